@@ -1,0 +1,615 @@
+/*
+ * myqc_oracle.c -- CPU restatement of myQC's int2e / int1e arithmetic.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity oracle for the CUDA ERI
+ * engine.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load it.  The product (myqc_b200/) never links,
+ * imports or calls anything in oracle/.
+ *
+ * Parity status: the reference (Fortran) cannot be compiled in this image (no
+ * gfortran) and ships no per-integral golden vectors, so per-integral parity is
+ * pinned only through the reference's own SCF outputs: examples/O/singlet/MOLDEN,
+ * examples/Be/MOLDEN (1e-8) and examples/NO/MOLDEN (2e-7) -- see
+ * tests/test_oracle_pins.py and tests/golden/.
+ *
+ * Every routine cites the reference file:line it follows (paths under
+ * /root/reference/src).  Arrays are the 0-based contents of the Fortran
+ * DIMENSION(0:) arrays; xyz is Fortran xyz(0:nnuc-1,0:2) i.e. xyz[i + nnuc*c].
+ *
+ * Deliberate fidelity points:
+ *   T1  Pi is the float32 value widened to double (no D0 suffix in the source).
+ *   T2  Boys values come from the Ftab bytes, never from a formula.
+ *   T3  Boys start order Q = 3*(la+lb+lc+ld) with l* the SET's max l.
+ *   T4  screen is EIJ*EGH < 1e-14 only.
+ *   T5  BoysG is undefined for T >= 30 in the reference; we return 0.490 there
+ *       (the last defined branch); the term it scales is < 3e-15.
+ *   T7  NINT rounds half away from zero (lround).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* REAL(KIND=8),PARAMETER :: Pi = 3.1415926535897931  (int2e.f90:621, auxilary.f90:169,196,711) */
+static const double PI_REF = (double)3.1415926535897931f;
+
+#define FT(t, j) ft[(t) + 121 * (j)] /* Ft(0:120,0:22) column-major, int2e.f90:118 */
+
+/* ------------------------------------------------------------------ */
+/* auxilary.f90:290-312 factR8                                          */
+static double factR8(int n) {
+    double val = 1.0;
+    for (int i = n; i >= 2; --i) val = val * i;
+    return val;
+}
+
+/* auxilary.f90:265-285 BoysG (T5: value for T>=30 is our documented choice) */
+static double BoysG(double T) {
+    if (T >= 12.0 && T < 15.0)
+        return 0.4999489092 - 0.2473631686 * pow(T, -1.0) + 0.321180909 * pow(T, -2.0) -
+               0.3811559346 * pow(T, -3.0);
+    if (T >= 15.0 && T < 18.0)
+        return 0.4998436875 - 0.24249438 * pow(T, -1.0) + 0.24642845 * pow(T, -2.0);
+    if (T >= 18.0 && T < 24.0) return 0.499093162 - 0.2152832 * pow(T, -1.0);
+    return 0.490; /* 24<=T<30 in the reference; undefined beyond */
+}
+
+/* auxilary.f90:85-215 Boys, Boys1, Boys2, Boys3.  Fj has Q+1 entries. */
+static void Boys(double *Fj, int Q, double T, const double *ft) {
+    if (T >= 0 && T < 12) { /* Boys1 :130-162 */
+        for (int j = 0; j <= Q; ++j) Fj[j] = 0.0;
+        int Tk = (int)lround(T * 10); /* NINT, :152 */
+        for (int k = 0; k <= 6; ++k)
+            Fj[Q] = Fj[Q] + FT(Tk, Q + k) * pow(Tk / 10.0 - T, (double)k) / factR8(k);
+        for (int j = Q - 1; j >= 0; --j) Fj[j] = (2 * T * Fj[j + 1] + exp(-T)) / (2.0 * j + 1.0);
+    } else if (T >= 12 && T < 2 * Q + 36) { /* Boys2 :167-189 */
+        double g = BoysG(T);
+        Fj[0] = 0.5 * pow(PI_REF, 0.5) * pow(T, -0.5) - exp(-T) * g / T;
+        for (int j = 1; j <= Q; ++j)
+            Fj[j] = pow(2.0 * T, -1.0) * ((2.0 * (j - 1) + 1) * Fj[j - 1] - exp(-T));
+    } else { /* Boys3 :194-215 */
+        Fj[0] = 0.5 * pow(PI_REF, 0.5) * pow(T, -0.5);
+        for (int j = 1; j <= Q; ++j) Fj[j] = pow(2.0 * T, -1.0) * (2.0 * (j - 1) + 1.0) * Fj[j - 1];
+    }
+}
+
+/* auxilary.f90:704-726 gtoD */
+static double gtoD(int l, double a) {
+    if (l == 0) return pow(2.0 * a / PI_REF, 3.0 / 4.0);
+    if (l == 1) return pow(128.0 * pow(a, 5.0) / pow(PI_REF, 3.0), 1.0 / 4.0);
+    return pow(2048.0 * pow(a, 7.0) / (9.0 * pow(PI_REF, 3.0)), 1.0 / 4.0);
+}
+
+/* ------------------------------------------------------------------ */
+/* R_NLM^j memoised recursion, auxilary.f90:22-80.                      */
+typedef struct {
+    int nmax, lmax, mmax, jmax; /* table is (-2:nmax,-2:lmax,-2:mmax,0:jmax) */
+    double *tab;
+    unsigned char *bol;
+} rtab_t;
+
+static inline size_t ridx(const rtab_t *r, int N, int L, int M, int j) {
+    return (size_t)(N + 2) +
+           (size_t)(r->nmax + 3) * ((size_t)(L + 2) + (size_t)(r->lmax + 3) * ((size_t)(M + 2) + (size_t)(r->mmax + 3) * (size_t)j));
+}
+
+static void RNLMj(double a, double b, double c, int N, int L, int M, int j, double al,
+                  const double *Fj, rtab_t *r) {
+    size_t id = ridx(r, N, L, M, j);
+    if (r->bol[id]) return;
+    if (N < 0 || L < 0 || M < 0) {
+        r->tab[id] = 0.0;
+        r->bol[id] = 1;
+        return;
+    } else if (N == 0 && L == 0 && M == 0) {
+        r->tab[id] = pow(-2.0 * al, (double)j) * Fj[j];
+        r->bol[id] = 1;
+        return;
+    }
+    if (N != 0) {
+        RNLMj(a, b, c, N - 1, L, M, j + 1, al, Fj, r);
+        RNLMj(a, b, c, N - 2, L, M, j + 1, al, Fj, r);
+        r->tab[id] = a * r->tab[ridx(r, N - 1, L, M, j + 1)] + (N - 1) * r->tab[ridx(r, N - 2, L, M, j + 1)];
+    } else if (L != 0) {
+        RNLMj(a, b, c, 0, L - 1, M, j + 1, al, Fj, r);
+        RNLMj(a, b, c, 0, L - 2, M, j + 1, al, Fj, r);
+        r->tab[id] = b * r->tab[ridx(r, 0, L - 1, M, j + 1)] + (L - 1) * r->tab[ridx(r, 0, L - 2, M, j + 1)];
+    } else {
+        RNLMj(a, b, c, 0, 0, M - 1, j + 1, al, Fj, r);
+        RNLMj(a, b, c, 0, 0, M - 2, j + 1, al, Fj, r);
+        r->tab[id] = c * r->tab[ridx(r, 0, 0, M - 1, j + 1)] + (M - 1) * r->tab[ridx(r, 0, 0, M - 2, j + 1)];
+    }
+    r->bol[id] = 1;
+}
+
+static void rtab_alloc(rtab_t *r, int nmax, int lmax, int mmax, int jmax) {
+    r->nmax = nmax; r->lmax = lmax; r->mmax = mmax; r->jmax = jmax;
+    size_t n = (size_t)(nmax + 3) * (lmax + 3) * (mmax + 3) * (jmax + 1);
+    r->tab = (double *)calloc(n, sizeof(double));      /* zeroed, int2e.f90:671-680 */
+    r->bol = (unsigned char *)calloc(n, 1);
+}
+static void rtab_free(rtab_t *r) { free(r->tab); free(r->bol); }
+
+/* ------------------------------------------------------------------ */
+/* Hermite expansion coefficients: getcoef / lrec / rrec, auxilary.f90:349-536.
+ * M(0:2, -2:imax, -2:jmax, -2:kmax) with imax=max(amax)+max(bmax), jmax=max(amax)+2, kmax=max(bmax)+2 */
+typedef struct {
+    int imax, jmax, kmax;
+    double *m;
+    unsigned char *f;
+} ctab_t;
+
+static inline size_t cidx(const ctab_t *t, int l, int i, int j, int k) {
+    return (size_t)l + 3 * ((size_t)(i + 2) + (size_t)(t->imax + 3) * ((size_t)(j + 2) + (size_t)(t->jmax + 3) * (size_t)(k + 2)));
+}
+
+static void rrec(ctab_t *t, int l, int i, int j, int k, const double *PA, const double *PB, double pp);
+
+static void lrec(ctab_t *t, int l, int i, int j, int k, const double *PA, const double *PB, double pp) {
+    size_t id = cidx(t, l, i, j, k);
+    if (t->f[id]) return;
+    if (i < 0 || j < 0 || k < 0 || i > j + k) { t->m[id] = 0.0; t->f[id] = 1; return; }
+    if (i == 0 && j == 0 && k == 0) { t->m[id] = 1.0; t->f[id] = 1; return; }
+    if (j <= k) { /* auxilary.f90:443-452 */
+        lrec(t, l, i - 1, j - 1, k, PA, PB, pp);
+        lrec(t, l, i, j - 1, k, PA, PB, pp);
+        lrec(t, l, i + 1, j - 1, k, PA, PB, pp);
+        rrec(t, l, i - 1, j, k - 1, PA, PB, pp);
+        rrec(t, l, i, j, k - 1, PA, PB, pp);
+        rrec(t, l, i + 1, j, k - 1, PA, PB, pp);
+        t->m[id] = t->m[cidx(t, l, i - 1, j, k - 1)] / (2.0 * pp) + PB[l] * t->m[cidx(t, l, i, j, k - 1)] +
+                   (i + 1) * t->m[cidx(t, l, i + 1, j, k - 1)];
+    } else { /* :453-462 */
+        lrec(t, l, i - 1, j - 1, k, PA, PB, pp);
+        lrec(t, l, i, j - 1, k, PA, PB, pp);
+        lrec(t, l, i + 1, j - 1, k, PA, PB, pp);
+        t->m[id] = t->m[cidx(t, l, i - 1, j - 1, k)] / (2.0 * pp) + PA[l] * t->m[cidx(t, l, i, j - 1, k)] +
+                   (i + 1) * t->m[cidx(t, l, i + 1, j - 1, k)];
+        rrec(t, l, i - 1, j, k - 1, PA, PB, pp);
+        rrec(t, l, i, j, k - 1, PA, PB, pp);
+        rrec(t, l, i + 1, j, k - 1, PA, PB, pp);
+    }
+    t->f[id] = 1;
+}
+
+static void rrec(ctab_t *t, int l, int i, int j, int k, const double *PA, const double *PB, double pp) {
+    /* auxilary.f90:473-536: identical body to lrec */
+    size_t id = cidx(t, l, i, j, k);
+    if (t->f[id]) return;
+    if (i < 0 || j < 0 || k < 0 || i > j + k) { t->m[id] = 0.0; t->f[id] = 1; return; }
+    if (i == 0 && j == 0 && k == 0) { t->m[id] = 1.0; t->f[id] = 1; return; }
+    if (j <= k) {
+        lrec(t, l, i - 1, j - 1, k, PA, PB, pp);
+        lrec(t, l, i, j - 1, k, PA, PB, pp);
+        lrec(t, l, i + 1, j - 1, k, PA, PB, pp);
+        rrec(t, l, i - 1, j, k - 1, PA, PB, pp);
+        rrec(t, l, i, j, k - 1, PA, PB, pp);
+        rrec(t, l, i + 1, j, k - 1, PA, PB, pp);
+        t->m[id] = t->m[cidx(t, l, i - 1, j, k - 1)] / (2.0 * pp) + PB[l] * t->m[cidx(t, l, i, j, k - 1)] +
+                   (i + 1) * t->m[cidx(t, l, i + 1, j, k - 1)];
+    } else {
+        lrec(t, l, i - 1, j - 1, k, PA, PB, pp);
+        lrec(t, l, i, j - 1, k, PA, PB, pp);
+        lrec(t, l, i + 1, j - 1, k, PA, PB, pp);
+        t->m[id] = t->m[cidx(t, l, i - 1, j - 1, k)] / (2.0 * pp) + PA[l] * t->m[cidx(t, l, i, j - 1, k)] +
+                   (i + 1) * t->m[cidx(t, l, i + 1, j - 1, k)];
+        rrec(t, l, i - 1, j, k - 1, PA, PB, pp);
+        rrec(t, l, i, j, k - 1, PA, PB, pp);
+        rrec(t, l, i + 1, j, k - 1, PA, PB, pp);
+    }
+    t->f[id] = 1;
+}
+
+/* getcoef, auxilary.f90:349-401.  amax/bmax are per-axis (all three equal in every caller). */
+static void getcoef(ctab_t *t, const double *PA, const double *PB, double aa, double bb,
+                    const int *amax, const int *bmax) {
+    int am = amax[0], bm = bmax[0];
+    for (int l = 1; l < 3; ++l) { if (amax[l] > am) am = amax[l]; if (bmax[l] > bm) bm = bmax[l]; }
+    t->imax = am + bm; t->jmax = am + 2; t->kmax = bm + 2;
+    size_t n = 3 * (size_t)(t->imax + 3) * (t->jmax + 3) * (t->kmax + 3);
+    t->m = (double *)calloc(n, sizeof(double));
+    t->f = (unsigned char *)calloc(n, 1);
+    double pp = aa + bb;
+    for (int l = 0; l < 3; ++l) {
+        lrec(t, l, 0, amax[l], bmax[l], PA, PB, pp);
+        rrec(t, l, 0, amax[l], bmax[l], PA, PB, pp);
+    }
+}
+static void ctab_free(ctab_t *t) { free(t->m); free(t->f); }
+
+/* ------------------------------------------------------------------ */
+/* getDk, auxilary.f90:541-633.  seta = setinfo(1+a*setl+1 : ...), i.e. seta[0]=#orbs,
+ * seta[1]=max l, seta[2]=centre, seta[3+i]=orbital ids.  basinfo(1+5*o+2)=l, (1+5*o+3)=ori. */
+typedef struct {
+    int kmax;      /* last valid index, -1 if none */
+    double Dk[512];
+    int Ck[512];
+    int Ok[1024];
+} dk_t;
+
+static void orb_lvec(const int *basinfo, int orb, int *ll) {
+    int ori = basinfo[1 + 5 * orb + 3];
+    int l = basinfo[1 + 5 * orb + 2];
+    if (ori == -1) { ll[0] = l; ll[1] = l; ll[2] = l; }
+    else { ll[0] = ll[1] = ll[2] = 0; ll[ori] = l; }
+}
+
+static void getDk(const ctab_t *coef, const int *seta, const int *setb, const double *basa,
+                  const double *basb, const int *basinfo, dk_t *o, double EIJ, double aa, double bb) {
+    const double tol = 0.1e-15;
+    o->kmax = -1;
+    for (int i = 0; i < seta[0]; ++i) {
+        int orba = seta[3 + i];
+        int ll[3]; orb_lvec(basinfo, orba, ll);
+        for (int j = 0; j < setb[0]; ++j) {
+            int orbb = setb[3 + j];
+            int rr[3]; orb_lvec(basinfo, orbb, rr);
+            int Nmax = ll[0] + rr[0], Lmax = ll[1] + rr[1], Mmax = ll[2] + rr[2];
+            for (int M = 0; M <= Mmax; ++M) {
+                if (fabs(coef->m[cidx(coef, 2, M, ll[2], rr[2])]) < tol) continue;
+                for (int L = 0; L <= Lmax; ++L) {
+                    if (fabs(coef->m[cidx(coef, 1, L, ll[1], rr[1])]) < tol) continue;
+                    for (int N = 0; N <= Nmax; ++N) {
+                        if (fabs(coef->m[cidx(coef, 0, N, ll[0], rr[0])]) < tol) continue;
+                        int k = ++o->kmax;
+                        o->Ck[k] = 300 * N + 20 * L + M;
+                        double d = coef->m[cidx(coef, 0, N, ll[0], rr[0])] * coef->m[cidx(coef, 1, L, ll[1], rr[1])] *
+                                   coef->m[cidx(coef, 2, M, ll[2], rr[2])];
+                        d = d * EIJ * gtoD(basinfo[1 + 5 * orba + 2], aa) * gtoD(basinfo[1 + 5 * orbb + 2], bb);
+                        d = d * basa[i] * basb[j];
+                        o->Dk[k] = d;
+                        o->Ok[2 * k] = orba;
+                        o->Ok[2 * k + 1] = orbb;
+                    }
+                }
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ */
+/* Per set-pair quantities, int2e.f90:193-229 (and :236-263 for the ket). */
+typedef struct {
+    double p, PP[3], E;
+    int lmax; /* set a max l + set b max l */
+    dk_t dk;
+} setpair_t;
+
+static void make_setpair(setpair_t *sp, int a, int b, int nnuc, const double *xyz, const double *set,
+                         const int *setinfo, const double *bas, const int *basinfo) {
+    int setl = setinfo[1], OpS = basinfo[0];
+    double aa = set[a], bb = set[b];
+    int u = setinfo[1 + a * setl + 3], v = setinfo[1 + b * setl + 3];
+    int la = setinfo[1 + a * setl + 2], lb = setinfo[1 + b * setl + 2];
+    double p = aa + bb, mm = aa * bb, AB[3], PA[3], PB[3];
+    for (int i = 0; i < 3; ++i) {
+        AB[i] = xyz[u + nnuc * i] - xyz[v + nnuc * i];
+        sp->PP[i] = (aa * xyz[u + nnuc * i] + bb * xyz[v + nnuc * i]) / p;
+        PA[i] = sp->PP[i] - xyz[u + nnuc * i];
+        PB[i] = sp->PP[i] - xyz[v + nnuc * i];
+    }
+    sp->p = p;
+    sp->E = exp(-mm * (pow(AB[0], 2.0) + pow(AB[1], 2.0) + pow(AB[2], 2.0)) / p);
+    sp->lmax = la + lb;
+    int amax[3] = {la + 2, la + 2, la + 2}, bmax[3] = {lb + 2, lb + 2, lb + 2}; /* int2e.f90:227 */
+    ctab_t coef;
+    getcoef(&coef, PA, PB, aa, bb, amax, bmax);
+    getDk(&coef, &setinfo[1 + a * setl + 1], &setinfo[1 + b * setl + 1], &bas[a * OpS], &bas[b * OpS],
+          basinfo, &sp->dk, sp->E, aa, bb);
+    ctab_free(&coef);
+}
+
+/* Only the pre-exponential (for the screen), int2e.f90:248-257 */
+static double setpair_E(int c, int d, int nnuc, const double *xyz, const double *set, const int *setinfo) {
+    int setl = setinfo[1];
+    double cc = set[c], dd = set[d];
+    int s = setinfo[1 + c * setl + 3], t = setinfo[1 + d * setl + 3];
+    double q = cc + dd, nn = cc * dd, CD[3];
+    for (int j = 0; j < 3; ++j) CD[j] = xyz[s + nnuc * j] - xyz[t + nnuc * j];
+    return exp(-nn * (pow(CD[0], 2.0) + pow(CD[1], 2.0) + pow(CD[2], 2.0)) / q);
+}
+
+/* clmnew, int2e.f90:618-726.  sink(i,j,g,h,value) receives every kept term. */
+typedef void (*sink_fn)(void *ctx, int i, int j, int g, int h, double v);
+
+static void clmnew(const setpair_t *ab, const setpair_t *cd, int norb, const double *ft, sink_fn sink, void *ctx) {
+    double p = ab->p, q = cd->p, PQ[3];
+    for (int j = 0; j < 3; ++j) PQ[j] = ab->PP[j] - cd->PP[j]; /* :266-268 */
+    int S = ab->lmax + cd->lmax;  /* Nmax = Lmax = Mmax, :654-656 */
+    int Q = 3 * S;
+    double Fj[16];
+    double ll = 2 * pow(PI_REF, 2.5) / (p * q * sqrt(p + q));                                  /* :663 */
+    double TT = p * q * (pow(PQ[0], 2.0) + pow(PQ[1], 2.0) + pow(PQ[2], 2.0)) / (p + q);      /* :664 */
+    for (int i = 0; i <= Q; ++i) Fj[i] = 0.0;
+    Boys(Fj, Q, TT, ft);
+    rtab_t r;
+    rtab_alloc(&r, S, S, S, Q);
+    for (int k = 0; k <= ab->dk.kmax; ++k) {
+        int i = ab->dk.Ok[2 * k], j = ab->dk.Ok[2 * k + 1];
+        if (j < i) continue;
+        for (int kp = 0; kp <= cd->dk.kmax; ++kp) {
+            int g = cd->dk.Ok[2 * kp], h = cd->dk.Ok[2 * kp + 1];
+            if (h < g) continue;
+            if ((g * norb + h) < (i * norb + j)) continue;
+            int foo = ab->dk.Ck[k];
+            int N = foo / 300; foo -= N * 300; int L = foo / 20; int M = foo - L * 20;
+            foo = cd->dk.Ck[kp];
+            int Np = foo / 300; foo -= Np * 300; int Lp = foo / 20; int Mp = foo - Lp * 20;
+            RNLMj(PQ[0], PQ[1], PQ[2], N + Np, L + Lp, M + Mp, 0, p * q / (p + q), Fj, &r);
+            double sgn = ((Np + Lp + Mp) & 1) ? -1.0 : 1.0;
+            double v = sgn * ll * cd->dk.Dk[kp] * r.tab[ridx(&r, N + Np, L + Lp, M + Mp, 0)] * ab->dk.Dk[k]; /* :716-717 */
+            sink(ctx, i, j, g, h, v);
+        }
+    }
+    rtab_free(&r);
+}
+
+/* ------------------------------------------------------------------ */
+/* Literal dense driver: proc2e, int2e.f90:78-351 (+ fillsym :540-554). */
+typedef struct { double *xx; long long n; } dense_ctx;
+static void dense_sink(void *c, int i, int j, int g, int h, double v) {
+    dense_ctx *d = (dense_ctx *)c;
+    long long n = d->n;
+    d->xx[i + n * (j + n * (g + n * (long long)h))] += v;
+}
+
+static void null_sink(void *c, int i, int j, int g, int h, double v) {
+    (void)i; (void)j; (void)g; (void)h;
+    *(volatile double *)c += v;
+}
+
+static void fillsym(double *xx, long long n, int i, int j, int g, int h) {
+#define XX(a, b, c, d) xx[(a) + n * ((b) + n * ((c) + n * (long long)(d)))]
+    double v = XX(i, j, g, h);
+    XX(i, j, h, g) = v; XX(j, i, g, h) = v; XX(j, i, h, g) = v; XX(g, h, i, j) = v;
+    XX(g, h, j, i) = v; XX(h, g, i, j) = v; XX(h, g, j, i) = v;
+#undef XX
+}
+
+/* a_stride/a_offset: process only sets a with a % a_stride == a_offset (bounded CPU-baseline
+ * samples); pass 1,0 for the full reference loop.  stats[0] = surviving ordered set quartets
+ * (clmnew calls), stats[1] = ordered quartets visited.  do_fill: run the fillsym pass. */
+int oracle_int2e_dense(int nnuc, const double *xyz, const double *set, const int *setinfo,
+                       const double *bas, const int *basinfo, const double *ft, double *xx,
+                       int do_fill, int a_stride, int a_offset, long long *stats) {
+    int nset = setinfo[0];
+    long long norb = basinfo[1];
+    if (xx) memset(xx, 0, sizeof(double) * norb * norb * norb * norb);
+    dense_ctx ctx = {xx, norb};
+    long long ncall = 0, nvisit = 0;
+    double sink_acc = 0.0;
+    setpair_t *ab = (setpair_t *)malloc(sizeof(setpair_t));
+    setpair_t *cd = (setpair_t *)malloc(sizeof(setpair_t));
+    for (int a = 0; a < nset; ++a) {
+        if (a % a_stride != a_offset) continue;
+        for (int b = 0; b < nset; ++b) {
+            make_setpair(ab, a, b, nnuc, xyz, set, setinfo, bas, basinfo);
+            for (int c = 0; c < nset; ++c) {
+                for (int d = 0; d < nset; ++d) {
+                    ++nvisit;
+                    double EGH = setpair_E(c, d, nnuc, xyz, set, setinfo);
+                    if (EGH * ab->E < 1.0e-14) continue; /* :257 */
+                    make_setpair(cd, c, d, nnuc, xyz, set, setinfo, bas, basinfo);
+                    ++ncall;
+                    if (xx) clmnew(ab, cd, (int)norb, ft, dense_sink, &ctx);
+                    else { /* timing-only mode still does the arithmetic */
+                        clmnew(ab, cd, (int)norb, ft, null_sink, &sink_acc);
+                    }
+                }
+            }
+        }
+    }
+    free(ab); free(cd);
+    if (xx && do_fill) { /* :290-304 */
+        for (int i = 0; i < norb; ++i)
+            for (int j = i; j < norb; ++j) {
+                for (int h = j; h < norb; ++h) fillsym(xx, norb, i, j, i, h);
+                for (int g = i + 1; g < norb; ++g)
+                    for (int h = g; h < norb; ++h) fillsym(xx, norb, i, j, g, h);
+            }
+    }
+    if (stats) { stats[0] = ncall; stats[1] = nvisit; }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* Packed canonical layout shared with the product's C-ABI:
+ *   pair index P(i,j) = i*norb - i(i-1)/2 + (j-i), i<=j
+ *   quartet index     = P*npair - P(P-1)/2 + (P'-P), P<=P'                      */
+static inline long long pair_index(long long i, long long j, long long n) { return i * n - i * (i - 1) / 2 + (j - i); }
+
+typedef struct { double *out; long long norb, npair; } packed_ctx;
+static void packed_sink(void *c, int i, int j, int g, int h, double v) {
+    packed_ctx *d = (packed_ctx *)c;
+    long long P = pair_index(i, j, d->norb), Pp = pair_index(g, h, d->norb);
+    d->out[P * d->npair - P * (P - 1) / 2 + (Pp - P)] += v;
+}
+
+/* Canonical driver: the same per-quartet arithmetic as the literal loop (same ordered set
+ * quartets contribute to each canonical integral, in the same a,b,c,d order), but ordered set
+ * quartets that can only produce filtered-out terms are not visited, and set-pair tables are
+ * built once.  out has npair(npair+1)/2 entries.  Equality with the literal driver is tested
+ * on the small examples (tests/test_oracle_pins.py). */
+int oracle_int2e_packed(int nnuc, const double *xyz, const double *set, const int *setinfo,
+                        const double *bas, const int *basinfo, const double *ft, double *out) {
+    int nset = setinfo[0], setl = setinfo[1];
+    long long norb = basinfo[1], npair = norb * (norb + 1) / 2;
+    memset(out, 0, sizeof(double) * (size_t)(npair * (npair + 1) / 2));
+    packed_ctx ctx = {out, norb, npair};
+    /* min/max orbital id per set */
+    int *omin = (int *)malloc(sizeof(int) * nset), *omax = (int *)malloc(sizeof(int) * nset);
+    for (int s = 0; s < nset; ++s) {
+        const int *si = &setinfo[1 + s * setl + 1];
+        omin[s] = 1 << 30; omax[s] = -1;
+        for (int i = 0; i < si[0]; ++i) { if (si[3 + i] < omin[s]) omin[s] = si[3 + i]; if (si[3 + i] > omax[s]) omax[s] = si[3 + i]; }
+    }
+    /* all ordered set pairs that can hold a function pair with i<=j and E >= 1e-14 */
+    long long np = 0;
+    int *pa = (int *)malloc(sizeof(int) * (size_t)nset * nset), *pb = (int *)malloc(sizeof(int) * (size_t)nset * nset);
+    for (int a = 0; a < nset; ++a)
+        for (int b = 0; b < nset; ++b) {
+            if (omax[b] < omin[a]) continue; /* every j<i: all terms skipped at int2e.f90:686/692 */
+            if (setpair_E(a, b, nnuc, xyz, set, setinfo) < 1.0e-14) continue; /* E<=1 so product fails too */
+            pa[np] = a; pb[np] = b; ++np;
+        }
+    setpair_t *sp = (setpair_t *)malloc(sizeof(setpair_t) * (size_t)np);
+    for (long long k = 0; k < np; ++k) make_setpair(&sp[k], pa[k], pb[k], nnuc, xyz, set, setinfo, bas, basinfo);
+    for (long long k = 0; k < np; ++k)
+        for (long long m = 0; m < np; ++m) {
+            if (sp[m].E * sp[k].E < 1.0e-14) continue;
+            /* ket keys g*norb+h must be able to reach >= smallest bra key */
+            if ((long long)omax[pa[m]] * norb + omax[pb[m]] < (long long)omin[pa[k]] * norb + omin[pb[k]]) continue;
+            clmnew(&sp[k], &sp[m], (int)norb, ft, packed_sink, &ctx);
+        }
+    free(sp); free(pa); free(pb); free(omin); free(omax);
+    return 0;
+}
+
+/* Row oracle for molecules whose packed array is too big for a second host copy:
+ * rows[r] is a canonical bra pair index P; out[r*npair + P'] receives (P|P') for every P'
+ * (entries with P' < P are produced with the roles the reference uses, i.e. as (P'|P)). */
+typedef struct { double *row; long long norb, npair, P; int want_lower; } row_ctx;
+static void row_sink(void *c, int i, int j, int g, int h, double v) {
+    row_ctx *d = (row_ctx *)c;
+    long long P = pair_index(i, j, d->norb), Pp = pair_index(g, h, d->norb);
+    if (!d->want_lower) { if (P == d->P) d->row[Pp] += v; }
+    else { if (Pp == d->P && P != Pp) d->row[P] += v; }
+}
+
+int oracle_int2e_rows(int nnuc, const double *xyz, const double *set, const int *setinfo,
+                      const double *bas, const int *basinfo, const double *ft, int nrows,
+                      const long long *rows, double *out) {
+    int nset = setinfo[0], setl = setinfo[1];
+    long long norb = basinfo[1], npair = norb * (norb + 1) / 2;
+    memset(out, 0, sizeof(double) * (size_t)nrows * npair);
+    /* set membership of each orbital */
+    setpair_t *ab = (setpair_t *)malloc(sizeof(setpair_t));
+    setpair_t *cd = (setpair_t *)malloc(sizeof(setpair_t));
+    double *Eall = (double *)malloc(sizeof(double) * (size_t)nset * nset);
+    for (int c = 0; c < nset; ++c)
+        for (int d = 0; d < nset; ++d) Eall[(size_t)c * nset + d] = setpair_E(c, d, nnuc, xyz, set, setinfo);
+    for (int r = 0; r < nrows; ++r) {
+        long long P = rows[r];
+        /* invert P -> (i,j) */
+        long long i = 0;
+        while (pair_index(i + 1, i + 1, norb) <= P) ++i;
+        long long j = i + (P - pair_index(i, i, norb));
+        row_ctx ctx = {&out[(size_t)r * npair], norb, npair, P, 0};
+        for (int a = 0; a < nset; ++a) {
+            const int *sa = &setinfo[1 + a * setl + 1];
+            int has_i = 0; for (int k = 0; k < sa[0]; ++k) if (sa[3 + k] == i) has_i = 1;
+            if (!has_i) continue;
+            for (int b = 0; b < nset; ++b) {
+                const int *sb = &setinfo[1 + b * setl + 1];
+                int has_j = 0; for (int k = 0; k < sb[0]; ++k) if (sb[3 + k] == j) has_j = 1;
+                if (!has_j) continue;
+                if (Eall[(size_t)a * nset + b] < 1.0e-14) continue;
+                make_setpair(ab, a, b, nnuc, xyz, set, setinfo, bas, basinfo);
+                for (int c = 0; c < nset; ++c)
+                    for (int d = 0; d < nset; ++d) {
+                        if (Eall[(size_t)c * nset + d] * ab->E < 1.0e-14) continue;
+                        make_setpair(cd, c, d, nnuc, xyz, set, setinfo, bas, basinfo);
+                        ctx.want_lower = 0; clmnew(ab, cd, (int)norb, ft, row_sink, &ctx); /* (P|P'>=P) */
+                        ctx.want_lower = 1; clmnew(cd, ab, (int)norb, ft, row_sink, &ctx); /* (P'<P|P) */
+                    }
+            }
+        }
+    }
+    free(ab); free(cd); free(Eall);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* int1e: overlap, kinetic, nuclear attraction; int1e.f90:132-280,321-582.
+ * Needed only to anchor the oracle to the reference's MOLDEN orbital energies.
+ * S, H are norb x norb column-major. */
+int oracle_int1e(int nnuc, const double *xyz, const int *atoms, const double *set, const int *setinfo,
+                 const double *bas, const int *basinfo, const double *ft, double *S, double *H) {
+    int nset = setinfo[0], setl = setinfo[1], OpS = basinfo[0];
+    long long norb = basinfo[1];
+    memset(S, 0, sizeof(double) * norb * norb);
+    memset(H, 0, sizeof(double) * norb * norb);
+    dk_t *dk = (dk_t *)malloc(sizeof(dk_t));
+    for (int a = 0; a < nset; ++a) {
+        double aa = set[a];
+        int u = setinfo[1 + a * setl + 3];
+        int la = setinfo[1 + a * setl + 2];
+        for (int b = 0; b < nset; ++b) {
+            double bb = set[b];
+            int v = setinfo[1 + b * setl + 3];
+            int lb = setinfo[1 + b * setl + 2];
+            int amax[3] = {la, la, la}, bmax[3] = {lb + 2, lb + 2, lb + 2}; /* :216-232 */
+            double p = aa + bb, m = aa * bb, AB[3], PP[3], PA[3], PB[3];
+            for (int i = 0; i < 3; ++i) {
+                AB[i] = xyz[u + nnuc * i] - xyz[v + nnuc * i];
+                PP[i] = (aa * xyz[u + nnuc * i] + bb * xyz[v + nnuc * i]) / p;
+                PA[i] = PP[i] - xyz[u + nnuc * i];
+                PB[i] = PP[i] - xyz[v + nnuc * i];
+            }
+            double EIJ = exp(-m * (pow(AB[0], 2.0) + pow(AB[1], 2.0) + pow(AB[2], 2.0)) / p);
+            if (EIJ < 1.0e-14) continue; /* :246-248 */
+            ctab_t coef;
+            getcoef(&coef, PA, PB, aa, bb, amax, bmax);
+            const int *seta = &setinfo[1 + a * setl + 1], *setb = &setinfo[1 + b * setl + 1];
+            const double *basa = &bas[a * OpS], *basb = &bas[b * OpS];
+            getDk(&coef, seta, setb, basa, basb, basinfo, dk, EIJ, aa, bb);
+#define C(l, i, j, k) coef.m[cidx(&coef, l, i, j, k)]
+            for (int i = 0; i < seta[0]; ++i) {
+                int orba = seta[3 + i];
+                int na[3]; orb_lvec(basinfo, orba, na);
+                for (int j = 0; j < setb[0]; ++j) {
+                    int orbb = setb[3 + j];
+                    int nb[3]; orb_lvec(basinfo, orbb, nb);
+                    /* overlap :321-386 */
+                    double temp = EIJ * pow(PI_REF / p, 3.0 / 2.0) * basa[i] * basb[j];
+                    temp = temp * gtoD(basinfo[1 + 5 * orba + 2], aa);
+                    temp = temp * gtoD(basinfo[1 + 5 * orbb + 2], bb);
+                    temp = temp * C(0, 0, na[0], nb[0]) * C(1, 0, na[1], nb[1]) * C(2, 0, na[2], nb[2]);
+                    S[orba + norb * orbb] += temp;
+                    /* kinetic :391-474 */
+                    double val = 0.0;
+                    for (int w = 0; w < 3; ++w) {
+                        int w1 = (w + 1) % 3, w2 = (w + 2) % 3;
+                        double t = nb[w] * (nb[w] - 1) * C(w, 0, na[w], nb[w] - 2);
+                        t = t - 2.0 * bb * nb[w] * C(w, 0, na[w], nb[w]);
+                        t = t - 2.0 * bb * (nb[w] + 1) * C(w, 0, na[w], nb[w]);
+                        t = t + 4.0 * pow(bb, 2.0) * C(w, 0, na[w], nb[w] + 2);
+                        t = t * C(w1, 0, na[w1], nb[w1]) * C(w2, 0, na[w2], nb[w2]);
+                        val = val + t;
+                    }
+                    val = val * (-0.5) * EIJ * pow(PI_REF / p, 3.0 / 2.0);
+                    val = val * basa[i] * basb[j];
+                    val = val * gtoD(basinfo[1 + 5 * orba + 2], aa);
+                    val = val * gtoD(basinfo[1 + 5 * orbb + 2], bb);
+                    H[orba + norb * orbb] += val;
+                }
+            }
+#undef C
+            /* coulomb :479-582 */
+            int S3 = la + lb, Q = 3 * S3;
+            for (int c = 0; c < nnuc; ++c) {
+                double CP[3], Fj[16];
+                for (int i = 0; i < 3; ++i) CP[i] = xyz[c + nnuc * i] - PP[i];
+                double TT = p * (pow(CP[0], 2.0) + pow(CP[1], 2.0) + pow(CP[2], 2.0));
+                for (int i = 0; i <= Q; ++i) Fj[i] = 0.0;
+                Boys(Fj, Q, TT, ft);
+                rtab_t r;
+                rtab_alloc(&r, S3, S3, S3, Q);
+                for (int k = 0; k <= dk->kmax; ++k) {
+                    int foo = dk->Ck[k];
+                    int N = foo / 300; foo -= N * 300; int L = foo / 20; int M = foo - L * 20;
+                    RNLMj(-CP[0], -CP[1], -CP[2], N, L, M, 0, p, Fj, &r);
+                    double temp = atoms[c] * (2.0 * PI_REF / p) * r.tab[ridx(&r, N, L, M, 0)] * dk->Dk[k];
+                    H[dk->Ok[2 * k] + norb * dk->Ok[2 * k + 1]] -= temp;
+                }
+                rtab_free(&r);
+            }
+            ctab_free(&coef);
+        }
+    }
+    free(dk);
+    return 0;
+}
+
+/* Exposed for unit tests of the Boys restatement. */
+void oracle_boys(double *Fj, int Q, double T, const double *ft) { Boys(Fj, Q, T, ft); }
