@@ -1,0 +1,135 @@
+/*
+ * myqc_eri.h -- C-ABI of the B200-native two-electron-integral (ERI) engine that replaces
+ * myQC's `int2e` hot path.
+ *
+ * The reference has no FFI/plugin interface: its boundary is (i) the executable `int2e`
+ * spawned by the driver (src/myQC/myQC.f90:54) and (ii) inside it the single call
+ *     CALL proc2e(bas,basinfo,atoms,options,fmem,nnuc,xyz,set,setinfo,maxL)
+ * (src/integrals/int2e.f90:66, interface :78-112).  The entry points below are what an
+ * iso_c_binding shim for that call binds (INTEGRATION.md shows the Fortran side), plus the
+ * file-level pieces of PROGRAM int2e (int2e.f90:14-69) used by our drop-in `int2e` binary.
+ *
+ * Conventions
+ *   - plain C types only; every array is the 0-based content of the Fortran DIMENSION(0:)
+ *     array of the same name, passed by reference.
+ *   - xyz is Fortran xyz(0:nnuc-1,0:2): element (i,c) at xyz[i + nnuc*c], bohr.
+ *   - set[nset], setinfo[2+setl*nset] (setinfo[0]=nset, setinfo[1]=setl=7),
+ *     bas[ops*nset] (ops=4), basinfo[2+5*norb] (basinfo[0]=ops, basinfo[1]=norb):
+ *     exactly what buildBasis produces (src/myQC/basis.f90:101-205).
+ *   - ftab[t + 121*j] = Ft(t,j), t=0..120, j=0..22: the bytes of the `Ftab` record
+ *     (int2e.f90:118,161-163).  Never regenerated from a formula.
+ *   - caller owns all pointers; the library copies inputs, owns all device memory, keeps
+ *     nothing after return (plans own their device buffers until destroyed).
+ *   - return 0 on success, negative MYQC_ERR_* otherwise; the library never exits the process.
+ *     The shim maps non-zero to `touch error` (int2e.f90:174-178).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns
+ *     MYQC_ERR_NO_DEVICE.
+ *
+ * Packed layout (8-fold-symmetry-unique integrals)
+ *   pair index   P(i,j) = i*norb - i(i-1)/2 + (j-i),       0 <= i <= j < norb
+ *   npair        = norb(norb+1)/2
+ *   quartet index(P,P') = P*npair - P(P-1)/2 + (P'-P),     P <= P'
+ *   P is monotone in the reference's key i*norb+j, so {P <= P'} is exactly the reference's
+ *   canonical set (int2e.f90:686,692,695).
+ */
+#ifndef MYQC_ERI_H
+#define MYQC_ERI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MYQC_OK 0
+#define MYQC_ERR_NO_DEVICE (-1)   /* no CUDA device / driver */
+#define MYQC_ERR_CUDA (-2)        /* a CUDA call failed; see myqc_last_error() */
+#define MYQC_ERR_UNSUPPORTED (-3) /* l > 1, or a set layout other than S / SP / P */
+#define MYQC_ERR_BAD_ARG (-4)     /* inconsistent sizes / null pointers */
+#define MYQC_ERR_IO (-5)          /* file missing or malformed */
+#define MYQC_ERR_NOMEM (-6)       /* host or device allocation failed */
+
+/* Human-readable description of the last error on this thread ("" if none). */
+const char *myqc_last_error(void);
+
+/* Number of visible CUDA devices (0 if none; never fails). */
+int myqc_device_count(void);
+
+/* ---- one-shot calls with HOST buffers: the body of proc2e (int2e.f90:78-351) ---------------
+ * xx:     out, caller-allocated 8*norb^4 bytes, Fortran XX(0:n-1,0:n-1,0:n-1,0:n-1) column-major,
+ *         offset of (i,j,g,h) = i + n*(j + n*(g + n*h)), all 8 symmetry images filled
+ *         (what fillsym leaves, int2e.f90:290-304,540-554).
+ * packed: out, caller-allocated npair(npair+1)/2 doubles, layout above.
+ * ngpu:   number of devices to shard over (1..myqc_device_count()); 0 = all visible.      */
+int myqc_eri_dense(int nnuc, const double *xyz, int nset, int setl, const double *set,
+                   const int32_t *setinfo, int ops, const double *bas, const int32_t *basinfo,
+                   const double *ftab, double *xx, int ngpu);
+
+int myqc_eri_packed(int nnuc, const double *xyz, int nset, int setl, const double *set,
+                    const int32_t *setinfo, int ops, const double *bas, const int32_t *basinfo,
+                    const double *ftab, double *packed, int ngpu);
+
+/* ---- plan API: device-resident execution, one plan per (GPU, shard) -------------------------
+ * A plan holds the shell-pair tables of one shard of the canonical quartet space on one device.
+ * Shard s of nshards owns a contiguous block of rows of the packed array (rows = bra pair index
+ * P), cut at shell boundaries and balanced by model flops; shards are independent (no
+ * collective).  nshards=1 is the whole problem.                                               */
+typedef struct myqc_eri_plan myqc_eri_plan;
+
+int myqc_eri_plan_create(int nnuc, const double *xyz, int nset, int setl, const double *set,
+                         const int32_t *setinfo, int ops, const double *bas,
+                         const int32_t *basinfo, const double *ftab, int device, int shard,
+                         int nshards, myqc_eri_plan **plan);
+
+/* Offset (in doubles) of this shard's slice inside the full packed array, and its length. */
+int64_t myqc_eri_plan_out_offset(const myqc_eri_plan *plan);
+int64_t myqc_eri_plan_out_elems(const myqc_eri_plan *plan);
+
+/* Compute the shard: d_out is a DEVICE pointer to myqc_eri_plan_out_elems() doubles on the
+ * plan's device; stream is a cudaStream_t (NULL = default stream).  Asynchronous: returns
+ * after enqueueing.  Every element of the slice is written (zeros where the reference's
+ * screen leaves zeros).                                                                      */
+int myqc_eri_plan_execute(myqc_eri_plan *plan, double *d_out, void *stream);
+
+/* Work statistics of the shard (all optional, may be NULL):
+ *   nquartets[6]  canonical primitive quartets surviving the reference screen per class
+ *                 {0,0},{0,1},{0,2},{1,1},{1,2},{2,2} (class = #SP sets in bra pair, ket pair)
+ *   model_flops   sum_class nquartets*W_class, W = {60,99,228,228,693,2691}
+ *   nlaunch       kernels one execute() enqueues                                              */
+int myqc_eri_plan_stats(const myqc_eri_plan *plan, int64_t *nquartets, double *model_flops,
+                        int *nlaunch);
+
+void myqc_eri_plan_destroy(myqc_eri_plan *plan);
+
+/* Expand a packed DEVICE array into the dense DEVICE array XX(n,n,n,n) (all 8 images).      */
+int myqc_eri_expand_dense(const double *d_packed, int norb, double *d_xx, void *stream);
+
+/* ---- file layer of PROGRAM int2e (int2e.f90:14-69) ------------------------------------------ */
+/* getenv, src/myQC/env.f90:16-73: read envdat / nucpos / fmem from `dir`.
+ * atoms[cap_nuc], xyz[3*cap_nuc] (Fortran layout with leading dim = returned nnuc),
+ * options[cap_opt].                                                                          */
+int myqc_read_env(const char *dir, int cap_nuc, int cap_opt, int *nnuc, int *nelcA, int *nelcB,
+                  int32_t *atoms, double *xyz, double *fmem, int *nopt, int32_t *options);
+
+/* buildBasis, src/myQC/basis.f90:23-226.  First call with null outputs to get sizes.
+ * Also (re)writes `basinfo` and `setinfo` text files into out_dir unless out_dir is NULL.    */
+int myqc_build_basis(const char *mybasis_path, int bkey, int nnuc, const int32_t *atoms,
+                     int *nset_cap, int *norb_cap, double *set, int32_t *setinfo, double *bas,
+                     int32_t *basinfo, int *maxN, int *maxL, const char *out_dir);
+
+/* READ(1) Ft, int2e.f90:161-163.  ftab receives 2783 doubles.                               */
+int myqc_read_ftab(const char *path, double *ftab);
+
+/* WRITE(42) XX, int2e.f90:166,306-307: one Fortran unformatted sequential record, split into
+ * gfortran subrecords above 2147483639 payload bytes.                                        */
+int myqc_write_xx(const char *path, const double *xx, int norb);
+int myqc_read_xx(const char *path, double *xx, int norb);
+
+/* The whole program: what the `int2e` executable does in directory `dir`.
+ * verbose mirrors the reference's stdout lines.                                              */
+int myqc_int2e_main(const char *dir, int ngpu);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYQC_ERI_H */

@@ -1,0 +1,301 @@
+"""myqc_b200 -- B200-native replacement for myQC's `int2e` two-electron-integral engine.
+
+Host-side mirror of the reference boundary (src/integrals/int2e.f90):
+
+    PROGRAM int2e            -> int2e_main(workdir)            (file in, `XX` file out)
+    CALL proc2e(...)         -> proc2e(...) / eri_dense(...)   (arrays in, dense XX out)
+                                eri_packed(...)                (8-fold-unique packed array)
+    getenv / buildBasis      -> read_env(dir), build_basis(path, atoms)
+    READ(1) Ft               -> read_ftab(path)
+    WRITE(42) XX             -> write_xx(path, xx), read_xx(path, norb)
+
+Everything computes through the C-ABI shared library `csrc/libmyqc_eri.so`
+(include/myqc_eri.h) whose kernels are hand-written CUDA for sm_100a.  There is no CPU
+fallback: importing works without a GPU (so the symbols can be checked), computing does not.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmyqc_eri.so")
+
+MYQC_OK = 0
+ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_BAD_ARG, ERR_IO, ERR_NOMEM = -1, -2, -3, -4, -5, -6
+
+# every symbol include/myqc_eri.h declares
+EXPORTS = [
+    "myqc_last_error", "myqc_device_count", "myqc_eri_dense", "myqc_eri_packed",
+    "myqc_eri_plan_create", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
+    "myqc_eri_plan_execute", "myqc_eri_plan_stats", "myqc_eri_plan_destroy",
+    "myqc_eri_expand_dense", "myqc_read_env", "myqc_build_basis", "myqc_read_ftab",
+    "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main",
+]
+
+
+class MyQCError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"myqc_eri error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+
+
+def lib() -> ctypes.CDLL:
+    """Load libmyqc_eri.so; fail loudly if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C myqc_b200/csrc` or "
+            "`python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    c_int, c_void_p, c_char_p = ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p
+    common = [c_int, _dp, c_int, c_int, _dp, _ip, c_int, _dp, _ip, _dp]
+    L.myqc_last_error.restype = c_char_p
+    L.myqc_device_count.restype = c_int
+    L.myqc_eri_dense.argtypes = common + [_dp, c_int]
+    L.myqc_eri_packed.argtypes = common + [_dp, c_int]
+    L.myqc_eri_plan_create.argtypes = common + [c_int, c_int, c_int, ctypes.POINTER(c_void_p)]
+    L.myqc_eri_plan_out_offset.argtypes = [c_void_p]
+    L.myqc_eri_plan_out_offset.restype = ctypes.c_int64
+    L.myqc_eri_plan_out_elems.argtypes = [c_void_p]
+    L.myqc_eri_plan_out_elems.restype = ctypes.c_int64
+    L.myqc_eri_plan_execute.argtypes = [c_void_p, c_void_p, c_void_p]
+    L.myqc_eri_plan_stats.argtypes = [c_void_p, _i64p, _dp, ctypes.POINTER(c_int)]
+    L.myqc_eri_plan_destroy.argtypes = [c_void_p]
+    L.myqc_eri_plan_destroy.restype = None
+    L.myqc_eri_expand_dense.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
+    L.myqc_read_env.argtypes = [c_char_p, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+                                ctypes.POINTER(c_int), _ip, _dp, _dp, ctypes.POINTER(c_int), _ip]
+    L.myqc_build_basis.argtypes = [c_char_p, c_int, c_int, _ip, ctypes.POINTER(c_int),
+                                   ctypes.POINTER(c_int), _dp, _ip, _dp, _ip, ctypes.POINTER(c_int),
+                                   ctypes.POINTER(c_int), c_char_p]
+    L.myqc_read_ftab.argtypes = [c_char_p, _dp]
+    L.myqc_write_xx.argtypes = [c_char_p, _dp, c_int]
+    L.myqc_read_xx.argtypes = [c_char_p, _dp, c_int]
+    L.myqc_int2e_main.argtypes = [c_char_p, c_int]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("myqc_last_error", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
+                        "myqc_eri_plan_destroy"):
+            fn.restype = c_int
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != MYQC_OK:
+        raise MyQCError(rc, lib().myqc_last_error().decode())
+
+
+def device_count() -> int:
+    return lib().myqc_device_count()
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+@dataclass
+class System:
+    """The arrays the reference passes to proc2e (int2e.f90:66,78-112), 0-based contents."""
+    nnuc: int
+    atoms: np.ndarray    # int32 [nnuc]
+    xyz: np.ndarray      # float64 [3*nnuc], Fortran xyz(0:nnuc-1,0:2): xyz[i + nnuc*c]
+    set: np.ndarray      # float64
+    setinfo: np.ndarray  # int32
+    bas: np.ndarray      # float64
+    basinfo: np.ndarray  # int32
+    ftab: np.ndarray     # float64 [2783]
+    options: np.ndarray | None = None
+    maxN: int = 2
+    maxL: int = 1
+
+    @property
+    def nset(self) -> int:
+        return int(self.setinfo[0])
+
+    @property
+    def setl(self) -> int:
+        return int(self.setinfo[1])
+
+    @property
+    def ops(self) -> int:
+        return int(self.basinfo[0])
+
+    @property
+    def norb(self) -> int:
+        return int(self.basinfo[1])
+
+    @property
+    def npair(self) -> int:
+        return self.norb * (self.norb + 1) // 2
+
+    @property
+    def nunique(self) -> int:
+        return self.npair * (self.npair + 1) // 2
+
+    def _common(self):
+        return (self.nnuc, _d(self.xyz), self.nset, self.setl, _d(self.set), _i(self.setinfo),
+                self.ops, _d(self.bas), _i(self.basinfo), _d(self.ftab))
+
+
+# ---- file layer ---------------------------------------------------------------------------
+def read_env(workdir: str):
+    """getenv (env.f90:16-73): returns (atoms, xyz_fortran, nelcA, nelcB, fmem, options)."""
+    L = lib()
+    n, na, nb, no = (ctypes.c_int() for _ in range(4))
+    fmem = ctypes.c_double()
+    _check(L.myqc_read_env(workdir.encode(), 0, 0, n, na, nb, None, None, fmem, no, None))
+    atoms = np.zeros(n.value, dtype=np.int32)
+    xyz = np.zeros(3 * n.value)
+    opts = np.zeros(max(no.value, 17), dtype=np.int32)
+    _check(L.myqc_read_env(workdir.encode(), n.value, len(opts), n, na, nb, _i(atoms), _d(xyz), fmem, no, _i(opts)))
+    return atoms, xyz, na.value, nb.value, fmem.value, opts[:no.value]
+
+
+def build_basis(mybasis_path: str, atoms, bkey: int = 0, out_dir: str | None = None):
+    """buildBasis (basis.f90:23-226): returns (set, setinfo, bas, basinfo, maxN, maxL)."""
+    L = lib()
+    atoms = np.ascontiguousarray(atoms, dtype=np.int32)
+    nsc, noc, mN, mL = (ctypes.c_int() for _ in range(4))
+    _check(L.myqc_build_basis(mybasis_path.encode(), bkey, len(atoms), _i(atoms), nsc, noc, None, None, None, None, mN, mL, None))
+    ops, setl = 4, 7
+    set_ = np.zeros(nsc.value)
+    bas = np.zeros(nsc.value * ops)
+    setinfo = np.zeros(2 + nsc.value * setl, dtype=np.int32)
+    basinfo = np.zeros(2 + 5 * noc.value, dtype=np.int32)
+    _check(L.myqc_build_basis(mybasis_path.encode(), bkey, len(atoms), _i(atoms), nsc, noc, _d(set_), _i(setinfo),
+                              _d(bas), _i(basinfo), mN, mL, out_dir.encode() if out_dir else None))
+    return set_, setinfo, bas, basinfo, mN.value, mL.value
+
+
+def read_ftab(path: str) -> np.ndarray:
+    ft = np.zeros(121 * 23)
+    _check(lib().myqc_read_ftab(path.encode(), _d(ft)))
+    return ft
+
+
+def write_xx(path: str, xx: np.ndarray, norb: int):
+    flat = np.ascontiguousarray(np.asarray(xx).reshape(-1, order="F"))
+    assert flat.size == norb ** 4
+    _check(lib().myqc_write_xx(path.encode(), _d(flat), norb))
+
+
+def read_xx(path: str, norb: int) -> np.ndarray:
+    flat = np.zeros(norb ** 4)
+    _check(lib().myqc_read_xx(path.encode(), _d(flat), norb))
+    return flat.reshape((norb,) * 4, order="F")
+
+
+def load_system(workdir: str, mybasis: str | None = None, ftab: str | None = None) -> System:
+    """What PROGRAM int2e reads before calling proc2e (int2e.f90:50-55,161-163)."""
+    atoms, xyz, _, _, _, opts = read_env(workdir)
+    set_, setinfo, bas, basinfo, mN, mL = build_basis(mybasis or os.path.join(workdir, "mybasis"), atoms,
+                                                      int(opts[2]) if len(opts) > 2 else 0)
+    ft = read_ftab(ftab or os.path.join(workdir, "Ftab"))
+    return System(nnuc=len(atoms), atoms=atoms, xyz=xyz, set=set_, setinfo=setinfo, bas=bas, basinfo=basinfo,
+                  ftab=ft, options=opts, maxN=mN, maxL=mL)
+
+
+def int2e_main(workdir: str, ngpu: int = 1) -> int:
+    """PROGRAM int2e (int2e.f90:14-69) in `workdir`; returns the library status (0 = ok)."""
+    return lib().myqc_int2e_main(workdir.encode(), ngpu)
+
+
+# ---- compute ------------------------------------------------------------------------------
+def eri_packed(s: System, ngpu: int = 1, out: np.ndarray | None = None) -> np.ndarray:
+    """Packed 8-fold-unique ERIs into a host array (layout: include/myqc_eri.h)."""
+    if out is None:
+        out = np.empty(s.nunique)
+    assert out.size == s.nunique and out.dtype == np.float64 and out.flags.c_contiguous
+    _check(lib().myqc_eri_packed(*s._common(), _d(out), ngpu))
+    return out
+
+
+def eri_dense(s: System, ngpu: int = 1) -> np.ndarray:
+    """Dense XX(i,j,g,h) with all 8 images filled: the array proc2e writes (int2e.f90:290-307)."""
+    n = s.norb
+    flat = np.empty(n ** 4)
+    _check(lib().myqc_eri_dense(*s._common(), _d(flat), ngpu))
+    return flat.reshape((n, n, n, n), order="F")
+
+
+def proc2e(bas, basinfo, atoms, options, fmem, nnuc, xyz, set, setinfo, maxL, ftab, ngpu: int = 1):
+    """Argument-for-argument mirror of the reference's
+    `proc2e(bas,basinfo,atoms,options,fmem,nnuc,xyz,set,setinfo,maxL)` (int2e.f90:78); `ftab` is the
+    table the reference reads from the `Ftab` file inside the routine.  Returns XX."""
+    s = System(nnuc=nnuc, atoms=np.asarray(atoms, dtype=np.int32), xyz=np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1),
+               set=np.ascontiguousarray(set, dtype=np.float64), setinfo=np.ascontiguousarray(setinfo, dtype=np.int32),
+               bas=np.ascontiguousarray(bas, dtype=np.float64), basinfo=np.ascontiguousarray(basinfo, dtype=np.int32),
+               ftab=np.ascontiguousarray(ftab, dtype=np.float64), options=options, maxL=maxL)
+    return eri_dense(s, ngpu)
+
+
+class Plan:
+    """Device-resident execution plan for one shard on one GPU (myqc_eri_plan_*)."""
+
+    def __init__(self, s: System, device: int = 0, shard: int = 0, nshards: int = 1):
+        self._h = ctypes.c_void_p()
+        self._s = s
+        _check(lib().myqc_eri_plan_create(*s._common(), device, shard, nshards, ctypes.byref(self._h)))
+        self.device = device
+        self.out_offset = lib().myqc_eri_plan_out_offset(self._h)
+        self.out_elems = lib().myqc_eri_plan_out_elems(self._h)
+
+    def execute(self, d_out_ptr: int, stream: int = 0):
+        """d_out_ptr: device pointer (int) to out_elems doubles; stream: cudaStream_t as int."""
+        _check(lib().myqc_eri_plan_execute(self._h, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(stream)))
+
+    def stats(self):
+        nq = (ctypes.c_int64 * 6)()
+        fl = ctypes.c_double()
+        nl = ctypes.c_int()
+        _check(lib().myqc_eri_plan_stats(self._h, nq, ctypes.byref(fl), ctypes.byref(nl)))
+        return {"nquartets": list(nq), "model_flops": fl.value, "nlaunch": nl.value}
+
+    def close(self):
+        if self._h:
+            lib().myqc_eri_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pair_index(i: int, j: int, norb: int) -> int:
+    return i * norb - i * (i - 1) // 2 + (j - i)
+
+
+# ---- job helpers ----------------------------------------------------------------------------
+def make_job(workdir: str, zmat_text: str, inputs_dir: str) -> System:
+    """Create a myQC job directory (ZMAT + mybasis + Ftab), run the `parse` stage
+    (myqc_b200.parse) and load what int2e would read."""
+    import shutil
+
+    from . import parse as _parse
+
+    os.makedirs(workdir, exist_ok=True)
+    with open(os.path.join(workdir, "ZMAT"), "w") as f:
+        f.write(zmat_text)
+    for name in ("mybasis", "Ftab"):
+        shutil.copyfile(os.path.join(inputs_dir, name), os.path.join(workdir, name))
+    _parse.parse(workdir)
+    return load_system(workdir)

@@ -1,0 +1,472 @@
+// C-ABI of the ERI engine (include/myqc_eri.h): plans, one-shot host-buffer calls.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/myqc_eri.h"
+#include "eri_kernels.cuh"
+#include "pairs.hpp"
+
+namespace myqc {
+
+thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(MYQC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+// model flops per canonical primitive quartet, SURVEY.md 8d
+static const double kW[6] = {60, 99, 228, 228, 693, 2691};
+static int class_id(int la, int lb) {
+    if (la > lb) std::swap(la, lb);
+    static const int id[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    return id[la][lb];
+}
+
+struct DevList {  // device copy of a PairList
+    int type = 0, n = 0, npad = 0;
+    double *aos = nullptr, *soa = nullptr;
+    int32_t *nprim = nullptr, *fi = nullptr, *fj = nullptr, *diag = nullptr;
+    std::vector<double> emax;  // host copy for the prefix computation
+};
+
+struct Launch {
+    int UT, TT;
+    ClassArgs args;
+};
+
+}  // namespace myqc
+
+using namespace myqc;
+
+struct myqc_eri_plan {
+    int device = 0, num_sms = 0;
+    int norb = 0, nset = 0;
+    int64_t npair = 0;
+    int64_t out_offset = 0, out_elems = 0;
+    std::vector<void*> dev_allocs;
+    std::vector<DevList> lists;
+    std::vector<Launch> launches;
+    double* d_ftab = nullptr;  // [5][121][8]
+    // stats (canonical primitive-quartet counts of the whole shard)
+    int64_t nquartets[6] = {0, 0, 0, 0, 0, 0};
+    double model_flops = 0.0;
+    int nlaunch = 0;
+};
+
+namespace myqc {
+
+template <class T>
+static int upload(myqc_eri_plan* pl, const std::vector<T>& h, T** d) {
+    *d = nullptr;
+    if (h.empty()) return MYQC_OK;
+    CU(cudaMalloc((void**)d, h.size() * sizeof(T)));
+    pl->dev_allocs.push_back(*d);
+    CU(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return MYQC_OK;
+}
+
+static int upload_list(myqc_eri_plan* pl, const PairList& src, DevList& d) {
+    d.type = src.type; d.n = src.n; d.npad = src.npad; d.emax = src.emax;
+    int rc;
+    if ((rc = upload(pl, src.aos, &d.aos))) return rc;
+    if ((rc = upload(pl, src.soa, &d.soa))) return rc;
+    if ((rc = upload(pl, src.nprim, &d.nprim))) return rc;
+    if ((rc = upload(pl, src.fi, &d.fi))) return rc;
+    if ((rc = upload(pl, src.fj, &d.fj))) return rc;
+    if ((rc = upload(pl, src.diag, &d.diag))) return rc;
+    return MYQC_OK;
+}
+
+// number of lane-side pairs v with emax_u*emax_v >= 1e-14 (lane list sorted descending)
+static std::vector<int32_t> prefix_counts(const std::vector<double>& eu, const std::vector<double>& et) {
+    std::vector<int32_t> out(eu.size());
+    for (size_t u = 0; u < eu.size(); ++u) {
+        const double e = eu[u];
+        size_t lo = 0, hi = et.size();
+        while (lo < hi) {  // first index with e*et < 1e-14
+            const size_t mid = (lo + hi) / 2;
+            if (e * et[mid] < 1.0e-14) hi = mid; else lo = mid + 1;
+        }
+        out[u] = (int32_t)lo;
+    }
+    return out;
+}
+
+static int add_launch(myqc_eri_plan* pl, int ui, int ti, bool tri) {
+    const DevList& U = pl->lists[ui];
+    const DevList& T = pl->lists[ti];
+    if (U.n == 0 || T.n == 0) return MYQC_OK;
+    Launch L;
+    L.UT = U.type; L.TT = T.type;
+    ClassArgs& a = L.args;
+    std::memset(&a, 0, sizeof(a));
+    a.u_aos = U.aos; a.u_nprim = U.nprim; a.u_fi = U.fi; a.u_fj = U.fj; a.u_diag = U.diag; a.nU = U.n;
+    std::vector<int32_t> ntv = prefix_counts(U.emax, T.emax);
+    int32_t* d_ntv = nullptr;
+    int rc = upload(pl, ntv, &d_ntv);
+    if (rc) return rc;
+    a.u_ntv = d_ntv;
+    a.t_soa = T.soa; a.t_nprim = T.nprim; a.t_fi = T.fi; a.t_fj = T.fj; a.t_diag = T.diag;
+    a.t_npad = T.npad; a.nT = T.n; a.tri = tri ? 1 : 0;
+    a.ftab_q = pl->d_ftab + (size_t)(U.type + T.type) * 121 * 8;
+    a.out = nullptr;
+    a.out_offset = pl->out_offset; a.out_elems = pl->out_elems;
+    a.norb = pl->norb; a.npair = pl->npair;
+    pl->launches.push_back(L);
+    pl->nlaunch += class_nlaunch(L.UT, L.TT);
+    return MYQC_OK;
+}
+
+// canonical primitive-quartet statistics: unordered primitive pairs {a<=b},
+// unordered pairs of pairs, kept iff EIJ*EGH >= 1e-14; restricted to the shard by `owner`.
+static void canonical_stats(int nnuc, const double* xyz, int nset, int setl, const double* set,
+                            const int32_t* setinfo, int64_t nq[6], double* flops) {
+    std::vector<double> E[3];
+    for (int a = 0; a < nset; ++a)
+        for (int b = a; b < nset; ++b) {
+            const double aa = set[a], bb = set[b];
+            const int u = setinfo[1 + a * setl + 3], v = setinfo[1 + b * setl + 3];
+            double r2 = 0;
+            for (int i = 0; i < 3; ++i) { const double d = xyz[u + nnuc * i] - xyz[v + nnuc * i]; r2 += d * d; }
+            const double e = std::exp(-aa * bb * r2 / (aa + bb));
+            if (e < 1.0e-14) continue;
+            E[setinfo[1 + a * setl + 2] + setinfo[1 + b * setl + 2]].push_back(e);
+        }
+    for (int t = 0; t < 3; ++t) std::sort(E[t].begin(), E[t].end(), std::greater<double>());
+    for (int c = 0; c < 6; ++c) nq[c] = 0;
+    for (int ta = 0; ta < 3; ++ta)
+        for (int tb = ta; tb < 3; ++tb) {
+            const std::vector<int32_t> cnt = prefix_counts(E[ta], E[tb]);
+            int64_t n = 0;
+            if (ta == tb) {
+                for (size_t u = 0; u < cnt.size(); ++u)
+                    if ((int64_t)cnt[u] > (int64_t)u) n += cnt[u] - (int64_t)u;  // v >= u
+            } else {
+                for (size_t u = 0; u < cnt.size(); ++u) n += cnt[u];
+            }
+            nq[class_id(ta, tb)] += n;
+        }
+    *flops = 0;
+    for (int c = 0; c < 6; ++c) *flops += kW[c] * (double)nq[c];
+}
+
+static int check_args(int nnuc, const double* xyz, int nset, int setl, const double* set,
+                      const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
+                      const double* ftab) {
+    if (!xyz || !set || !setinfo || !bas || !basinfo || !ftab) return fail(MYQC_ERR_BAD_ARG, "null input pointer");
+    if (nnuc < 1 || nset < 1) return fail(MYQC_ERR_BAD_ARG, "nnuc/nset must be positive");
+    if (setinfo[0] != nset || setinfo[1] != setl) return fail(MYQC_ERR_BAD_ARG, "setinfo header does not match nset/setl");
+    if (basinfo[0] != ops || basinfo[1] < 1) return fail(MYQC_ERR_BAD_ARG, "basinfo header does not match ops/norb");
+    for (int s = 0; s < nset; ++s) {
+        const int c = setinfo[1 + s * setl + 3];
+        if (c < 0 || c >= nnuc) return fail(MYQC_ERR_BAD_ARG, "set centre out of range");
+        if (!(set[s] > 0.0)) return fail(MYQC_ERR_BAD_ARG, "non-positive exponent");
+    }
+    return MYQC_OK;
+}
+
+}  // namespace myqc
+
+extern "C" {
+
+const char* myqc_last_error(void) { return g_last_error.c_str(); }
+
+int myqc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const double* set,
+                         const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
+                         const double* ftab, int device, int shard, int nshards, myqc_eri_plan** plan) {
+    if (!plan) return fail(MYQC_ERR_BAD_ARG, "plan is null");
+    *plan = nullptr;
+    int rc = check_args(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab);
+    if (rc) return rc;
+    if (nshards < 1 || shard < 0 || shard >= nshards) return fail(MYQC_ERR_BAD_ARG, "bad shard/nshards");
+    const int ndev = myqc_device_count();
+    if (ndev == 0) return fail(MYQC_ERR_NO_DEVICE, "no CUDA device: the ERI engine has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(MYQC_ERR_BAD_ARG, "device index out of range");
+    CU(cudaSetDevice(device));
+
+    std::unique_ptr<myqc_eri_plan> pl(new myqc_eri_plan());
+    pl->device = device;
+    CU(cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, device));
+    pl->norb = basinfo[1];
+    pl->nset = nset;
+    pl->npair = (int64_t)pl->norb * (pl->norb + 1) / 2;
+
+    std::string err;
+    std::vector<Shell> shells;
+    if ((rc = build_shells(nnuc, nset, setl, setinfo, ops, basinfo, shells, err))) return fail(rc, err);
+    PairList all[3];
+    if ((rc = build_pairs(nnuc, xyz, set, setinfo, setl, ops, bas, basinfo, shells, all, err))) return fail(rc, err);
+
+    // Boys tables for the five start orders Q = 0,3,6,9,12: row t = {Ft(t,Q+k)/k!, k<7 ; t/10}
+    {
+        std::vector<double> h(5 * 121 * 8);
+        for (int qi = 0; qi < 5; ++qi)
+            for (int t = 0; t <= 120; ++t) {
+                double fact = 1.0;
+                for (int k = 0; k < 7; ++k) {
+                    if (k > 1) fact *= k;
+                    h[((size_t)qi * 121 + t) * 8 + k] = ftab[t + 121 * (3 * qi + k)] / fact;
+                }
+                h[((size_t)qi * 121 + t) * 8 + 7] = t / 10.0;
+            }
+        if ((rc = upload(pl.get(), h, &pl->d_ftab))) return rc;
+    }
+
+    // ---- sharding: contiguous blocks of packed rows, cut where a shell's functions start -------
+    // owner key of a quartet = smallest first-function id of its shells; see DESIGN.md.
+    int fn_lo = 0, fn_hi = pl->norb;  // this shard owns rows whose first index is in [fn_lo, fn_hi)
+    if (nshards > 1) {
+        // shells must own contiguous function ranges for row blocks to be closed
+        for (const Shell& sh : shells) {
+            int cnt = 0, mx = -1;
+            for (int k = 0; k < 4; ++k) if (sh.fn[k] >= 0) { ++cnt; mx = std::max(mx, sh.fn[k]); }
+            if (mx - sh.first_fn + 1 != cnt) return fail(MYQC_ERR_UNSUPPORTED, "sharding needs contiguous orbital ids per shell");
+        }
+        std::vector<int> cuts;  // candidate cut points: first function of each shell
+        for (const Shell& sh : shells) cuts.push_back(sh.first_fn);
+        std::sort(cuts.begin(), cuts.end());
+        // weight of a candidate block [c_k, c_{k+1}) ~ model flops of the quartets it owns.
+        // estimate: for every pair list, a pair u with owner key o(u) owns the quartets (u,v) with
+        // o(v) >= o(u) (ties split evenly); count them with per-list cumulative histograms.
+        const int nc = (int)cuts.size();
+        auto cut_of = [&](int fn) { return (int)(std::upper_bound(cuts.begin(), cuts.end(), fn) - cuts.begin()) - 1; };
+        std::vector<double> w(nc, 0.0);
+        // cumulative histogram over lane list positions is too large for big lists; use the fact
+        // that the prefix of a list sorted by emax is an unbiased sample of owners: weight of row
+        // u split between o(u) and the owners of its prefix proportionally to a global histogram.
+        for (int ta = 0; ta < 3; ++ta)
+            for (int tb = ta; tb < 3; ++tb) {
+                const PairList& A = all[ta];
+                const PairList& B = all[tb];
+                if (A.n == 0 || B.n == 0) continue;
+                const double wq = kW[class_id(ta, tb)] * 81.0;
+                std::vector<int32_t> cnt = prefix_counts(A.emax, B.emax);
+                // suffix histogram of B owners: frac_ge[c] = fraction of B pairs with cut >= c
+                std::vector<double> hist(nc + 1, 0.0);
+                for (int k = 0; k < B.n; ++k) hist[cut_of(B.owner_fn[k])] += 1.0;
+                std::vector<double> ge(nc + 1, 0.0);
+                for (int c = nc - 1; c >= 0; --c) ge[c] = ge[c + 1] + hist[c];
+                for (int u = 0; u < A.n; ++u) {
+                    double nrow = cnt[u];
+                    if (ta == tb) nrow = std::max(0.0, nrow - u);  // v >= u
+                    const int cu = cut_of(A.owner_fn[u]);
+                    const double f_ge = ge[cu] / B.n;  // share of partners owned by u's block
+                    w[cu] += wq * nrow * f_ge;
+                    // the rest goes to lower blocks proportionally to their histogram
+                    if (cu > 0 && f_ge < 1.0) {
+                        const double rest = wq * nrow / B.n;
+                        for (int c = 0; c < cu; ++c) w[c] += rest * hist[c];
+                    }
+                }
+            }
+        double tot = 0;
+        for (double x : w) tot += x;
+        // greedy contiguous cut into nshards blocks of ~equal weight
+        std::vector<int> bound(nshards + 1, nc);
+        bound[0] = 0;
+        double acc = 0;
+        int s = 1;
+        for (int c = 0; c < nc && s < nshards; ++c) {
+            acc += w[c];
+            if (acc >= tot * s / nshards) bound[s++] = c + 1;
+        }
+        for (; s < nshards; ++s) bound[s] = nc;
+        for (int k = 1; k <= nshards; ++k) bound[k] = std::max(bound[k], bound[k - 1]);
+        bound[nshards] = nc;
+        fn_lo = bound[shard] < nc ? cuts[bound[shard]] : pl->norb;
+        fn_hi = bound[shard + 1] < nc ? cuts[bound[shard + 1]] : pl->norb;
+        if (bound[shard] == 0) fn_lo = 0;
+    }
+    {
+        const int64_t n = pl->norb, np = pl->npair;
+        auto row0 = [&](int64_t i) { return i * n - i * (i - 1) / 2; };            // P(i,i)
+        auto qoff = [&](int64_t P) { return P * np - P * (P - 1) / 2; };            // index(P,P)
+        const int64_t Plo = fn_lo >= n ? np : row0(fn_lo), Phi = fn_hi >= n ? np : row0(fn_hi);
+        pl->out_offset = Plo >= np ? np * (np + 1) / 2 : qoff(Plo);
+        const int64_t end = Phi >= np ? np * (np + 1) / 2 : qoff(Phi);
+        pl->out_elems = end - pl->out_offset;
+    }
+
+    // lists: "mine" (owner key in [fn_lo,fn_hi)) and "later" (owner key >= fn_hi)
+    pl->lists.reserve(6);
+    int mine_id[3], later_id[3];
+    for (int t = 0; t < 3; ++t) {
+        std::vector<char> pm(all[t].n), pl8(all[t].n);
+        bool any_later = false;
+        for (int k = 0; k < all[t].n; ++k) {
+            pm[k] = (all[t].owner_fn[k] >= fn_lo && all[t].owner_fn[k] < fn_hi);
+            pl8[k] = (all[t].owner_fn[k] >= fn_hi);
+            any_later = any_later || pl8[k];
+        }
+        pl->lists.emplace_back();
+        mine_id[t] = (int)pl->lists.size() - 1;
+        if ((rc = upload_list(pl.get(), nshards == 1 ? all[t] : sublist(all[t], pm), pl->lists.back()))) return rc;
+        later_id[t] = -1;
+        if (any_later) {
+            pl->lists.emplace_back();
+            later_id[t] = (int)pl->lists.size() - 1;
+            if ((rc = upload_list(pl.get(), sublist(all[t], pl8), pl->lists.back()))) return rc;
+        }
+    }
+    // launches.  Class (ta,tb), ta <= tb, uniform side = ta, lane side = tb.
+    for (int ta = 0; ta < 3; ++ta)
+        for (int tb = ta; tb < 3; ++tb) {
+            if (ta == tb) {
+                if ((rc = add_launch(pl.get(), mine_id[ta], mine_id[ta], true))) return rc;
+                if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), mine_id[ta], later_id[ta], false))) return rc;
+            } else {
+                if ((rc = add_launch(pl.get(), mine_id[ta], mine_id[tb], false))) return rc;
+                if (later_id[tb] >= 0 && (rc = add_launch(pl.get(), mine_id[ta], later_id[tb], false))) return rc;
+                if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), later_id[ta], mine_id[tb], false))) return rc;
+            }
+        }
+    pl->nlaunch += 1;  // zero fill
+
+    if (nshards == 1) canonical_stats(nnuc, xyz, nset, setl, set, setinfo, pl->nquartets, &pl->model_flops);
+    *plan = pl.release();
+    return MYQC_OK;
+}
+
+int64_t myqc_eri_plan_out_offset(const myqc_eri_plan* plan) { return plan ? plan->out_offset : -1; }
+int64_t myqc_eri_plan_out_elems(const myqc_eri_plan* plan) { return plan ? plan->out_elems : -1; }
+
+int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
+    if (!plan || (!d_out && plan->out_elems > 0)) return fail(MYQC_ERR_BAD_ARG, "null plan or output");
+    CU(cudaSetDevice(plan->device));
+    int e = launch_fill_zero(d_out, plan->out_elems, plan->num_sms, stream);
+    if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
+    for (Launch& L : plan->launches) {
+        L.args.out = d_out;
+        e = launch_class(L.UT, L.TT, L.args, plan->num_sms, stream);
+        if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+    }
+    return MYQC_OK;
+}
+
+int myqc_eri_plan_stats(const myqc_eri_plan* plan, int64_t* nquartets, double* model_flops, int* nlaunch) {
+    if (!plan) return fail(MYQC_ERR_BAD_ARG, "null plan");
+    if (nquartets) for (int c = 0; c < 6; ++c) nquartets[c] = plan->nquartets[c];
+    if (model_flops) *model_flops = plan->model_flops;
+    if (nlaunch) *nlaunch = plan->nlaunch;
+    return MYQC_OK;
+}
+
+void myqc_eri_plan_destroy(myqc_eri_plan* plan) {
+    if (!plan) return;
+    cudaSetDevice(plan->device);
+    for (void* p : plan->dev_allocs) cudaFree(p);
+    delete plan;
+}
+
+int myqc_eri_expand_dense(const double* d_packed, int norb, double* d_xx, void* stream) {
+    if (!d_packed || !d_xx || norb < 1) return fail(MYQC_ERR_BAD_ARG, "bad arguments");
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int e = launch_expand_dense(d_packed, norb, d_xx, sms, stream);
+    if (e) return cuda_fail((cudaError_t)e, "expand_dense launch");
+    return MYQC_OK;
+}
+
+// one-shot, host buffers ---------------------------------------------------------------------
+static int run_packed_host(int nnuc, const double* xyz, int nset, int setl, const double* set,
+                           const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
+                           const double* ftab, double* packed, int ngpu) {
+    const int ndev = myqc_device_count();
+    if (ndev == 0) return fail(MYQC_ERR_NO_DEVICE, "no CUDA device: the ERI engine has no CPU fallback");
+    if (ngpu <= 0 || ngpu > ndev) ngpu = (ngpu <= 0) ? ndev : ndev;
+    if (!packed) return fail(MYQC_ERR_BAD_ARG, "null output");
+    std::vector<int> rcs(ngpu, 0);
+    std::vector<std::string> errs(ngpu);
+    auto work = [&](int g) {
+        myqc_eri_plan* pl = nullptr;
+        int rc = myqc_eri_plan_create(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab, g, g, ngpu, &pl);
+        if (rc) { rcs[g] = rc; errs[g] = g_last_error; return; }
+        double* d_out = nullptr;
+        const int64_t n = pl->out_elems;
+        cudaError_t e = cudaSuccess;
+        if (n > 0) e = cudaMalloc((void**)&d_out, (size_t)n * sizeof(double));
+        if (e != cudaSuccess) { rcs[g] = MYQC_ERR_NOMEM; errs[g] = cudaGetErrorString(e); myqc_eri_plan_destroy(pl); return; }
+        rc = myqc_eri_plan_execute(pl, d_out, nullptr);
+        if (!rc && n > 0) {
+            e = cudaMemcpy(packed + pl->out_offset, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { rc = MYQC_ERR_CUDA; g_last_error = cudaGetErrorString(e); }
+        }
+        if (rc) { rcs[g] = rc; errs[g] = g_last_error; }
+        cudaFree(d_out);
+        myqc_eri_plan_destroy(pl);
+    };
+    if (ngpu == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < ngpu; ++g) th.emplace_back(work, g);
+        for (auto& t : th) t.join();
+    }
+    for (int g = 0; g < ngpu; ++g)
+        if (rcs[g]) return fail(rcs[g], errs[g]);
+    return MYQC_OK;
+}
+
+int myqc_eri_packed(int nnuc, const double* xyz, int nset, int setl, const double* set,
+                    const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
+                    const double* ftab, double* packed, int ngpu) {
+    int rc = check_args(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab);
+    if (rc) return rc;
+    return run_packed_host(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab, packed, ngpu);
+}
+
+int myqc_eri_dense(int nnuc, const double* xyz, int nset, int setl, const double* set,
+                   const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
+                   const double* ftab, double* xx, int ngpu) {
+    int rc = check_args(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab);
+    if (rc) return rc;
+    if (!xx) return fail(MYQC_ERR_BAD_ARG, "null output");
+    const int ndev = myqc_device_count();
+    if (ndev == 0) return fail(MYQC_ERR_NO_DEVICE, "no CUDA device: the ERI engine has no CPU fallback");
+    (void)ngpu;  // the dense array is assembled on device 0; sharding applies to the packed path
+    myqc_eri_plan* pl = nullptr;
+    rc = myqc_eri_plan_create(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab, 0, 0, 1, &pl);
+    if (rc) return rc;
+    const int64_t n = pl->norb;
+    double *d_packed = nullptr, *d_xx = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_packed, (size_t)pl->out_elems * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_xx, (size_t)(n * n * n * n) * sizeof(double));
+    if (e != cudaSuccess) {
+        cudaFree(d_packed); myqc_eri_plan_destroy(pl);
+        return fail(MYQC_ERR_NOMEM, std::string("device allocation for dense XX: ") + cudaGetErrorString(e));
+    }
+    rc = myqc_eri_plan_execute(pl, d_packed, nullptr);
+    if (!rc) rc = myqc_eri_expand_dense(d_packed, (int)n, d_xx, nullptr);
+    if (!rc) {
+        e = cudaMemcpy(xx, d_xx, (size_t)(n * n * n * n) * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "copy dense XX to host");
+    }
+    cudaFree(d_packed); cudaFree(d_xx);
+    myqc_eri_plan_destroy(pl);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,274 @@
+// Host-side shell-pair builder (see pairs.hpp).  Built with -ffp-contract=off so the
+// prefactor EIJ is bit-identical to what the reference's gfortran build computes: the
+// EIJ*EGH >= 1e-14 inclusion rule (int2e.f90:257) must make the same decisions.
+#include "pairs.hpp"
+#include "terms.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "../../include/myqc_eri.h"
+
+namespace myqc {
+
+// REAL(KIND=8),PARAMETER :: Pi = 3.1415926535897931 -- a default-REAL literal, i.e. float32
+// pi widened (int2e.f90:621, auxilary.f90:711).  SURVEY.md T1.
+static const double kPiRef = (double)3.1415926535897931f;
+
+// auxilary.f90:704-726
+static double gtoD(int l, double a) {
+    if (l == 0) return std::pow(2.0 * a / kPiRef, 3.0 / 4.0);
+    return std::pow(128.0 * std::pow(a, 5.0) / std::pow(kPiRef, 3.0), 1.0 / 4.0);
+}
+
+int build_shells(int nnuc, int nset, int setl, const int32_t* setinfo, int ops,
+                 const int32_t* basinfo, std::vector<Shell>& shells, std::string& err) {
+    (void)nnuc;
+    shells.clear();
+    if (setl < 4 || ops < 1 || ops > 4 || setl != 3 + ops) {
+        err = "setl/ops not of the form 3+OpS with OpS<=4";
+        return MYQC_ERR_BAD_ARG;
+    }
+    const int norb = basinfo[1];
+    for (int s = 0; s < nset; ++s) {
+        const int32_t* si = &setinfo[1 + s * setl + 1];  // {#orbs, max l, centre, orbital ids...}
+        const int no = si[0];
+        if (no < 1 || no > ops) { err = "set with no orbitals or more than OpS"; return MYQC_ERR_BAD_ARG; }
+        for (int k = 0; k < no; ++k)
+            if (si[3 + k] < 0 || si[3 + k] >= norb) { err = "orbital id out of range"; return MYQC_ERR_BAD_ARG; }
+        // look for an existing shell with the same centre and orbital list
+        int found = -1;
+        for (size_t h = 0; h < shells.size() && found < 0; ++h) {
+            const Shell& sh = shells[h];
+            if (sh.centre != si[2]) continue;
+            const int32_t* s0 = &setinfo[1 + sh.sets[0] * setl + 1];
+            if (s0[0] != no) continue;
+            bool same = true;
+            for (int k = 0; k < no; ++k) same = same && (s0[3 + k] == si[3 + k]);
+            if (same) found = (int)h;
+        }
+        if (found >= 0) { shells[found].sets.push_back(s); continue; }
+        Shell sh;
+        sh.centre = si[2];
+        sh.fn[0] = sh.fn[1] = sh.fn[2] = sh.fn[3] = -1;
+        sh.sets.push_back(s);
+        auto L = [&](int o) { return basinfo[1 + 5 * o + 2]; };
+        auto ORI = [&](int o) { return basinfo[1 + 5 * o + 3]; };
+        for (int k = 0; k < no; ++k)
+            if (L(si[3 + k]) > 1) { err = "angular momentum l > 1 is not implemented (basis.f90:170-174)"; return MYQC_ERR_UNSUPPORTED; }
+        if (no == 1 && L(si[3]) == 0 && ORI(si[3]) == -1) {
+            sh.type = 0;
+            sh.fn[0] = si[3];
+        } else if (no == 4 && L(si[3]) == 0 && ORI(si[3]) == -1 && L(si[4]) == 1 && ORI(si[4]) == 0 &&
+                   L(si[5]) == 1 && ORI(si[5]) == 1 && L(si[6]) == 1 && ORI(si[6]) == 2) {
+            sh.type = 1;
+            for (int k = 0; k < 4; ++k) sh.fn[k] = si[3 + k];
+        } else if (no == 3 && L(si[3]) == 1 && ORI(si[3]) == 0 && L(si[4]) == 1 && ORI(si[4]) == 1 &&
+                   L(si[5]) == 1 && ORI(si[5]) == 2) {
+            sh.type = 1;  // p-only set: an SP shell whose s function is absent
+            for (int k = 0; k < 3; ++k) sh.fn[1 + k] = si[3 + k];
+        } else {
+            err = "unsupported set layout (only S, SP and P sets are implemented)";
+            return MYQC_ERR_UNSUPPORTED;
+        }
+        if (si[1] != sh.type) { err = "set max-l inconsistent with its orbitals"; return MYQC_ERR_BAD_ARG; }
+        sh.first_fn = norb;
+        for (int k = 0; k < 4; ++k)
+            if (sh.fn[k] >= 0) sh.first_fn = std::min(sh.first_fn, sh.fn[k]);
+        shells.push_back(sh);
+    }
+    for (const Shell& sh : shells)
+        if ((int)sh.sets.size() > 3) { err = "more than 3 primitives per shell"; return MYQC_ERR_UNSUPPORTED; }
+    return MYQC_OK;
+}
+
+namespace {
+
+struct PrimRec {
+    double E;
+    double f[5 + 46 + 1];
+};
+
+// contraction coefficient of function slot mu (0=s,1..3=p) of `shell` in primitive set `s`
+double slot_coef(const Shell& sh, int s, int mu, const int32_t* setinfo, int setl, int ops,
+                 const double* bas) {
+    const int32_t* si = &setinfo[1 + s * setl + 1];
+    if (sh.fn[mu] < 0) return 0.0;
+    for (int k = 0; k < si[0]; ++k)
+        if (si[3 + k] == sh.fn[mu]) return bas[s * ops + k];
+    return 0.0;
+}
+
+}  // namespace
+
+int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* setinfo, int setl,
+                int ops, const double* bas, const int32_t* basinfo,
+                const std::vector<Shell>& shells, PairList lists[3], std::string& err) {
+    (void)basinfo;
+    (void)err;
+    const double tol = 0.1e-15;  // auxilary.f90:573
+    struct Tmp {
+        int type, A, B, nprim;
+        double emax;
+        std::vector<PrimRec> prims;
+    };
+    std::vector<Tmp> tmp[3];
+    const int ns = (int)shells.size();
+    for (int A = 0; A < ns; ++A) {
+        for (int B = A; B < ns; ++B) {
+            const Shell& sa = shells[A];
+            const Shell& sb = shells[B];
+            const int type = sa.type + sb.type;
+            const int nterm = pt_nterm(type);
+            Tmp t;
+            t.type = type; t.A = A; t.B = B; t.emax = 0.0;
+            for (int a : sa.sets) {
+                for (int b : sb.sets) {
+                    // int2e.f90:215-223
+                    const double aa = set[a], bb = set[b];
+                    const int u = sa.centre, v = sb.centre;
+                    const double p = aa + bb, mm = aa * bb;
+                    double AB[3], PP[3], PA[3], PB[3];
+                    for (int i = 0; i < 3; ++i) {
+                        AB[i] = xyz[u + nnuc * i] - xyz[v + nnuc * i];
+                        PP[i] = (aa * xyz[u + nnuc * i] + bb * xyz[v + nnuc * i]) / p;
+                        PA[i] = PP[i] - xyz[u + nnuc * i];
+                        PB[i] = PP[i] - xyz[v + nnuc * i];
+                    }
+                    const double EIJ = std::exp(-mm * (AB[0] * AB[0] + AB[1] * AB[1] + AB[2] * AB[2]) / p);
+                    if (EIJ < 1.0e-14) continue;  // EGH <= 1, so EIJ*EGH < 1e-14 for every ket (:257)
+                    // closed forms of lrec/rrec for n,nbar <= 1 (auxilary.f90:443-462)
+                    const double half = 1.0 / (2.0 * p);
+                    double d[3][2][2][3];  // [axis][n][nbar][N]
+                    for (int w = 0; w < 3; ++w) {
+                        d[w][0][0][0] = 1.0;  d[w][0][0][1] = 0.0;  d[w][0][0][2] = 0.0;
+                        d[w][1][0][0] = PA[w]; d[w][1][0][1] = half; d[w][1][0][2] = 0.0;
+                        d[w][0][1][0] = PB[w]; d[w][0][1][1] = half; d[w][0][1][2] = 0.0;
+                        d[w][1][1][0] = PB[w] * PA[w] + half;
+                        d[w][1][1][1] = PA[w] / (2.0 * p) + PB[w] * half;
+                        d[w][1][1][2] = half / (2.0 * p);
+                    }
+                    const double ga[2] = {gtoD(0, aa), gtoD(1, aa)};
+                    const double gb[2] = {gtoD(0, bb), gtoD(1, bb)};
+                    // 2 Pi^2.5 / (p q sqrt(p+q)) is split as scale(p)*scale(q)/sqrt(p+q)
+                    const double scale = std::sqrt(2.0) * std::pow(kPiRef, 1.25) / p;
+                    auto term = [&](int mu, int nu, int N, int L, int M) -> double {
+                        // mu,nu in {0=s,1=x,2=y,3=z}; getDk, auxilary.f90:610-622
+                        int n[3] = {mu == 1, mu == 2, mu == 3};
+                        int nb[3] = {nu == 1, nu == 2, nu == 3};
+                        const double cx = d[0][n[0]][nb[0]][N], cy = d[1][n[1]][nb[1]][L], cz = d[2][n[2]][nb[2]][M];
+                        if (std::fabs(cz) < tol || std::fabs(cy) < tol || std::fabs(cx) < tol) return 0.0;
+                        double Dk = cx * cy * cz;
+                        Dk = Dk * EIJ * ga[mu != 0] * gb[nu != 0];
+                        Dk = Dk * slot_coef(sa, a, mu, setinfo, setl, ops, bas) * slot_coef(sb, b, nu, setinfo, setl, ops, bas);
+                        return Dk * scale;
+                    };
+                    PrimRec r;
+                    std::memset(&r, 0, sizeof(r));
+                    r.E = EIJ;
+                    r.f[0] = p; r.f[1] = PP[0]; r.f[2] = PP[1]; r.f[3] = PP[2]; r.f[4] = EIJ;
+                    double* c = &r.f[5];
+                    const bool a_is_sp = (sa.type == 1);
+                    for (int k = 0; k < nterm; ++k) {
+                        const int f = term_fn(type, k), h = term_h(type, k);
+                        int mu = 0, nu = 0;
+                        if (type == PT_SSP) { mu = a_is_sp ? f : 0; nu = a_is_sp ? 0 : f; }
+                        else if (type == PT_SPSP) { mu = f / 4; nu = f % 4; }
+                        c[k] = term(mu, nu, h_N(h), h_L(h), h_M(h));
+                    }
+                    t.prims.push_back(r);
+                    t.emax = std::max(t.emax, EIJ);
+                }
+            }
+            if (t.prims.empty()) continue;
+            std::stable_sort(t.prims.begin(), t.prims.end(), [](const PrimRec& x, const PrimRec& y) { return x.E > y.E; });
+            t.nprim = (int)t.prims.size();
+            if (t.nprim > kMaxPrim) { err = "more than 9 primitive pairs per shell pair"; return MYQC_ERR_UNSUPPORTED; }
+            tmp[type].push_back(std::move(t));
+        }
+    }
+    for (int type = 0; type < 3; ++type) {
+        std::vector<Tmp>& v = tmp[type];
+        std::stable_sort(v.begin(), v.end(), [](const Tmp& x, const Tmp& y) { return x.emax > y.emax; });
+        PairList& pl = lists[type];
+        pl = PairList();
+        pl.type = type;
+        pl.n = (int)v.size();
+        pl.npad = (pl.n + 31) / 32 * 32;
+        const int nf = pt_nf(type), nfield = pt_nfield(type);
+        pl.emax.resize(pl.n); pl.nprim.resize(pl.n); pl.diag.resize(pl.n);
+        pl.shA.resize(pl.n); pl.shB.resize(pl.n); pl.owner_fn.resize(pl.n);
+        pl.fi.assign((size_t)pl.n * nf, -1); pl.fj.assign((size_t)pl.n * nf, -1);
+        pl.aos.assign((size_t)pl.n * kMaxPrim * nfield, 0.0);
+        pl.soa.assign((size_t)kMaxPrim * nfield * pl.npad, 0.0);
+        for (int k = 0; k < pl.n; ++k) {
+            const Tmp& t = v[k];
+            const Shell& sa = shells[t.A];
+            const Shell& sb = shells[t.B];
+            pl.emax[k] = t.emax; pl.nprim[k] = t.nprim; pl.diag[k] = (t.A == t.B);
+            pl.shA[k] = t.A; pl.shB[k] = t.B;
+            pl.owner_fn[k] = std::min(sa.first_fn, sb.first_fn);
+            if (type == PT_SS) {
+                pl.fi[k] = sa.fn[0]; pl.fj[k] = sb.fn[0];
+            } else if (type == PT_SSP) {
+                const bool a_is_sp = (sa.type == 1);
+                for (int w = 0; w < 4; ++w) {
+                    pl.fi[(size_t)k * 4 + w] = a_is_sp ? sa.fn[w] : sa.fn[0];
+                    pl.fj[(size_t)k * 4 + w] = a_is_sp ? sb.fn[0] : sb.fn[w];
+                }
+            } else {
+                for (int mu = 0; mu < 4; ++mu)
+                    for (int nu = 0; nu < 4; ++nu) {
+                        pl.fi[(size_t)k * 16 + 4 * mu + nu] = sa.fn[mu];
+                        pl.fj[(size_t)k * 16 + 4 * mu + nu] = sb.fn[nu];
+                    }
+            }
+            // a function pair with an absent member is marked absent on both sides
+            for (int f = 0; f < nf; ++f)
+                if (pl.fi[(size_t)k * nf + f] < 0 || pl.fj[(size_t)k * nf + f] < 0)
+                    pl.fi[(size_t)k * nf + f] = pl.fj[(size_t)k * nf + f] = -1;
+            for (int q = 0; q < t.nprim; ++q)
+                for (int f = 0; f < nfield; ++f) {
+                    const double val = t.prims[q].f[f];
+                    pl.aos[((size_t)k * kMaxPrim + q) * nfield + f] = val;
+                    pl.soa[((size_t)q * nfield + f) * pl.npad + k] = val;
+                }
+        }
+    }
+    return MYQC_OK;
+}
+
+PairList sublist(const PairList& src, const std::vector<char>& pred) {
+    PairList d;
+    d.type = src.type;
+    const int nf = pt_nf(src.type), nfield = pt_nfield(src.type);
+    std::vector<int> idx;
+    for (int k = 0; k < src.n; ++k)
+        if (pred[k]) idx.push_back(k);
+    d.n = (int)idx.size();
+    d.npad = (d.n + 31) / 32 * 32;
+    d.emax.resize(d.n); d.nprim.resize(d.n); d.diag.resize(d.n);
+    d.shA.resize(d.n); d.shB.resize(d.n); d.owner_fn.resize(d.n);
+    d.fi.resize((size_t)d.n * nf); d.fj.resize((size_t)d.n * nf);
+    d.aos.assign((size_t)d.n * kMaxPrim * nfield, 0.0);
+    d.soa.assign((size_t)kMaxPrim * nfield * d.npad, 0.0);
+    for (int k = 0; k < d.n; ++k) {
+        const int s = idx[k];
+        d.emax[k] = src.emax[s]; d.nprim[k] = src.nprim[s]; d.diag[k] = src.diag[s];
+        d.shA[k] = src.shA[s]; d.shB[k] = src.shB[s]; d.owner_fn[k] = src.owner_fn[s];
+        for (int f = 0; f < nf; ++f) {
+            d.fi[(size_t)k * nf + f] = src.fi[(size_t)s * nf + f];
+            d.fj[(size_t)k * nf + f] = src.fj[(size_t)s * nf + f];
+        }
+        std::memcpy(&d.aos[(size_t)k * kMaxPrim * nfield], &src.aos[(size_t)s * kMaxPrim * nfield],
+                    sizeof(double) * kMaxPrim * nfield);
+        for (int q = 0; q < kMaxPrim; ++q)
+            for (int f = 0; f < nfield; ++f)
+                d.soa[((size_t)q * nfield + f) * d.npad + k] = src.soa[((size_t)q * nfield + f) * src.npad + s];
+    }
+    return d;
+}
+
+}  // namespace myqc

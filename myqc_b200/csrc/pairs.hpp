@@ -1,0 +1,72 @@
+// Host-side shell-pair builder for the B200 ERI engine.
+//
+// Replaces the per-(a,b) / per-(c,d) work of the reference's quartet loop
+// (src/integrals/int2e.f90:192-263: p, P, PA, PB, EIJ, getcoef, getDk) by tables built once:
+// contracted shells are recovered from the reference's "set" arrays, every shell pair gets its
+// primitive-pair records (exponent sum, centre, prefactor, Hermite coefficients folded with
+// normalisation and contraction coefficients), pairs are classed by the number of SP sets
+// (0: S.S, 1: S.SP, 2: SP.SP) and sorted by their largest prefactor so that the reference's
+// EIJ*EGH >= 1e-14 screen becomes a prefix of the list (a Schwarz-like bound that is *exactly*
+// the reference's inclusion rule).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace myqc {
+
+constexpr int kMaxPrim = 9;  // primitive pairs per shell pair (STO-nG with n<=3)
+
+// Pair types
+enum PairType { PT_SS = 0, PT_SSP = 1, PT_SPSP = 2 };
+
+// number of function pairs, Hermite terms and padded fields per primitive record
+constexpr int pt_nf(int t) { return t == 0 ? 1 : (t == 1 ? 4 : 16); }
+constexpr int pt_nterm(int t) { return t == 0 ? 1 : (t == 1 ? 7 : 46); }
+// fields: p, Px, Py, Pz, E, coef[nterm], padded to a multiple of 2 doubles (16 B, TMA granule)
+constexpr int pt_nfield(int t) { return ((5 + pt_nterm(t)) + 1) / 2 * 2; }
+
+struct Shell {
+    int centre;
+    int type;         // 0 = S (one s function), 1 = SP (s,px,py,pz; s may be absent)
+    int fn[4];        // orbital ids of (s,px,py,pz); -1 if absent (S shells use fn[0] only)
+    std::vector<int> sets;  // primitive sets (indices into set[]) in reference order
+    int first_fn;     // smallest orbital id (ownership of packed rows)
+};
+
+struct PairList {
+    int type = 0;
+    int n = 0;     // number of shell pairs kept
+    int npad = 0;  // n rounded up to 32 (SoA leading dimension)
+    // per pair, sorted by emax descending
+    std::vector<double> emax;
+    std::vector<int32_t> nprim;
+    std::vector<int32_t> fi, fj;  // [n][nf] orbital ids of each function pair (-1: absent)
+    std::vector<int32_t> diag;    // shell A == shell B
+    std::vector<int32_t> shA, shB;
+    std::vector<int32_t> owner_fn;  // min(first_fn(A), first_fn(B)) -> shard ownership key
+    // primitive records (prims sorted by E descending inside each pair, unused slots zero)
+    std::vector<double> aos;  // [n][kMaxPrim][nfield]   (uniform / TMA side)
+    std::vector<double> soa;  // [kMaxPrim][nfield][npad] (per-lane side)
+};
+
+struct Basis {
+    int nnuc = 0, nset = 0, norb = 0;
+    std::vector<Shell> shells;
+    PairList lists[3];
+};
+
+// Returns 0 or a negative MYQC_ERR_* code; err receives a message.
+int build_shells(int nnuc, int nset, int setl, const int32_t* setinfo, int ops,
+                 const int32_t* basinfo, std::vector<Shell>& shells, std::string& err);
+
+// Build the three pair lists restricted to shells for which keep_shell[s] != 0 on BOTH sides
+// (keep_shell == nullptr keeps all).
+int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* setinfo,
+                int setl, int ops, const double* bas, const int32_t* basinfo,
+                const std::vector<Shell>& shells, PairList lists[3], std::string& err);
+
+// Select a sub-list (keeping order) of the pairs for which pred[k] != 0.
+PairList sublist(const PairList& src, const std::vector<char>& pred);
+
+}  // namespace myqc
