@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- unique ERIs/s of the int2e hot path on N B200s (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload h2o_64] [--impl ours|reference]
+  (N > 1: launched by torchrun, one rank per GPU; ranks shard the packed quartet space, no
+   collective on the data path; only the timing barrier / max-over-ranks use NCCL.)
+
+A "step" is one full evaluation of this rank's shard of the packed 8-fold-unique ERI array of the
+workload molecule: zero fill + six quartet-class kernels, inputs (shell-pair tables, Boys table)
+already resident in HBM.  `value` = unique ERIs of the whole molecule / max-over-ranks step time.
+`e2e` is the same metric through the host-buffer C-ABI call a user makes (plan build, H2D of the
+pair tables, kernels, D2H of the packed slice into pinned host memory inside the timed region).
+
+`--impl reference` times the CPU restatement of the reference's own loop (oracle/, the reference
+is Fortran and cannot be built in this image) on all host cores over a bounded sample of the
+same workload, extrapolated to the whole molecule.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+INPUTS = os.path.join(ROOT, "tests", "golden", "inputs")
+METRIC = "unique_eris_per_s"
+UNIT = "ERI/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_system(workload: str):
+    import myqc_b200 as Q
+    from myqc_b200 import molecules
+    d = os.path.join(INPUTS, workload)
+    zm = open(os.path.join(d, "ZMAT")).read() if os.path.isdir(d) else molecules.zmat(workload)
+    with tempfile.TemporaryDirectory() as tmp:
+        return Q.make_job(tmp, zm, INPUTS), zm
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_sample(zm: str, seconds: float, nthreads: int, offset: int = 0):
+    """Bounded sample of the reference's loop on the host (oracle port).  Returns
+    (unique ERIs/s extrapolated to the whole molecule, description)."""
+    from oracle import oracle as O
+    mol = O.parse_zmat(zm)
+    b = O.build_basis(open(os.path.join(INPUTS, "mybasis")).read(), mol.atoms)
+    ft = O.read_ftab(os.path.join(INPUTS, "Ftab"))
+    n = b.nset
+    total = n * n
+    npair = b.norb * (b.norb + 1) // 2
+    nunique = npair * (npair + 1) // 2
+    # calibrate on a small stride sample, then size the real sample for `seconds`
+    ncal = min(total, 4 * nthreads)
+    idx = (np.arange(ncal, dtype=np.int64) * (total // ncal) + offset) % total
+    dt, _ = O.int2e_sample(mol, b, ft, idx // n, idx % n, nthreads)
+    per = max(dt / ncal, 1e-7)
+    ns = int(min(total, max(ncal, seconds / per)))
+    idx = (np.arange(ns, dtype=np.int64) * (total // ns) + offset) % total
+    dt, surv = O.int2e_sample(mol, b, ft, idx // n, idx % n, nthreads)
+    full = dt * total / ns
+    desc = (f"oracle port of int2e.f90 loop: {ns} of {total} ordered (a,b) set-pair rows "
+            f"(stride sample, {surv} surviving quartets, {dt:.1f} s), "
+            + ("full run" if ns == total else "extrapolated by row count"))
+    return nunique / full, desc, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    s, zm = build_system(args.workload)
+    nthreads = os.cpu_count() or 1
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for w in range(args.warmup):
+        cpu_sample(zm, min(per_step, 2.0), nthreads, offset=w)
+    vals, descs, t_tot = [], [], 0.0
+    for k in range(args.steps):
+        v, d, dt = cpu_sample(zm, per_step, nthreads, offset=args.warmup + k)
+        vals.append(v); descs.append(d); t_tot += dt
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s.nunique / value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": args.workload, "norb": s.norb, "nset": s.nset,
+                                          "unique_eris": s.nunique},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": descs[-1]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import myqc_b200 as Q
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the ERI engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    s, zm = build_system(args.workload)
+    nq, model_flops = Q.canonical_stats(s)
+    plan = Q.Plan(s, device=local, shard=rank, nshards=world)
+    out = torch.empty(max(plan.out_elems, 1), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    nlaunch = plan.stats()["nlaunch"]
+    log(f"[rank {rank}] {args.workload}: norb={s.norb} unique={s.nunique} shard elems={plan.out_elems} "
+        f"({8 * plan.out_elems / 1e9:.2f} GB) launches/step={nlaunch}")
+
+    fp64_peak = Q.fp64_peak(local) if rank == 0 else 0.0
+    hbm_peak, peak_src = measured_peaks()
+
+    # L2: the slice each step writes is far larger than the 126 MB L2 for the headline workload;
+    # for small workloads flush L2 between steps by writing a 256 MB scratch buffer.
+    need_flush = 8 * plan.out_elems < 512e6
+    scratch = torch.empty(32 * 1024 * 1024, dtype=torch.float64, device="cuda") if need_flush else None
+
+    def step():
+        if scratch is not None:
+            scratch.zero_()
+        plan.execute(out.data_ptr(), stream)
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    barrier()
+    for k in range(args.steps):
+        if scratch is not None:
+            scratch.zero_()
+        ev[2 * k].record()
+        plan.execute(out.data_ptr(), stream)
+        ev[2 * k + 1].record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_local = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)) / args.steps
+    ms = allmax(ms_local)
+    value = s.nunique / (ms * 1e-3)
+
+    # per-launch breakdown (CUDA events around every launch, on the launching stream)
+    launches = plan.launches()
+    acc = np.zeros(len(launches))
+    nrep = max(1, min(args.steps, 5))
+    for _ in range(nrep):
+        if scratch is not None:
+            scratch.zero_()
+        acc += np.array(plan.execute_timed(out.data_ptr(), stream))
+    acc /= nrep
+    barrier()
+    checksum = float(out[:plan.out_elems].sum().item()) if plan.out_elems else 0.0
+    checksum = allsum(checksum)
+
+    # ---- end to end through the host-buffer C-ABI call ------------------------------------------
+    e2e = None
+    try:
+        off = Q.shard_layout(s, world)
+        nloc = int(off[rank + 1] - off[rank])
+        host = torch.empty(max(nloc, 1), dtype=torch.float64, pin_memory=True)
+        harr = host.numpy()
+        Q.eri_packed_shard(s, harr[:nloc], device=local, shard=rank, nshards=world)  # warm-up
+        barrier()
+        ne2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(ne2e):
+            Q.eri_packed_shard(s, harr[:nloc], device=local, shard=rank, nshards=world)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / ne2e
+        dt = allmax(dt)
+        h2d = Q.plan_h2d_bytes(s)
+        e2e = {"value": s.nunique / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(8 * s.nunique), "ms_per_step": dt * 1e3, "steps": ne2e,
+               "host_checksum": float(allsum(float(harr[:nloc].sum())))}
+    except Exception as exc:  # report, do not hide
+        e2e = {"value": None, "unit": UNIT, "error": repr(exc)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant launch ---------------------------------------------------------
+    per_class_ms = {}
+    for (cls, tri, rows), t in zip(launches, acc):
+        per_class_ms[cls] = per_class_ms.get(cls, 0.0) + float(t)
+    kernels = []
+    for cls, t in sorted(per_class_ms.items()):
+        if cls < 0:
+            gb = 8.0 * plan.out_elems / 1e9
+            kernels.append({"kernel": "fill_zero", "ms": t, "bound": "hbm", "achieved": gb / (t * 1e-3) if t > 0 else 0.0,
+                            "peak": hbm_peak, "unit": "GB/s"})
+        else:
+            # shard-local model flops are only known for the whole molecule at N=1
+            fl = Q.CLASS_W[cls] * float(nq[cls]) / world
+            kernels.append({"kernel": "eri_class" + Q.CLASS_NAMES[cls], "ms": t, "bound": "fp64",
+                            "achieved": fl / (t * 1e-3) / 1e12 if t > 0 else 0.0, "peak": fp64_peak, "unit": "TFLOP/s"})
+    for k in kernels:
+        k["frac"] = k["achieved"] / k["peak"] if k["peak"] else None
+    dom = max(kernels, key=lambda k: k["ms"])
+    roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
+                "unit": dom["unit"], "frac": dom["frac"], "traffic": None,
+                "peak_source": peak_src if dom["bound"] == "hbm" else "measured DFMA microbenchmark in this run (myqc_fp64_peak)",
+                "share_of_step": dom["ms"] / float(acc.sum()) if acc.sum() > 0 else None}
+    whole = {"fp64_tflops_model": model_flops / (ms * 1e-3) / 1e12 / 1.0,
+             "fp64_frac_of_measured_dfma_peak": model_flops / (ms * 1e-3) / 1e12 / (fp64_peak * world) if fp64_peak else None,
+             "hbm_gbs_algorithmic": 8.0 * s.nunique / 1e9 / (ms * 1e-3),
+             "hbm_frac": 8.0 * s.nunique / 1e9 / (ms * 1e-3) / (hbm_peak * world)}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, desc, _ = cpu_sample(zm, args.cpu_seconds, 1)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "norb": s.norb, "nset": s.nset, "unique_eris": s.nunique,
+                   "canonical_prim_quartets": int(nq.sum()), "model_flops": model_flops,
+                   "l2": "flushed between steps (256 MB scratch write)" if need_flush else
+                         "output slice per step (%.1f GB) is larger than L2" % (8 * plan.out_elems / 1e9),
+                   "parallelism": f"quartet-space row shards x{world}, no collective"},
+        "roofline": roofline, "kernels": kernels, "whole_step": whole,
+        "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(nlaunch * args.steps),
+        "clocks": clk, "fp64_peak_tflops_measured": fp64_peak, "checksum": checksum,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="h2o_64")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

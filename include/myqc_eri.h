@@ -69,6 +69,14 @@ int myqc_eri_packed(int nnuc, const double *xyz, int nset, int setl, const doubl
                     const int32_t *setinfo, int ops, const double *bas, const int32_t *basinfo,
                     const double *ftab, double *packed, int ngpu);
 
+/* One shard of the packed array into a HOST buffer of (offsets[shard+1]-offsets[shard]) doubles
+ * (myqc_eri_shard_layout), computed on `device`: what one rank of a one-process-per-GPU job calls.
+ * h2d_bytes (optional) receives the bytes of pair/Boys tables uploaded for the call.          */
+int myqc_eri_packed_shard(int nnuc, const double *xyz, int nset, int setl, const double *set,
+                          const int32_t *setinfo, int ops, const double *bas, const int32_t *basinfo,
+                          const double *ftab, double *packed_slice, int device, int shard, int nshards,
+                          int64_t *h2d_bytes);
+
 /* ---- plan API: device-resident execution, one plan per (GPU, shard) -------------------------
  * A plan holds the shell-pair tables of one shard of the canonical quartet space on one device.
  * Shard s of nshards owns a contiguous block of rows of the packed array (rows = bra pair index
@@ -100,6 +108,29 @@ int myqc_eri_plan_stats(const myqc_eri_plan *plan, int64_t *nquartets, double *m
                         int *nlaunch);
 
 void myqc_eri_plan_destroy(myqc_eri_plan *plan);
+
+/* Host-only (no device needed): offsets[0..nshards] of the shard slices in the packed array;
+ * shard s owns [offsets[s], offsets[s+1]).  Every rank computes the same layout independently. */
+int myqc_eri_shard_layout(int nnuc, const double *xyz, int nset, int setl, const double *set,
+                          const int32_t *setinfo, int ops, const double *bas, const int32_t *basinfo,
+                          int nshards, int64_t *offsets);
+
+/* Host-only: canonical surviving primitive-quartet counts per class and their model flops for
+ * the whole molecule (same definition as myqc_eri_plan_stats).                  */
+int myqc_eri_canonical_stats(int nnuc, const double *xyz, int nset, int setl, const double *set,
+                              const int32_t *setinfo, int64_t *nquartets, double *model_flops);
+
+/* Measurement hooks (bench.py): launches of one execute() = 1 zero fill + the class kernels.
+ * launch_info: cls = -1 for the zero fill, else the class id 0..5 in the order of nquartets[];
+ * rows = elements filled / uniform-side rows.  execute_timed brackets every launch with CUDA
+ * events on `stream`, synchronises, and returns the per-launch milliseconds in ms[launch_count]. */
+int myqc_eri_plan_launch_count(const myqc_eri_plan *plan);
+int myqc_eri_plan_launch_info(const myqc_eri_plan *plan, int k, int *cls, int *tri, int64_t *rows);
+int myqc_eri_plan_execute_timed(myqc_eri_plan *plan, double *d_out, void *stream, float *ms);
+
+/* Register-resident DFMA microbenchmark: the FP64 (non-tensor) roofline denominator, measured
+ * on the device the plan runs on (MEASURED_PEAKS.json has no FP64 figure).                    */
+int myqc_fp64_peak(int device, double *tflops);
 
 /* Expand a packed DEVICE array into the dense DEVICE array XX(n,n,n,n) (all 8 images).      */
 int myqc_eri_expand_dense(const double *d_packed, int norb, double *d_xx, void *stream);

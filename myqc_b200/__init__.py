@@ -33,7 +33,9 @@ EXPORTS = [
     "myqc_eri_plan_create", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
     "myqc_eri_plan_execute", "myqc_eri_plan_stats", "myqc_eri_plan_destroy",
     "myqc_eri_expand_dense", "myqc_read_env", "myqc_build_basis", "myqc_read_ftab",
-    "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main",
+    "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main", "myqc_eri_shard_layout",
+    "myqc_eri_canonical_stats", "myqc_eri_plan_launch_count", "myqc_eri_plan_launch_info",
+    "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard",
 ]
 
 
@@ -84,6 +86,13 @@ def lib() -> ctypes.CDLL:
     L.myqc_write_xx.argtypes = [c_char_p, _dp, c_int]
     L.myqc_read_xx.argtypes = [c_char_p, _dp, c_int]
     L.myqc_int2e_main.argtypes = [c_char_p, c_int]
+    L.myqc_eri_shard_layout.argtypes = common[:-1] + [c_int, _i64p]
+    L.myqc_eri_canonical_stats.argtypes = [c_int, _dp, c_int, c_int, _dp, _ip, _i64p, _dp]
+    L.myqc_eri_plan_launch_count.argtypes = [c_void_p]
+    L.myqc_eri_plan_launch_info.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), _i64p]
+    L.myqc_eri_plan_execute_timed.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ctypes.c_float)]
+    L.myqc_fp64_peak.argtypes = [c_int, _dp]
+    L.myqc_eri_packed_shard.argtypes = common + [_dp, c_int, c_int, c_int, _i64p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("myqc_last_error", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
@@ -227,6 +236,24 @@ def eri_packed(s: System, ngpu: int = 1, out: np.ndarray | None = None) -> np.nd
     return out
 
 
+_last_h2d_bytes = 0
+
+
+def eri_packed_shard(s: System, out: np.ndarray, device: int = 0, shard: int = 0, nshards: int = 1) -> np.ndarray:
+    """One shard of the packed array into the host array `out` (length from shard_layout)."""
+    global _last_h2d_bytes
+    assert out.dtype == np.float64 and out.flags.c_contiguous
+    h2d = ctypes.c_int64()
+    _check(lib().myqc_eri_packed_shard(*s._common(), _d(out), device, shard, nshards, ctypes.byref(h2d)))
+    _last_h2d_bytes = h2d.value
+    return out
+
+
+def plan_h2d_bytes(s: System) -> int:
+    """Bytes of pair/Boys tables the last eri_packed_shard call uploaded."""
+    return _last_h2d_bytes
+
+
 def eri_dense(s: System, ngpu: int = 1) -> np.ndarray:
     """Dense XX(i,j,g,h) with all 8 images filled: the array proc2e writes (int2e.f90:290-307)."""
     n = s.norb
@@ -261,6 +288,22 @@ class Plan:
         """d_out_ptr: device pointer (int) to out_elems doubles; stream: cudaStream_t as int."""
         _check(lib().myqc_eri_plan_execute(self._h, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(stream)))
 
+    def launches(self):
+        """[(class id or -1 for the zero fill, tri flag, rows)] in launch order."""
+        out = []
+        for k in range(lib().myqc_eri_plan_launch_count(self._h)):
+            c, t, r = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+            _check(lib().myqc_eri_plan_launch_info(self._h, k, ctypes.byref(c), ctypes.byref(t), ctypes.byref(r)))
+            out.append((c.value, t.value, r.value))
+        return out
+
+    def execute_timed(self, d_out_ptr: int, stream: int = 0):
+        """Like execute(), but synchronises and returns per-launch milliseconds (CUDA events)."""
+        n = lib().myqc_eri_plan_launch_count(self._h)
+        ms = (ctypes.c_float * n)()
+        _check(lib().myqc_eri_plan_execute_timed(self._h, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(stream), ms))
+        return list(ms)
+
     def stats(self):
         nq = (ctypes.c_int64 * 6)()
         fl = ctypes.c_double()
@@ -278,6 +321,33 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+CLASS_NAMES = ["{0,0}", "{0,1}", "{0,2}", "{1,1}", "{1,2}", "{2,2}"]
+CLASS_W = [60.0, 99.0, 228.0, 228.0, 693.0, 2691.0]  # model flop per canonical primitive quartet
+
+
+def shard_layout(s: System, nshards: int) -> np.ndarray:
+    """Host-only: packed-array offsets [nshards+1] of the shard slices."""
+    off = np.zeros(nshards + 1, dtype=np.int64)
+    _check(lib().myqc_eri_shard_layout(*s._common()[:-1], nshards, off.ctypes.data_as(_i64p)))
+    return off
+
+
+def canonical_stats(s: System):
+    """Host-only: (nquartets[6], model_flops) of the whole molecule."""
+    nq = np.zeros(6, dtype=np.int64)
+    fl = ctypes.c_double()
+    _check(lib().myqc_eri_canonical_stats(s.nnuc, _d(s.xyz), s.nset, s.setl, _d(s.set), _i(s.setinfo),
+                                          nq.ctypes.data_as(_i64p), ctypes.byref(fl)))
+    return nq, fl.value
+
+
+def fp64_peak(device: int = 0) -> float:
+    """Measured DFMA peak of `device` in TFLOP/s (register-resident microbenchmark)."""
+    v = ctypes.c_double()
+    _check(lib().myqc_fp64_peak(device, ctypes.byref(v)))
+    return v.value
 
 
 def pair_index(i: int, j: int, norb: int) -> int:

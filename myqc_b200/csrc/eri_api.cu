@@ -68,6 +68,7 @@ struct myqc_eri_plan {
     int64_t nquartets[6] = {0, 0, 0, 0, 0, 0};
     double model_flops = 0.0;
     int nlaunch = 0;
+    int64_t h2d_bytes = 0;  // bytes uploaded at plan creation (pair tables, Boys tables, prefixes)
 };
 
 namespace myqc {
@@ -79,6 +80,7 @@ static int upload(myqc_eri_plan* pl, const std::vector<T>& h, T** d) {
     CU(cudaMalloc((void**)d, h.size() * sizeof(T)));
     pl->dev_allocs.push_back(*d);
     CU(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    pl->h2d_bytes += (int64_t)(h.size() * sizeof(T));
     return MYQC_OK;
 }
 
@@ -167,6 +169,80 @@ static void canonical_stats(int nnuc, const double* xyz, int nset, int setl, con
     for (int c = 0; c < 6; ++c) *flops += kW[c] * (double)nq[c];
 }
 
+// packed index of the first element of the first row whose leading orbital is `fn`
+static int64_t packed_row_offset(int64_t fn, int64_t norb) {
+    const int64_t np = norb * (norb + 1) / 2;
+    if (fn >= norb) return np * (np + 1) / 2;
+    const int64_t P = fn * norb - fn * (fn - 1) / 2;  // P(fn,fn)
+    return P * np - P * (P - 1) / 2;
+}
+
+// Ownership rule (multi-GPU): a shell quartet belongs to the shard that owns the
+// smallest first-orbital id among its four shells; all its canonical integrals then lie in packed
+// rows whose leading orbital is inside that shell.  Shards are contiguous blocks of such rows.
+// fn_bounds[s] .. fn_bounds[s+1] are the leading-orbital ranges, balanced by estimated model
+// flops.  Pure host arithmetic: every rank computes the same answer independently.
+static int shard_fn_bounds(const std::vector<Shell>& shells, const PairList all[3], int norb, int nshards,
+                           std::vector<int>& fn_bounds, std::string& err) {
+    fn_bounds.assign(nshards + 1, norb);
+    fn_bounds[0] = 0;
+    if (nshards == 1) return MYQC_OK;
+    for (const Shell& sh : shells) {  // row blocks are closed only for contiguous orbital ranges
+        int cnt = 0, mx = -1;
+        for (int k = 0; k < 4; ++k) if (sh.fn[k] >= 0) { ++cnt; mx = std::max(mx, sh.fn[k]); }
+        if (mx - sh.first_fn + 1 != cnt) { err = "sharding needs contiguous orbital ids per shell"; return MYQC_ERR_UNSUPPORTED; }
+    }
+    std::vector<int> cuts;  // candidate cut points: first orbital of each shell
+    for (const Shell& sh : shells) cuts.push_back(sh.first_fn);
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    const int nc = (int)cuts.size();
+    auto cut_of = [&](int fn) { return (int)(std::upper_bound(cuts.begin(), cuts.end(), fn) - cuts.begin()) - 1; };
+    // weight of block c ~ model flops of the quartets it owns.  A row u of class (ta,tb) has
+    // cnt[u] partners (the emax prefix); the prefix of a list sorted by emax is treated as an
+    // unbiased sample of owners, so the row's weight is split between cut(u) (partners with
+    // cut >= cut(u)) and the lower cuts in proportion to the partner histogram.
+    std::vector<double> w(nc, 0.0);
+    for (int ta = 0; ta < 3; ++ta)
+        for (int tb = ta; tb < 3; ++tb) {
+            const PairList& A = all[ta];
+            const PairList& B = all[tb];
+            if (A.n == 0 || B.n == 0) continue;
+            const std::vector<int32_t> cnt = prefix_counts(A.emax, B.emax);
+            std::vector<double> hist(nc + 1, 0.0), ge(nc + 2, 0.0);
+            double mean_prim = 0.0;
+            for (int k = 0; k < B.n; ++k) {
+                hist[cut_of(B.owner_fn[k])] += 1.0;
+                mean_prim += B.nprim[k];
+            }
+            mean_prim /= B.n;
+            for (int c = nc - 1; c >= 0; --c) ge[c] = ge[c + 1] + hist[c];
+            const double wq = kW[class_id(ta, tb)] * mean_prim / B.n;
+            for (int u = 0; u < A.n; ++u) {
+                double nrow = cnt[u];
+                if (ta == tb) nrow = std::max(0.0, nrow - u);
+                const double wr = wq * nrow * (double)A.nprim[u];
+                const int cu = cut_of(A.owner_fn[u]);
+                w[cu] += wr * ge[cu];
+                for (int c = 0; c < cu; ++c) w[c] += wr * hist[c];
+            }
+        }
+    double tot = 0;
+    for (double x : w) tot += x;
+    std::vector<int> bound(nshards + 1, nc);
+    bound[0] = 0;
+    double acc = 0;
+    int sidx = 1;
+    for (int c = 0; c < nc && sidx < nshards; ++c) {
+        acc += w[c];
+        while (sidx < nshards && acc >= tot * sidx / nshards) bound[sidx++] = c + 1;
+    }
+    for (int k = 1; k <= nshards; ++k) bound[k] = std::max(bound[k], bound[k - 1]);
+    bound[nshards] = nc;
+    for (int k = 1; k < nshards; ++k) fn_bounds[k] = bound[k] < nc ? cuts[bound[k]] : norb;
+    return MYQC_OK;
+}
+
 static int check_args(int nnuc, const double* xyz, int nset, int setl, const double* set,
                       const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
                       const double* ftab) {
@@ -236,78 +312,14 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
     }
 
     // ---- sharding: contiguous blocks of packed rows, cut where a shell's functions start -------
-    // owner key of a quartet = smallest first-function id of its shells; see DESIGN.md.
     int fn_lo = 0, fn_hi = pl->norb;  // this shard owns rows whose first index is in [fn_lo, fn_hi)
-    if (nshards > 1) {
-        // shells must own contiguous function ranges for row blocks to be closed
-        for (const Shell& sh : shells) {
-            int cnt = 0, mx = -1;
-            for (int k = 0; k < 4; ++k) if (sh.fn[k] >= 0) { ++cnt; mx = std::max(mx, sh.fn[k]); }
-            if (mx - sh.first_fn + 1 != cnt) return fail(MYQC_ERR_UNSUPPORTED, "sharding needs contiguous orbital ids per shell");
-        }
-        std::vector<int> cuts;  // candidate cut points: first function of each shell
-        for (const Shell& sh : shells) cuts.push_back(sh.first_fn);
-        std::sort(cuts.begin(), cuts.end());
-        // weight of a candidate block [c_k, c_{k+1}) ~ model flops of the quartets it owns.
-        // estimate: for every pair list, a pair u with owner key o(u) owns the quartets (u,v) with
-        // o(v) >= o(u) (ties split evenly); count them with per-list cumulative histograms.
-        const int nc = (int)cuts.size();
-        auto cut_of = [&](int fn) { return (int)(std::upper_bound(cuts.begin(), cuts.end(), fn) - cuts.begin()) - 1; };
-        std::vector<double> w(nc, 0.0);
-        // cumulative histogram over lane list positions is too large for big lists; use the fact
-        // that the prefix of a list sorted by emax is an unbiased sample of owners: weight of row
-        // u split between o(u) and the owners of its prefix proportionally to a global histogram.
-        for (int ta = 0; ta < 3; ++ta)
-            for (int tb = ta; tb < 3; ++tb) {
-                const PairList& A = all[ta];
-                const PairList& B = all[tb];
-                if (A.n == 0 || B.n == 0) continue;
-                const double wq = kW[class_id(ta, tb)] * 81.0;
-                std::vector<int32_t> cnt = prefix_counts(A.emax, B.emax);
-                // suffix histogram of B owners: frac_ge[c] = fraction of B pairs with cut >= c
-                std::vector<double> hist(nc + 1, 0.0);
-                for (int k = 0; k < B.n; ++k) hist[cut_of(B.owner_fn[k])] += 1.0;
-                std::vector<double> ge(nc + 1, 0.0);
-                for (int c = nc - 1; c >= 0; --c) ge[c] = ge[c + 1] + hist[c];
-                for (int u = 0; u < A.n; ++u) {
-                    double nrow = cnt[u];
-                    if (ta == tb) nrow = std::max(0.0, nrow - u);  // v >= u
-                    const int cu = cut_of(A.owner_fn[u]);
-                    const double f_ge = ge[cu] / B.n;  // share of partners owned by u's block
-                    w[cu] += wq * nrow * f_ge;
-                    // the rest goes to lower blocks proportionally to their histogram
-                    if (cu > 0 && f_ge < 1.0) {
-                        const double rest = wq * nrow / B.n;
-                        for (int c = 0; c < cu; ++c) w[c] += rest * hist[c];
-                    }
-                }
-            }
-        double tot = 0;
-        for (double x : w) tot += x;
-        // greedy contiguous cut into nshards blocks of ~equal weight
-        std::vector<int> bound(nshards + 1, nc);
-        bound[0] = 0;
-        double acc = 0;
-        int s = 1;
-        for (int c = 0; c < nc && s < nshards; ++c) {
-            acc += w[c];
-            if (acc >= tot * s / nshards) bound[s++] = c + 1;
-        }
-        for (; s < nshards; ++s) bound[s] = nc;
-        for (int k = 1; k <= nshards; ++k) bound[k] = std::max(bound[k], bound[k - 1]);
-        bound[nshards] = nc;
-        fn_lo = bound[shard] < nc ? cuts[bound[shard]] : pl->norb;
-        fn_hi = bound[shard + 1] < nc ? cuts[bound[shard + 1]] : pl->norb;
-        if (bound[shard] == 0) fn_lo = 0;
-    }
     {
-        const int64_t n = pl->norb, np = pl->npair;
-        auto row0 = [&](int64_t i) { return i * n - i * (i - 1) / 2; };            // P(i,i)
-        auto qoff = [&](int64_t P) { return P * np - P * (P - 1) / 2; };            // index(P,P)
-        const int64_t Plo = fn_lo >= n ? np : row0(fn_lo), Phi = fn_hi >= n ? np : row0(fn_hi);
-        pl->out_offset = Plo >= np ? np * (np + 1) / 2 : qoff(Plo);
-        const int64_t end = Phi >= np ? np * (np + 1) / 2 : qoff(Phi);
-        pl->out_elems = end - pl->out_offset;
+        std::vector<int> fn_bounds;
+        if ((rc = shard_fn_bounds(shells, all, pl->norb, nshards, fn_bounds, err))) return fail(rc, err);
+        fn_lo = fn_bounds[shard];
+        fn_hi = fn_bounds[shard + 1];
+        pl->out_offset = packed_row_offset(fn_lo, pl->norb);
+        pl->out_elems = packed_row_offset(fn_hi, pl->norb) - pl->out_offset;
     }
 
     // lists: "mine" (owner key in [fn_lo,fn_hi)) and "later" (owner key >= fn_hi)
@@ -350,6 +362,32 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
     return MYQC_OK;
 }
 
+int myqc_eri_canonical_stats(int nnuc, const double* xyz, int nset, int setl, const double* set,
+                              const int32_t* setinfo, int64_t* nquartets, double* model_flops) {
+    if (!xyz || !set || !setinfo || !nquartets || !model_flops) return fail(MYQC_ERR_BAD_ARG, "null pointer");
+    canonical_stats(nnuc, xyz, nset, setl, set, setinfo, nquartets, model_flops);
+    return MYQC_OK;
+}
+
+int myqc_eri_shard_layout(int nnuc, const double* xyz, int nset, int setl, const double* set,
+                          const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
+                          int nshards, int64_t* offsets) {
+    // host only: no device is touched
+    static const double dummy_ft[1] = {0.0};
+    int rc = check_args(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, dummy_ft);
+    if (rc) return rc;
+    if (nshards < 1 || !offsets) return fail(MYQC_ERR_BAD_ARG, "bad nshards/offsets");
+    std::string err;
+    std::vector<Shell> shells;
+    if ((rc = build_shells(nnuc, nset, setl, setinfo, ops, basinfo, shells, err))) return fail(rc, err);
+    PairList all[3];
+    if ((rc = build_pairs(nnuc, xyz, set, setinfo, setl, ops, bas, basinfo, shells, all, err))) return fail(rc, err);
+    std::vector<int> fb;
+    if ((rc = shard_fn_bounds(shells, all, basinfo[1], nshards, fb, err))) return fail(rc, err);
+    for (int k = 0; k <= nshards; ++k) offsets[k] = packed_row_offset(fb[k], basinfo[1]);
+    return MYQC_OK;
+}
+
 int64_t myqc_eri_plan_out_offset(const myqc_eri_plan* plan) { return plan ? plan->out_offset : -1; }
 int64_t myqc_eri_plan_out_elems(const myqc_eri_plan* plan) { return plan ? plan->out_elems : -1; }
 
@@ -363,6 +401,63 @@ int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
         e = launch_class(L.UT, L.TT, L.args, plan->num_sms, stream);
         if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
     }
+    return MYQC_OK;
+}
+
+int myqc_eri_plan_launch_count(const myqc_eri_plan* plan) {
+    if (!plan) return 0;
+    return 1 + (int)plan->launches.size();
+}
+
+int myqc_eri_plan_launch_info(const myqc_eri_plan* plan, int k, int* cls, int* tri, int64_t* rows) {
+    if (!plan || k < 0 || k > (int)plan->launches.size()) return fail(MYQC_ERR_BAD_ARG, "bad launch index");
+    if (k == 0) {  // the zero fill
+        if (cls) *cls = -1;
+        if (tri) *tri = 0;
+        if (rows) *rows = plan->out_elems;
+        return MYQC_OK;
+    }
+    const Launch& L = plan->launches[k - 1];
+    if (cls) *cls = class_id(L.UT, L.TT);
+    if (tri) *tri = L.args.tri;
+    if (rows) *rows = L.args.nU;
+    return MYQC_OK;
+}
+
+int myqc_eri_plan_execute_timed(myqc_eri_plan* plan, double* d_out, void* stream, float* ms) {
+    if (!plan || !ms || (!d_out && plan->out_elems > 0)) return fail(MYQC_ERR_BAD_ARG, "null plan/output/ms");
+    CU(cudaSetDevice(plan->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n = 1 + (int)plan->launches.size();
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) CU(cudaEventCreate(&e));
+    CU(cudaEventRecord(ev[0], st));
+    int e = launch_fill_zero(d_out, plan->out_elems, plan->num_sms, stream);
+    if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
+    CU(cudaEventRecord(ev[1], st));
+    for (int k = 0; k < n - 1; ++k) {
+        Launch& L = plan->launches[k];
+        L.args.out = d_out;
+        e = launch_class(L.UT, L.TT, L.args, plan->num_sms, stream);
+        if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+        CU(cudaEventRecord(ev[k + 2], st));
+    }
+    CU(cudaEventSynchronize(ev[n]));
+    for (int k = 0; k < n; ++k) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
+    for (auto& x : ev) cudaEventDestroy(x);
+    return MYQC_OK;
+}
+
+int myqc_fp64_peak(int device, double* tflops) {
+    if (!tflops) return fail(MYQC_ERR_BAD_ARG, "null output");
+    if (myqc_device_count() == 0) return fail(MYQC_ERR_NO_DEVICE, "no CUDA device");
+    CU(cudaSetDevice(device));
+    int sms = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double best = 0.0;
+    int e = measure_dfma_peak(sms, &best);
+    if (e) return cuda_fail((cudaError_t)e, "dfma peak kernel");
+    *tflops = best;
     return MYQC_OK;
 }
 
@@ -392,32 +487,51 @@ int myqc_eri_expand_dense(const double* d_packed, int norb, double* d_xx, void* 
 }
 
 // one-shot, host buffers ---------------------------------------------------------------------
+int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const double* set,
+                          const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
+                          const double* ftab, double* packed_slice, int device, int shard, int nshards,
+                          int64_t* h2d_bytes) {
+    myqc_eri_plan* pl = nullptr;
+    int rc = myqc_eri_plan_create(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab, device, shard, nshards, &pl);
+    if (rc) return rc;
+    if (h2d_bytes) *h2d_bytes = pl->h2d_bytes;
+    const int64_t n = pl->out_elems;
+    if (n > 0 && !packed_slice) { myqc_eri_plan_destroy(pl); return fail(MYQC_ERR_BAD_ARG, "null output"); }
+    double* d_out = nullptr;
+    if (n > 0) {
+        cudaError_t e = cudaMalloc((void**)&d_out, (size_t)n * sizeof(double));
+        if (e != cudaSuccess) {
+            myqc_eri_plan_destroy(pl);
+            return fail(MYQC_ERR_NOMEM, std::string("device allocation of the packed slice: ") + cudaGetErrorString(e));
+        }
+    }
+    rc = myqc_eri_plan_execute(pl, d_out, nullptr);
+    if (!rc && n > 0) {
+        // pinned destinations run at PCIe speed; pageable ones are staged by the driver
+        cudaError_t e = cudaMemcpy(packed_slice, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = cuda_fail(e, "copy packed slice to host");
+    }
+    cudaFree(d_out);
+    myqc_eri_plan_destroy(pl);
+    return rc;
+}
+
 static int run_packed_host(int nnuc, const double* xyz, int nset, int setl, const double* set,
                            const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
                            const double* ftab, double* packed, int ngpu) {
     const int ndev = myqc_device_count();
     if (ndev == 0) return fail(MYQC_ERR_NO_DEVICE, "no CUDA device: the ERI engine has no CPU fallback");
-    if (ngpu <= 0 || ngpu > ndev) ngpu = (ngpu <= 0) ? ndev : ndev;
+    if (ngpu <= 0 || ngpu > ndev) ngpu = ndev;
     if (!packed) return fail(MYQC_ERR_BAD_ARG, "null output");
+    std::vector<int64_t> off(ngpu + 1, 0);
+    int rc = myqc_eri_shard_layout(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ngpu, off.data());
+    if (rc) return rc;
     std::vector<int> rcs(ngpu, 0);
     std::vector<std::string> errs(ngpu);
     auto work = [&](int g) {
-        myqc_eri_plan* pl = nullptr;
-        int rc = myqc_eri_plan_create(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab, g, g, ngpu, &pl);
-        if (rc) { rcs[g] = rc; errs[g] = g_last_error; return; }
-        double* d_out = nullptr;
-        const int64_t n = pl->out_elems;
-        cudaError_t e = cudaSuccess;
-        if (n > 0) e = cudaMalloc((void**)&d_out, (size_t)n * sizeof(double));
-        if (e != cudaSuccess) { rcs[g] = MYQC_ERR_NOMEM; errs[g] = cudaGetErrorString(e); myqc_eri_plan_destroy(pl); return; }
-        rc = myqc_eri_plan_execute(pl, d_out, nullptr);
-        if (!rc && n > 0) {
-            e = cudaMemcpy(packed + pl->out_offset, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) { rc = MYQC_ERR_CUDA; g_last_error = cudaGetErrorString(e); }
-        }
-        if (rc) { rcs[g] = rc; errs[g] = g_last_error; }
-        cudaFree(d_out);
-        myqc_eri_plan_destroy(pl);
+        rcs[g] = myqc_eri_packed_shard(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab,
+                                       packed + off[g], g, g, ngpu, nullptr);
+        if (rcs[g]) errs[g] = g_last_error;
     };
     if (ngpu == 1) work(0);
     else {

@@ -413,6 +413,45 @@ static int launch_one(const ClassArgs& a, int num_sms, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// FP64 roofline denominator: 8 independent DFMA chains per thread, 256 threads, 8 CTAs per SM.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+int measure_dfma_peak(int num_sms, double* tflops) {
+    const int grid = num_sms * 8, iters = 4096;
+    double* d = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d, (size_t)grid * 256 * sizeof(double));
+    if (e != cudaSuccess) return (int)e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(t0);
+        dfma_peak_kernel<<<grid, 256>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1);
+        const double flops = 2.0 * 8 * 16 * (double)iters * 256.0 * grid;
+        if (rep > 0) best = best > flops / (ms * 1e-3) / 1e12 ? best : flops / (ms * 1e-3) / 1e12;
+    }
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    cudaFree(d);
+    *tflops = best;
+    return (int)e;
+}
+
 int class_nlaunch(int UT, int TT) { return (UT == 2 && TT == 2) ? 4 : 1; }
 
 int launch_class(int UT, int TT, const ClassArgs& a, int num_sms, void* stream) {

@@ -40,6 +40,7 @@ int launch_class(int UT, int TT, const ClassArgs& a, int num_sms, void* stream);
 // number of kernel launches launch_class issues for (UT,TT)
 int class_nlaunch(int UT, int TT);
 
+int measure_dfma_peak(int num_sms, double* tflops);
 int launch_fill_zero(double* out, int64_t n, int num_sms, void* stream);
 int launch_expand_dense(const double* packed, int norb, double* xx, int num_sms, void* stream);
 

@@ -26,6 +26,7 @@
  *   T7  NINT rounds half away from zero (lround).
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -409,6 +410,62 @@ int oracle_int2e_dense(int nnuc, const double *xyz, const double *set, const int
             }
     }
     if (stats) { stats[0] = ncall; stats[1] = nvisit; }
+    return 0;
+}
+
+/* CPU-baseline sampler: the reference's per-(a,b) work (int2e.f90:199-283: pair set-up, the full
+ * c,d loops with their EXP and screen, getcoef/getDk and clmnew for every survivor) for the listed
+ * ordered set pairs only.  Results are discarded; stats[0] = surviving ordered quartets processed.
+ * nthreads > 1 distributes the listed pairs over POSIX threads (the reference itself is serial). */
+typedef struct {
+    int nnuc; const double *xyz, *set; const int *setinfo; const double *bas; const int *basinfo; const double *ft;
+    int npairs; const int *a_list, *b_list;
+    int next;              /* shared work counter */
+    long long ncall; double sink;
+    pthread_mutex_t mu;
+} sample_job;
+
+static void *sample_worker(void *arg) {
+    sample_job *J = (sample_job *)arg;
+    int nset = J->setinfo[0];
+    long long norb = J->basinfo[1];
+    setpair_t *ab = (setpair_t *)malloc(sizeof(setpair_t));
+    setpair_t *cd = (setpair_t *)malloc(sizeof(setpair_t));
+    long long ncall = 0;
+    double acc = 0.0;
+    for (;;) {
+        pthread_mutex_lock(&J->mu);
+        int k = J->next++;
+        pthread_mutex_unlock(&J->mu);
+        if (k >= J->npairs) break;
+        make_setpair(ab, J->a_list[k], J->b_list[k], J->nnuc, J->xyz, J->set, J->setinfo, J->bas, J->basinfo);
+        for (int c = 0; c < nset; ++c)
+            for (int d = 0; d < nset; ++d) {
+                double EGH = setpair_E(c, d, J->nnuc, J->xyz, J->set, J->setinfo);
+                if (EGH * ab->E < 1.0e-14) continue;
+                make_setpair(cd, c, d, J->nnuc, J->xyz, J->set, J->setinfo, J->bas, J->basinfo);
+                ++ncall;
+                clmnew(ab, cd, (int)norb, J->ft, null_sink, &acc);
+            }
+    }
+    pthread_mutex_lock(&J->mu);
+    J->ncall += ncall; J->sink += acc;
+    pthread_mutex_unlock(&J->mu);
+    free(ab); free(cd);
+    return NULL;
+}
+
+int oracle_int2e_sample(int nnuc, const double *xyz, const double *set, const int *setinfo,
+                        const double *bas, const int *basinfo, const double *ft, int npairs,
+                        const int *a_list, const int *b_list, int nthreads, long long *stats) {
+    sample_job J = {nnuc, xyz, set, setinfo, bas, basinfo, ft, npairs, a_list, b_list, 0, 0, 0.0, PTHREAD_MUTEX_INITIALIZER};
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    pthread_t th[256];
+    for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, sample_worker, &J);
+    sample_worker(&J);
+    for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+    if (stats) { stats[0] = J.ncall; stats[1] = (long long)(J.sink != 12345.678); }
     return 0;
 }
 

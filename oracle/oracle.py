@@ -62,6 +62,8 @@ def lib():
         L.oracle_int2e_rows.restype = ctypes.c_int
         L.oracle_int1e.argtypes = [ctypes.c_int, dp, ip, dp, ip, dp, ip, dp, dp, dp]
         L.oracle_int1e.restype = ctypes.c_int
+        L.oracle_int2e_sample.argtypes = [ctypes.c_int, dp, dp, ip, dp, ip, dp, ctypes.c_int, ip, ip, ctypes.c_int, llp]
+        L.oracle_int2e_sample.restype = ctypes.c_int
         L.oracle_boys.argtypes = [dp, ctypes.c_int, ctypes.c_double, dp]
         L.oracle_boys.restype = None
         _lib = L
@@ -263,6 +265,22 @@ def int2e_rows(mol, b, ft, rows):
     assert lib().oracle_int2e_rows(*a, len(rows), rows.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
                                    _dp(out)) == 0
     return out
+
+
+def int2e_sample(mol, b, ft, a_list, b_list, nthreads=1):
+    """Time-only run of the reference's per-(a,b) work for the listed ordered set pairs.
+    Returns (seconds, surviving ordered quartets processed)."""
+    import time
+    keep, a = _args(mol, b, ft)
+    al = np.ascontiguousarray(a_list, dtype=np.int32)
+    bl = np.ascontiguousarray(b_list, dtype=np.int32)
+    stats = np.zeros(2, dtype=np.int64)
+    t0 = time.perf_counter()
+    rc = lib().oracle_int2e_sample(*a, len(al), _ip(al), _ip(bl), int(nthreads),
+                                   stats.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)))
+    dt = time.perf_counter() - t0
+    assert rc == 0
+    return dt, int(stats[0])
 
 
 def int1e(mol, b, ft):
