@@ -154,6 +154,8 @@ int myqc_read_ftab(const char *path, double *ftab);
 /* WRITE(42) XX, int2e.f90:166,306-307: one Fortran unformatted sequential record, split into
  * gfortran subrecords above 2147483639 payload bytes.                                        */
 int myqc_write_xx(const char *path, const double *xx, int norb);
+/* same with an explicit maximum subrecord payload (bytes); used to test the subrecord framing */
+int myqc_write_xx_ex(const char *path, const double *xx, int norb, int64_t max_subrecord);
 int myqc_read_xx(const char *path, double *xx, int norb);
 
 /* The whole program: what the `int2e` executable does in directory `dir`.

@@ -35,7 +35,7 @@ EXPORTS = [
     "myqc_eri_expand_dense", "myqc_read_env", "myqc_build_basis", "myqc_read_ftab",
     "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main", "myqc_eri_shard_layout",
     "myqc_eri_canonical_stats", "myqc_eri_plan_launch_count", "myqc_eri_plan_launch_info",
-    "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard",
+    "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard", "myqc_write_xx_ex",
 ]
 
 
@@ -85,6 +85,7 @@ def lib() -> ctypes.CDLL:
     L.myqc_read_ftab.argtypes = [c_char_p, _dp]
     L.myqc_write_xx.argtypes = [c_char_p, _dp, c_int]
     L.myqc_read_xx.argtypes = [c_char_p, _dp, c_int]
+    L.myqc_write_xx_ex.argtypes = [c_char_p, _dp, c_int, ctypes.c_int64]
     L.myqc_int2e_main.argtypes = [c_char_p, c_int]
     L.myqc_eri_shard_layout.argtypes = common[:-1] + [c_int, _i64p]
     L.myqc_eri_canonical_stats.argtypes = [c_int, _dp, c_int, c_int, _dp, _ip, _i64p, _dp]
@@ -199,10 +200,13 @@ def read_ftab(path: str) -> np.ndarray:
     return ft
 
 
-def write_xx(path: str, xx: np.ndarray, norb: int):
+def write_xx(path: str, xx: np.ndarray, norb: int, max_subrecord: int | None = None):
     flat = np.ascontiguousarray(np.asarray(xx).reshape(-1, order="F"))
     assert flat.size == norb ** 4
-    _check(lib().myqc_write_xx(path.encode(), _d(flat), norb))
+    if max_subrecord is None:
+        _check(lib().myqc_write_xx(path.encode(), _d(flat), norb))
+    else:
+        _check(lib().myqc_write_xx_ex(path.encode(), _d(flat), norb, max_subrecord))
 
 
 def read_xx(path: str, norb: int) -> np.ndarray:

@@ -42,8 +42,8 @@ static int class_id(int la, int lb) {
 struct DevList {  // device copy of a PairList
     int type = 0, n = 0, npad = 0;
     double *aos = nullptr, *soa = nullptr;
-    int32_t *nprim = nullptr, *fi = nullptr, *fj = nullptr, *diag = nullptr;
-    std::vector<double> emax;  // host copy for the prefix computation
+    int32_t *nprim = nullptr, *pidx = nullptr;
+    PairList host;  // host copy (without the bulky record arrays) for the prefix computation
 };
 
 struct Launch {
@@ -63,7 +63,10 @@ struct myqc_eri_plan {
     std::vector<void*> dev_allocs;
     std::vector<DevList> lists;
     std::vector<Launch> launches;
-    double* d_ftab = nullptr;  // [5][121][8]
+    double* d_ftab = nullptr;    // [5][121][8]
+    double* d_exptab = nullptr;  // [601][2] {exp(-k/10), k/10}
+    int* d_counters = nullptr;   // one row counter per class-kernel launch
+    int ncounters = 0;
     // stats (canonical primitive-quartet counts of the whole shard)
     int64_t nquartets[6] = {0, 0, 0, 0, 0, 0};
     double model_flops = 0.0;
@@ -85,14 +88,13 @@ static int upload(myqc_eri_plan* pl, const std::vector<T>& h, T** d) {
 }
 
 static int upload_list(myqc_eri_plan* pl, const PairList& src, DevList& d) {
-    d.type = src.type; d.n = src.n; d.npad = src.npad; d.emax = src.emax;
+    d.type = src.type; d.n = src.n; d.npad = src.npad;
+    d.host.type = src.type; d.host.n = src.n; d.host.emax = src.emax; d.host.bucket = src.bucket;
     int rc;
     if ((rc = upload(pl, src.aos, &d.aos))) return rc;
     if ((rc = upload(pl, src.soa, &d.soa))) return rc;
     if ((rc = upload(pl, src.nprim, &d.nprim))) return rc;
-    if ((rc = upload(pl, src.fi, &d.fi))) return rc;
-    if ((rc = upload(pl, src.fj, &d.fj))) return rc;
-    if ((rc = upload(pl, src.diag, &d.diag))) return rc;
+    if ((rc = upload(pl, src.pidx, &d.pidx))) return rc;
     return MYQC_OK;
 }
 
@@ -119,18 +121,27 @@ static int add_launch(myqc_eri_plan* pl, int ui, int ti, bool tri) {
     L.UT = U.type; L.TT = T.type;
     ClassArgs& a = L.args;
     std::memset(&a, 0, sizeof(a));
-    a.u_aos = U.aos; a.u_nprim = U.nprim; a.u_fi = U.fi; a.u_fj = U.fj; a.u_diag = U.diag; a.nU = U.n;
-    std::vector<int32_t> ntv = prefix_counts(U.emax, T.emax);
-    int32_t* d_ntv = nullptr;
-    int rc = upload(pl, ntv, &d_ntv);
+    a.u_aos = U.aos; a.u_nprim = U.nprim; a.u_pidx = U.pidx; a.nU = U.n;
+    const std::vector<int32_t> ntv = row_prefix(U.host, T.host);
+    std::vector<int4> tasks;
+    for (int u = 0; u < U.n; ++u)
+        for (int v0 = tri ? u : 0; v0 < ntv[u]; v0 += kTaskPairs)
+            tasks.push_back(make_int4(u, v0, std::min(v0 + kTaskPairs, (int)ntv[u]), 0));
+    if (tasks.empty()) return MYQC_OK;
+    int4* d_tasks = nullptr;
+    int rc = upload(pl, tasks, &d_tasks);
     if (rc) return rc;
-    a.u_ntv = d_ntv;
-    a.t_soa = T.soa; a.t_nprim = T.nprim; a.t_fi = T.fi; a.t_fj = T.fj; a.t_diag = T.diag;
+    a.tasks = d_tasks;
+    a.ntasks = (int)tasks.size();
+    a.t_soa = T.soa; a.t_nprim = T.nprim; a.t_pidx = T.pidx;
     a.t_npad = T.npad; a.nT = T.n; a.tri = tri ? 1 : 0;
     a.ftab_q = pl->d_ftab + (size_t)(U.type + T.type) * 121 * 8;
+    a.exptab = reinterpret_cast<const double2*>(pl->d_exptab);
+    a.row_counter = pl->d_counters + pl->ncounters;
+    pl->ncounters += class_nlaunch(L.UT, L.TT);
     a.out = nullptr;
-    a.out_offset = pl->out_offset; a.out_elems = pl->out_elems;
-    a.norb = pl->norb; a.npair = pl->npair;
+    a.out_offset = pl->out_offset;
+    a.npair = pl->npair;
     pl->launches.push_back(L);
     pl->nlaunch += class_nlaunch(L.UT, L.TT);
     return MYQC_OK;
@@ -208,7 +219,7 @@ static int shard_fn_bounds(const std::vector<Shell>& shells, const PairList all[
             const PairList& A = all[ta];
             const PairList& B = all[tb];
             if (A.n == 0 || B.n == 0) continue;
-            const std::vector<int32_t> cnt = prefix_counts(A.emax, B.emax);
+            const std::vector<int32_t> cnt = row_prefix(A, B);
             std::vector<double> hist(nc + 1, 0.0), ge(nc + 2, 0.0);
             double mean_prim = 0.0;
             for (int k = 0; k < B.n; ++k) {
@@ -306,9 +317,14 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
                     if (k > 1) fact *= k;
                     h[((size_t)qi * 121 + t) * 8 + k] = ftab[t + 121 * (3 * qi + k)] / fact;
                 }
-                h[((size_t)qi * 121 + t) * 8 + 7] = t / 10.0;
+                h[((size_t)qi * 121 + t) * 8 + 7] = 0.0;
             }
         if ((rc = upload(pl.get(), h, &pl->d_ftab))) return rc;
+        std::vector<double> ex(2 * 608, 0.0);
+        for (int k = 0; k <= 600; ++k) { ex[2 * k] = std::exp(-(k / 10.0)); ex[2 * k + 1] = k / 10.0; }
+        if ((rc = upload(pl.get(), ex, &pl->d_exptab))) return rc;
+        std::vector<int> zeros(64, 0);
+        if ((rc = upload(pl.get(), zeros, &pl->d_counters))) return rc;
     }
 
     // ---- sharding: contiguous blocks of packed rows, cut where a shell's functions start -------
@@ -394,7 +410,7 @@ int64_t myqc_eri_plan_out_elems(const myqc_eri_plan* plan) { return plan ? plan-
 int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
     if (!plan || (!d_out && plan->out_elems > 0)) return fail(MYQC_ERR_BAD_ARG, "null plan or output");
     CU(cudaSetDevice(plan->device));
-    int e = launch_fill_zero(d_out, plan->out_elems, plan->num_sms, stream);
+    int e = launch_fill_zero(d_out, plan->out_elems, plan->d_counters, plan->ncounters, plan->num_sms, stream);
     if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
     for (Launch& L : plan->launches) {
         L.args.out = d_out;
@@ -432,7 +448,7 @@ int myqc_eri_plan_execute_timed(myqc_eri_plan* plan, double* d_out, void* stream
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) CU(cudaEventCreate(&e));
     CU(cudaEventRecord(ev[0], st));
-    int e = launch_fill_zero(d_out, plan->out_elems, plan->num_sms, stream);
+    int e = launch_fill_zero(d_out, plan->out_elems, plan->d_counters, plan->ncounters, plan->num_sms, stream);
     if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
     CU(cudaEventRecord(ev[1], st));
     for (int k = 0; k < n - 1; ++k) {

@@ -4,27 +4,33 @@
 // for every canonical contracted shell quartet (u | v) that passes the reference's
 // EIJ*EGH >= 1e-14 rule, the sum over primitive quartets of
 //     ll * sum_{k,k'} (-1)^{N'+L'+M'} D_k D'_k' R_{N+N',L+L',M+M'}(alpha, P-Q)
-// with Boys values F_j(T) obtained exactly as the reference does (7-term Taylor expansion
-// about the nearest Ftab node for T < 12 starting at order Q = 3*(number of SP sets) and
-// recurring downwards; asymptotic forms above).
+// with Boys values F_j(T) obtained exactly as the reference does: 7-term Taylor expansion about
+// the nearest Ftab node for T < 12, starting at order Q = 3*(number of SP sets) and recurring
+// downwards (Boys1); F0 = sqrt(pi)/2/sqrt(T) - exp(-T) g(T)/T with upward recursion for
+// 12 <= T < 2Q+36 (Boys2); the bare asymptotic form above (Boys3).
 //
 // Mapping onto the B200:
 //   * one kernel instantiation per quartet class (UT, TT) = (#SP sets in the uniform-side pair,
-//     #SP sets in the lane-side pair); all loops over Hermite terms are compile-time unrolled,
-//     so K-, R- and output accumulators live in registers (FP64 DFMA pipe bound).
-//   * persistent CTAs; each CTA iteration owns one row u: its primitive-pair record block
-//     (<= 3.7 KB) is staged into shared memory with one TMA bulk copy (cp.async.bulk +
-//     mbarrier) and then read as warp-uniform broadcasts.
-//   * each lane owns one lane-side pair v (coalesced SoA loads) and loops over primitive
-//     pairs: for each lane-side primitive, accumulate K[f][H'] over the uniform-side primitives
-//     (step A: |terms_U| x |H_T| DFMA per primitive quartet), then fold the lane-side
-//     coefficients once (step B), i.e. the second half-contraction is hoisted out of the
-//     primitive-quartet loop.
-//   * the Boys table of the class (121 x 8 doubles, pre-divided by k!) lives in shared memory.
-//   * (SP SP|SP SP) is split into four mu-slices of the uniform side so that 40 K- and 64
-//     output accumulators fit; outputs of the big classes are kept in lane-private shared
-//     memory between lane-side primitives.
-//   * no tensor cores: this is not a dense contraction.
+//     #SP sets in the lane-side pair); all loops over Hermite terms are unrolled at compile time
+//     (static_for), so the K-, R- and output accumulators live in registers and the inner loop is
+//     straight-line DFMA code (FP64 pipe bound; no tensor cores: this is not a dense contraction).
+//   * warps are autonomous: each warp pulls rows u of the quartet space from a global counter,
+//     stages the row's primitive-pair record block (<= 3.7 KB) into its own shared-memory double
+//     buffer with a TMA bulk copy (cp.async.bulk + mbarrier) while it still works on the previous
+//     row, and reads it back as warp-uniform broadcasts.  No CTA-wide barrier in the main loop.
+//   * each lane owns one lane-side pair v (coalesced SoA loads).  Pair lists are ordered by
+//     prefactor bucket and Morton code of the pair centre, so the 32 pairs of a warp are spatially
+//     close: they sit in the same Boys regime and lose the same primitives to the screen.
+//   * for each lane-side primitive, K[f][H'] is accumulated over the uniform-side primitives
+//     (step A: |terms_U| x |H_T| DFMA per primitive quartet); the lane-side coefficients are folded
+//     once afterwards (step B) -- the second half-contraction is hoisted out of the inner loop.
+//   * far-field quartets (T >= 2Q+36, the bulk of a large molecule) need one reciprocal square
+//     root and no exponential: G_j = sqrt(pi)/2 /sqrt(p q) (2j-1)!! (-1)^j / R^(2j+1).
+//   * the Boys Taylor table of the class (121 x 8 doubles, pre-divided by k!) and an exp(-k/10)
+//     table live in shared memory; exp(-T) = exp(-k/10) * exp(k/10 - T) with a 9-term series.
+//   * (SP SP|SP SP) is split into four mu-slices of the uniform side so that 40 K- and 64 output
+//     accumulators fit; outputs of the two big classes are kept in lane-private shared memory
+//     between lane-side primitives.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -38,6 +44,8 @@ namespace myqc {
 namespace {
 
 constexpr double kScreen = 1.0e-14;  // int2e.f90:257
+// 0.5 * Pi**0.5 with the reference's float32 Pi = 3.1415927410125732 (auxilary.f90:169,182,196,208)
+constexpr double kHalfSqrtPi = 0.8862269377835134;
 
 // compile-time loop: f(std::integral_constant<int,I>) for I in [0,N).  Forces every table lookup
 // (term_fn, term_h, h_add ...) to be evaluated by the front end, so all accumulator indices are
@@ -87,11 +95,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Boys function, auxilary.f90:85-215.  F[0..LN] are returned; the T < 12 branch starts at order
-// Q like the reference and recurs downwards through all orders (T3 in SURVEY.md).
-// s_ft row t: {Ft(t,Q+k)/k!, k=0..6 ; t/10.0}.
+// 1/sqrt(x) for positive normal x: MUFU.RSQ64H seed + one third-order correction (the arithmetic
+// of CUDA's rsqrt() without its special-case branch).
+__device__ __forceinline__ double rsqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double r = fma(x, -(y * y), 1.0);
+    const double c = fma(r, 0.375, 0.5);
+    return fma(c, y * r, y);
+}
+
+// exp(d) for |d| <= 0.06: 9-term series (truncation < 3e-20)
+__device__ __forceinline__ double exp_small(double d) {
+    double e = 1.0 / 362880.0;
+    e = fma(e, d, 1.0 / 40320.0);
+    e = fma(e, d, 1.0 / 5040.0);
+    e = fma(e, d, 1.0 / 720.0);
+    e = fma(e, d, 1.0 / 120.0);
+    e = fma(e, d, 1.0 / 24.0);
+    e = fma(e, d, 1.0 / 6.0);
+    e = fma(e, d, 0.5);
+    e = fma(e, d, 1.0);
+    return fma(e, d, 1.0);
+}
+
+// NINT(x) for x >= 0: round half away from zero (auxilary.f90:152)
+__device__ __forceinline__ int nint_pos(double x) {
+    int k = (int)x;
+    if (x - (double)k >= 0.5) ++k;
+    return k;
+}
+
+// auxilary.f90:265-285; T >= 30 is undefined in the reference, we keep 0.490
 __device__ __forceinline__ double boys_g(double T, double invT) {
-    // auxilary.f90:265-285; T >= 30 is undefined in the reference, we keep 0.490 (T5)
     double c0 = 0.490, c1 = 0.0, c2 = 0.0, c3 = 0.0;
     if (T < 15.0) { c0 = 0.4999489092; c1 = -0.2473631686; c2 = 0.321180909; c3 = -0.3811559346; }
     else if (T < 18.0) { c0 = 0.4998436875; c1 = -0.24249438; c2 = 0.24642845; }
@@ -99,51 +135,55 @@ __device__ __forceinline__ double boys_g(double T, double invT) {
     return fma(invT, fma(invT, fma(invT, c3, c2), c1), c0);
 }
 
-template <int Q, int LN>
-__device__ __forceinline__ void boys(double T, double (&F)[LN + 1], const double* __restrict__ s_ft) {
-    // 0.5 * Pi**0.5 with the reference's float32 Pi (auxilary.f90:169,182)
-    constexpr double kHalfSqrtPi = 0.8862269377835134;  // 0.5*sqrt(3.1415927410125732)
+// G_j = (-2 alpha)^j F_j(T) / sqrt(p+q), j = 0..LT, for the two regimes that need alpha and T
+// (auxilary.f90:130-189).  s_ft row t: {Ft(t,Q+k)/k!, k=0..6 ; unused}; s_exp[k] = {exp(-k/10), k/10}.
+template <int Q, int LT>
+__device__ __forceinline__ void boys_near_mid(double T, double alpha, double rs, double (&G)[LT + 1],
+                                              const double* __restrict__ s_ft,
+                                              const double2* __restrict__ s_exp) {
+    double F[LT + 1];
+    const int Tk = nint_pos(T * 10.0);
+    const double2 ex = s_exp[Tk];
+    const double d = ex.y - T;  // Tk/10.0D0 - T
     if (T < 12.0) {
-        // Tk = NINT(T*10): round half away from zero (T7)
-        const double x = T * 10.0;
-        int Tk = (int)x;
-        if (x - (double)Tk >= 0.5) ++Tk;
         const double2* row = reinterpret_cast<const double2*>(s_ft + Tk * 8);
-        const double2 c01 = row[0], c23 = row[1], c45 = row[2], c6t = row[3];
-        const double d = c6t.y - T;  // Tk/10.0D0 - T
-        double f = c6t.x;
+        const double2 c01 = row[0], c23 = row[1], c45 = row[2], c6 = row[3];
+        double f = c6.x;
         f = fma(f, d, c45.y);
         f = fma(f, d, c45.x);
         f = fma(f, d, c23.y);
         f = fma(f, d, c23.x);
         f = fma(f, d, c01.y);
         f = fma(f, d, c01.x);
-        if (Q <= LN) F[Q] = f;
+        if (Q <= LT) F[Q] = f;
         if (Q > 0) {
-            const double e = exp(-T);
+            const double e = ex.x * exp_small(d);  // exp(-T)
             const double t2 = 2.0 * T;
 #pragma unroll
             for (int j = Q - 1; j >= 0; --j) {
                 f = fma(t2, f, e) * (1.0 / (2.0 * j + 1.0));
-                if (j <= LN) F[j] = f;
+                if (j <= LT) F[j] = f;
             }
         }
     } else {
-        const double r = rsqrt(T);
-        const double invT = r * r;
-        double f = kHalfSqrtPi * r;
-        double e = 0.0;
-        if (T < (double)(2 * Q + 36)) {
-            e = exp(-T);
-            f = fma(-e * boys_g(T, invT), invT, f);
-        }
+        const double rT = rsqrt_pos(T);
+        const double invT = rT * rT;
+        const double e = ex.x * exp_small(d);
+        double f = fma(-e * boys_g(T, invT), invT, kHalfSqrtPi * rT);
         F[0] = f;
         const double h = 0.5 * invT;
 #pragma unroll
-        for (int j = 1; j <= LN; ++j) {
+        for (int j = 1; j <= LT; ++j) {
             f = h * fma((double)(2 * j - 1), f, -e);
             F[j] = f;
         }
+    }
+    const double m2a = -2.0 * alpha;
+    double w = rs;
+#pragma unroll
+    for (int j = 0; j <= LT; ++j) {
+        G[j] = w * F[j];
+        w *= m2a;
     }
 }
 
@@ -178,87 +218,130 @@ __device__ __forceinline__ void build_R(const double (&G)[LT + 1], double X, dou
     });
 }
 
+template <int UT, int TT, int USL>
+struct Cfg {
+    static constexpr int LT = UT + TT;
+    static constexpr int Q = 3 * LT;  // Boys start order, int2e.f90:654-658,668
+    static constexpr int NR = h_count(LT);
+    static constexpr int NHT = tt_nh(TT);
+    static constexpr int NFU = (USL >= 0) ? 4 : tt_nf(UT);
+    static constexpr int NFU_FULL = tt_nf(UT);
+    static constexpr int NFT = tt_nf(TT);
+    static constexpr int NTU = tt_nterm(UT);
+    static constexpr int NTT = tt_nterm(TT);
+    static constexpr int FU = tt_nfield(UT);
+    static constexpr int FT = tt_nfield(TT);
+    static constexpr int NOUT = NFU * NFT;
+    static constexpr bool OUT_SMEM = (NOUT > 16);
+    static constexpr int NTHREADS = OUT_SMEM ? 128 : 256;
+    static constexpr int NWARPS = NTHREADS / 32;
+    static constexpr uint32_t U_BYTES = 9 * FU * 8;
+    // shared memory: Taylor table | exp table | per-warp U double buffers | mbarriers | out staging
+    static constexpr size_t OFF_EXP = 121 * 8 * 8;
+    static constexpr size_t OFF_U = OFF_EXP + 608 * 16;
+    static constexpr size_t OFF_BAR = OFF_U + (size_t)NWARPS * 2 * U_BYTES;
+    static constexpr size_t OFF_OUT = OFF_BAR + (size_t)NWARPS * 2 * 8;
+    static constexpr size_t SMEM = OFF_OUT + (OUT_SMEM ? (size_t)NOUT * NTHREADS * 8 : 0);
+};
+
 }  // namespace
 
-// smem layout: [ftab 121*8 doubles][u record 9*FU doubles][mbarrier 8 B (+8 pad)][out staging]
 template <int UT, int TT, int USL>
-static constexpr size_t smem_bytes() {
-    size_t b = 121 * 8 * 8 + 9 * tt_nfield(UT) * 8 + 16;
-    constexpr int nout = ((USL >= 0) ? 4 : tt_nf(UT)) * tt_nf(TT);
-    if (nout > 16) b += (size_t)nout * 128 * 8;
-    return b;
-}
+__global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS) eri_class_kernel(const ClassArgs a) {
+    using C = Cfg<UT, TT, USL>;
+    constexpr int LT = C::LT, Q = C::Q, NR = C::NR, NHT = C::NHT, NFU = C::NFU, NFT = C::NFT;
+    constexpr int NTU = C::NTU, NTT = C::NTT, FU = C::FU, FT = C::FT, NOUT = C::NOUT;
+    constexpr int NTHREADS = C::NTHREADS;
+    constexpr bool OUT_SMEM = C::OUT_SMEM;
 
-template <int UT, int TT, int USL>
-__global__ void __launch_bounds__(((((USL >= 0) ? 4 : tt_nf(UT)) * tt_nf(TT)) > 16) ? 128 : 256)
-    eri_class_kernel(const ClassArgs a) {
-    constexpr int LT = UT + TT;
-    constexpr int Q = 3 * LT;
-    constexpr int NR = h_count(LT);
-    constexpr int NHT = tt_nh(TT);
-    constexpr int NFU = (USL >= 0) ? 4 : tt_nf(UT);
-    constexpr int NFU_FULL = tt_nf(UT);
-    constexpr int NFT = tt_nf(TT);
-    constexpr int NTU = tt_nterm(UT);
-    constexpr int NTT = tt_nterm(TT);
-    constexpr int FU = tt_nfield(UT);
-    constexpr int FT = tt_nfield(TT);
-    constexpr int NOUT = NFU * NFT;
-    constexpr bool OUT_SMEM = (NOUT > 16);
-    constexpr int NTHREADS = OUT_SMEM ? 128 : 256;
-    constexpr int NWARPS = NTHREADS / 32;
-    constexpr uint32_t U_BYTES = 9 * FU * 8;
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* s_ft = reinterpret_cast<double*>(smem_raw);
-    double* s_u = s_ft + 121 * 8;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_u + 9 * FU);
-    double* s_out = reinterpret_cast<double*>(s_bar + 2);
+    double2* s_exp = reinterpret_cast<double2*>(smem_raw + C::OFF_EXP);
+    double* s_out = reinterpret_cast<double*>(smem_raw + C::OFF_OUT);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    double* s_ubuf = reinterpret_cast<double*>(smem_raw + C::OFF_U) + (size_t)warp * 2 * 9 * FU;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + C::OFF_BAR) + warp * 2;
 
     for (int i = tid; i < 121 * 8; i += NTHREADS) s_ft[i] = a.ftab_q[i];
-    if (tid == 0) {
-        mbar_init(s_bar, 1);
+    for (int i = tid; i < 601; i += NTHREADS) s_exp[i] = a.exptab[i];
+    if (lane == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    uint32_t parity = 0;
-    for (int u = blockIdx.x; u < a.nU; u += gridDim.x) {
-        if (tid == 0) {
-            mbar_expect_tx(s_bar, U_BYTES);
-            tma_bulk_g2s(s_u, a.u_aos + (size_t)u * 9 * FU, U_BYTES, s_bar);
+    // ---- warp-autonomous task loop with a two-deep TMA prefetch ------------------------------
+    // task = (row u, lane-side range [vb0, vend)): rows are cut into pieces of at most
+    // kTaskPairs lane-side pairs so that no warp owns more than a sliver of the launch.
+    int t = 0;
+    int4 task = make_int4(0, 0, 0, 0);
+    if (lane == 0) {
+        t = atomicAdd(a.row_counter, 1);
+        if (t < a.ntasks) {
+            task = a.tasks[t];
+            mbar_expect_tx(&s_bar[0], C::U_BYTES);
+            tma_bulk_g2s(s_ubuf, a.u_aos + (size_t)task.x * 9 * FU, C::U_BYTES, &s_bar[0]);
         }
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    task.x = __shfl_sync(0xffffffffu, task.x, 0);
+    task.y = __shfl_sync(0xffffffffu, task.y, 0);
+    task.z = __shfl_sync(0xffffffffu, task.z, 0);
+    int buf = 0;
+    uint32_t parity0 = 0, parity1 = 0;
+    while (t < a.ntasks) {
+        int tn = 0;
+        int4 taskn = make_int4(0, 0, 0, 0);
+        if (lane == 0) {
+            tn = atomicAdd(a.row_counter, 1);
+            if (tn < a.ntasks) {
+                taskn = a.tasks[tn];
+                mbar_expect_tx(&s_bar[buf ^ 1], C::U_BYTES);
+                tma_bulk_g2s(s_ubuf + (size_t)(buf ^ 1) * 9 * FU, a.u_aos + (size_t)taskn.x * 9 * FU, C::U_BYTES,
+                             &s_bar[buf ^ 1]);
+            }
+        }
+        tn = __shfl_sync(0xffffffffu, tn, 0);
+        taskn.x = __shfl_sync(0xffffffffu, taskn.x, 0);
+        taskn.y = __shfl_sync(0xffffffffu, taskn.y, 0);
+        taskn.z = __shfl_sync(0xffffffffu, taskn.z, 0);
+        const int u = task.x;
+        const int v0 = task.y;
+        const int ntv = task.z;
         const int npu = a.u_nprim[u];
-        const int ntv = a.u_ntv[u];
-        const int v0 = a.tri ? u : 0;
-        const int udiag = a.u_diag[u];
-        mbar_wait(s_bar, parity);
-        parity ^= 1;
+        int P1[NFU];
+#pragma unroll
+        for (int f = 0; f < NFU; ++f) P1[f] = a.u_pidx[(size_t)u * C::NFU_FULL + ((USL >= 0) ? (4 * USL + f) : f)];
+        if (buf == 0) { mbar_wait(&s_bar[0], parity0); parity0 ^= 1; }
+        else          { mbar_wait(&s_bar[1], parity1); parity1 ^= 1; }
+        const double* s_u = s_ubuf + (size_t)buf * 9 * FU;
         const double eu_max = s_u[4];
 
-        for (int vb = v0 + warp * 32; vb < ntv; vb += NWARPS * 32) {
+        for (int vb = v0; vb < ntv; vb += 32) {
             const int v = vb + lane;
             if (v < ntv) {
                 double out_r[OUT_SMEM ? 1 : NOUT];
-                if (OUT_SMEM) {
+                if constexpr (OUT_SMEM) {
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o) s_out[o * NTHREADS + tid] = 0.0;
                 } else {
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o) out_r[o] = 0.0;
                 }
+                bool any = false;
                 const int npt = a.t_nprim[v];
+                const size_t ld = (size_t)a.t_npad;
                 for (int kt = 0; kt < npt; ++kt) {
-                    const double* tp = a.t_soa + (size_t)kt * FT * a.t_npad + v;
-                    const double et = tp[4 * (size_t)a.t_npad];
-                    if (eu_max * et < kScreen) break;  // prims sorted by E descending
+                    const double* tp = a.t_soa + (size_t)kt * FT * ld + v;
+                    const double et = tp[4 * ld];
+                    if (eu_max * et < kScreen) break;  // primitives are sorted by E, descending
                     const double q = tp[0];
-                    const double Qx = tp[(size_t)a.t_npad], Qy = tp[2 * (size_t)a.t_npad],
-                                 Qz = tp[3 * (size_t)a.t_npad];
+                    const double Qx = tp[ld], Qy = tp[2 * ld], Qz = tp[3 * ld];
+                    const double cfar = kHalfSqrtPi * tp[5 * ld];  // sqrt(pi)/2 / sqrt(q)
                     double K[NFU][NHT];
 #pragma unroll
                     for (int f = 0; f < NFU; ++f)
@@ -267,25 +350,30 @@ __global__ void __launch_bounds__(((((USL >= 0) ? 4 : tt_nf(UT)) * tt_nf(TT)) > 
 
                     for (int ku = 0; ku < npu; ++ku) {
                         const double* up = s_u + ku * FU;
-                        if (up[4] * et < kScreen) break;  // IF (EGH*EIJ .LT. 1.0D-14) CYCLE
+                        if (up[4] * et < kScreen) break;  // IF (EGH*EIJ .LT. 1.0D-14) CYCLE  (int2e.f90:257)
+                        any = true;
                         const double p = up[0];
                         const double X = up[1] - Qx, Y = up[2] - Qy, Z = up[3] - Qz;
+                        const double R2 = fma(X, X, fma(Y, Y, Z * Z));
                         const double s = p + q;
-                        const double rs = rsqrt(s);
-                        const double alpha = p * q * (rs * rs);
-                        const double T = alpha * (X * X + Y * Y + Z * Z);
-                        double F[LT + 1];
-                        boys<Q, LT>(T, F, s_ft);
-                        // G_j = (-2 alpha)^j F_j / sqrt(p+q)   (R_000^j, auxilary.f90:51; ll folded)
+                        const double pq = p * q;
+                        const double w = pq * R2;  // T*(p+q)
                         double G[LT + 1];
-                        {
-                            const double m2a = -2.0 * alpha;
-                            double w = rs;
+                        if (w >= (double)(2 * Q + 36) * s) {
+                            // Boys3 (auxilary.f90:194-215): G_j = sqrt(pi)/2 /sqrt(pq) (2j-1)!! (-1)^j R^-(2j+1)
+                            const double rinv = rsqrt_pos(R2);
+                            const double m = -(rinv * rinv);
+                            double g = cfar * up[5] * rinv;
+                            G[0] = g;
 #pragma unroll
-                            for (int j = 0; j <= LT; ++j) {
-                                G[j] = w * F[j];
-                                w *= m2a;
+                            for (int j = 1; j <= LT; ++j) {
+                                g *= (double)(2 * j - 1) * m;
+                                G[j] = g;
                             }
+                        } else {
+                            const double rs = rsqrt_pos(s);
+                            const double alpha = pq * (rs * rs);
+                            boys_near_mid<Q, LT>(alpha * R2, alpha, rs, G, s_ft, s_exp);
                         }
                         double R[NR];
                         build_R<LT>(G, X, Y, Z, R);
@@ -296,7 +384,7 @@ __global__ void __launch_bounds__(((((USL >= 0) ? 4 : tt_nf(UT)) * tt_nf(TT)) > 
                             if constexpr (USL < 0 || f / 4 == USL) {
                                 constexpr int lf = (USL >= 0) ? (f % 4) : f;
                                 constexpr int hk = term_h(UT, k);
-                                const double cu = up[5 + k];
+                                const double cu = up[kRecCoef + k];
                                 static_for<0, NHT>([&](auto hc) {
                                     constexpr int hp = decltype(hc)::value;
                                     constexpr int ri = h_add(hk, hp);
@@ -310,7 +398,7 @@ __global__ void __launch_bounds__(((((USL >= 0) ? 4 : tt_nf(UT)) * tt_nf(TT)) > 
                         constexpr int k = decltype(kc)::value;
                         constexpr int fp = term_fn(TT, k);
                         constexpr int hp = term_h(TT, k);
-                        double ct = tp[(size_t)(5 + k) * a.t_npad];
+                        double ct = tp[(size_t)(kRecCoef + k) * ld];
                         if constexpr (h_parity(hp) != 0) ct = -ct;
 #pragma unroll
                         for (int f = 0; f < NFU; ++f) {
@@ -323,41 +411,42 @@ __global__ void __launch_bounds__(((((USL >= 0) ? 4 : tt_nf(UT)) * tt_nf(TT)) > 
                         }
                     });
                 }
-                // store the distinct canonical integrals of this shell quartet
-                const int tdiag = a.t_diag[v];
-                const bool same_pair = a.tri && (v == u);
-                const int64_t n = a.norb;
+                // store the distinct canonical integrals of this shell quartet (the slice was zero
+                // filled: quartets the screen removes entirely keep the reference's exact zeros)
+                if (any) {
+                    const bool same_pair = a.tri && (v == u);
+                    const int64_t np = a.npair;
+                    int P2[NFT];
 #pragma unroll
-                for (int f = 0; f < NFU; ++f) {
-                    const int fu = (USL >= 0) ? (4 * USL + f) : f;
-                    const int i0 = a.u_fi[(size_t)u * NFU_FULL + fu];
-                    const int j0 = a.u_fj[(size_t)u * NFU_FULL + fu];
-                    if (i0 < 0 || (udiag && i0 > j0)) continue;
-                    const int64_t i = i0 < j0 ? i0 : j0, j = i0 < j0 ? j0 : i0;
-                    const int64_t P1 = i * n - i * (i - 1) / 2 + (j - i);
+                    for (int fp = 0; fp < NFT; ++fp) P2[fp] = a.t_pidx[(size_t)v * NFT + fp];
 #pragma unroll
-                    for (int fp = 0; fp < NFT; ++fp) {
-                        const int g0 = a.t_fi[(size_t)v * NFT + fp];
-                        const int h0 = a.t_fj[(size_t)v * NFT + fp];
-                        if (g0 < 0 || (tdiag && g0 > h0)) continue;
-                        const int64_t g = g0 < h0 ? g0 : h0, h = g0 < h0 ? h0 : g0;
-                        const int64_t P2 = g * n - g * (g - 1) / 2 + (h - g);
-                        if (same_pair && P1 > P2) continue;
-                        const int64_t lo = P1 < P2 ? P1 : P2, hi = P1 < P2 ? P2 : P1;
-                        const int64_t idx = lo * a.npair - lo * (lo - 1) / 2 + (hi - lo) - a.out_offset;
-                        const double val = OUT_SMEM ? s_out[(f * NFT + fp) * NTHREADS + tid] : out_r[f * NFT + fp];
-                        a.out[idx] = val;
+                    for (int f = 0; f < NFU; ++f) {
+                        if (P1[f] < 0) continue;
+#pragma unroll
+                        for (int fp = 0; fp < NFT; ++fp) {
+                            if (P2[fp] < 0) continue;
+                            if (same_pair && P1[f] > P2[fp]) continue;
+                            const int64_t lo = P1[f] < P2[fp] ? P1[f] : P2[fp];
+                            const int64_t hi = P1[f] < P2[fp] ? P2[fp] : P1[f];
+                            const int64_t idx = lo * np - ((lo * (lo - 1)) >> 1) + (hi - lo) - a.out_offset;
+                            a.out[idx] = OUT_SMEM ? s_out[(f * NFT + fp) * NTHREADS + tid] : out_r[f * NFT + fp];
+                        }
                     }
                 }
             }
         }
-        __syncthreads();  // every warp is done with s_u before the next row's TMA overwrites it
+        __syncwarp();  // every lane is done with this buffer before the TMA two tasks ahead reuses it
+        t = tn;
+        task = taskn;
+        buf ^= 1;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void fill_zero_kernel(double* __restrict__ out, int64_t n) {
-    // 128-bit stores, grid-stride; a slice may start on an odd element
+__global__ void fill_zero_kernel(double* __restrict__ out, int64_t n, int* __restrict__ counters, int ncounters) {
+    // 128-bit stores, grid-stride; a slice may start on an odd element.  Also resets the per-launch
+    // row counters of the class kernels that follow on the same stream.
+    if (blockIdx.x == 0 && (int)threadIdx.x < ncounters) counters[threadIdx.x] = 0;
     const int64_t head = ((reinterpret_cast<uintptr_t>(out) & 15) != 0 && n > 0) ? 1 : 0;
     const int64_t n2 = (n - head) / 2;
     double2* o2 = reinterpret_cast<double2*>(out + head);
@@ -396,20 +485,52 @@ __global__ void expand_dense_kernel(const double* __restrict__ packed, int norb,
 // ------------------------------------------------------------------------------------------
 template <int UT, int TT, int USL>
 static int launch_one(const ClassArgs& a, int num_sms, cudaStream_t st) {
-    if (a.nU <= 0 || a.nT <= 0) return 0;
-    constexpr int nout = ((USL >= 0) ? 4 : tt_nf(UT)) * tt_nf(TT);
-    constexpr int nthreads = nout > 16 ? 128 : 256;
-    const size_t smem = smem_bytes<UT, TT, USL>();
+    if (a.nU <= 0 || a.nT <= 0 || a.ntasks <= 0) return 0;
+    using C = Cfg<UT, TT, USL>;
     auto kern = eri_class_kernel<UT, TT, USL>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return (int)e;
     int occ = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NTHREADS, C::SMEM);
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) occ = 1;
     int grid = num_sms * occ;
-    if (grid > a.nU) grid = a.nU;
-    kern<<<grid, nthreads, smem, st>>>(a);
+    const int need = (a.ntasks + C::NWARPS - 1) / C::NWARPS;
+    if (grid > need) grid = need;
+    kern<<<grid, C::NTHREADS, C::SMEM, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int class_nlaunch(int UT, int TT) { return (UT == 2 && TT == 2) ? 4 : 1; }
+
+int launch_class(int UT, int TT, const ClassArgs& a0, int num_sms, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ClassArgs a = a0;
+    if (UT == 0 && TT == 0) return launch_one<0, 0, -1>(a, num_sms, st);
+    if (UT == 0 && TT == 1) return launch_one<0, 1, -1>(a, num_sms, st);
+    if (UT == 0 && TT == 2) return launch_one<0, 2, -1>(a, num_sms, st);
+    if (UT == 1 && TT == 1) return launch_one<1, 1, -1>(a, num_sms, st);
+    if (UT == 1 && TT == 2) return launch_one<1, 2, -1>(a, num_sms, st);
+    if (UT == 2 && TT == 2) {  // four mu-slices, each with its own row counter
+        int e = launch_one<2, 2, 0>(a, num_sms, st);
+        a.row_counter = a0.row_counter + 1;
+        if (!e) e = launch_one<2, 2, 1>(a, num_sms, st);
+        a.row_counter = a0.row_counter + 2;
+        if (!e) e = launch_one<2, 2, 2>(a, num_sms, st);
+        a.row_counter = a0.row_counter + 3;
+        if (!e) e = launch_one<2, 2, 3>(a, num_sms, st);
+        return e;
+    }
+    return (int)cudaErrorInvalidValue;
+}
+
+int launch_fill_zero(double* out, int64_t n, int* counters, int ncounters, int num_sms, void* stream) {
+    fill_zero_kernel<<<num_sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, counters, ncounters);
+    return (int)cudaGetLastError();
+}
+
+int launch_expand_dense(const double* packed, int norb, double* xx, int num_sms, void* stream) {
+    expand_dense_kernel<<<num_sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(packed, norb, xx);
     return (int)cudaGetLastError();
 }
 
@@ -444,42 +565,13 @@ int measure_dfma_peak(int num_sms, double* tflops) {
         float ms = 0;
         cudaEventElapsedTime(&ms, t0, t1);
         const double flops = 2.0 * 8 * 16 * (double)iters * 256.0 * grid;
-        if (rep > 0) best = best > flops / (ms * 1e-3) / 1e12 ? best : flops / (ms * 1e-3) / 1e12;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
     }
     cudaEventDestroy(t0); cudaEventDestroy(t1);
     cudaFree(d);
     *tflops = best;
     return (int)e;
-}
-
-int class_nlaunch(int UT, int TT) { return (UT == 2 && TT == 2) ? 4 : 1; }
-
-int launch_class(int UT, int TT, const ClassArgs& a, int num_sms, void* stream) {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (UT == 0 && TT == 0) return launch_one<0, 0, -1>(a, num_sms, st);
-    if (UT == 0 && TT == 1) return launch_one<0, 1, -1>(a, num_sms, st);
-    if (UT == 0 && TT == 2) return launch_one<0, 2, -1>(a, num_sms, st);
-    if (UT == 1 && TT == 1) return launch_one<1, 1, -1>(a, num_sms, st);
-    if (UT == 1 && TT == 2) return launch_one<1, 2, -1>(a, num_sms, st);
-    if (UT == 2 && TT == 2) {
-        int e = launch_one<2, 2, 0>(a, num_sms, st);
-        if (!e) e = launch_one<2, 2, 1>(a, num_sms, st);
-        if (!e) e = launch_one<2, 2, 2>(a, num_sms, st);
-        if (!e) e = launch_one<2, 2, 3>(a, num_sms, st);
-        return e;
-    }
-    return (int)cudaErrorInvalidValue;
-}
-
-int launch_fill_zero(double* out, int64_t n, int num_sms, void* stream) {
-    if (n <= 0) return 0;
-    fill_zero_kernel<<<num_sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n);
-    return (int)cudaGetLastError();
-}
-
-int launch_expand_dense(const double* packed, int norb, double* xx, int num_sms, void* stream) {
-    expand_dense_kernel<<<num_sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(packed, norb, xx);
-    return (int)cudaGetLastError();
 }
 
 }  // namespace myqc

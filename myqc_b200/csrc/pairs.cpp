@@ -88,8 +88,22 @@ namespace {
 
 struct PrimRec {
     double E;
-    double f[5 + 46 + 1];
+    double f[kCoefField + 46 + 2];
 };
+
+// 30-bit Morton code of a point inside the bounding box [lo, lo+ext]^3
+uint32_t morton3(const double* r, const double* lo, double ext) {
+    uint32_t code = 0;
+    uint32_t q[3];
+    for (int c = 0; c < 3; ++c) {
+        double t = ext > 0 ? (r[c] - lo[c]) / ext : 0.0;
+        t = t < 0 ? 0 : (t > 1 ? 1 : t);
+        q[c] = (uint32_t)(t * 1023.0);
+    }
+    for (int b = 9; b >= 0; --b)
+        for (int c = 0; c < 3; ++c) code = (code << 1) | ((q[c] >> b) & 1u);
+    return code;
+}
 
 // contraction coefficient of function slot mu (0=s,1..3=p) of `shell` in primitive set `s`
 double slot_coef(const Shell& sh, int s, int mu, const int32_t* setinfo, int setl, int ops,
@@ -106,14 +120,21 @@ double slot_coef(const Shell& sh, int s, int mu, const int32_t* setinfo, int set
 int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* setinfo, int setl,
                 int ops, const double* bas, const int32_t* basinfo,
                 const std::vector<Shell>& shells, PairList lists[3], std::string& err) {
-    (void)basinfo;
-    (void)err;
     const double tol = 0.1e-15;  // auxilary.f90:573
     struct Tmp {
-        int type, A, B, nprim;
+        int type, A, B, nprim, bucket;
+        uint32_t morton;
         double emax;
+        double centre[3];
         std::vector<PrimRec> prims;
     };
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < nnuc; ++i)
+        for (int c = 0; c < 3; ++c) {
+            lo[c] = std::min(lo[c], xyz[i + nnuc * c]);
+            hi[c] = std::max(hi[c], xyz[i + nnuc * c]);
+        }
+    const double ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
     std::vector<Tmp> tmp[3];
     const int ns = (int)shells.size();
     for (int A = 0; A < ns; ++A) {
@@ -169,7 +190,8 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
                     std::memset(&r, 0, sizeof(r));
                     r.E = EIJ;
                     r.f[0] = p; r.f[1] = PP[0]; r.f[2] = PP[1]; r.f[3] = PP[2]; r.f[4] = EIJ;
-                    double* c = &r.f[5];
+                    r.f[5] = 1.0 / std::sqrt(p);
+                    double* c = &r.f[kCoefField];
                     const bool a_is_sp = (sa.type == 1);
                     for (int k = 0; k < nterm; ++k) {
                         const int f = term_fn(type, k), h = term_h(type, k);
@@ -186,49 +208,50 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
             std::stable_sort(t.prims.begin(), t.prims.end(), [](const PrimRec& x, const PrimRec& y) { return x.E > y.E; });
             t.nprim = (int)t.prims.size();
             if (t.nprim > kMaxPrim) { err = "more than 9 primitive pairs per shell pair"; return MYQC_ERR_UNSUPPORTED; }
+            t.bucket = emax_bucket(t.emax);
+            for (int c = 0; c < 3; ++c) t.centre[c] = t.prims[0].f[1 + c];  // centre of the dominant primitive
+            t.morton = morton3(t.centre, lo, ext);
             tmp[type].push_back(std::move(t));
         }
     }
     for (int type = 0; type < 3; ++type) {
         std::vector<Tmp>& v = tmp[type];
-        std::stable_sort(v.begin(), v.end(), [](const Tmp& x, const Tmp& y) { return x.emax > y.emax; });
+        std::stable_sort(v.begin(), v.end(), [](const Tmp& x, const Tmp& y) {
+            if (x.bucket != y.bucket) return x.bucket < y.bucket;
+            return x.morton < y.morton;
+        });
         PairList& pl = lists[type];
         pl = PairList();
         pl.type = type;
         pl.n = (int)v.size();
         pl.npad = (pl.n + 31) / 32 * 32;
         const int nf = pt_nf(type), nfield = pt_nfield(type);
-        pl.emax.resize(pl.n); pl.nprim.resize(pl.n); pl.diag.resize(pl.n);
+        pl.emax.resize(pl.n); pl.nprim.resize(pl.n); pl.bucket.resize(pl.n);
         pl.shA.resize(pl.n); pl.shB.resize(pl.n); pl.owner_fn.resize(pl.n);
-        pl.fi.assign((size_t)pl.n * nf, -1); pl.fj.assign((size_t)pl.n * nf, -1);
+        pl.pidx.assign((size_t)pl.n * nf, -1);
         pl.aos.assign((size_t)pl.n * kMaxPrim * nfield, 0.0);
         pl.soa.assign((size_t)kMaxPrim * nfield * pl.npad, 0.0);
+        const int64_t norb = basinfo[1];
         for (int k = 0; k < pl.n; ++k) {
             const Tmp& t = v[k];
             const Shell& sa = shells[t.A];
             const Shell& sb = shells[t.B];
-            pl.emax[k] = t.emax; pl.nprim[k] = t.nprim; pl.diag[k] = (t.A == t.B);
+            pl.emax[k] = t.emax; pl.nprim[k] = t.nprim; pl.bucket[k] = t.bucket;
             pl.shA[k] = t.A; pl.shB[k] = t.B;
             pl.owner_fn[k] = std::min(sa.first_fn, sb.first_fn);
-            if (type == PT_SS) {
-                pl.fi[k] = sa.fn[0]; pl.fj[k] = sb.fn[0];
-            } else if (type == PT_SSP) {
-                const bool a_is_sp = (sa.type == 1);
-                for (int w = 0; w < 4; ++w) {
-                    pl.fi[(size_t)k * 4 + w] = a_is_sp ? sa.fn[w] : sa.fn[0];
-                    pl.fj[(size_t)k * 4 + w] = a_is_sp ? sb.fn[0] : sb.fn[w];
-                }
-            } else {
-                for (int mu = 0; mu < 4; ++mu)
-                    for (int nu = 0; nu < 4; ++nu) {
-                        pl.fi[(size_t)k * 16 + 4 * mu + nu] = sa.fn[mu];
-                        pl.fj[(size_t)k * 16 + 4 * mu + nu] = sb.fn[nu];
-                    }
+            for (int f = 0; f < nf; ++f) {
+                int fi, fj;
+                if (type == PT_SS) { fi = sa.fn[0]; fj = sb.fn[0]; }
+                else if (type == PT_SSP) {
+                    const bool a_is_sp = (sa.type == 1);
+                    fi = a_is_sp ? sa.fn[f] : sa.fn[0];
+                    fj = a_is_sp ? sb.fn[0] : sb.fn[f];
+                } else { fi = sa.fn[f / 4]; fj = sb.fn[f % 4]; }
+                if (fi < 0 || fj < 0) continue;            // absent function (p-only set)
+                if (t.A == t.B && fi > fj) continue;       // (j,i) duplicate inside a diagonal shell pair
+                const int64_t i = std::min(fi, fj), j = std::max(fi, fj);
+                pl.pidx[(size_t)k * nf + f] = (int32_t)(i * norb - i * (i - 1) / 2 + (j - i));
             }
-            // a function pair with an absent member is marked absent on both sides
-            for (int f = 0; f < nf; ++f)
-                if (pl.fi[(size_t)k * nf + f] < 0 || pl.fj[(size_t)k * nf + f] < 0)
-                    pl.fi[(size_t)k * nf + f] = pl.fj[(size_t)k * nf + f] = -1;
             for (int q = 0; q < t.nprim; ++q)
                 for (int f = 0; f < nfield; ++f) {
                     const double val = t.prims[q].f[f];
@@ -249,19 +272,16 @@ PairList sublist(const PairList& src, const std::vector<char>& pred) {
         if (pred[k]) idx.push_back(k);
     d.n = (int)idx.size();
     d.npad = (d.n + 31) / 32 * 32;
-    d.emax.resize(d.n); d.nprim.resize(d.n); d.diag.resize(d.n);
+    d.emax.resize(d.n); d.nprim.resize(d.n); d.bucket.resize(d.n);
     d.shA.resize(d.n); d.shB.resize(d.n); d.owner_fn.resize(d.n);
-    d.fi.resize((size_t)d.n * nf); d.fj.resize((size_t)d.n * nf);
+    d.pidx.resize((size_t)d.n * nf);
     d.aos.assign((size_t)d.n * kMaxPrim * nfield, 0.0);
     d.soa.assign((size_t)kMaxPrim * nfield * d.npad, 0.0);
     for (int k = 0; k < d.n; ++k) {
         const int s = idx[k];
-        d.emax[k] = src.emax[s]; d.nprim[k] = src.nprim[s]; d.diag[k] = src.diag[s];
+        d.emax[k] = src.emax[s]; d.nprim[k] = src.nprim[s]; d.bucket[k] = src.bucket[s];
         d.shA[k] = src.shA[s]; d.shB[k] = src.shB[s]; d.owner_fn[k] = src.owner_fn[s];
-        for (int f = 0; f < nf; ++f) {
-            d.fi[(size_t)k * nf + f] = src.fi[(size_t)s * nf + f];
-            d.fj[(size_t)k * nf + f] = src.fj[(size_t)s * nf + f];
-        }
+        for (int f = 0; f < nf; ++f) d.pidx[(size_t)k * nf + f] = src.pidx[(size_t)s * nf + f];
         std::memcpy(&d.aos[(size_t)k * kMaxPrim * nfield], &src.aos[(size_t)s * kMaxPrim * nfield],
                     sizeof(double) * kMaxPrim * nfield);
         for (int q = 0; q < kMaxPrim; ++q)
@@ -269,6 +289,32 @@ PairList sublist(const PairList& src, const std::vector<char>& pred) {
                 d.soa[((size_t)q * nfield + f) * d.npad + k] = src.soa[((size_t)q * nfield + f) * src.npad + s];
     }
     return d;
+}
+
+int emax_bucket(double emax) {
+    // Fine groups: symmetry-equivalent pairs share emax up to rounding noise, so a 1e-6 relative
+    // grid keeps pairs of one kind (same primitive survival pattern) together while the Morton
+    // order inside a group keeps them spatially close.
+    if (!(emax > 0.0)) return 1 << 30;
+    const double b = std::floor(-std::log(emax) * 1.0e6);
+    return b < 0 ? 0 : (b > 1.0e9 ? 1000000000 : (int)b);
+}
+
+std::vector<int32_t> row_prefix(const PairList& U, const PairList& T) {
+    // suffix maximum of T.emax is non-increasing: binary search for the last index that can still
+    // hold a pair passing emax_u*emax_v >= 1e-14
+    std::vector<double> smax(T.n + 1, 0.0);
+    for (int k = T.n - 1; k >= 0; --k) smax[k] = std::max(smax[k + 1], T.emax[k]);
+    std::vector<int32_t> out(U.n, 0);
+    for (int u = 0; u < U.n; ++u) {
+        int lo = 0, hi = T.n;  // first index with emax_u*smax < 1e-14
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (U.emax[u] * smax[mid] < 1.0e-14) hi = mid; else lo = mid + 1;
+        }
+        out[u] = lo;
+    }
+    return out;
 }
 
 }  // namespace myqc

@@ -23,8 +23,10 @@ enum PairType { PT_SS = 0, PT_SSP = 1, PT_SPSP = 2 };
 // number of function pairs, Hermite terms and padded fields per primitive record
 constexpr int pt_nf(int t) { return t == 0 ? 1 : (t == 1 ? 4 : 16); }
 constexpr int pt_nterm(int t) { return t == 0 ? 1 : (t == 1 ? 7 : 46); }
-// fields: p, Px, Py, Pz, E, coef[nterm], padded to a multiple of 2 doubles (16 B, TMA granule)
-constexpr int pt_nfield(int t) { return ((5 + pt_nterm(t)) + 1) / 2 * 2; }
+// fields: p, Px, Py, Pz, E, 1/sqrt(p), coef[nterm], padded to a multiple of 2 doubles (16 B, the
+// TMA bulk-copy granule)
+constexpr int kCoefField = 6;
+constexpr int pt_nfield(int t) { return ((kCoefField + pt_nterm(t)) + 1) / 2 * 2; }
 
 struct Shell {
     int centre;
@@ -38,11 +40,15 @@ struct PairList {
     int type = 0;
     int n = 0;     // number of shell pairs kept
     int npad = 0;  // n rounded up to 32 (SoA leading dimension)
-    // per pair, sorted by emax descending
+    // Order: groups of decreasing largest-prefactor (emax equal to 1e-6 relative, i.e. pairs of
+    // one symmetry-equivalent kind), and inside a group the Morton order of the pair centre, so
+    // that the 32 pairs a warp holds are of one kind (same primitive survival pattern) and
+    // spatially close (same Boys regime against a given row).
     std::vector<double> emax;
+    std::vector<int32_t> bucket;  // [n] non-decreasing bucket id
     std::vector<int32_t> nprim;
-    std::vector<int32_t> fi, fj;  // [n][nf] orbital ids of each function pair (-1: absent)
-    std::vector<int32_t> diag;    // shell A == shell B
+    std::vector<int32_t> pidx;    // [n][nf] packed pair index P(i,j) of each function pair; -1: not stored
+                                  // (absent function, or the (j,i) duplicate of a diagonal shell pair)
     std::vector<int32_t> shA, shB;
     std::vector<int32_t> owner_fn;  // min(first_fn(A), first_fn(B)) -> shard ownership key
     // primitive records (prims sorted by E descending inside each pair, unused slots zero)
@@ -59,6 +65,14 @@ struct Basis {
 // Returns 0 or a negative MYQC_ERR_* code; err receives a message.
 int build_shells(int nnuc, int nset, int setl, const int32_t* setinfo, int ops,
                  const int32_t* basinfo, std::vector<Shell>& shells, std::string& err);
+
+// Group id of a largest-prefactor value (1e-6 relative grid, emax = 1 -> group 0).
+int emax_bucket(double emax);
+
+// For every row u of `U`: the number of leading pairs of `T` that must be visited so that every
+// pair v with emax_u*emax_v >= 1e-14 is included (pairs inside the prefix that fail the product
+// test simply find no surviving primitive quartet).
+std::vector<int32_t> row_prefix(const PairList& U, const PairList& T);
 
 // Build the three pair lists restricted to shells for which keep_shell[s] != 0 on BOTH sides
 // (keep_shell == nullptr keeps all).

@@ -259,6 +259,11 @@ int myqc_read_ftab(const char* path, double* ftab) {
 static const int64_t kMaxSub = 2147483639;
 
 int myqc_write_xx(const char* path, const double* xx, int norb) {
+    return myqc_write_xx_ex(path, xx, norb, kMaxSub);
+}
+
+int myqc_write_xx_ex(const char* path, const double* xx, int norb, int64_t max_subrecord) {
+    if (max_subrecord < 8 || max_subrecord > kMaxSub) max_subrecord = kMaxSub;
     FILE* f = std::fopen(path, "wb");
     if (!f) return io_fail("cannot open XX for writing");
     const int64_t n = norb;
@@ -266,7 +271,7 @@ int myqc_write_xx(const char* path, const double* xx, int norb) {
     const char* p = reinterpret_cast<const char*>(xx);
     bool first = true, ok = true;
     do {
-        const int64_t chunk = left > kMaxSub ? kMaxSub : left;
+        const int64_t chunk = left > max_subrecord ? max_subrecord : left;
         const bool more = left > chunk;
         // leading marker negative: continued in the next subrecord; trailing negative: has a predecessor
         const int32_t lead = (int32_t)(more ? -chunk : chunk);

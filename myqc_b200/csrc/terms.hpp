@@ -53,7 +53,9 @@ MYQC_HD constexpr int h_parity(int a) { return (h_N(a) + h_L(a) + h_M(a)) & 1; }
 MYQC_HD constexpr int tt_nf(int t) { return t == 0 ? 1 : (t == 1 ? 4 : 16); }
 MYQC_HD constexpr int tt_nterm(int t) { return t == 0 ? 1 : (t == 1 ? 7 : 46); }
 MYQC_HD constexpr int tt_nh(int t) { return h_count(t); }  // 1, 4, 10 Hermite indices
-MYQC_HD constexpr int tt_nfield(int t) { return ((5 + tt_nterm(t)) + 1) / 2 * 2; }
+// primitive record: p, Px, Py, Pz, E, 1/sqrt(p), coef[nterm], padded to an even number of doubles
+constexpr int kRecCoef = 6;
+MYQC_HD constexpr int tt_nfield(int t) { return ((kRecCoef + tt_nterm(t)) + 1) / 2 * 2; }
 
 // unit vector index of axis w (1..3) -> Hermite index of e_w is simply w
 // SP.SP function pair f = 4*mu + nu, mu,nu in {0=s,1=x,2=y,3=z}.

@@ -1,0 +1,197 @@
+"""Parity tests proper (need a B200): the CUDA path through the C-ABI against the CPU oracle and
+the committed golden fixtures.  Tolerance: BASELINE.json's north star -- 1e-10 Hartree absolute per
+integral."""
+import os
+
+import numpy as np
+import pytest
+
+import myqc_b200 as Q
+from conftest import EXAMPLES, GOLDEN, INPUTS, example_zmat, oracle_system, product_system
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1.0e-10  # Hartree, absolute, per integral (BASELINE.json north_star)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if Q.device_count() < 1:
+        pytest.fail("GPU tests need a CUDA device; the ERI engine has no CPU fallback")
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_examples_against_golden_and_oracle(name, tmp_path, oracle_inputs):
+    s = product_system(name, tmp_path)
+    got = Q.eri_packed(s)
+    gold = np.load(os.path.join(GOLDEN, f"packed_{name}.npy"))
+    assert got.shape == gold.shape
+    assert np.abs(got - gold).max() < TOL
+    mol, b, ft = oracle_system(name, oracle_inputs)
+    assert np.abs(got - O.int2e_packed(mol, b, ft)).max() < TOL
+    # what the reference's screen leaves exactly zero stays (numerically) zero
+    assert np.abs(got[gold == 0.0]).max(initial=0.0) < 1e-14
+
+
+@pytest.mark.parametrize("name", ["CO2", "NO", "h2o_2"])
+def test_dense_xx_all_eight_images(name, tmp_path, oracle_inputs):
+    """proc2e mirror: dense XX(i,j,g,h) with fillsym's 8 images (int2e.f90:290-304,540-554)."""
+    s = product_system(name, tmp_path)
+    xx = Q.proc2e(s.bas, s.basinfo, s.atoms, s.options, 1000.0, s.nnuc, s.xyz, s.set, s.setinfo, s.maxL, s.ftab)
+    mol, b, ft = oracle_system(name, oracle_inputs)
+    ref, _ = O.int2e_dense(mol, b, ft)
+    assert xx.shape == ref.shape and np.abs(xx - ref).max() < TOL
+    for perm in [(1, 0, 2, 3), (0, 1, 3, 2), (1, 0, 3, 2), (2, 3, 0, 1), (3, 2, 0, 1), (2, 3, 1, 0), (3, 2, 1, 0)]:
+        assert np.array_equal(xx, xx.transpose(perm))
+
+
+@pytest.mark.parametrize("name", ["CO2", "OH"])
+def test_int2e_drop_in_writes_the_reference_xx_record(name, tmp_path, oracle_inputs):
+    """PROGRAM int2e in a job directory: same inputs, same XX record (consumers do READ(9) XX)."""
+    s = product_system(name, tmp_path)
+    assert Q.int2e_main(str(tmp_path), 1) == 0
+    assert not (tmp_path / "error").exists()
+    raw = open(tmp_path / "XX", "rb").read()
+    n = s.norb
+    assert len(raw) == 8 * n ** 4 + 8
+    xx = np.frombuffer(raw[4:-4], dtype="<f8").reshape((n,) * 4, order="F")
+    mol, b, ft = oracle_system(name, oracle_inputs)
+    ref, _ = O.int2e_dense(mol, b, ft)
+    assert np.abs(xx - ref).max() < TOL
+    # basinfo was (re)written for the downstream stages; fmem is net unchanged and readable
+    assert int(open(tmp_path / "basinfo").read().split()[1]) == n
+    assert abs(float(open(tmp_path / "fmem").read().split()[0]) - 1000.0) < 1e-6
+    # the SCF energy the consumers would get from this XX
+    S, H = O.int1e(mol, b, ft)
+    nA, nB = O.electrons(mol)
+    if nA == nB:
+        E, _, _ = O.scf_rhf(S, H, np.array(xx), nA + nB, O.nuclear_repulsion(mol))
+        assert abs(E - (-183.32315970625)) < 1e-9  # 1e-9 Eh, north star
+
+
+@pytest.mark.parametrize("name", ["h2o", "h2o_4", "c4h10", "h2o_8"])
+def test_small_clusters_full_compare(name, tmp_path, oracle_inputs):
+    s = product_system(name, tmp_path)
+    got = Q.eri_packed(s)
+    mol, b, ft = oracle_system(name, oracle_inputs)
+    ref = O.int2e_packed(mol, b, ft)
+    assert np.abs(got - ref).max() < TOL
+    assert np.abs(got[ref == 0.0]).max(initial=0.0) < 1e-14
+
+
+def test_h2o16_baseline_config_full_compare(tmp_path, oracle_inputs):
+    """BASELINE.json configs[2]: (H2O)_16, 112 basis functions, every one of the 20 024 956 unique
+    integrals against the oracle."""
+    s = product_system("h2o_16", tmp_path)
+    assert (s.norb, s.nunique) == (112, 20024956)
+    got = Q.eri_packed(s)
+    mol, b, ft = oracle_system("h2o_16", oracle_inputs)
+    ref = O.int2e_packed(mol, b, ft)
+    assert np.abs(got - ref).max() < TOL
+    assert np.array_equal(got == 0.0, ref == 0.0) or np.abs(got[ref == 0.0]).max(initial=0.0) < 1e-14
+
+
+def _rows_check(name, tmp_path, oracle_inputs, nrows):
+    """Full-size configs: the whole packed array stays on the device side of the call; a fixed
+    sample of complete rows is compared with the row oracle, plus size-independent properties."""
+    s = product_system(name, tmp_path)
+    got = Q.eri_packed(s)
+    mol, b, ft = oracle_system(name, oracle_inputs)
+    npair = s.npair
+    rng = np.random.default_rng(20261017)
+    rows = np.unique(np.concatenate([[0, npair - 1], rng.integers(0, npair, nrows)]))
+    ref = O.int2e_rows(mol, b, ft, rows)
+
+    def packed_index(P, Pp):
+        lo, hi = np.minimum(P, Pp), np.maximum(P, Pp)
+        return lo * npair - lo * (lo - 1) // 2 + (hi - lo)
+    cols = np.arange(npair, dtype=np.int64)
+    worst = 0.0
+    for r, P in enumerate(rows):
+        g = got[packed_index(np.int64(P), cols)]
+        worst = max(worst, float(np.abs(g - ref[r]).max()))
+    assert worst < TOL, worst
+    # Schwarz inequality |(P|P')| <= sqrt((P|P)(P'|P')) on the sampled rows (size independent).
+    # Slack 1e-6: the reference's EIJ*EGH >= 1e-14 rule zeroes a diagonal (P'|P') once E_P' < 1e-7
+    # while (P|P') with a compact P survives, so the inequality only holds up to ~E_P' itself.
+    diag = got[packed_index(cols, cols)]
+    assert diag.min() > -1e-12
+    for P in rows:
+        g = got[packed_index(np.int64(P), cols)]
+        assert np.all(np.abs(g) <= np.sqrt(np.abs(diag[P]) * np.abs(diag)) + 1e-6)
+    return s, got
+
+
+def test_c20h42_rows(tmp_path, oracle_inputs):
+    """BASELINE.json configs[3]: C20H42, 142 basis functions."""
+    s, got = _rows_check("c20h42", tmp_path, oracle_inputs, 24)
+    assert (s.norb, s.nunique) == (142, 51546781)
+
+
+def test_h2o64_rows(tmp_path, oracle_inputs):
+    """BASELINE.json configs[4]: (H2O)_64, 448 basis functions, 5.06e9 unique integrals (40.5 GB)."""
+    s, got = _rows_check("h2o_64", tmp_path, oracle_inputs, 10)
+    assert (s.norb, s.nunique) == (448, 5057816176)
+    # translation invariance of the lattice: molecule (0,0,0) and molecule (1,0,0) have the same
+    # intramolecular integrals (7 functions each, 16 molecules apart in orbital order)
+    n, npair = s.norb, s.npair
+
+    def idx(i, j, g, h):
+        i, j = min(i, j), max(i, j)
+        g, h = min(g, h), max(g, h)
+        P, Pp = Q.pair_index(i, j, n), Q.pair_index(g, h, n)
+        P, Pp = min(P, Pp), max(P, Pp)
+        return P * npair - P * (P - 1) // 2 + (Pp - P)
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        i, j, g, h = rng.integers(0, 7, 4)
+        a = got[idx(i, j, g, h)]
+        bshift = got[idx(i + 7 * 16, j + 7 * 16, g + 7 * 16, h + 7 * 16)]
+        assert abs(a - bshift) < 1e-11
+
+
+@pytest.mark.parametrize("name,nsh", [("CO2", 2), ("h2o_4", 3), ("h2o_8", 4), ("h2o_16", 8)])
+def test_shards_reproduce_the_unsharded_array_bitwise(name, nsh, tmp_path):
+    """Multi-GPU path on one device: every shard computes its slice independently; the
+    concatenation must be bit-identical to the single-shard result."""
+    s = product_system(name, tmp_path)
+    whole = Q.eri_packed(s)
+    off = Q.shard_layout(s, nsh)
+    parts = np.empty_like(whole)
+    for k in range(nsh):
+        Q.eri_packed_shard(s, parts[off[k]:off[k + 1]], device=0, shard=k, nshards=nsh)
+    assert np.array_equal(parts, whole)
+
+
+def test_plan_api_device_buffers(tmp_path):
+    import torch
+    s = product_system("h2o_4", tmp_path)
+    plan = Q.Plan(s, device=0)
+    out = torch.full((plan.out_elems,), float("nan"), dtype=torch.float64, device="cuda:0")
+    plan.execute(out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref = Q.eri_packed(s)
+    assert np.array_equal(out.cpu().numpy(), ref)  # every element written, deterministic
+    ms = plan.execute_timed(out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert len(ms) == len(plan.launches()) and all(m >= 0 for m in ms)
+    st = plan.stats()
+    assert sum(st["nquartets"]) == int(Q.canonical_stats(s)[0].sum())
+    # dense expansion on device
+    n = s.norb
+    xx = torch.empty(n ** 4, dtype=torch.float64, device="cuda:0")
+    Q._check(Q.lib().myqc_eri_expand_dense(out.data_ptr(), n, xx.data_ptr(), None))
+    torch.cuda.synchronize()
+    assert np.array_equal(xx.cpu().numpy().reshape((n,) * 4, order="F"), Q.eri_dense(s))
+    plan.close()
+
+
+def test_permuting_atoms_permutes_integrals(tmp_path, oracle_inputs):
+    """Relabelling the nuclei only relabels the integrals (size-independent property)."""
+    zm = example_zmat("h2o_2").splitlines()
+    atoms = zm[1:7]
+    perm_lines = [zm[0]] + atoms[3:] + atoms[:3] + zm[7:]
+    s1 = Q.make_job(str(tmp_path / "a"), "\n".join(zm) + "\n", INPUTS)
+    s2 = Q.make_job(str(tmp_path / "b"), "\n".join(perm_lines) + "\n", INPUTS)
+    x1, x2 = Q.eri_dense(s1), Q.eri_dense(s2)
+    p = np.concatenate([np.arange(7, 14), np.arange(0, 7)])
+    assert np.abs(x1 - x2[np.ix_(p, p, p, p)]).max() < 1e-12

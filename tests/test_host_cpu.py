@@ -1,0 +1,162 @@
+"""Host-side logic of the product, no GPU needed: the C-ABI library loads and exports what
+include/myqc_eri.h declares, the file layer restates getenv/buildBasis/Ftab/XX exactly, the
+parse stage matches the oracle's restatement, sharding tiles the packed array."""
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import myqc_b200 as Q
+from myqc_b200 import molecules, parse
+from conftest import EXAMPLES, INPUTS, ROOT, example_zmat, oracle_system, product_system
+from oracle import oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "myqc_eri.h")).read()
+    declared = set(re.findall(r"\b(myqc_[a-z0-9_]+)\s*\(", hdr))
+    L = Q.lib()
+    missing = [n for n in declared if not hasattr(L, n)]
+    assert not missing, missing
+    assert declared == set(Q.EXPORTS)
+
+
+def test_no_cpu_fallback(tmp_path):
+    """Without a device the compute entry points fail loudly instead of falling back."""
+    if Q.device_count() > 0:
+        pytest.skip("a GPU is present")
+    s = product_system("H2", tmp_path)
+    with pytest.raises(Q.MyQCError) as e:
+        Q.eri_packed(s)
+    assert e.value.code == Q.ERR_NO_DEVICE
+    with pytest.raises(Q.MyQCError):
+        Q.Plan(s)
+
+
+@pytest.mark.parametrize("name", EXAMPLES + ["h2o_4", "c4h10"])
+def test_input_layer_matches_oracle(name, tmp_path, oracle_inputs):
+    s = product_system(name, tmp_path)
+    mol, b, ft = oracle_system(name, oracle_inputs)
+    assert np.array_equal(s.atoms, mol.atoms)
+    assert np.array_equal(s.xyz, mol.xyz_fortran())          # parse: COM shift + A2B, bit for bit
+    assert np.array_equal(s.set, b.set) and np.array_equal(s.bas, b.bas)
+    assert np.array_equal(s.setinfo, b.setinfo) and np.array_equal(s.basinfo, b.basinfo)
+    assert np.array_equal(s.ftab, ft)
+    # basinfo text file: downstream stages read tokens 0-1 = OpS, norb (RHFI2G.f90:48-51)
+    Q.build_basis(os.path.join(INPUTS, "mybasis"), s.atoms, 0, out_dir=str(tmp_path))
+    toks = open(tmp_path / "basinfo").read().split()
+    assert int(toks[0]) == 4 and int(toks[1]) == s.norb
+    stoks = open(tmp_path / "setinfo").read().split()
+    assert int(stoks[0]) == s.nset and int(stoks[1]) == 7
+
+
+def test_sizes_of_baseline_configs(tmp_path):
+    for name, norb, nset in [("CO2", 15, 18), ("HF", 6, 9), ("CO", 10, 12), ("NO", 10, 12),
+                             ("h2o_16", 112, 192), ("c20h42", 142, 246), ("h2o_64", 448, 768)]:
+        atoms, xyz, opts = parse.parse_zmat(example_zmat(name))
+        set_, setinfo, bas, basinfo, _, _ = Q.build_basis(os.path.join(INPUTS, "mybasis"), atoms)
+        assert (basinfo[1], setinfo[0]) == (norb, nset)
+
+
+def test_canonical_work_counts_match_survey(tmp_path):
+    """SURVEY.md 8d work totals (exact canonical primitive-quartet counts and model flops)."""
+    want = {"CO2": (11901, 6.462e6), "HF": (1035, 2.50e5), "CO": (2823, 1.455e6), "NO": (2714, 1.440e6),
+            "h2o_16": (24634506, 3.520e9), "c20h42": (39864177, 6.748e9), "h2o_64": (1071129508, 1.397e11)}
+    for name, (nq, fl) in want.items():
+        s = product_system(name, tmp_path / name)
+        got, flops = Q.canonical_stats(s)
+        assert int(got.sum()) == nq
+        assert abs(flops - fl) / fl < 2e-3
+
+
+def test_ftab_reader_rejects_garbage(tmp_path):
+    bad = tmp_path / "Ftab"
+    bad.write_bytes(b"\x00" * 100)
+    with pytest.raises(Q.MyQCError) as e:
+        Q.read_ftab(str(bad))
+    assert e.value.code == Q.ERR_IO
+    with pytest.raises(Q.MyQCError):
+        Q.read_ftab(str(tmp_path / "missing"))
+
+
+def test_xx_record_framing(tmp_path):
+    """One Fortran unformatted sequential record; gfortran subrecords above the limit: leading
+    marker negative when continued, trailing marker negative when it has a predecessor."""
+    n = 5
+    xx = np.arange(n ** 4, dtype=np.float64).reshape((n,) * 4, order="F")
+    p = str(tmp_path / "XX")
+    Q.write_xx(p, xx, n)
+    raw = open(p, "rb").read()
+    assert len(raw) == 8 * n ** 4 + 8
+    assert struct.unpack("<i", raw[:4])[0] == 8 * n ** 4 == struct.unpack("<i", raw[-4:])[0]
+    assert np.array_equal(np.frombuffer(raw[4:-4], dtype="<f8"), xx.reshape(-1, order="F"))
+    assert np.array_equal(Q.read_xx(p, n), xx)
+    # force three subrecords of at most 2000 bytes (5000-byte payload)
+    Q.write_xx(p, xx, n, max_subrecord=2000)
+    raw = open(p, "rb").read()
+    assert len(raw) == 8 * n ** 4 + 3 * 8
+    marks, pos = [], 0
+    while pos < len(raw):
+        lead = struct.unpack("<i", raw[pos:pos + 4])[0]
+        size = abs(lead)
+        trail = struct.unpack("<i", raw[pos + 4 + size:pos + 8 + size])[0]
+        marks.append((lead, trail))
+        pos += 8 + size
+    assert marks == [(-2000, 2000), (-2000, -2000), (1000, -1000)]
+    assert np.array_equal(Q.read_xx(p, n), xx)
+
+
+def test_int2e_main_error_paths(tmp_path):
+    """Missing inputs -> `touch error`, non-zero status, no XX (int2e.f90:174-178, env.f90:37-53)."""
+    rc = Q.int2e_main(str(tmp_path), 1)
+    assert rc == Q.ERR_IO and (tmp_path / "error").exists() and not (tmp_path / "XX").exists()
+    # existing XX -> skipped untouched (int2e.f90:58-63)
+    d = tmp_path / "job"
+    s = product_system("H2", d)
+    (d / "XX").write_bytes(b"keep")
+    assert Q.int2e_main(str(d), 1) == 0
+    assert (d / "XX").read_bytes() == b"keep" and not (d / "error").exists()
+
+
+def test_unsupported_inputs_are_rejected(tmp_path):
+    s = product_system("HF", tmp_path)
+    bad = np.array(s.setinfo, copy=True)
+    bad[0] = s.nset + 1  # header does not match
+    with pytest.raises(Q.MyQCError) as e:
+        Q.shard_layout(Q.System(s.nnuc, s.atoms, s.xyz, s.set, bad, s.bas, s.basinfo, s.ftab), 2)
+    assert e.value.code == Q.ERR_BAD_ARG
+    bi = np.array(s.basinfo, copy=True)
+    bi[1 + 5 * 1 + 2] = 2  # a d function
+    with pytest.raises(Q.MyQCError) as e:
+        Q.shard_layout(Q.System(s.nnuc, s.atoms, s.xyz, s.set, s.setinfo, s.bas, bi, s.ftab), 2)
+    assert e.value.code == Q.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("name,nsh", [("CO2", 2), ("h2o_4", 3), ("h2o_16", 8), ("c20h42", 4), ("h2o_64", 8)])
+def test_shard_layout_tiles_the_packed_array(name, nsh, tmp_path):
+    s = product_system(name, tmp_path)
+    off = Q.shard_layout(s, nsh)
+    assert off[0] == 0 and off[-1] == s.nunique and np.all(np.diff(off) >= 0)
+    # every cut is the start of a packed row whose leading orbital starts a shell
+    n, npair = s.norb, s.npair
+    starts = {0, s.nunique}
+    for i in range(n):
+        P = i * n - i * (i - 1) // 2
+        starts.add(P * npair - P * (P - 1) // 2)
+    assert all(int(o) in starts for o in off)
+    if name in ("h2o_16", "h2o_64"):
+        assert np.count_nonzero(np.diff(off)) == nsh  # no empty shard on the benchmark workloads
+
+
+def test_synthetic_geometries(tmp_path):
+    """deterministic lattices, atom order O,H,H, 3.0 A spacing."""
+    atoms, xyz, _ = parse.parse_zmat(molecules.zmat("h2o_16"))
+    assert len(atoms) == 48 and list(atoms[:3]) == [8, 1, 1]
+    d = np.linalg.norm(xyz[3] - xyz[0]) / parse.A2B
+    assert abs(d - 3.0) < 1e-12
+    atoms, xyz, _ = parse.parse_zmat(molecules.zmat("c20h42"))
+    assert (atoms == 6).sum() == 20 and (atoms == 1).sum() == 42
+    cc = np.linalg.norm(xyz[1] - xyz[0]) / parse.A2B
+    assert abs(cc - 1.54) < 1e-6

@@ -1,0 +1,117 @@
+"""The oracle is pinned before it is trusted (CPU only).
+
+The reference ships no per-integral golden vectors and cannot be compiled here, so the pins are
+  (1) the orbital energies the reference itself printed (examples/*/MOLDEN -> golden/molden.json),
+      reached through the oracle's int1e + SCF restatement, and
+  (2) the SCF energies / (00|00) integrals recorded in BASELINE.md section 2.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import EXAMPLES, GOLDEN, INPUTS, oracle_system
+from oracle import oracle as O
+
+MOLDEN = json.load(open(os.path.join(GOLDEN, "molden.json")))
+
+# BASELINE.md section 2 (values obtained in the survey session from an independent scratch
+# restatement; agreement expected to ~1e-9)
+BASELINE_MD = {
+    "CO2": (-183.32315970625, 3.541947441699492), "CO": (-111.14366962864, None),
+    "HF": (-98.57048757208, None), "OH": (-74.36468492502, None),
+    "HeH": (-2.85292120403, 1.055712738104997), "H2": (-1.04299387882, 0.774605771027572),
+    "H": (-0.46658182071, None), "NO": (-127.53356293, None),
+}
+
+
+def _scf(name, oracle_inputs):
+    mol, b, ft = oracle_system(name, oracle_inputs)
+    xx, _ = O.int2e_dense(mol, b, ft)
+    S, H = O.int1e(mol, b, ft)
+    nA, nB = O.electrons(mol)
+    enr = O.nuclear_repulsion(mol)
+    if nA == nB:
+        E, eps, _ = O.scf_rhf(S, H, xx, nA + nB, enr)
+        return E, eps, eps, xx
+    E, ea, eb, _ = O.scf_uhf(S, H, xx, nA, nB, enr)
+    return E, ea, eb, xx
+
+
+@pytest.mark.parametrize("name,tol", [("O_singlet", 1e-8), ("Be", 1e-8), ("NO", 4e-7)])
+def test_molden_orbital_energies(name, tol, oracle_inputs):
+    """examples/O/singlet/MOLDEN, examples/Be/MOLDEN (print precision 1e-8) and examples/NO/MOLDEN
+    (the reference ran at SCF_Conv=7, so ~2e-7)."""
+    _, ea, eb, _ = _scf(name, oracle_inputs)
+    ma = np.array(MOLDEN[name]["alpha"])
+    assert np.abs(np.sort(ea) - np.sort(ma)).max() < tol
+    if MOLDEN[name]["beta"]:
+        assert np.abs(np.sort(eb) - np.sort(np.array(MOLDEN[name]["beta"]))).max() < tol
+
+
+def test_true_pi_would_fail(oracle_inputs):
+    """T1: with float32 pi the O atom 1s1s1s1s integral is 4.785064768; true pi gives ...834."""
+    _, b_, ft = oracle_system("O_singlet", oracle_inputs)
+    mol = O.parse_zmat(open(os.path.join(INPUTS, "O_singlet", "ZMAT")).read())
+    xx, _ = O.int2e_dense(mol, b_, ft)
+    assert abs(xx[0, 0, 0, 0] - 4.785064768) < 5e-9
+    assert abs(xx[0, 0, 0, 0] - 4.785064834) > 5e-8
+
+
+@pytest.mark.parametrize("name", sorted(BASELINE_MD))
+def test_baseline_md_anchors(name, oracle_inputs):
+    E, _, _, xx = _scf(name, oracle_inputs)
+    Eref, x0 = BASELINE_MD[name]
+    assert abs(E - Eref) < 5e-9
+    if x0 is not None:
+        assert abs(xx[0, 0, 0, 0] - x0) < 1e-14
+
+
+@pytest.mark.parametrize("name", EXAMPLES)
+def test_literal_equals_canonical_and_golden(name, oracle_inputs):
+    """The canonical (packed) driver visits fewer set quartets but must reproduce the literal
+    nset^4 loop bit for bit; both must equal the committed fixture."""
+    mol, b, ft = oracle_system(name, oracle_inputs)
+    xx, stats = O.int2e_dense(mol, b, ft)
+    pk = O.int2e_packed(mol, b, ft)
+    assert np.array_equal(pk, O.packed_from_dense(xx))
+    gold = np.load(os.path.join(GOLDEN, f"packed_{name}.npy"))
+    assert np.array_equal(pk, gold)
+    # fillsym left all 8 images equal
+    assert np.array_equal(xx, xx.transpose(1, 0, 2, 3)) and np.array_equal(xx, xx.transpose(2, 3, 0, 1))
+    assert np.array_equal(O.dense_from_packed(pk, b.norb), xx)
+
+
+def test_rows_oracle_matches_packed(oracle_inputs):
+    mol, b, ft = oracle_system("h2o_2", oracle_inputs)
+    pk = O.int2e_packed(mol, b, ft)
+    n = b.norb
+    full = O.dense_from_packed(pk, n)
+    ii, jj = np.triu_indices(n)
+    rows = np.array([0, 5, 17, 40, len(ii) - 1])
+    got = O.int2e_rows(mol, b, ft, rows)
+    for r, P in enumerate(rows):
+        want = full[ii[P], jj[P]][ii, jj]
+        assert np.abs(got[r] - want).max() < 1e-13
+
+
+def test_boys_regimes(oracle_inputs):
+    """Boys restatement: Taylor/downward below T=12, asymptotic forms above, table errors kept."""
+    import mpmath as mp
+    ft = oracle_inputs[0]
+
+    def exact(j, T):
+        return float(mp.quad(lambda t: t ** (2 * j) * mp.e ** (-T * t * t), [0, 1]))
+    for Q in (0, 3, 6, 12):
+        for T in (0.0, 0.31, 3.77, 11.96):
+            F = O.boys(Q, T, ft)
+            for j in range(Q + 1):
+                assert abs(F[j] - exact(j, T)) < 5e-8  # table typos / float pi limit the accuracy
+    # the four known bad table entries are used as they are: Ft(36,2)
+    F = O.boys(2, 3.6, ft)
+    assert abs(F[2] - ft[36 + 121 * 2]) < 1e-15
+    # T >= 12: float32 pi shows up at the 1e-8 level
+    F = O.boys(0, 40.0, ft)
+    assert abs(F[0] - 0.5 * np.sqrt(float(np.float32(np.pi)) / 40.0)) < 1e-16
+    assert abs(F[0] - 0.5 * np.sqrt(np.pi / 40.0)) > 1e-10
