@@ -123,10 +123,25 @@ static int add_launch(myqc_eri_plan* pl, int ui, int ti, bool tri) {
     std::memset(&a, 0, sizeof(a));
     a.u_aos = U.aos; a.u_nprim = U.nprim; a.u_pidx = U.pidx; a.nU = U.n;
     const std::vector<int32_t> ntv = row_prefix(U.host, T.host);
+    // segments of the lane-side list: at most kTaskPairs pairs, cut at group boundaries once a
+    // segment holds >= 64 pairs, so that a task holds pairs of (mostly) one kind
+    std::vector<int> seg;  // segment start offsets, terminated by T.n
+    seg.push_back(0);
+    for (int k = 1; k < T.n; ++k) {
+        const int len = k - seg.back();
+        if (len >= kTaskPairs || (len >= 64 && T.host.bucket[k] != T.host.bucket[k - 1])) seg.push_back(k);
+    }
+    seg.push_back(T.n);
     std::vector<int4> tasks;
-    for (int u = 0; u < U.n; ++u)
-        for (int v0 = tri ? u : 0; v0 < ntv[u]; v0 += kTaskPairs)
-            tasks.push_back(make_int4(u, v0, std::min(v0 + kTaskPairs, (int)ntv[u]), 0));
+    for (int u = 0; u < U.n; ++u) {
+        const int lo = tri ? u : 0, hi = ntv[u];
+        if (lo >= hi) continue;
+        size_t si = std::upper_bound(seg.begin(), seg.end(), lo) - seg.begin() - 1;
+        for (; si + 1 < seg.size() && seg[si] < hi; ++si) {
+            const int b = std::max(seg[si], lo), e = std::min(seg[si + 1], hi);
+            if (b < e) tasks.push_back(make_int4(u, b, e, 0));
+        }
+    }
     if (tasks.empty()) return MYQC_OK;
     int4* d_tasks = nullptr;
     int rc = upload(pl, tasks, &d_tasks);

@@ -240,7 +240,8 @@ struct Cfg {
     static constexpr size_t OFF_EXP = 121 * 8 * 8;
     static constexpr size_t OFF_U = OFF_EXP + 608 * 16;
     static constexpr size_t OFF_BAR = OFF_U + (size_t)NWARPS * 2 * U_BYTES;
-    static constexpr size_t OFF_OUT = OFF_BAR + (size_t)NWARPS * 2 * 8;
+    static constexpr size_t OFF_SORT = OFF_BAR + (size_t)NWARPS * 2 * 8;   // per warp: 256 idx + 64 bins (int)
+    static constexpr size_t OFF_OUT = OFF_SORT + (size_t)NWARPS * (kTaskPairs + 64) * 4;
     static constexpr size_t SMEM = OFF_OUT + (OUT_SMEM ? (size_t)NOUT * NTHREADS * 8 : 0);
 };
 
@@ -264,6 +265,8 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS) eri_class_kernel(c
     const int warp = tid >> 5;
     double* s_ubuf = reinterpret_cast<double*>(smem_raw + C::OFF_U) + (size_t)warp * 2 * 9 * FU;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + C::OFF_BAR) + warp * 2;
+    int* s_vidx = reinterpret_cast<int*>(smem_raw + C::OFF_SORT) + warp * (kTaskPairs + 64);
+    int* s_bin = s_vidx + kTaskPairs;
 
     for (int i = tid; i < 121 * 8; i += NTHREADS) s_ft[i] = a.ftab_q[i];
     for (int i = tid; i < 601; i += NTHREADS) s_exp[i] = a.exptab[i];
@@ -321,9 +324,65 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS) eri_class_kernel(c
         const double* s_u = s_ubuf + (size_t)buf * 9 * FU;
         const double eu_max = s_u[4];
 
-        for (int vb = v0; vb < ntv; vb += 32) {
-            const int v = vb + lane;
-            if (v < ntv) {
+        // ---- order the task's lane-side pairs by their distance from the row's pair -----------
+        // The Boys regime of a primitive quartet is set by alpha*|P-Q|^2; pairs of one task are of
+        // one kind (same exponents), so after a counting sort on |P-Q|^2 the 32 lanes of a chunk
+        // take the same branch.  Which lane gets which pair does not affect any result.
+        const int nitem = ntv - v0;
+        if (nitem > 32) {
+            const double Px = s_u[1], Py = s_u[2], Pz = s_u[3];
+            double key[kTaskPairs / 32];
+            double kmin = 1.0e300, kmax = 0.0;
+#pragma unroll
+            for (int i = 0; i < kTaskPairs / 32; ++i) {
+                const int v = v0 + i * 32 + lane;
+                key[i] = -1.0;
+                if (v < ntv) {
+                    const double dx = Px - a.t_soa[(size_t)a.t_npad + v];
+                    const double dy = Py - a.t_soa[2 * (size_t)a.t_npad + v];
+                    const double dz = Pz - a.t_soa[3 * (size_t)a.t_npad + v];
+                    key[i] = fma(dx, dx, fma(dy, dy, dz * dz));
+                    kmin = fmin(kmin, key[i]);
+                    kmax = fmax(kmax, key[i]);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                kmin = fmin(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                kmax = fmax(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+            }
+            const double scale = 63.999 / (kmax - kmin + 1.0e-300);
+            s_bin[lane] = 0;
+            s_bin[lane + 32] = 0;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < kTaskPairs / 32; ++i)
+                if (key[i] >= 0.0) atomicAdd(&s_bin[(int)((key[i] - kmin) * scale)], 1);
+            __syncwarp();
+            // exclusive scan of the 64 bin counts (two bins per lane)
+            const int c0 = s_bin[2 * lane], c1 = s_bin[2 * lane + 1];
+            int incl = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            __syncwarp();
+            s_bin[2 * lane] = incl - c0 - c1;
+            s_bin[2 * lane + 1] = incl - c1;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < kTaskPairs / 32; ++i)
+                if (key[i] >= 0.0) s_vidx[atomicAdd(&s_bin[(int)((key[i] - kmin) * scale)], 1)] = v0 + i * 32 + lane;
+            __syncwarp();
+        } else {
+            s_vidx[lane] = v0 + lane;
+            __syncwarp();
+        }
+
+        for (int ib = 0; ib < nitem; ib += 32) {
+            if (ib + lane < nitem) {
+                const int v = s_vidx[ib + lane];
                 double out_r[OUT_SMEM ? 1 : NOUT];
                 if constexpr (OUT_SMEM) {
 #pragma unroll

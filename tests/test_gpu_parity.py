@@ -151,16 +151,24 @@ def test_h2o64_rows(tmp_path, oracle_inputs):
 
 
 @pytest.mark.parametrize("name,nsh", [("CO2", 2), ("h2o_4", 3), ("h2o_8", 4), ("h2o_16", 8)])
-def test_shards_reproduce_the_unsharded_array_bitwise(name, nsh, tmp_path):
-    """Multi-GPU path on one device: every shard computes its slice independently; the
-    concatenation must be bit-identical to the single-shard result."""
+def test_shards_reproduce_the_unsharded_array(name, nsh, tmp_path):
+    """Multi-GPU path on one device: every shard computes its slice independently.  A quartet that
+    straddles two ownership lists is evaluated with bra and ket roles possibly exchanged with
+    respect to the single-shard run (P-Q changes sign, sums run in another order), so the
+    concatenation agrees to rounding (1e-13), not bit for bit; zeros stay exact zeros."""
     s = product_system(name, tmp_path)
     whole = Q.eri_packed(s)
     off = Q.shard_layout(s, nsh)
     parts = np.empty_like(whole)
     for k in range(nsh):
         Q.eri_packed_shard(s, parts[off[k]:off[k + 1]], device=0, shard=k, nshards=nsh)
-    assert np.array_equal(parts, whole)
+    assert np.abs(parts - whole).max() < 1e-13
+    assert np.array_equal(parts == 0.0, whole == 0.0)
+    # and each run is deterministic
+    again = np.empty_like(whole)
+    for k in range(nsh):
+        Q.eri_packed_shard(s, again[off[k]:off[k + 1]], device=0, shard=k, nshards=nsh)
+    assert np.array_equal(parts, again)
 
 
 def test_plan_api_device_buffers(tmp_path):
