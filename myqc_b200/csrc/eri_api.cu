@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -51,9 +52,17 @@ struct Launch {
     ClassArgs args;
 };
 
+constexpr int kMaxCounters = 1024;
+
 }  // namespace myqc
 
 using namespace myqc;
+
+struct Sub {  // one virtual sub-shard: a contiguous piece of the plan's slice with its own launches
+    int64_t out_offset = 0, out_elems = 0;  // absolute packed offsets
+    std::vector<Launch> launches;
+    int counter_base = 0, ncounters = 0;
+};
 
 struct myqc_eri_plan {
     int device = 0, num_sms = 0;
@@ -62,11 +71,17 @@ struct myqc_eri_plan {
     int64_t out_offset = 0, out_elems = 0;
     std::vector<void*> dev_allocs;
     std::vector<DevList> lists;
-    std::vector<Launch> launches;
+    std::vector<Sub> subs;
     double* d_ftab = nullptr;    // [5][121][8]
     double* d_exptab = nullptr;  // [601][2] {exp(-k/10), k/10}
     int* d_counters = nullptr;   // one row counter per class-kernel launch
     int ncounters = 0;
+    // internal streams: the zero fill of sub-shard k+1 overlaps the FP64 kernels of sub-shard k,
+    // and class kernels of one sub-shard overlap each other's tails
+    static constexpr int kNumCompute = 4;
+    cudaStream_t s_fill = nullptr, s_comp[kNumCompute] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t e_start = nullptr, e_done[kNumCompute + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> e_fill;
     // stats (canonical primitive-quartet counts of the whole shard)
     int64_t nquartets[6] = {0, 0, 0, 0, 0, 0};
     double model_flops = 0.0;
@@ -113,7 +128,7 @@ static std::vector<int32_t> prefix_counts(const std::vector<double>& eu, const s
     return out;
 }
 
-static int add_launch(myqc_eri_plan* pl, int ui, int ti, bool tri) {
+static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
     const DevList& U = pl->lists[ui];
     const DevList& T = pl->lists[ti];
     if (U.n == 0 || T.n == 0) return MYQC_OK;
@@ -152,12 +167,14 @@ static int add_launch(myqc_eri_plan* pl, int ui, int ti, bool tri) {
     a.t_npad = T.npad; a.nT = T.n; a.tri = tri ? 1 : 0;
     a.ftab_q = pl->d_ftab + (size_t)(U.type + T.type) * 121 * 8;
     a.exptab = reinterpret_cast<const double2*>(pl->d_exptab);
+    if (pl->ncounters + 4 > kMaxCounters) return fail(MYQC_ERR_UNSUPPORTED, "too many launches in one plan");
     a.row_counter = pl->d_counters + pl->ncounters;
     pl->ncounters += class_nlaunch(L.UT, L.TT);
+    sub.ncounters += class_nlaunch(L.UT, L.TT);
     a.out = nullptr;
-    a.out_offset = pl->out_offset;
+    a.out_offset = sub.out_offset;
     a.npair = pl->npair;
-    pl->launches.push_back(L);
+    sub.launches.push_back(L);
     pl->nlaunch += class_nlaunch(L.UT, L.TT);
     return MYQC_OK;
 }
@@ -206,29 +223,30 @@ static int64_t packed_row_offset(int64_t fn, int64_t norb) {
 // Ownership rule (multi-GPU): a shell quartet belongs to the shard that owns the
 // smallest first-orbital id among its four shells; all its canonical integrals then lie in packed
 // rows whose leading orbital is inside that shell.  Shards are contiguous blocks of such rows.
-// fn_bounds[s] .. fn_bounds[s+1] are the leading-orbital ranges, balanced by estimated model
-// flops.  Pure host arithmetic: every rank computes the same answer independently.
-static int shard_fn_bounds(const std::vector<Shell>& shells, const PairList all[3], int norb, int nshards,
-                           std::vector<int>& fn_bounds, std::string& err) {
-    fn_bounds.assign(nshards + 1, norb);
-    fn_bounds[0] = 0;
-    if (nshards == 1) return MYQC_OK;
+// Pure host arithmetic: every rank computes the same answer independently.
+struct CutTable {
+    std::vector<int> cuts;   // candidate cut points: first orbital of each shell, ascending
+    std::vector<double> w;   // estimated model flops owned by [cuts[c], cuts[c+1])
+};
+
+static int build_cut_table(const std::vector<Shell>& shells, const PairList all[3], CutTable& ct, std::string& err) {
     for (const Shell& sh : shells) {  // row blocks are closed only for contiguous orbital ranges
         int cnt = 0, mx = -1;
         for (int k = 0; k < 4; ++k) if (sh.fn[k] >= 0) { ++cnt; mx = std::max(mx, sh.fn[k]); }
         if (mx - sh.first_fn + 1 != cnt) { err = "sharding needs contiguous orbital ids per shell"; return MYQC_ERR_UNSUPPORTED; }
     }
-    std::vector<int> cuts;  // candidate cut points: first orbital of each shell
+    std::vector<int>& cuts = ct.cuts;
+    cuts.clear();
     for (const Shell& sh : shells) cuts.push_back(sh.first_fn);
     std::sort(cuts.begin(), cuts.end());
     cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
     const int nc = (int)cuts.size();
     auto cut_of = [&](int fn) { return (int)(std::upper_bound(cuts.begin(), cuts.end(), fn) - cuts.begin()) - 1; };
     // weight of block c ~ model flops of the quartets it owns.  A row u of class (ta,tb) has
-    // cnt[u] partners (the emax prefix); the prefix of a list sorted by emax is treated as an
-    // unbiased sample of owners, so the row's weight is split between cut(u) (partners with
-    // cut >= cut(u)) and the lower cuts in proportion to the partner histogram.
-    std::vector<double> w(nc, 0.0);
+    // cnt[u] partners (the emax prefix); the prefix is treated as an unbiased sample of owners, so
+    // the row's weight is split between cut(u) (partners with cut >= cut(u)) and the lower cuts
+    // in proportion to the partner histogram.
+    ct.w.assign(nc, 0.0);
     for (int ta = 0; ta < 3; ++ta)
         for (int tb = ta; tb < 3; ++tb) {
             const PairList& A = all[ta];
@@ -249,25 +267,31 @@ static int shard_fn_bounds(const std::vector<Shell>& shells, const PairList all[
                 if (ta == tb) nrow = std::max(0.0, nrow - u);
                 const double wr = wq * nrow * (double)A.nprim[u];
                 const int cu = cut_of(A.owner_fn[u]);
-                w[cu] += wr * ge[cu];
-                for (int c = 0; c < cu; ++c) w[c] += wr * hist[c];
+                ct.w[cu] += wr * ge[cu];
+                for (int c = 0; c < cu; ++c) ct.w[c] += wr * hist[c];
             }
         }
-    double tot = 0;
-    for (double x : w) tot += x;
-    std::vector<int> bound(nshards + 1, nc);
-    bound[0] = 0;
-    double acc = 0;
-    int sidx = 1;
-    for (int c = 0; c < nc && sidx < nshards; ++c) {
-        acc += w[c];
-        while (sidx < nshards && acc >= tot * sidx / nshards) bound[sidx++] = c + 1;
-    }
-    for (int k = 1; k <= nshards; ++k) bound[k] = std::max(bound[k], bound[k - 1]);
-    bound[nshards] = nc;
-    for (int k = 1; k < nshards; ++k) fn_bounds[k] = bound[k] < nc ? cuts[bound[k]] : norb;
     return MYQC_OK;
 }
+
+// cut the candidate range [c_lo, c_hi) into m contiguous parts of ~equal weight; returns m+1 indices
+static std::vector<int> split_range(const CutTable& ct, int c_lo, int c_hi, int m) {
+    std::vector<int> bound(m + 1, c_hi);
+    bound[0] = c_lo;
+    double tot = 0;
+    for (int c = c_lo; c < c_hi; ++c) tot += ct.w[c];
+    double acc = 0;
+    int sidx = 1;
+    for (int c = c_lo; c < c_hi && sidx < m; ++c) {
+        acc += ct.w[c];
+        while (sidx < m && acc >= tot * sidx / m) bound[sidx++] = c + 1;
+    }
+    for (int k = 1; k <= m; ++k) bound[k] = std::max(bound[k], bound[k - 1]);
+    bound[m] = c_hi;
+    return bound;
+}
+
+static int cut_to_fn(const CutTable& ct, int c, int norb) { return c < (int)ct.cuts.size() ? (c == 0 ? 0 : ct.cuts[c]) : norb; }
 
 static int check_args(int nnuc, const double* xyz, int nset, int setl, const double* set,
                       const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
@@ -338,55 +362,99 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
         std::vector<double> ex(2 * 608, 0.0);
         for (int k = 0; k <= 600; ++k) { ex[2 * k] = std::exp(-(k / 10.0)); ex[2 * k + 1] = k / 10.0; }
         if ((rc = upload(pl.get(), ex, &pl->d_exptab))) return rc;
-        std::vector<int> zeros(64, 0);
+        std::vector<int> zeros(kMaxCounters, 0);
         if ((rc = upload(pl.get(), zeros, &pl->d_counters))) return rc;
     }
 
     // ---- sharding: contiguous blocks of packed rows, cut where a shell's functions start -------
-    int fn_lo = 0, fn_hi = pl->norb;  // this shard owns rows whose first index is in [fn_lo, fn_hi)
+    // External shards (one per GPU) are cut first; this plan's shard is then cut again into
+    // virtual sub-shards so that the zero fill of piece k+1 overlaps the FP64 kernels of piece k.
+    CutTable ct;
+    ct.cuts.push_back(0);
+    ct.w.push_back(1.0);
+    int nvs = 1;
     {
-        std::vector<int> fn_bounds;
-        if ((rc = shard_fn_bounds(shells, all, pl->norb, nshards, fn_bounds, err))) return fail(rc, err);
-        fn_lo = fn_bounds[shard];
-        fn_hi = fn_bounds[shard + 1];
-        pl->out_offset = packed_row_offset(fn_lo, pl->norb);
-        pl->out_elems = packed_row_offset(fn_hi, pl->norb) - pl->out_offset;
+        const char* env = std::getenv("MYQC_VSHARDS");
+        const int64_t total = pl->npair * (pl->npair + 1) / 2;
+        // Measured on (H2O)_64 (profiles/r1_notes.md): cutting one GPU's shard into pieces overlaps the
+        // zero fill with the FP64 kernels but costs more in extra launches, shorter task lists and
+        // duplicated "later" lists than it wins (23.5 / 25.0 / 26.6 / 32.4 ms for 1 / 2 / 4 / 8 pieces),
+        // so the default is one piece; MYQC_VSHARDS overrides it for experiments.
+        (void)total;
+        nvs = env ? std::atoi(env) : 1;
+        if (nvs < 1) nvs = 1;
+        if (nvs > 16) nvs = 16;
     }
+    std::vector<int> sub_fn(2, 0);
+    sub_fn[1] = pl->norb;
+    if (nshards > 1 || nvs > 1) {
+        if ((rc = build_cut_table(shells, all, ct, err))) return fail(rc, err);
+        const int nc = (int)ct.cuts.size();
+        const std::vector<int> ext = split_range(ct, 0, nc, nshards);
+        const std::vector<int> sub = split_range(ct, ext[shard], ext[shard + 1], nvs);
+        sub_fn.clear();
+        for (int c : sub) sub_fn.push_back(cut_to_fn(ct, c, pl->norb));
+        // drop empty pieces
+        std::vector<int> keep;
+        for (size_t k = 0; k < sub_fn.size(); ++k)
+            if (k == 0 || sub_fn[k] > keep.back()) keep.push_back(sub_fn[k]);
+        if (keep.size() < 2) keep.push_back(keep.back());
+        sub_fn = keep;
+    }
+    pl->out_offset = packed_row_offset(sub_fn.front(), pl->norb);
+    pl->out_elems = packed_row_offset(sub_fn.back(), pl->norb) - pl->out_offset;
 
-    // lists: "mine" (owner key in [fn_lo,fn_hi)) and "later" (owner key >= fn_hi)
-    pl->lists.reserve(6);
-    int mine_id[3], later_id[3];
-    for (int t = 0; t < 3; ++t) {
-        std::vector<char> pm(all[t].n), pl8(all[t].n);
-        bool any_later = false;
-        for (int k = 0; k < all[t].n; ++k) {
-            pm[k] = (all[t].owner_fn[k] >= fn_lo && all[t].owner_fn[k] < fn_hi);
-            pl8[k] = (all[t].owner_fn[k] >= fn_hi);
-            any_later = any_later || pl8[k];
-        }
-        pl->lists.emplace_back();
-        mine_id[t] = (int)pl->lists.size() - 1;
-        if ((rc = upload_list(pl.get(), nshards == 1 ? all[t] : sublist(all[t], pm), pl->lists.back()))) return rc;
-        later_id[t] = -1;
-        if (any_later) {
+    const int nsub = (int)sub_fn.size() - 1;
+    pl->subs.resize(nsub);
+    pl->lists.reserve(6 * nsub);
+    for (int k = 0; k < nsub; ++k) {
+        Sub& sub = pl->subs[k];
+        const int fn_lo = sub_fn[k], fn_hi = sub_fn[k + 1];
+        sub.out_offset = packed_row_offset(fn_lo, pl->norb);
+        sub.out_elems = packed_row_offset(fn_hi, pl->norb) - sub.out_offset;
+        sub.counter_base = pl->ncounters;
+        // lists: "mine" (owner key in [fn_lo,fn_hi)) and "later" (owner key >= fn_hi)
+        int mine_id[3], later_id[3];
+        const bool whole = (fn_lo == 0 && fn_hi >= pl->norb);
+        for (int t = 0; t < 3; ++t) {
+            std::vector<char> pm(all[t].n), pl8(all[t].n);
+            bool any_later = false;
+            for (int q = 0; q < all[t].n; ++q) {
+                pm[q] = (all[t].owner_fn[q] >= fn_lo && all[t].owner_fn[q] < fn_hi);
+                pl8[q] = (all[t].owner_fn[q] >= fn_hi);
+                any_later = any_later || pl8[q];
+            }
             pl->lists.emplace_back();
-            later_id[t] = (int)pl->lists.size() - 1;
-            if ((rc = upload_list(pl.get(), sublist(all[t], pl8), pl->lists.back()))) return rc;
-        }
-    }
-    // launches.  Class (ta,tb), ta <= tb, uniform side = ta, lane side = tb.
-    for (int ta = 0; ta < 3; ++ta)
-        for (int tb = ta; tb < 3; ++tb) {
-            if (ta == tb) {
-                if ((rc = add_launch(pl.get(), mine_id[ta], mine_id[ta], true))) return rc;
-                if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), mine_id[ta], later_id[ta], false))) return rc;
-            } else {
-                if ((rc = add_launch(pl.get(), mine_id[ta], mine_id[tb], false))) return rc;
-                if (later_id[tb] >= 0 && (rc = add_launch(pl.get(), mine_id[ta], later_id[tb], false))) return rc;
-                if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), later_id[ta], mine_id[tb], false))) return rc;
+            mine_id[t] = (int)pl->lists.size() - 1;
+            if ((rc = upload_list(pl.get(), whole ? all[t] : sublist(all[t], pm), pl->lists.back()))) return rc;
+            later_id[t] = -1;
+            if (any_later) {
+                pl->lists.emplace_back();
+                later_id[t] = (int)pl->lists.size() - 1;
+                if ((rc = upload_list(pl.get(), sublist(all[t], pl8), pl->lists.back()))) return rc;
             }
         }
-    pl->nlaunch += 1;  // zero fill
+        // launches.  Class (ta,tb), ta <= tb, uniform side = ta, lane side = tb.
+        for (int ta = 0; ta < 3; ++ta)
+            for (int tb = ta; tb < 3; ++tb) {
+                if (ta == tb) {
+                    if ((rc = add_launch(pl.get(), sub, mine_id[ta], mine_id[ta], true))) return rc;
+                    if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), sub, mine_id[ta], later_id[ta], false))) return rc;
+                } else {
+                    if ((rc = add_launch(pl.get(), sub, mine_id[ta], mine_id[tb], false))) return rc;
+                    if (later_id[tb] >= 0 && (rc = add_launch(pl.get(), sub, mine_id[ta], later_id[tb], false))) return rc;
+                    if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), sub, later_id[ta], mine_id[tb], false))) return rc;
+                }
+            }
+        pl->nlaunch += 1;  // zero fill of this piece
+    }
+    // internal streams and events
+    CU(cudaStreamCreateWithFlags(&pl->s_fill, cudaStreamNonBlocking));
+    for (auto& st : pl->s_comp) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&pl->e_start, cudaEventDisableTiming));
+    for (auto& e : pl->e_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    pl->e_fill.resize(nsub);
+    for (auto& e : pl->e_fill) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
     if (nshards == 1) canonical_stats(nnuc, xyz, nset, setl, set, setinfo, pl->nquartets, &pl->model_flops);
     *plan = pl.release();
@@ -413,65 +481,109 @@ int myqc_eri_shard_layout(int nnuc, const double* xyz, int nset, int setl, const
     if ((rc = build_shells(nnuc, nset, setl, setinfo, ops, basinfo, shells, err))) return fail(rc, err);
     PairList all[3];
     if ((rc = build_pairs(nnuc, xyz, set, setinfo, setl, ops, bas, basinfo, shells, all, err))) return fail(rc, err);
-    std::vector<int> fb;
-    if ((rc = shard_fn_bounds(shells, all, basinfo[1], nshards, fb, err))) return fail(rc, err);
-    for (int k = 0; k <= nshards; ++k) offsets[k] = packed_row_offset(fb[k], basinfo[1]);
+    CutTable ct;
+    if (nshards == 1) { offsets[0] = 0; offsets[1] = packed_row_offset(basinfo[1], basinfo[1]); return MYQC_OK; }
+    if ((rc = build_cut_table(shells, all, ct, err))) return fail(rc, err);
+    const std::vector<int> ext = split_range(ct, 0, (int)ct.cuts.size(), nshards);
+    for (int k = 0; k <= nshards; ++k) offsets[k] = packed_row_offset(cut_to_fn(ct, ext[k], basinfo[1]), basinfo[1]);
     return MYQC_OK;
 }
 
 int64_t myqc_eri_plan_out_offset(const myqc_eri_plan* plan) { return plan ? plan->out_offset : -1; }
 int64_t myqc_eri_plan_out_elems(const myqc_eri_plan* plan) { return plan ? plan->out_elems : -1; }
 
+// serial order of launches: for each sub-shard its zero fill, then its class kernels
+static int plan_launch_total(const myqc_eri_plan* plan) {
+    int n = 0;
+    for (const Sub& sub : plan->subs) n += 1 + (int)sub.launches.size();
+    return n;
+}
+
 int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
     if (!plan || (!d_out && plan->out_elems > 0)) return fail(MYQC_ERR_BAD_ARG, "null plan or output");
     CU(cudaSetDevice(plan->device));
-    int e = launch_fill_zero(d_out, plan->out_elems, plan->d_counters, plan->ncounters, plan->num_sms, stream);
-    if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
-    for (Launch& L : plan->launches) {
-        L.args.out = d_out;
-        e = launch_class(L.UT, L.TT, L.args, plan->num_sms, stream);
-        if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nsub = (int)plan->subs.size();
+    // fork: internal streams start after whatever is already queued on the caller's stream
+    CU(cudaEventRecord(plan->e_start, st));
+    CU(cudaStreamWaitEvent(plan->s_fill, plan->e_start, 0));
+    for (auto& sc : plan->s_comp) CU(cudaStreamWaitEvent(sc, plan->e_start, 0));
+    for (int k = 0; k < nsub; ++k) {
+        Sub& sub = plan->subs[k];
+        int e = launch_fill_zero(d_out + (sub.out_offset - plan->out_offset), sub.out_elems,
+                                 plan->d_counters + sub.counter_base, sub.ncounters, plan->num_sms, plan->s_fill);
+        if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
+        CU(cudaEventRecord(plan->e_fill[k], plan->s_fill));
     }
+    int rr = 0;
+    for (int k = 0; k < nsub; ++k) {
+        Sub& sub = plan->subs[k];
+        bool waited[myqc_eri_plan::kNumCompute] = {false, false, false, false};
+        for (Launch& L : sub.launches) {
+            const int si = rr++ % myqc_eri_plan::kNumCompute;
+            if (!waited[si]) { CU(cudaStreamWaitEvent(plan->s_comp[si], plan->e_fill[k], 0)); waited[si] = true; }
+            L.args.out = d_out + (sub.out_offset - plan->out_offset);
+            int e = launch_class(L.UT, L.TT, L.args, plan->num_sms, plan->s_comp[si]);
+            if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+        }
+    }
+    // join
+    for (int i = 0; i < myqc_eri_plan::kNumCompute; ++i) {
+        CU(cudaEventRecord(plan->e_done[i], plan->s_comp[i]));
+        CU(cudaStreamWaitEvent(st, plan->e_done[i], 0));
+    }
+    CU(cudaEventRecord(plan->e_done[myqc_eri_plan::kNumCompute], plan->s_fill));
+    CU(cudaStreamWaitEvent(st, plan->e_done[myqc_eri_plan::kNumCompute], 0));
     return MYQC_OK;
 }
 
 int myqc_eri_plan_launch_count(const myqc_eri_plan* plan) {
     if (!plan) return 0;
-    return 1 + (int)plan->launches.size();
+    return plan_launch_total(plan);
 }
 
 int myqc_eri_plan_launch_info(const myqc_eri_plan* plan, int k, int* cls, int* tri, int64_t* rows) {
-    if (!plan || k < 0 || k > (int)plan->launches.size()) return fail(MYQC_ERR_BAD_ARG, "bad launch index");
-    if (k == 0) {  // the zero fill
-        if (cls) *cls = -1;
-        if (tri) *tri = 0;
-        if (rows) *rows = plan->out_elems;
+    if (!plan || k < 0 || k >= plan_launch_total(plan)) return fail(MYQC_ERR_BAD_ARG, "bad launch index");
+    for (const Sub& sub : plan->subs) {
+        const int n = 1 + (int)sub.launches.size();
+        if (k >= n) { k -= n; continue; }
+        if (k == 0) {  // the zero fill of this piece
+            if (cls) *cls = -1;
+            if (tri) *tri = 0;
+            if (rows) *rows = sub.out_elems;
+            return MYQC_OK;
+        }
+        const Launch& L = sub.launches[k - 1];
+        if (cls) *cls = class_id(L.UT, L.TT);
+        if (tri) *tri = L.args.tri;
+        if (rows) *rows = L.args.ntasks;
         return MYQC_OK;
     }
-    const Launch& L = plan->launches[k - 1];
-    if (cls) *cls = class_id(L.UT, L.TT);
-    if (tri) *tri = L.args.tri;
-    if (rows) *rows = L.args.nU;
-    return MYQC_OK;
+    return fail(MYQC_ERR_BAD_ARG, "bad launch index");
 }
 
+// Serialised pass on the caller's stream with CUDA events around every launch: the per-kernel
+// durations behind bench.py's roofline (the production execute() overlaps launches on internal streams).
 int myqc_eri_plan_execute_timed(myqc_eri_plan* plan, double* d_out, void* stream, float* ms) {
     if (!plan || !ms || (!d_out && plan->out_elems > 0)) return fail(MYQC_ERR_BAD_ARG, "null plan/output/ms");
     CU(cudaSetDevice(plan->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int n = 1 + (int)plan->launches.size();
+    const int n = plan_launch_total(plan);
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) CU(cudaEventCreate(&e));
     CU(cudaEventRecord(ev[0], st));
-    int e = launch_fill_zero(d_out, plan->out_elems, plan->d_counters, plan->ncounters, plan->num_sms, stream);
-    if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
-    CU(cudaEventRecord(ev[1], st));
-    for (int k = 0; k < n - 1; ++k) {
-        Launch& L = plan->launches[k];
-        L.args.out = d_out;
-        e = launch_class(L.UT, L.TT, L.args, plan->num_sms, stream);
-        if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
-        CU(cudaEventRecord(ev[k + 2], st));
+    int idx = 0;
+    for (Sub& sub : plan->subs) {
+        int e = launch_fill_zero(d_out + (sub.out_offset - plan->out_offset), sub.out_elems,
+                                 plan->d_counters + sub.counter_base, sub.ncounters, plan->num_sms, st);
+        if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
+        CU(cudaEventRecord(ev[++idx], st));
+        for (Launch& L : sub.launches) {
+            L.args.out = d_out + (sub.out_offset - plan->out_offset);
+            e = launch_class(L.UT, L.TT, L.args, plan->num_sms, st);
+            if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+            CU(cudaEventRecord(ev[++idx], st));
+        }
     }
     CU(cudaEventSynchronize(ev[n]));
     for (int k = 0; k < n; ++k) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
@@ -503,6 +615,11 @@ int myqc_eri_plan_stats(const myqc_eri_plan* plan, int64_t* nquartets, double* m
 void myqc_eri_plan_destroy(myqc_eri_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);
+    if (plan->s_fill) { cudaStreamSynchronize(plan->s_fill); cudaStreamDestroy(plan->s_fill); }
+    for (auto& st : plan->s_comp) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    if (plan->e_start) cudaEventDestroy(plan->e_start);
+    for (auto& e : plan->e_done) if (e) cudaEventDestroy(e);
+    for (auto& e : plan->e_fill) if (e) cudaEventDestroy(e);
     for (void* p : plan->dev_allocs) cudaFree(p);
     delete plan;
 }
