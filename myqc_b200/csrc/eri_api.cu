@@ -49,7 +49,8 @@ struct DevList {  // device copy of a PairList
 
 struct Launch {
     int UT, TT;
-    ClassArgs args;
+    ClassArgs args;                // args.tasks/ntasks describe the whole need-sorted task array
+    std::vector<int> region_task;  // [nregion+1] task ranges: region r = tasks whose writes end inside fill region r
 };
 
 constexpr int kMaxCounters = 1024;
@@ -62,6 +63,11 @@ struct Sub {  // one virtual sub-shard: a contiguous piece of the plan's slice w
     int64_t out_offset = 0, out_elems = 0;  // absolute packed offsets
     std::vector<Launch> launches;
     int counter_base = 0, ncounters = 0;
+    // Fill regions: the slice is zero-filled in nregion consecutive pieces; the tasks of every
+    // class kernel are sorted by the end of the last packed row they can write to, so the tasks
+    // of region r only touch memory that pieces 0..r have already zeroed and can run while the
+    // later pieces are still being filled (no extra lists, no extra arithmetic: same tasks).
+    std::vector<int64_t> region_end;  // [nregion] offsets relative to the sub-shard's slice
 };
 
 struct myqc_eri_plan {
@@ -104,7 +110,7 @@ static int upload(myqc_eri_plan* pl, const std::vector<T>& h, T** d) {
 
 static int upload_list(myqc_eri_plan* pl, const PairList& src, DevList& d) {
     d.type = src.type; d.n = src.n; d.npad = src.npad;
-    d.host.type = src.type; d.host.n = src.n; d.host.emax = src.emax; d.host.bucket = src.bucket;
+    d.host.type = src.type; d.host.n = src.n; d.host.emax = src.emax; d.host.bucket = src.bucket; d.host.pidx = src.pidx; d.host.nprim = src.nprim;
     int rc;
     if ((rc = upload(pl, src.aos, &d.aos))) return rc;
     if ((rc = upload(pl, src.soa, &d.soa))) return rc;
@@ -140,22 +146,63 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
     const std::vector<int32_t> ntv = row_prefix(U.host, T.host);
     // segments of the lane-side list: at most kTaskPairs pairs, cut at group boundaries once a
     // segment holds >= 64 pairs, so that a task holds pairs of (mostly) one kind
+    // The heavier the class, the shorter the tasks: a task is executed by one warp from start to
+    // finish, so its duration bounds the tail of the launch (a 256-pair (SP SP|SP SP) task with all
+    // 81 primitive quartets alive would run for more than a millisecond).
+    static const int kMaxPairsByClass[6] = {256, 256, 128, 128, 64, 32};
+    const int maxpairs = kMaxPairsByClass[class_id(U.type, T.type)];
+    const int mingroup = std::min(64, maxpairs);
     std::vector<int> seg;  // segment start offsets, terminated by T.n
     seg.push_back(0);
     for (int k = 1; k < T.n; ++k) {
         const int len = k - seg.back();
-        if (len >= kTaskPairs || (len >= 64 && T.host.bucket[k] != T.host.bucket[k - 1])) seg.push_back(k);
+        if (len >= maxpairs || (len >= mingroup && T.host.bucket[k] != T.host.bucket[k - 1])) seg.push_back(k);
     }
     seg.push_back(T.n);
-    std::vector<int4> tasks;
+    // last packed element a row u can write to: end of packed row max_f P(u,f)
+    std::vector<int64_t> need_u(U.n, 0);
+    {
+        const int nfu = pt_nf(U.type);
+        for (int u = 0; u < U.n; ++u) {
+            int64_t pmax = -1;
+            for (int f = 0; f < nfu; ++f) pmax = std::max<int64_t>(pmax, U.host.pidx[(size_t)u * nfu + f]);
+            need_u[u] = pmax < 0 ? 0 : (pmax + 1) * pl->npair - (pmax + 1) * pmax / 2 - sub.out_offset;  // row end, slice-relative
+        }
+    }
+    struct TaskN { int4 t; int64_t need; int region; double weight; };
+    std::vector<TaskN> tn;
+    std::vector<double> tprim_prefix(T.n + 1, 0.0);  // prefix sums of lane-side primitive counts
+    for (int k = 0; k < T.n; ++k) tprim_prefix[k + 1] = tprim_prefix[k] + T.host.nprim[k];
     for (int u = 0; u < U.n; ++u) {
         const int lo = tri ? u : 0, hi = ntv[u];
         if (lo >= hi) continue;
         size_t si = std::upper_bound(seg.begin(), seg.end(), lo) - seg.begin() - 1;
         for (; si + 1 < seg.size() && seg[si] < hi; ++si) {
             const int b = std::max(seg[si], lo), e = std::min(seg[si + 1], hi);
-            if (b < e) tasks.push_back(make_int4(u, b, e, 0));
+            if (b < e)
+                tn.push_back({make_int4(u, b, e, 0), need_u[u], 0,
+                              (double)U.host.nprim[u] * (tprim_prefix[e] - tprim_prefix[b])});
         }
+    }
+    // region of a task = first fill region that covers everything the task can write; inside a
+    // region the heaviest tasks (most primitive quartets) go first so that launches end on light ones
+    const int nregion = (int)sub.region_end.size();
+    for (TaskN& t : tn) {
+        int r = 0;
+        while (r + 1 < nregion && t.need > sub.region_end[r]) ++r;
+        t.region = r;
+    }
+    std::stable_sort(tn.begin(), tn.end(), [](const TaskN& x, const TaskN& y) {
+        if (x.region != y.region) return x.region < y.region;
+        return x.weight > y.weight;
+    });
+    std::vector<int4> tasks(tn.size());
+    for (size_t k = 0; k < tn.size(); ++k) tasks[k] = tn[k].t;
+    L.region_task.assign(nregion + 1, (int)tn.size());
+    L.region_task[0] = 0;
+    for (size_t k = 0, r = 0; r < (size_t)nregion; ++r) {
+        while (k < tn.size() && tn[k].region <= (int)r) ++k;
+        L.region_task[r + 1] = (int)k;
     }
     if (tasks.empty()) return MYQC_OK;
     int4* d_tasks = nullptr;
@@ -167,15 +214,16 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
     a.t_npad = T.npad; a.nT = T.n; a.tri = tri ? 1 : 0;
     a.ftab_q = pl->d_ftab + (size_t)(U.type + T.type) * 121 * 8;
     a.exptab = reinterpret_cast<const double2*>(pl->d_exptab);
-    if (pl->ncounters + 4 > kMaxCounters) return fail(MYQC_ERR_UNSUPPORTED, "too many launches in one plan");
+    const int ncnt = class_nlaunch(L.UT, L.TT) * nregion;  // one task counter per launch and region
+    if (pl->ncounters + ncnt > kMaxCounters) return fail(MYQC_ERR_UNSUPPORTED, "too many launches in one plan");
     a.row_counter = pl->d_counters + pl->ncounters;
-    pl->ncounters += class_nlaunch(L.UT, L.TT);
-    sub.ncounters += class_nlaunch(L.UT, L.TT);
+    pl->ncounters += ncnt;
+    sub.ncounters += ncnt;
     a.out = nullptr;
     a.out_offset = sub.out_offset;
     a.npair = pl->npair;
     sub.launches.push_back(L);
-    pl->nlaunch += class_nlaunch(L.UT, L.TT);
+    pl->nlaunch += class_nlaunch(L.UT, L.TT) * nregion;
     return MYQC_OK;
 }
 
@@ -413,6 +461,22 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
         sub.out_offset = packed_row_offset(fn_lo, pl->norb);
         sub.out_elems = packed_row_offset(fn_hi, pl->norb) - sub.out_offset;
         sub.counter_base = pl->ncounters;
+        {
+            const char* envr = std::getenv("MYQC_FILL_REGIONS");
+            // Default 1: on (H2O)_64 the fill of region r+1 and the kernels of region r do not co-run
+            // well (persistent grids starve each other): 23.2 / 24.2 / 24.8 ms for 1 / 2 / 4 regions
+            // (profiles/r1_notes.md).  MYQC_FILL_REGIONS overrides it for experiments.
+            int nreg = envr ? std::atoi(envr) : 1;
+            if (nreg < 1) nreg = 1;
+            if (nreg > 16) nreg = 16;
+            sub.region_end.resize(nreg);
+            for (int r = 0; r < nreg; ++r) {
+                int64_t e = sub.out_elems * (r + 1) / nreg;
+                e = (e + 1) & ~(int64_t)1;  // keep 16-byte aligned pieces
+                sub.region_end[r] = std::min(e, sub.out_elems);
+            }
+            sub.region_end[nreg - 1] = sub.out_elems;
+        }
         // lists: "mine" (owner key in [fn_lo,fn_hi)) and "later" (owner key >= fn_hi)
         int mine_id[3], later_id[3];
         const bool whole = (fn_lo == 0 && fn_hi >= pl->norb);
@@ -446,15 +510,19 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
                     if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), sub, later_id[ta], mine_id[tb], false))) return rc;
                 }
             }
-        pl->nlaunch += 1;  // zero fill of this piece
+        pl->nlaunch += (int)sub.region_end.size();  // zero fills of this piece
     }
     // internal streams and events
     CU(cudaStreamCreateWithFlags(&pl->s_fill, cudaStreamNonBlocking));
     for (auto& st : pl->s_comp) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&pl->e_start, cudaEventDisableTiming));
     for (auto& e : pl->e_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    pl->e_fill.resize(nsub);
-    for (auto& e : pl->e_fill) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    {
+        size_t nfill = 0;
+        for (const Sub& sub : pl->subs) nfill += sub.region_end.size();
+        pl->e_fill.resize(nfill);
+        for (auto& e : pl->e_fill) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
 
     if (nshards == 1) canonical_stats(nnuc, xyz, nset, setl, set, setinfo, pl->nquartets, &pl->model_flops);
     *plan = pl.release();
@@ -492,39 +560,63 @@ int myqc_eri_shard_layout(int nnuc, const double* xyz, int nset, int setl, const
 int64_t myqc_eri_plan_out_offset(const myqc_eri_plan* plan) { return plan ? plan->out_offset : -1; }
 int64_t myqc_eri_plan_out_elems(const myqc_eri_plan* plan) { return plan ? plan->out_elems : -1; }
 
-// serial order of launches: for each sub-shard its zero fill, then its class kernels
+// serial order of launches: for each sub-shard and fill region: its zero fill, then the class
+// kernels restricted to the tasks of that region
 static int plan_launch_total(const myqc_eri_plan* plan) {
     int n = 0;
-    for (const Sub& sub : plan->subs) n += 1 + (int)sub.launches.size();
+    for (const Sub& sub : plan->subs) n += (int)sub.region_end.size() * (1 + (int)sub.launches.size());
     return n;
+}
+
+// launch the tasks of fill region r of one class launch (its own task counter per region)
+static int launch_region(myqc_eri_plan* plan, Sub& sub, Launch& L, int r, double* d_sub_out, cudaStream_t st) {
+    const int t0 = L.region_task[r], t1 = L.region_task[r + 1];
+    if (t1 <= t0) return 0;
+    ClassArgs a = L.args;
+    a.out = d_sub_out;
+    a.tasks = L.args.tasks + t0;
+    a.ntasks = t1 - t0;
+    a.row_counter = L.args.row_counter + r * class_nlaunch(L.UT, L.TT);
+    return launch_class(L.UT, L.TT, a, plan->num_sms, st);
+}
+
+static int fill_region(myqc_eri_plan* plan, Sub& sub, int r, double* d_sub_out, cudaStream_t st) {
+    const int64_t b = r == 0 ? 0 : sub.region_end[r - 1], e = sub.region_end[r];
+    // the first fill of a sub-shard also resets all of its task counters
+    return launch_fill_zero(d_sub_out + b, e - b, plan->d_counters + sub.counter_base, r == 0 ? sub.ncounters : 0,
+                            plan->num_sms, st);
 }
 
 int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
     if (!plan || (!d_out && plan->out_elems > 0)) return fail(MYQC_ERR_BAD_ARG, "null plan or output");
     CU(cudaSetDevice(plan->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int nsub = (int)plan->subs.size();
     // fork: internal streams start after whatever is already queued on the caller's stream
     CU(cudaEventRecord(plan->e_start, st));
     CU(cudaStreamWaitEvent(plan->s_fill, plan->e_start, 0));
     for (auto& sc : plan->s_comp) CU(cudaStreamWaitEvent(sc, plan->e_start, 0));
-    for (int k = 0; k < nsub; ++k) {
-        Sub& sub = plan->subs[k];
-        int e = launch_fill_zero(d_out + (sub.out_offset - plan->out_offset), sub.out_elems,
-                                 plan->d_counters + sub.counter_base, sub.ncounters, plan->num_sms, plan->s_fill);
-        if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
-        CU(cudaEventRecord(plan->e_fill[k], plan->s_fill));
+    int ef = 0;
+    for (Sub& sub : plan->subs) {
+        double* d_sub = d_out + (sub.out_offset - plan->out_offset);
+        for (int r = 0; r < (int)sub.region_end.size(); ++r) {
+            int e = fill_region(plan, sub, r, d_sub, plan->s_fill);
+            if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
+            CU(cudaEventRecord(plan->e_fill[ef++], plan->s_fill));
+        }
     }
     int rr = 0;
-    for (int k = 0; k < nsub; ++k) {
-        Sub& sub = plan->subs[k];
-        bool waited[myqc_eri_plan::kNumCompute] = {false, false, false, false};
-        for (Launch& L : sub.launches) {
-            const int si = rr++ % myqc_eri_plan::kNumCompute;
-            if (!waited[si]) { CU(cudaStreamWaitEvent(plan->s_comp[si], plan->e_fill[k], 0)); waited[si] = true; }
-            L.args.out = d_out + (sub.out_offset - plan->out_offset);
-            int e = launch_class(L.UT, L.TT, L.args, plan->num_sms, plan->s_comp[si]);
-            if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+    ef = 0;
+    for (Sub& sub : plan->subs) {
+        double* d_sub = d_out + (sub.out_offset - plan->out_offset);
+        for (int r = 0; r < (int)sub.region_end.size(); ++r, ++ef) {
+            bool waited[myqc_eri_plan::kNumCompute] = {false, false, false, false};
+            for (Launch& L : sub.launches) {
+                if (L.region_task[r + 1] <= L.region_task[r]) continue;
+                const int si = rr++ % myqc_eri_plan::kNumCompute;
+                if (!waited[si]) { CU(cudaStreamWaitEvent(plan->s_comp[si], plan->e_fill[ef], 0)); waited[si] = true; }
+                int e = launch_region(plan, sub, L, r, d_sub, plan->s_comp[si]);
+                if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+            }
         }
     }
     // join
@@ -545,19 +637,21 @@ int myqc_eri_plan_launch_count(const myqc_eri_plan* plan) {
 int myqc_eri_plan_launch_info(const myqc_eri_plan* plan, int k, int* cls, int* tri, int64_t* rows) {
     if (!plan || k < 0 || k >= plan_launch_total(plan)) return fail(MYQC_ERR_BAD_ARG, "bad launch index");
     for (const Sub& sub : plan->subs) {
-        const int n = 1 + (int)sub.launches.size();
-        if (k >= n) { k -= n; continue; }
-        if (k == 0) {  // the zero fill of this piece
-            if (cls) *cls = -1;
-            if (tri) *tri = 0;
-            if (rows) *rows = sub.out_elems;
+        for (int r = 0; r < (int)sub.region_end.size(); ++r) {
+            const int n = 1 + (int)sub.launches.size();
+            if (k >= n) { k -= n; continue; }
+            if (k == 0) {  // the zero fill of this region
+                if (cls) *cls = -1;
+                if (tri) *tri = 0;
+                if (rows) *rows = sub.region_end[r] - (r == 0 ? 0 : sub.region_end[r - 1]);
+                return MYQC_OK;
+            }
+            const Launch& L = sub.launches[k - 1];
+            if (cls) *cls = class_id(L.UT, L.TT);
+            if (tri) *tri = L.args.tri;
+            if (rows) *rows = L.region_task[r + 1] - L.region_task[r];
             return MYQC_OK;
         }
-        const Launch& L = sub.launches[k - 1];
-        if (cls) *cls = class_id(L.UT, L.TT);
-        if (tri) *tri = L.args.tri;
-        if (rows) *rows = L.args.ntasks;
-        return MYQC_OK;
     }
     return fail(MYQC_ERR_BAD_ARG, "bad launch index");
 }
@@ -574,15 +668,16 @@ int myqc_eri_plan_execute_timed(myqc_eri_plan* plan, double* d_out, void* stream
     CU(cudaEventRecord(ev[0], st));
     int idx = 0;
     for (Sub& sub : plan->subs) {
-        int e = launch_fill_zero(d_out + (sub.out_offset - plan->out_offset), sub.out_elems,
-                                 plan->d_counters + sub.counter_base, sub.ncounters, plan->num_sms, st);
-        if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
-        CU(cudaEventRecord(ev[++idx], st));
-        for (Launch& L : sub.launches) {
-            L.args.out = d_out + (sub.out_offset - plan->out_offset);
-            e = launch_class(L.UT, L.TT, L.args, plan->num_sms, st);
-            if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+        double* d_sub = d_out + (sub.out_offset - plan->out_offset);
+        for (int r = 0; r < (int)sub.region_end.size(); ++r) {
+            int e = fill_region(plan, sub, r, d_sub, st);
+            if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
             CU(cudaEventRecord(ev[++idx], st));
+            for (Launch& L : sub.launches) {
+                e = launch_region(plan, sub, L, r, d_sub, st);
+                if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+                CU(cudaEventRecord(ev[++idx], st));
+            }
         }
     }
     CU(cudaEventSynchronize(ev[n]));

@@ -34,6 +34,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <type_traits>
 
 #include "eri_kernels.cuh"
@@ -584,7 +585,15 @@ int launch_class(int UT, int TT, const ClassArgs& a0, int num_sms, void* stream)
 }
 
 int launch_fill_zero(double* out, int64_t n, int* counters, int ncounters, int num_sms, void* stream) {
-    fill_zero_kernel<<<num_sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, counters, ncounters);
+    // A small footprint (default 2 CTAs of 256 threads per SM) is enough to saturate HBM with
+    // 128-bit stores and leaves the SMs to the FP64 kernels that run next to a later region's fill.
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        const char* e = getenv("MYQC_FILL_CTAS");
+        ctas_per_sm = e ? atoi(e) : 2;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    fill_zero_kernel<<<num_sms * ctas_per_sm, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, counters, ncounters);
     return (int)cudaGetLastError();
 }
 
