@@ -158,7 +158,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(args._stdout, json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -219,12 +219,13 @@ def run_ours(args):
             scratch.zero_()
         plan.execute(out.data_ptr(), stream)
 
-    for _ in range(max(args.warmup, 0)):
-        step()
-    barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+        time.sleep(0.5)  # nvidia-smi needs a moment before its first sample
+    for _ in range(max(args.warmup, 0)):
+        step()
+    barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
     barrier()
     for k in range(args.steps):
@@ -238,6 +239,13 @@ def run_ours(args):
     ms_local = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)) / args.steps
     ms = allmax(ms_local)
     value = s.nunique / (ms * 1e-3)
+    if world > 1:
+        tt = torch.tensor([ms_local, float(plan.out_elems)], dtype=torch.float64, device="cuda")
+        gl = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(gl, tt)
+        per_rank = [{"rank": r, "ms": float(g[0].item()), "slice_gb": 8e-9 * float(g[1].item())} for r, g in enumerate(gl)]
+    else:
+        per_rank = [{"rank": 0, "ms": ms_local, "slice_gb": 8e-9 * plan.out_elems}]
 
     # per-launch breakdown (CUDA events around every launch, on the launching stream)
     launches = plan.launches()
@@ -323,11 +331,27 @@ def run_ours(args):
                    "parallelism": f"quartet-space row shards x{world}, no collective"},
         "roofline": roofline, "kernels": kernels, "whole_step": whole,
         "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(nlaunch * args.steps),
-        "clocks": clk, "fp64_peak_tflops_measured": fp64_peak, "checksum": checksum,
+        "clocks": clk, "fp64_peak_tflops_measured": fp64_peak, "checksum": checksum, "per_rank": per_rank,
     }
-    print(json.dumps(line), flush=True)
+    _emit(args._stdout, json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def _quiet_stdout():
+    """Route fd 1 to stderr until the JSON line is printed, so that library banners (NCCL prints its
+    version to stdout) cannot end up in front of the one line the driver parses."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def _emit(saved_fd, line: str):
+    sys.stdout.flush()
+    os.dup2(saved_fd, 1)
+    os.close(saved_fd)
+    print(line, flush=True)
 
 
 def main():
@@ -340,6 +364,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args._stdout = _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
