@@ -309,7 +309,11 @@ static int build_cut_table(const std::vector<Shell>& shells, const PairList all[
             }
             mean_prim /= B.n;
             for (int c = nc - 1; c >= 0; --c) ge[c] = ge[c + 1] + hist[c];
-            const double wq = kW[class_id(ta, tb)] * mean_prim / B.n;
+            // seconds per primitive quartet: model flops / (measured class efficiency x DFMA peak);
+            // efficiencies from profiles/r1_notes.md ((H2O)_64, one B200)
+            static const double kEff[6] = {0.34, 0.31, 0.23, 0.23, 0.20, 0.12};
+            const int cid = class_id(ta, tb);
+            const double wq = kW[cid] / (kEff[cid] * 34.2e12) * mean_prim / B.n;
             for (int u = 0; u < A.n; ++u) {
                 double nrow = cnt[u];
                 if (ta == tb) nrow = std::max(0.0, nrow - u);
@@ -319,6 +323,17 @@ static int build_cut_table(const std::vector<Shell>& shells, const PairList all[
                 for (int c = 0; c < cu; ++c) ct.w[c] += wr * hist[c];
             }
         }
+    // plus the zero fill of the rows the block owns (HBM bound, ~6.2 TB/s)
+    {
+        int norb = 0;
+        for (const Shell& sh : shells)
+            for (int k = 0; k < 4; ++k) norb = std::max(norb, sh.fn[k] + 1);
+        for (int c = 0; c < nc; ++c) {
+            const int64_t b = packed_row_offset(c == 0 ? 0 : cuts[c], norb);
+            const int64_t e = packed_row_offset(c + 1 < nc ? cuts[c + 1] : norb, norb);
+            ct.w[c] += 8.0 * (double)(e - b) / 6.2e12;
+        }
+    }
     return MYQC_OK;
 }
 

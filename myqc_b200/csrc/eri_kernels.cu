@@ -234,7 +234,9 @@ struct Cfg {
     static constexpr int FT = tt_nfield(TT);
     static constexpr int NOUT = NFU * NFT;
     static constexpr bool OUT_SMEM = (NOUT > 16);
-    static constexpr int NTHREADS = OUT_SMEM ? 128 : 256;
+    // 128-thread CTAs for every class: (S SP|S SP) needs 140 registers, and a 256-thread CTA of it
+    // would leave an SM with a single resident CTA (8 warps); four-warp CTAs pack 3 per SM
+    static constexpr int NTHREADS = 128;
     static constexpr int NWARPS = NTHREADS / 32;
     static constexpr uint32_t U_BYTES = 9 * FU * 8;
     // shared memory: Taylor table | exp table | per-warp U double buffers | mbarriers | out staging
