@@ -288,6 +288,8 @@ def run_ours(args):
     # ---- end to end through the host-buffer C-ABI call ------------------------------------------
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
         off = Q.shard_layout(s, world)
         nloc = int(off[rank + 1] - off[rank])
         host = torch.empty(max(nloc, 1), dtype=torch.float64, pin_memory=True)
@@ -315,13 +317,16 @@ def run_ours(args):
 
     # ---- roofline of the dominant launch ---------------------------------------------------------
     per_class_ms = {}
+    fill_elems = 0
     for (cls, tri, rows), t in zip(launches, acc):
         per_class_ms[cls] = per_class_ms.get(cls, 0.0) + float(t)
+        if cls < 0:
+            fill_elems += int(rows)  # zeros the fill writes (all slice elements for the plain fill)
     kernels = []
     for cls, t in sorted(per_class_ms.items()):
         if cls < 0:
-            gb = 8.0 * plan.out_elems / 1e9
-            kernels.append({"kernel": "fill_zero", "ms": t, "bound": "hbm", "achieved": gb / (t * 1e-3) if t > 0 else 0.0,
+            gb = 8.0 * fill_elems / 1e9
+            kernels.append({"kernel": "fill_zero", "zeros_written": fill_elems, "ms": t, "bound": "hbm", "achieved": gb / (t * 1e-3) if t > 0 else 0.0,
                             "peak": hbm_peak, "unit": "GB/s"})
         else:
             # shard-local model flops are only known for the whole molecule at N=1
@@ -402,6 +407,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="experiments only: skip the host-buffer end-to-end leg")
     args = ap.parse_args()
     args._stdout = _quiet_stdout()
     if args.impl == "reference":

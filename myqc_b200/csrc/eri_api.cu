@@ -5,7 +5,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
+#include <climits>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <string>
 #include <thread>
@@ -51,6 +54,7 @@ struct Launch {
     int UT, TT;
     ClassArgs args;                // args.tasks/ntasks describe the whole need-sorted task array
     std::vector<int> region_task;  // [nregion+1] task ranges: region r = tasks whose writes end inside fill region r
+    double weight = 0.0;           // sum over tasks of (primitives of the row) x (primitives of the lane-side range)
 };
 
 constexpr int kMaxCounters = 1024;
@@ -68,6 +72,10 @@ struct Sub {  // one virtual sub-shard: a contiguous piece of the plan's slice w
     // of region r only touch memory that pieces 0..r have already zeroed and can run while the
     // later pieces are still being filled (no extra lists, no extra arithmetic: same tasks).
     std::vector<int64_t> region_end;  // [nregion] offsets relative to the sub-shard's slice
+    // screened fill (default): one launch that writes the zeros of exactly those elements no class
+    // kernel writes, so it needs no ordering against them
+    FillArgs fill;
+    int64_t fill_zero_elems = 0;  // zeros the screened fill writes (slice elements minus screened-in ones)
 };
 
 struct myqc_eri_plan {
@@ -93,6 +101,10 @@ struct myqc_eri_plan {
     double model_flops = 0.0;
     int nlaunch = 0;
     int64_t h2d_bytes = 0;  // bytes uploaded at plan creation (pair tables, Boys tables, prefixes)
+    bool screened_fill = true;
+    int32_t *d_rk = nullptr, *d_cut = nullptr;
+    std::vector<int32_t> h_rk, h_cut;
+    int nrank = 0;
 };
 
 namespace myqc {
@@ -192,12 +204,30 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
         while (r + 1 < nregion && t.need > sub.region_end[r]) ++r;
         t.region = r;
     }
-    std::stable_sort(tn.begin(), tn.end(), [](const TaskN& x, const TaskN& y) {
-        if (x.region != y.region) return x.region < y.region;
-        return x.weight > y.weight;
-    });
+    // MYQC_TASK_ORDER=0: plain heaviest-task-first order (23.5 ms on (H2O)_64 against 22.5 ms, profiles/r1_notes.md)
+    static const int task_order = std::getenv("MYQC_TASK_ORDER") ? std::atoi(std::getenv("MYQC_TASK_ORDER")) : 1;
+    if (task_order == 1) {
+        // rows heaviest first, the tasks of one row adjacent: everything a launch stores into the packed
+        // rows of one uniform-side pair is stored within a short time, so partial-sector stores of
+        // neighbouring lanes meet in L2
+        std::vector<double> roww(U.n, 0.0);
+        for (const TaskN& t : tn) roww[t.t.x] += t.weight;
+        std::stable_sort(tn.begin(), tn.end(), [&](const TaskN& x, const TaskN& y) {
+            if (x.region != y.region) return x.region < y.region;
+            if (x.t.x != y.t.x) {
+                if (roww[x.t.x] != roww[y.t.x]) return roww[x.t.x] > roww[y.t.x];
+                return x.t.x < y.t.x;
+            }
+            return x.t.y < y.t.y;
+        });
+    } else {
+        std::stable_sort(tn.begin(), tn.end(), [](const TaskN& x, const TaskN& y) {
+            if (x.region != y.region) return x.region < y.region;
+            return x.weight > y.weight;
+        });
+    }
     std::vector<int4> tasks(tn.size());
-    for (size_t k = 0; k < tn.size(); ++k) tasks[k] = tn[k].t;
+    for (size_t k = 0; k < tn.size(); ++k) { tasks[k] = tn[k].t; L.weight += tn[k].weight; }
     L.region_task.assign(nregion + 1, (int)tn.size());
     L.region_task[0] = 0;
     for (size_t k = 0, r = 0; r < (size_t)nregion; ++r) {
@@ -222,8 +252,91 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
     a.out = nullptr;
     a.out_offset = sub.out_offset;
     a.npair = pl->npair;
+    a.store_mask = std::getenv("MYQC_STORE_MASK") ? std::atoll(std::getenv("MYQC_STORE_MASK")) : -1;
     sub.launches.push_back(L);
     pl->nlaunch += class_nlaunch(L.UT, L.TT) * nregion;
+    return MYQC_OK;
+}
+
+// Rank / cut arrays of the screened fill (see fill_screened_kernel).  all[] are the complete pair
+// lists of the molecule: every function pair P belongs to exactly one shell pair.
+static int build_screen_ranks(myqc_eri_plan* pl, const PairList all[3]) {
+    std::vector<double> E;
+    for (int t = 0; t < 3; ++t) E.insert(E.end(), all[t].emax.begin(), all[t].emax.end());
+    std::sort(E.begin(), E.end(), std::greater<double>());
+    pl->nrank = (int)E.size();
+    pl->h_rk.assign((size_t)pl->npair, INT32_MAX);
+    pl->h_cut.assign((size_t)pl->npair, 0);
+    for (int t = 0; t < 3; ++t) {
+        const int nf = pt_nf(t);
+        for (int q = 0; q < all[t].n; ++q) {
+            const double e = all[t].emax[q];
+            // first occurrence of e in the descending list
+            const int32_t rank = (int32_t)(std::lower_bound(E.begin(), E.end(), e, std::greater<double>()) - E.begin());
+            size_t lo = 0, hi = E.size();
+            while (lo < hi) {  // first index whose product with e fails the reference's test
+                const size_t mid = (lo + hi) / 2;
+                if (e * E[mid] < 1.0e-14) hi = mid; else lo = mid + 1;
+            }
+            for (int f = 0; f < nf; ++f) {
+                const int32_t P = all[t].pidx[(size_t)q * nf + f];
+                if (P < 0) continue;
+                pl->h_rk[P] = rank;
+                pl->h_cut[P] = (int32_t)lo;
+            }
+        }
+    }
+    int rc;
+    if ((rc = upload(pl, pl->h_rk, &pl->d_rk))) return rc;
+    if ((rc = upload(pl, pl->h_cut, &pl->d_cut))) return rc;
+    return MYQC_OK;
+}
+
+static int build_sub_fill(myqc_eri_plan* pl, Sub& sub, int64_t row_lo, int64_t row_hi) {
+    FillArgs& f = sub.fill;
+    std::memset(&f, 0, sizeof(f));
+    f.out_offset = sub.out_offset;
+    f.npair = pl->npair;
+    f.row_lo = row_lo; f.row_hi = row_hi;
+    f.rk = pl->d_rk; f.cut = pl->d_cut;
+    f.all = std::getenv("MYQC_FILL_ALL") ? 1 : 0;
+    f.sleep_ns = std::getenv("MYQC_FILL_SLEEP_NS") ? std::atoi(std::getenv("MYQC_FILL_SLEEP_NS")) : 0;
+    sub.fill_zero_elems = 0;
+    if (row_hi <= row_lo) return MYQC_OK;
+    const int64_t ncb_all = (pl->npair + kFillCols - 1) / kFillCols;
+    f.cb0 = (int)(row_lo / kFillCols);
+    f.ncb = (int)(ncb_all - f.cb0);
+    std::vector<int32_t> ucb(f.ncb + 1, 0);
+    for (int k = 0; k < f.ncb; ++k) {
+        const int64_t cend = std::min<int64_t>(((int64_t)f.cb0 + k + 1) * kFillCols, pl->npair);  // one past the last column
+        const int64_t rows = std::min(row_hi, cend) - row_lo;                                    // rows r <= last column
+        const int64_t nrb = rows > 0 ? (rows + kFillRows - 1) / kFillRows : 0;
+        if ((int64_t)ucb[k] + nrb > INT32_MAX) return fail(MYQC_ERR_UNSUPPORTED, "too many fill units");
+        ucb[k + 1] = ucb[k] + (int32_t)nrb;
+    }
+    f.nunits = ucb[f.ncb];
+    int32_t* d_ucb = nullptr;
+    int rc = upload(pl, ucb, &d_ucb);
+    if (rc) return rc;
+    f.ucb = d_ucb;
+    if (pl->ncounters + 1 > kMaxCounters) return fail(MYQC_ERR_UNSUPPORTED, "too many launches in one plan");
+    f.counter = pl->d_counters + pl->ncounters;
+    pl->ncounters += 1;
+    // zeros written = elements of the rows minus the screened-in ones: count pairs (P <= P') with
+    // rk[P'] < cut[P] with a Fenwick tree over the ranks
+    std::vector<int32_t> bit((size_t)pl->nrank + 1, 0);
+    int64_t touched = 0;
+    for (int64_t P = pl->npair - 1; P >= row_lo; --P) {
+        const int32_t r = pl->h_rk[P];
+        if (r < pl->nrank)
+            for (int i = r + 1; i <= pl->nrank; i += i & (-i)) ++bit[i];
+        if (P < row_hi) {
+            int64_t c = 0;
+            for (int i = pl->h_cut[P]; i > 0; i -= i & (-i)) c += bit[i];
+            touched += c;
+        }
+    }
+    sub.fill_zero_elems = sub.out_elems - touched;
     return MYQC_OK;
 }
 
@@ -395,6 +508,10 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
     if (ndev == 0) return fail(MYQC_ERR_NO_DEVICE, "no CUDA device: the ERI engine has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(MYQC_ERR_BAD_ARG, "device index out of range");
     CU(cudaSetDevice(device));
+    {
+        const int e = prepare_kernels();
+        if (e) return cuda_fail((cudaError_t)e, "kernel preparation");
+    }
 
     std::unique_ptr<myqc_eri_plan> pl(new myqc_eri_plan());
     pl->device = device;
@@ -408,6 +525,14 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
     if ((rc = build_shells(nnuc, nset, setl, setinfo, ops, basinfo, shells, err))) return fail(rc, err);
     PairList all[3];
     if ((rc = build_pairs(nnuc, xyz, set, setinfo, setl, ops, bas, basinfo, shells, all, err))) return fail(rc, err);
+    {
+        // Default: zero the whole slice first (streaming 128-bit stores, 0.95 of HBM peak), class kernels
+        // after it.  MYQC_FILL_MODE=screened selects the order-independent screened fill that runs next
+        // to the class kernels; measured on (H2O)_64 it does not pay (profiles/r1_notes.md): the class
+        // kernels' scattered stores and the fill compete for DRAM, the co-run takes the sum of both.
+        const char* fm = std::getenv("MYQC_FILL_MODE");
+        pl->screened_fill = (fm && std::strcmp(fm, "screened") == 0);
+    }
 
     // Boys tables for the five start orders Q = 0,3,6,9,12: row t = {Ft(t,Q+k)/k!, k<7 ; t/10}
     {
@@ -428,6 +553,7 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
         std::vector<int> zeros(kMaxCounters, 0);
         if ((rc = upload(pl.get(), zeros, &pl->d_counters))) return rc;
     }
+    if (pl->screened_fill && (rc = build_screen_ranks(pl.get(), all))) return rc;
 
     // ---- sharding: contiguous blocks of packed rows, cut where a shell's functions start -------
     // External shards (one per GPU) are cut first; this plan's shard is then cut again into
@@ -482,7 +608,7 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
             // well (persistent grids starve each other): 23.2 / 24.2 / 24.8 ms for 1 / 2 / 4 regions
             // (profiles/r1_notes.md).  MYQC_FILL_REGIONS overrides it for experiments.
             int nreg = envr ? std::atoi(envr) : 1;
-            if (nreg < 1) nreg = 1;
+            if (nreg < 1 || pl->screened_fill) nreg = 1;
             if (nreg > 16) nreg = 16;
             sub.region_end.resize(nreg);
             for (int r = 0; r < nreg; ++r) {
@@ -526,7 +652,40 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
                 }
             }
         pl->nlaunch += (int)sub.region_end.size();  // zero fills of this piece
+        if (pl->screened_fill) {
+            // pacing table: one entry per class-kernel task counter, weighted by the launch's estimated
+            // duration (upper bound of its primitive quartets x measured time per quartet of its class)
+            static const double kPsPerQuartet[6] = {5.1, 9.8, 29.0, 31.0, 107.0, 640.0};  // (H2O)_64, profiles/r1_notes.md
+            std::vector<int32_t> pidx, pn;
+            std::vector<float> pw;
+            double wsum = 0.0;
+            for (const Launch& L : sub.launches) {
+                const int ns = class_nlaunch(L.UT, L.TT);
+                const double w = L.weight * kPsPerQuartet[class_id(L.UT, L.TT)] / ns;
+                for (int k = 0; k < ns; ++k) {
+                    pidx.push_back((int32_t)(L.args.row_counter - pl->d_counters) + k);
+                    pn.push_back(L.args.ntasks);
+                    pw.push_back((float)w);
+                    wsum += w;
+                }
+            }
+            for (float& w : pw) w = (float)(w / (wsum > 0 ? wsum : 1.0));
+            int32_t *d_pidx = nullptr, *d_pn = nullptr;
+            float* d_pw = nullptr;
+            if ((rc = upload(pl.get(), pidx, &d_pidx))) return rc;
+            if ((rc = upload(pl.get(), pn, &d_pn))) return rc;
+            if ((rc = upload(pl.get(), pw, &d_pw))) return rc;
+            const int64_t n = pl->norb;
+            const int64_t row_lo = (int64_t)fn_lo * n - (int64_t)fn_lo * (fn_lo - 1) / 2;
+            const int64_t row_hi = (int64_t)fn_hi * n - (int64_t)fn_hi * (fn_hi - 1) / 2;
+            if ((rc = build_sub_fill(pl.get(), sub, row_lo, row_hi))) return rc;
+            sub.fill.counters = pl->d_counters;
+            sub.fill.prog_idx = d_pidx; sub.fill.prog_n = d_pn; sub.fill.prog_w = d_pw;
+            sub.fill.nprog = (int)pidx.size();
+        }
     }
+    pl->h_rk.clear(); pl->h_rk.shrink_to_fit();
+    pl->h_cut.clear(); pl->h_cut.shrink_to_fit();
     // internal streams and events
     CU(cudaStreamCreateWithFlags(&pl->s_fill, cudaStreamNonBlocking));
     for (auto& st : pl->s_comp) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -595,7 +754,14 @@ static int launch_region(myqc_eri_plan* plan, Sub& sub, Launch& L, int r, double
     return launch_class(L.UT, L.TT, a, plan->num_sms, st);
 }
 
-static int fill_region(myqc_eri_plan* plan, Sub& sub, int r, double* d_sub_out, cudaStream_t st) {
+static int fill_region(myqc_eri_plan* plan, Sub& sub, int r, double* d_sub_out, cudaStream_t st, bool paced = false) {
+    if (plan->screened_fill) {
+        FillArgs f = sub.fill;
+        f.out = d_sub_out;
+        static const bool no_pace = std::getenv("MYQC_FILL_NOPACE") != nullptr;
+        if (!paced || no_pace) f.nprog = 0;
+        return launch_fill_screened(f, plan->num_sms, st);
+    }
     const int64_t b = r == 0 ? 0 : sub.region_end[r - 1], e = sub.region_end[r];
     // the first fill of a sub-shard also resets all of its task counters
     return launch_fill_zero(d_sub_out + b, e - b, plan->d_counters + sub.counter_base, r == 0 ? sub.ncounters : 0,
@@ -606,6 +772,19 @@ int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
     if (!plan || (!d_out && plan->out_elems > 0)) return fail(MYQC_ERR_BAD_ARG, "null plan or output");
     CU(cudaSetDevice(plan->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // MYQC_TIMELINE=1: completion time of every launch on its internal stream, printed on stderr
+    // (a debugging aid: it synchronises the device at the end of the call)
+    static const bool timeline = std::getenv("MYQC_TIMELINE") != nullptr;
+    std::vector<std::pair<std::string, cudaEvent_t>> tl;
+    auto mark = [&](const std::string& name, cudaStream_t s) {
+        if (!timeline) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        tl.emplace_back(name, e);
+    };
+    if (plan->screened_fill) CU(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)plan->ncounters, st));
+    mark("start", st);
     // fork: internal streams start after whatever is already queued on the caller's stream
     CU(cudaEventRecord(plan->e_start, st));
     CU(cudaStreamWaitEvent(plan->s_fill, plan->e_start, 0));
@@ -614,9 +793,10 @@ int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
     for (Sub& sub : plan->subs) {
         double* d_sub = d_out + (sub.out_offset - plan->out_offset);
         for (int r = 0; r < (int)sub.region_end.size(); ++r) {
-            int e = fill_region(plan, sub, r, d_sub, plan->s_fill);
-            if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
+            int e = fill_region(plan, sub, r, d_sub, plan->s_fill, true);
+            if (e) return cuda_fail((cudaError_t)e, "fill launch");
             CU(cudaEventRecord(plan->e_fill[ef++], plan->s_fill));
+            mark("fill", plan->s_fill);
         }
     }
     int rr = 0;
@@ -628,9 +808,12 @@ int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
             for (Launch& L : sub.launches) {
                 if (L.region_task[r + 1] <= L.region_task[r]) continue;
                 const int si = rr++ % myqc_eri_plan::kNumCompute;
-                if (!waited[si]) { CU(cudaStreamWaitEvent(plan->s_comp[si], plan->e_fill[ef], 0)); waited[si] = true; }
+                // plain fill: the slice must be zeroed before a class kernel stores into it; the
+                // screened fill writes a disjoint set of elements and needs no ordering
+                if (!waited[si] && !plan->screened_fill) { CU(cudaStreamWaitEvent(plan->s_comp[si], plan->e_fill[ef], 0)); waited[si] = true; }
                 int e = launch_region(plan, sub, L, r, d_sub, plan->s_comp[si]);
                 if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+                mark("class{" + std::to_string(L.UT) + "," + std::to_string(L.TT) + "} on stream " + std::to_string(si), plan->s_comp[si]);
             }
         }
     }
@@ -641,6 +824,16 @@ int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
     }
     CU(cudaEventRecord(plan->e_done[myqc_eri_plan::kNumCompute], plan->s_fill));
     CU(cudaStreamWaitEvent(st, plan->e_done[myqc_eri_plan::kNumCompute], 0));
+    if (timeline) {
+        mark("join", st);
+        cudaDeviceSynchronize();
+        for (size_t k = 1; k < tl.size(); ++k) {
+            float t = 0;
+            cudaEventElapsedTime(&t, tl[0].second, tl[k].second);
+            std::fprintf(stderr, "[myqc timeline] %-28s done at %8.3f ms\n", tl[k].first.c_str(), t);
+        }
+        for (auto& x : tl) cudaEventDestroy(x.second);
+    }
     return MYQC_OK;
 }
 
@@ -658,7 +851,7 @@ int myqc_eri_plan_launch_info(const myqc_eri_plan* plan, int k, int* cls, int* t
             if (k == 0) {  // the zero fill of this region
                 if (cls) *cls = -1;
                 if (tri) *tri = 0;
-                if (rows) *rows = sub.region_end[r] - (r == 0 ? 0 : sub.region_end[r - 1]);
+                if (rows) *rows = plan->screened_fill ? sub.fill_zero_elems : sub.region_end[r] - (r == 0 ? 0 : sub.region_end[r - 1]);
                 return MYQC_OK;
             }
             const Launch& L = sub.launches[k - 1];
@@ -680,6 +873,7 @@ int myqc_eri_plan_execute_timed(myqc_eri_plan* plan, double* d_out, void* stream
     const int n = plan_launch_total(plan);
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) CU(cudaEventCreate(&e));
+    if (plan->screened_fill) CU(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)plan->ncounters, st));
     CU(cudaEventRecord(ev[0], st));
     int idx = 0;
     for (Sub& sub : plan->subs) {
@@ -749,9 +943,17 @@ int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const
                           const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
                           const double* ftab, double* packed_slice, int device, int shard, int nshards,
                           int64_t* h2d_bytes) {
+    // MYQC_TRACE=1: wall-clock breakdown of the one-shot call on stderr
+    const bool trace = std::getenv("MYQC_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto t0 = now();
     myqc_eri_plan* pl = nullptr;
     int rc = myqc_eri_plan_create(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab, device, shard, nshards, &pl);
     if (rc) return rc;
+    const auto t1 = now();
     if (h2d_bytes) *h2d_bytes = pl->h2d_bytes;
     const int64_t n = pl->out_elems;
     if (n > 0 && !packed_slice) { myqc_eri_plan_destroy(pl); return fail(MYQC_ERR_BAD_ARG, "null output"); }
@@ -763,14 +965,23 @@ int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const
             return fail(MYQC_ERR_NOMEM, std::string("device allocation of the packed slice: ") + cudaGetErrorString(e));
         }
     }
+    const auto t2 = now();
     rc = myqc_eri_plan_execute(pl, d_out, nullptr);
+    if (trace) cudaDeviceSynchronize();
+    const auto t3 = now();
     if (!rc && n > 0) {
         // pinned destinations run at PCIe speed; pageable ones are staged by the driver
         cudaError_t e = cudaMemcpy(packed_slice, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) rc = cuda_fail(e, "copy packed slice to host");
     }
+    const auto t4 = now();
     cudaFree(d_out);
     myqc_eri_plan_destroy(pl);
+    const auto t5 = now();
+    if (trace)
+        std::fprintf(stderr, "[myqc trace] shard %d/%d: plan %.1f ms, cudaMalloc %.1f ms, execute %.1f ms, D2H %.1f ms (%.2f GB, %.1f GB/s), free %.1f ms\n",
+                     shard, nshards, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), 8e-9 * (double)n,
+                     8e-9 * (double)n / (ms(t3, t4) * 1e-3 + 1e-12), ms(t4, t5));
     return rc;
 }
 

@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS) eri_class_kernel(c
                             const int64_t lo = P1[f] < P2[fp] ? P1[f] : P2[fp];
                             const int64_t hi = P1[f] < P2[fp] ? P2[fp] : P1[f];
                             const int64_t idx = lo * np - ((lo * (lo - 1)) >> 1) + (hi - lo) - a.out_offset;
-                            a.out[idx] = OUT_SMEM ? s_out[(f * NFT + fp) * NTHREADS + tid] : out_r[f * NFT + fp];
+                            a.out[idx & a.store_mask] = OUT_SMEM ? s_out[(f * NFT + fp) * NTHREADS + tid] : out_r[f * NFT + fp];
                         }
                     }
                 }
@@ -521,6 +521,123 @@ __global__ void fill_zero_kernel(double* __restrict__ out, int64_t n, int* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Screened zero fill.  An element (P,P') of the packed array is written by a class kernel iff its
+// two shell pairs pass the reference's test on their largest prefactors,
+// fl(emax_P * emax_P') >= 1e-14 (int2e.f90:257); the product is monotone in each factor, so with
+// rk[] = rank of emax in the descending list of all shell-pair prefactors and cut[P] = number of
+// list entries whose product with emax_P passes, the test is the integer compare rk[P'] < cut[P].
+// This kernel writes the zeros of exactly the other elements: every element of the slice is
+// written once, by one kernel, and the fill needs no ordering against the FP64 kernels -- it runs
+// next to them (HBM-write bound next to DFMA bound) instead of in front of them.
+//
+// Work unit = kFillRows packed rows x kFillCols columns; thread t owns columns cb*kFillCols +
+// j*256 + t and keeps their ranks in registers for all rows of the unit, so rk[] is read once per
+// unit, and a warp writes 256 contiguous bytes per store.  Units are enumerated column block by
+// column block (ucb[] = prefix sums of the row blocks each column block needs: only rows <= the
+// block's last column exist in the upper triangle) and pulled from a global counter.
+constexpr int kFillThreads = 256;
+constexpr int kFillColsPerThread = kFillCols / kFillThreads;
+constexpr int kFillUcbSmem = 1024;  // column-block prefix entries cached in shared memory
+
+__global__ void __launch_bounds__(kFillThreads) fill_screened_kernel(const FillArgs a) {
+    __shared__ int s_unit[2];
+    __shared__ int s_ucb[kFillUcbSmem];
+    const int tid = threadIdx.x;
+    const int64_t np = a.npair;
+    const bool ucb_smem = a.ncb + 1 <= kFillUcbSmem;
+    if (ucb_smem)
+        for (int i = tid; i <= a.ncb; i += kFillThreads) s_ucb[i] = a.ucb[i];
+    // thread 0 claims units; with pacing it first waits until the class kernels have got far enough
+    bool pace = a.nprog > 0;  // thread 0 only
+    auto claim = [&]() -> int {
+        if (pace) {
+            unsigned long long t_wait0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_wait0));
+            for (;;) {
+                float p = 0.0f;
+                for (int k = 0; k < a.nprog; ++k) {
+                    const int n = a.prog_n[k];
+                    int c = *reinterpret_cast<const volatile int*>(a.counters + a.prog_idx[k]);
+                    c = c < n ? c : n;
+                    p += a.prog_w[k] * (float)c / (float)n;
+                }
+                // a little ahead of the compute (tasks are sorted heaviest first, so the task count
+                // lags the time), everything once the class kernels are done (p == 1 -> 1.2)
+                const float allowed = (0.04f + 1.16f * p) * (float)a.nunits;
+                const int cur = *reinterpret_cast<const volatile int*>(a.counter);
+                if ((float)cur < allowed || p >= 0.999f) break;
+                // safety net: never wait more than 2 ms on the class kernels (they advance every few
+                // microseconds when they run; if they cannot run, throttling must not become a deadlock)
+                unsigned long long t_now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+                if (t_now - t_wait0 > 2000000ull) { pace = false; break; }
+                __nanosleep(2000);
+            }
+        }
+        return atomicAdd(a.counter, 1);
+    };
+    if (tid == 0) s_unit[0] = claim();
+    __syncthreads();
+    int unit = s_unit[0];
+    for (int it = 0; unit < a.nunits; ++it) {
+        // the next unit is claimed while this one is written (one barrier per unit)
+        if (tid == 0) s_unit[(it + 1) & 1] = claim();
+        // column block of this unit: last cb with ucb[cb] <= unit
+        int lo = 0, hi = a.ncb;
+        if (ucb_smem) {
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_ucb[mid] <= unit) lo = mid; else hi = mid;
+            }
+        } else {
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(a.ucb + mid) <= unit) lo = mid; else hi = mid;
+            }
+        }
+        const int ulo = ucb_smem ? s_ucb[lo] : __ldg(a.ucb + lo);
+        const int64_t r0 = a.row_lo + (int64_t)(unit - ulo) * kFillRows;
+        const int64_t c0 = (int64_t)(a.cb0 + lo) * kFillCols;
+        int rk[kFillColsPerThread];
+#pragma unroll
+        for (int j = 0; j < kFillColsPerThread; ++j) {
+            const int64_t c = c0 + j * kFillThreads + tid;
+            rk[j] = c < np ? __ldg(a.rk + c) : -1;  // -1: column does not exist, never stored
+        }
+        int64_t rend = r0 + kFillRows;
+        if (rend > a.row_hi) rend = a.row_hi;
+        const bool interior = (r0 + kFillRows - 1 <= c0);  // every row of the unit is <= every column
+        // element (r,c) lives at out[off(r) - out_offset + (c - r)], off(r) = r*np - r(r-1)/2
+        double* o = a.out + (r0 * np - ((r0 * (r0 - 1)) >> 1) - a.out_offset - r0 + c0 + tid);
+        int64_t r = r0;
+        if (interior) {
+            for (; r + 4 <= rend; r += 4) {
+                int cut[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cut[i] = a.all ? 0 : __ldg(a.cut + r + i);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int j = 0; j < kFillColsPerThread; ++j)
+                        if (rk[j] >= cut[i]) __stcs(o + j * kFillThreads, 0.0);
+                    o += np - (r + i) - 1;  // off(r+1) - (r+1) - (off(r) - r)
+                }
+                if (a.sleep_ns > 0) __nanosleep(a.sleep_ns);
+            }
+        }
+        for (; r < rend; ++r) {
+            const int cut = a.all ? 0 : __ldg(a.cut + r);
+#pragma unroll
+            for (int j = 0; j < kFillColsPerThread; ++j)
+                if (rk[j] >= cut && c0 + j * kFillThreads + tid >= r) __stcs(o + j * kFillThreads, 0.0);
+            o += np - r - 1;
+        }
+        __syncthreads();
+        unit = s_unit[(it + 1) & 1];
+    }
+}
+
 // dense XX(i,j,g,h) (column-major, i fastest) from the packed array: the fillsym pass of the
 // reference (int2e.f90:290-304,540-554) done as a gather so that the 8n^4-byte stream is written
 // once, coalesced.
@@ -545,17 +662,87 @@ __global__ void expand_dense_kernel(const double* __restrict__ packed, int norb,
 }
 
 // ------------------------------------------------------------------------------------------
+// Kernels that are meant to share SMs (the class kernels and the screened fill) must ask for the
+// same L1/shared split; with the default fill mode the split of every kernel is left to the driver
+// (a larger L1 is worth ~2 % on the small classes).
+static bool common_carveout() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MYQC_FILL_MODE");
+        v = (e && e[0] == 's') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+// Kernel attributes are set (and the kernels loaded: CUDA loads modules lazily, and a first-time load
+// cannot complete while the paced fill kernel is waiting on the device for that very kernel) once
+// per device, before the first launch of a plan.
 template <int UT, int TT, int USL>
-static int launch_one(const ClassArgs& a, int num_sms, cudaStream_t st) {
-    if (a.nU <= 0 || a.nT <= 0 || a.ntasks <= 0) return 0;
+static int prepare_one(int* occ_out) {
     using C = Cfg<UT, TT, USL>;
     auto kern = eri_class_kernel<UT, TT, USL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return (int)e;
+    // Every kernel of a plan asks for the same (maximum) shared-memory carve-out: an SM cannot hold
+    // CTAs of kernels with different L1/shared splits at the same time (measured:
+    // tools/probes/concurrency_probe.cu), and the class kernels and the screened fill share SMs.
+    if (common_carveout()) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+    }
     int occ = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NTHREADS, C::SMEM);
     if (e != cudaSuccess) return (int)e;
-    if (occ < 1) occ = 1;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return (int)e;
+    *occ_out = occ < 1 ? 1 : occ;
+    return 0;
+}
+
+constexpr int kMaxDevices = 64;
+static int g_occ[kMaxDevices][10];
+static bool g_prepared[kMaxDevices];
+
+int prepare_kernels() {
+    int dev = 0;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return (int)ce;
+    if (dev < 0 || dev >= kMaxDevices) return (int)cudaErrorInvalidDevice;
+    if (g_prepared[dev]) return 0;
+    int e = 0;
+    if (!e) e = prepare_one<0, 0, -1>(&g_occ[dev][0]);
+    if (!e) e = prepare_one<0, 1, -1>(&g_occ[dev][1]);
+    if (!e) e = prepare_one<0, 2, -1>(&g_occ[dev][2]);
+    if (!e) e = prepare_one<1, 1, -1>(&g_occ[dev][3]);
+    if (!e) e = prepare_one<1, 2, -1>(&g_occ[dev][4]);
+    if (!e) e = prepare_one<2, 2, 0>(&g_occ[dev][5]);
+    if (!e) e = prepare_one<2, 2, 1>(&g_occ[dev][6]);
+    if (!e) e = prepare_one<2, 2, 2>(&g_occ[dev][7]);
+    if (!e) e = prepare_one<2, 2, 3>(&g_occ[dev][8]);
+    if (e) return e;
+    if (common_carveout()) {
+        ce = cudaFuncSetAttribute(fill_screened_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared);
+        if (ce != cudaSuccess) return (int)ce;
+    }
+    cudaFuncAttributes fa;
+    ce = cudaFuncGetAttributes(&fa, fill_screened_kernel);
+    if (ce != cudaSuccess) return (int)ce;
+    g_prepared[dev] = true;
+    return 0;
+}
+
+template <int UT, int TT, int USL>
+static int launch_one(const ClassArgs& a, int num_sms, cudaStream_t st, int slot) {
+    if (a.nU <= 0 || a.nT <= 0 || a.ntasks <= 0) return 0;
+    using C = Cfg<UT, TT, USL>;
+    auto kern = eri_class_kernel<UT, TT, USL>;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int e0 = prepare_kernels();
+    if (e0) return e0;
+    const int occ = g_occ[dev][slot];
     int grid = num_sms * occ;
     const int need = (a.ntasks + C::NWARPS - 1) / C::NWARPS;
     if (grid > need) grid = need;
@@ -568,19 +755,19 @@ int class_nlaunch(int UT, int TT) { return (UT == 2 && TT == 2) ? 4 : 1; }
 int launch_class(int UT, int TT, const ClassArgs& a0, int num_sms, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ClassArgs a = a0;
-    if (UT == 0 && TT == 0) return launch_one<0, 0, -1>(a, num_sms, st);
-    if (UT == 0 && TT == 1) return launch_one<0, 1, -1>(a, num_sms, st);
-    if (UT == 0 && TT == 2) return launch_one<0, 2, -1>(a, num_sms, st);
-    if (UT == 1 && TT == 1) return launch_one<1, 1, -1>(a, num_sms, st);
-    if (UT == 1 && TT == 2) return launch_one<1, 2, -1>(a, num_sms, st);
+    if (UT == 0 && TT == 0) return launch_one<0, 0, -1>(a, num_sms, st, 0);
+    if (UT == 0 && TT == 1) return launch_one<0, 1, -1>(a, num_sms, st, 1);
+    if (UT == 0 && TT == 2) return launch_one<0, 2, -1>(a, num_sms, st, 2);
+    if (UT == 1 && TT == 1) return launch_one<1, 1, -1>(a, num_sms, st, 3);
+    if (UT == 1 && TT == 2) return launch_one<1, 2, -1>(a, num_sms, st, 4);
     if (UT == 2 && TT == 2) {  // four mu-slices, each with its own row counter
-        int e = launch_one<2, 2, 0>(a, num_sms, st);
+        int e = launch_one<2, 2, 0>(a, num_sms, st, 5);
         a.row_counter = a0.row_counter + 1;
-        if (!e) e = launch_one<2, 2, 1>(a, num_sms, st);
+        if (!e) e = launch_one<2, 2, 1>(a, num_sms, st, 6);
         a.row_counter = a0.row_counter + 2;
-        if (!e) e = launch_one<2, 2, 2>(a, num_sms, st);
+        if (!e) e = launch_one<2, 2, 2>(a, num_sms, st, 7);
         a.row_counter = a0.row_counter + 3;
-        if (!e) e = launch_one<2, 2, 3>(a, num_sms, st);
+        if (!e) e = launch_one<2, 2, 3>(a, num_sms, st, 8);
         return e;
     }
     return (int)cudaErrorInvalidValue;
@@ -596,6 +783,24 @@ int launch_fill_zero(double* out, int64_t n, int* counters, int ncounters, int n
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
     fill_zero_kernel<<<num_sms * ctas_per_sm, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, counters, ncounters);
+    return (int)cudaGetLastError();
+}
+
+int launch_fill_screened(const FillArgs& a, int num_sms, void* stream) {
+    if (a.nunits <= 0) return 0;
+    // persistent: a few CTAs per SM are enough to keep HBM busy with posted stores, and leave the
+    // register file to the FP64 kernels that run next to the fill
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        const char* e = getenv("MYQC_FILL_CTAS");
+        ctas_per_sm = e ? atoi(e) : 1;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    int grid = num_sms * ctas_per_sm;
+    if (grid > a.nunits) grid = a.nunits;
+    const int e0 = prepare_kernels();
+    if (e0) return e0;
+    fill_screened_kernel<<<grid, kFillThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
     return (int)cudaGetLastError();
 }
 

@@ -38,7 +38,37 @@ struct ClassArgs {
     double* out;         // this shard's slice of the packed array
     int64_t out_offset;  // packed index of out[0]
     int64_t npair;
+    int64_t store_mask;  // -1; experiments: a small mask folds all stores into an L2-resident window
 };
+
+// Screened zero fill (see fill_screened_kernel): rows [row_lo,row_hi) of the packed upper triangle
+constexpr int kFillRows = 64;
+constexpr int kFillCols = 2048;
+struct FillArgs {
+    double* out;         // this slice of the packed array
+    int64_t out_offset;  // packed index of out[0]
+    int64_t npair;
+    int64_t row_lo, row_hi;
+    const int32_t* rk;   // [npair] rank of the function pair's shell-pair prefactor (INT32_MAX: no shell pair kept)
+    const int32_t* cut;  // [npair] number of ranks that pass the screen against this row
+    const int32_t* ucb;  // [ncb+1] prefix sums of row blocks per column block, column blocks cb0..cb0+ncb-1
+    int cb0, ncb, nunits;
+    int* counter;        // unit counter (zeroed before the launch)
+    int all;             // experiments: ignore the screen, zero every element (only valid before the class kernels)
+    // pacing: the fill is throttled to the progress of the class kernels that run next to it, so that
+    // its stores are spread over their whole duration instead of saturating the memory pipeline up front.
+    // progress = sum_k prog_w[k] * min(counters[prog_idx[k]], prog_n[k]) / prog_n[k]  (weights sum to 1);
+    // nprog = 0: no pacing (serial timing pass, or nothing to pace against)
+    const int* counters;
+    const int32_t* prog_idx;
+    const int32_t* prog_n;
+    const float* prog_w;
+    int nprog;
+    int sleep_ns;  // experiments: fixed delay per four rows written (a constant-rate fill)
+};
+int launch_fill_screened(const FillArgs& a, int num_sms, void* stream);
+// sets the kernel attributes and forces the (lazily loaded) kernels of the current device to load
+int prepare_kernels();
 
 // returns cudaError_t as int; `slice` selects the mu-slice for (2,2), ignored otherwise
 int launch_class(int UT, int TT, const ClassArgs& a, int num_sms, void* stream);
