@@ -158,11 +158,7 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
     const std::vector<int32_t> ntv = row_prefix(U.host, T.host);
     // segments of the lane-side list: at most kTaskPairs pairs, cut at group boundaries once a
     // segment holds >= 64 pairs, so that a task holds pairs of (mostly) one kind
-    // The heavier the class, the shorter the tasks: a task is executed by one warp from start to
-    // finish, so its duration bounds the tail of the launch (a 256-pair (SP SP|SP SP) task with all
-    // 81 primitive quartets alive would run for more than a millisecond).
-    static const int kMaxPairsByClass[6] = {256, 256, 128, 128, 64, 32};
-    const int maxpairs = kMaxPairsByClass[class_id(U.type, T.type)];
+    const int maxpairs = class_task_pairs(U.type, T.type);
     const int mingroup = std::min(64, maxpairs);
     std::vector<int> seg;  // segment start offsets, terminated by T.n
     seg.push_back(0);
@@ -240,7 +236,7 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
     if (rc) return rc;
     a.tasks = d_tasks;
     a.ntasks = (int)tasks.size();
-    a.t_soa = T.soa; a.t_nprim = T.nprim; a.t_pidx = T.pidx;
+    a.t_soa = T.soa; a.t_aos = T.aos; a.t_nprim = T.nprim; a.t_pidx = T.pidx;
     a.t_npad = T.npad; a.nT = T.n; a.tri = tri ? 1 : 0;
     a.ftab_q = pl->d_ftab + (size_t)(U.type + T.type) * 121 * 8;
     a.exptab = reinterpret_cast<const double2*>(pl->d_exptab);
@@ -252,7 +248,6 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
     a.out = nullptr;
     a.out_offset = sub.out_offset;
     a.npair = pl->npair;
-    a.store_mask = std::getenv("MYQC_STORE_MASK") ? std::atoll(std::getenv("MYQC_STORE_MASK")) : -1;
     sub.launches.push_back(L);
     pl->nlaunch += class_nlaunch(L.UT, L.TT) * nregion;
     return MYQC_OK;
@@ -743,7 +738,7 @@ static int plan_launch_total(const myqc_eri_plan* plan) {
 }
 
 // launch the tasks of fill region r of one class launch (its own task counter per region)
-static int launch_region(myqc_eri_plan* plan, Sub& sub, Launch& L, int r, double* d_sub_out, cudaStream_t st) {
+static int launch_region(myqc_eri_plan* plan, Sub& sub, Launch& L, int r, int slice, double* d_sub_out, cudaStream_t st) {
     const int t0 = L.region_task[r], t1 = L.region_task[r + 1];
     if (t1 <= t0) return 0;
     ClassArgs a = L.args;
@@ -751,7 +746,7 @@ static int launch_region(myqc_eri_plan* plan, Sub& sub, Launch& L, int r, double
     a.tasks = L.args.tasks + t0;
     a.ntasks = t1 - t0;
     a.row_counter = L.args.row_counter + r * class_nlaunch(L.UT, L.TT);
-    return launch_class(L.UT, L.TT, a, plan->num_sms, st);
+    return launch_class(L.UT, L.TT, slice, a, plan->num_sms, st);
 }
 
 static int fill_region(myqc_eri_plan* plan, Sub& sub, int r, double* d_sub_out, cudaStream_t st, bool paced = false) {
@@ -807,13 +802,16 @@ int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
             bool waited[myqc_eri_plan::kNumCompute] = {false, false, false, false};
             for (Launch& L : sub.launches) {
                 if (L.region_task[r + 1] <= L.region_task[r]) continue;
-                const int si = rr++ % myqc_eri_plan::kNumCompute;
-                // plain fill: the slice must be zeroed before a class kernel stores into it; the
-                // screened fill writes a disjoint set of elements and needs no ordering
-                if (!waited[si] && !plan->screened_fill) { CU(cudaStreamWaitEvent(plan->s_comp[si], plan->e_fill[ef], 0)); waited[si] = true; }
-                int e = launch_region(plan, sub, L, r, d_sub, plan->s_comp[si]);
-                if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
-                mark("class{" + std::to_string(L.UT) + "," + std::to_string(L.TT) + "} on stream " + std::to_string(si), plan->s_comp[si]);
+                // the mu-slices of (SP SP|SP SP) are independent launches: one internal stream each
+                for (int slice = 0; slice < class_nlaunch(L.UT, L.TT); ++slice) {
+                    const int si = rr++ % myqc_eri_plan::kNumCompute;
+                    // plain fill: the slice must be zeroed before a class kernel stores into it; the
+                    // screened fill writes a disjoint set of elements and needs no ordering
+                    if (!waited[si] && !plan->screened_fill) { CU(cudaStreamWaitEvent(plan->s_comp[si], plan->e_fill[ef], 0)); waited[si] = true; }
+                    int e = launch_region(plan, sub, L, r, slice, d_sub, plan->s_comp[si]);
+                    if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+                    mark("class{" + std::to_string(L.UT) + "," + std::to_string(L.TT) + "} on stream " + std::to_string(si), plan->s_comp[si]);
+                }
             }
         }
     }
@@ -883,7 +881,7 @@ int myqc_eri_plan_execute_timed(myqc_eri_plan* plan, double* d_out, void* stream
             if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
             CU(cudaEventRecord(ev[++idx], st));
             for (Launch& L : sub.launches) {
-                e = launch_region(plan, sub, L, r, d_sub, st);
+                for (int slice = 0; slice < class_nlaunch(L.UT, L.TT) && !e; ++slice) e = launch_region(plan, sub, L, r, slice, d_sub, st);
                 if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
                 CU(cudaEventRecord(ev[++idx], st));
             }

@@ -238,20 +238,25 @@ struct Cfg {
     // would leave an SM with a single resident CTA (8 warps); four-warp CTAs pack 3 per SM
     static constexpr int NTHREADS = 128;
     static constexpr int NWARPS = NTHREADS / 32;
+    // resident CTAs per SM the register allocation is held to: 72 / 80 / 128 / 140 registers for the
+    // four small classes, two CTAs for the two large ones
+    static constexpr int MINB = (LT == 0) ? 7 : (LT == 1) ? 6 : (UT == 0 && TT == 2) ? 4 : (LT == 2) ? 3 : 2;
     static constexpr uint32_t U_BYTES = 9 * FU * 8;
     // shared memory: Taylor table | exp table | per-warp U double buffers | mbarriers | out staging
     static constexpr size_t OFF_EXP = 121 * 8 * 8;
     static constexpr size_t OFF_U = OFF_EXP + 608 * 16;
     static constexpr size_t OFF_BAR = OFF_U + (size_t)NWARPS * 2 * U_BYTES;
-    static constexpr size_t OFF_SORT = OFF_BAR + (size_t)NWARPS * 2 * 8;   // per warp: 256 idx + 64 bins (int)
-    static constexpr size_t OFF_OUT = OFF_SORT + (size_t)NWARPS * (kTaskPairs + 64) * 4;
+    static constexpr bool LANE_AOS = (UT >= 1);  // measured: pays for {1,1},{1,2},{2,2}, costs for {0,x}
+    static constexpr int TASKP = class_task_pairs(UT, TT);                 // lane-side pairs per task
+    static constexpr size_t OFF_SORT = OFF_BAR + (size_t)NWARPS * 2 * 8;   // per warp: TASKP idx + 64 bins (int)
+    static constexpr size_t OFF_OUT = OFF_SORT + (size_t)NWARPS * (TASKP + 64) * 4;
     static constexpr size_t SMEM = OFF_OUT + (OUT_SMEM ? (size_t)NOUT * NTHREADS * 8 : 0);
 };
 
 }  // namespace
 
 template <int UT, int TT, int USL>
-__global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS) eri_class_kernel(const ClassArgs a) {
+__global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::MINB) eri_class_kernel(const ClassArgs a) {
     using C = Cfg<UT, TT, USL>;
     constexpr int LT = C::LT, Q = C::Q, NR = C::NR, NHT = C::NHT, NFU = C::NFU, NFT = C::NFT;
     constexpr int NTU = C::NTU, NTT = C::NTT, FU = C::FU, FT = C::FT, NOUT = C::NOUT;
@@ -268,8 +273,8 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS) eri_class_kernel(c
     const int warp = tid >> 5;
     double* s_ubuf = reinterpret_cast<double*>(smem_raw + C::OFF_U) + (size_t)warp * 2 * 9 * FU;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + C::OFF_BAR) + warp * 2;
-    int* s_vidx = reinterpret_cast<int*>(smem_raw + C::OFF_SORT) + warp * (kTaskPairs + 64);
-    int* s_bin = s_vidx + kTaskPairs;
+    int* s_vidx = reinterpret_cast<int*>(smem_raw + C::OFF_SORT) + warp * (C::TASKP + 64);
+    int* s_bin = s_vidx + C::TASKP;
 
     for (int i = tid; i < 121 * 8; i += NTHREADS) s_ft[i] = a.ftab_q[i];
     for (int i = tid; i < 601; i += NTHREADS) s_exp[i] = a.exptab[i];
@@ -332,18 +337,26 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS) eri_class_kernel(c
         // one kind (same exponents), so after a counting sort on |P-Q|^2 the 32 lanes of a chunk
         // take the same branch.  Which lane gets which pair does not affect any result.
         const int nitem = ntv - v0;
-        if (nitem > 32) {
+        if (C::TASKP > 32 && nitem > 32) {
             const double Px = s_u[1], Py = s_u[2], Pz = s_u[3];
-            double key[kTaskPairs / 32];
+            double key[C::TASKP / 32];
             double kmin = 1.0e300, kmax = 0.0;
 #pragma unroll
-            for (int i = 0; i < kTaskPairs / 32; ++i) {
+            for (int i = 0; i < C::TASKP / 32; ++i) {
                 const int v = v0 + i * 32 + lane;
                 key[i] = -1.0;
                 if (v < ntv) {
-                    const double dx = Px - a.t_soa[(size_t)a.t_npad + v];
-                    const double dy = Py - a.t_soa[2 * (size_t)a.t_npad + v];
-                    const double dz = Pz - a.t_soa[3 * (size_t)a.t_npad + v];
+                    double dx, dy, dz;
+                    if constexpr (C::LANE_AOS) {
+                        const double* r0 = a.t_aos + (size_t)v * 9 * FT;
+                        dx = Px - __ldg(r0 + 1);
+                        dy = Py - __ldg(r0 + 2);
+                        dz = Pz - __ldg(r0 + 3);
+                    } else {
+                        dx = Px - a.t_soa[(size_t)a.t_npad + v];
+                        dy = Py - a.t_soa[2 * (size_t)a.t_npad + v];
+                        dz = Pz - a.t_soa[3 * (size_t)a.t_npad + v];
+                    }
                     key[i] = fma(dx, dx, fma(dy, dy, dz * dz));
                     kmin = fmin(kmin, key[i]);
                     kmax = fmax(kmax, key[i]);
@@ -359,7 +372,7 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS) eri_class_kernel(c
             s_bin[lane + 32] = 0;
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < kTaskPairs / 32; ++i)
+            for (int i = 0; i < C::TASKP / 32; ++i)
                 if (key[i] >= 0.0) atomicAdd(&s_bin[(int)((key[i] - kmin) * scale)], 1);
             __syncwarp();
             // exclusive scan of the 64 bin counts (two bins per lane)
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS) eri_class_kernel(c
             s_bin[2 * lane + 1] = incl - c1;
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < kTaskPairs / 32; ++i)
+            for (int i = 0; i < C::TASKP / 32; ++i)
                 if (key[i] >= 0.0) s_vidx[atomicAdd(&s_bin[(int)((key[i] - kmin) * scale)], 1)] = v0 + i * 32 + lane;
             __syncwarp();
         } else {
@@ -396,14 +409,37 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS) eri_class_kernel(c
                 }
                 bool any = false;
                 const int npt = a.t_nprim[v];
-                const size_t ld = (size_t)a.t_npad;
+                // Lane-side records.  Small classes read the structure-of-arrays copy (a task's pairs are
+                // a contiguous range, so the 8 chunks of a task share its lines in L1).  The classes with
+                // many Hermite coefficients read the lane's own contiguous [9][FT] block instead: one base
+                // pointer and compile-time offsets instead of a 64-bit multiply-add per field (this alone
+                // removes the register spills of (S SP|SP SP) and (SP SP|SP SP)), and the next
+                // primitive's lines are prefetched into L1 while this one is contracted.
+                const size_t ld = C::LANE_AOS ? (size_t)1 : (size_t)a.t_npad;
+                const double* trec = C::LANE_AOS ? a.t_aos + (size_t)v * 9 * FT : a.t_soa + v;
                 for (int kt = 0; kt < npt; ++kt) {
-                    const double* tp = a.t_soa + (size_t)kt * FT * ld + v;
-                    const double et = tp[4 * ld];
-                    if (eu_max * et < kScreen) break;  // primitives are sorted by E, descending
-                    const double q = tp[0];
-                    const double Qx = tp[ld], Qy = tp[2 * ld], Qz = tp[3 * ld];
-                    const double cfar = kHalfSqrtPi * tp[5 * ld];  // sqrt(pi)/2 / sqrt(q)
+                    const double* tp = C::LANE_AOS ? trec + kt * FT : trec + (size_t)kt * FT * ld;
+                    double et, q, Qx, Qy, Qz, cfar;
+                    if constexpr (C::LANE_AOS) {
+                        const double2 t45 = __ldg(reinterpret_cast<const double2*>(tp) + 2);
+                        et = t45.x;
+                        if (eu_max * et < kScreen) break;  // primitives are sorted by E, descending
+                        const double2 t01 = __ldg(reinterpret_cast<const double2*>(tp));
+                        const double2 t23 = __ldg(reinterpret_cast<const double2*>(tp) + 1);
+                        if (kt + 1 < npt) {
+#pragma unroll
+                            for (int b = 0; b < FT * 8; b += 128)
+                                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(tp + FT) + b));
+                        }
+                        q = t01.x; Qx = t01.y; Qy = t23.x; Qz = t23.y;
+                        cfar = kHalfSqrtPi * t45.y;  // sqrt(pi)/2 / sqrt(q)
+                    } else {
+                        et = tp[4 * ld];
+                        if (eu_max * et < kScreen) break;  // primitives are sorted by E, descending
+                        q = tp[0];
+                        Qx = tp[ld]; Qy = tp[2 * ld]; Qz = tp[3 * ld];
+                        cfar = kHalfSqrtPi * tp[5 * ld];  // sqrt(pi)/2 / sqrt(q)
+                    }
                     double K[NFU][NHT];
 #pragma unroll
                     for (int f = 0; f < NFU; ++f)
@@ -460,7 +496,7 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS) eri_class_kernel(c
                         constexpr int k = decltype(kc)::value;
                         constexpr int fp = term_fn(TT, k);
                         constexpr int hp = term_h(TT, k);
-                        double ct = tp[(size_t)(kRecCoef + k) * ld];
+                        double ct = C::LANE_AOS ? __ldg(tp + kRecCoef + k) : tp[(size_t)(kRecCoef + k) * ld];
                         if constexpr (h_parity(hp) != 0) ct = -ct;
 #pragma unroll
                         for (int f = 0; f < NFU; ++f) {
@@ -491,7 +527,7 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS) eri_class_kernel(c
                             const int64_t lo = P1[f] < P2[fp] ? P1[f] : P2[fp];
                             const int64_t hi = P1[f] < P2[fp] ? P2[fp] : P1[f];
                             const int64_t idx = lo * np - ((lo * (lo - 1)) >> 1) + (hi - lo) - a.out_offset;
-                            a.out[idx & a.store_mask] = OUT_SMEM ? s_out[(f * NFT + fp) * NTHREADS + tid] : out_r[f * NFT + fp];
+                            a.out[idx] = OUT_SMEM ? s_out[(f * NFT + fp) * NTHREADS + tid] : out_r[f * NFT + fp];
                         }
                     }
                 }
@@ -752,23 +788,20 @@ static int launch_one(const ClassArgs& a, int num_sms, cudaStream_t st, int slot
 
 int class_nlaunch(int UT, int TT) { return (UT == 2 && TT == 2) ? 4 : 1; }
 
-int launch_class(int UT, int TT, const ClassArgs& a0, int num_sms, void* stream) {
+int launch_class(int UT, int TT, int slice, const ClassArgs& a0, int num_sms, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ClassArgs a = a0;
+    a.row_counter = a0.row_counter + slice;
     if (UT == 0 && TT == 0) return launch_one<0, 0, -1>(a, num_sms, st, 0);
     if (UT == 0 && TT == 1) return launch_one<0, 1, -1>(a, num_sms, st, 1);
     if (UT == 0 && TT == 2) return launch_one<0, 2, -1>(a, num_sms, st, 2);
     if (UT == 1 && TT == 1) return launch_one<1, 1, -1>(a, num_sms, st, 3);
     if (UT == 1 && TT == 2) return launch_one<1, 2, -1>(a, num_sms, st, 4);
-    if (UT == 2 && TT == 2) {  // four mu-slices, each with its own row counter
-        int e = launch_one<2, 2, 0>(a, num_sms, st, 5);
-        a.row_counter = a0.row_counter + 1;
-        if (!e) e = launch_one<2, 2, 1>(a, num_sms, st, 6);
-        a.row_counter = a0.row_counter + 2;
-        if (!e) e = launch_one<2, 2, 2>(a, num_sms, st, 7);
-        a.row_counter = a0.row_counter + 3;
-        if (!e) e = launch_one<2, 2, 3>(a, num_sms, st, 8);
-        return e;
+    if (UT == 2 && TT == 2) {  // four mu-slices, each with its own task counter
+        if (slice == 0) return launch_one<2, 2, 0>(a, num_sms, st, 5);
+        if (slice == 1) return launch_one<2, 2, 1>(a, num_sms, st, 6);
+        if (slice == 2) return launch_one<2, 2, 2>(a, num_sms, st, 7);
+        if (slice == 3) return launch_one<2, 2, 3>(a, num_sms, st, 8);
     }
     return (int)cudaErrorInvalidValue;
 }

@@ -6,7 +6,13 @@
 
 namespace myqc {
 
-constexpr int kTaskPairs = 256;  // lane-side pairs per task (8 warp chunks)
+constexpr int kTaskPairs = 256;  // most lane-side pairs per task (8 warp chunks)
+// The heavier the class, the shorter the tasks: a task is executed by one warp from start to finish,
+// so its duration bounds the tail of the launch (a 256-pair (SP SP|SP SP) task with all 81 primitive
+// quartets alive would run for more than a millisecond).
+constexpr int class_task_pairs(int UT, int TT) {
+    return (UT + TT <= 1) ? 256 : (UT + TT == 2) ? 128 : (UT + TT == 3) ? 64 : 32;
+}
 
 // One launch = all quartets (u, v) with u in a "uniform-side" pair list (records staged to
 // shared memory by TMA bulk copy, one row of the quartet space per CTA iteration) and v in a
@@ -23,6 +29,7 @@ struct ClassArgs {
     int ntasks;
     // lane side (SoA [9][nfield(TT)][t_npad])
     const double* t_soa;
+    const double* t_aos;     // the same records as [nT][9][nfield(TT)]: one lane reads its own pair contiguously
     const int32_t* t_nprim;  // [nT]
     const int32_t* t_pidx;   // [nT][nf(TT)]
     int t_npad;
@@ -38,7 +45,6 @@ struct ClassArgs {
     double* out;         // this shard's slice of the packed array
     int64_t out_offset;  // packed index of out[0]
     int64_t npair;
-    int64_t store_mask;  // -1; experiments: a small mask folds all stores into an L2-resident window
 };
 
 // Screened zero fill (see fill_screened_kernel): rows [row_lo,row_hi) of the packed upper triangle
@@ -70,8 +76,9 @@ int launch_fill_screened(const FillArgs& a, int num_sms, void* stream);
 // sets the kernel attributes and forces the (lazily loaded) kernels of the current device to load
 int prepare_kernels();
 
-// returns cudaError_t as int; `slice` selects the mu-slice for (2,2), ignored otherwise
-int launch_class(int UT, int TT, const ClassArgs& a, int num_sms, void* stream);
+// returns cudaError_t as int; `slice` < class_nlaunch(UT,TT) selects the mu-slice of (2,2) (0 otherwise);
+// slice k uses the task counter a.row_counter + k
+int launch_class(int UT, int TT, int slice, const ClassArgs& a, int num_sms, void* stream);
 // number of kernel launches launch_class issues for (UT,TT)
 int class_nlaunch(int UT, int TT);
 
