@@ -36,6 +36,8 @@ EXPORTS = [
     "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main", "myqc_eri_shard_layout",
     "myqc_eri_canonical_stats", "myqc_eri_plan_launch_count", "myqc_eri_plan_launch_info",
     "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard", "myqc_write_xx_ex",
+    # include/myqc_fock.h
+    "myqc_fock_rhf", "myqc_fock_uhf", "myqc_fock_rhf_host", "myqc_fock_uhf_host",
 ]
 
 
@@ -94,6 +96,11 @@ def lib() -> ctypes.CDLL:
     L.myqc_eri_plan_execute_timed.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ctypes.c_float)]
     L.myqc_fp64_peak.argtypes = [c_int, _dp]
     L.myqc_eri_packed_shard.argtypes = common + [_dp, c_int, c_int, c_int, _i64p]
+    c_i64 = ctypes.c_int64
+    L.myqc_fock_rhf.argtypes = [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p]
+    L.myqc_fock_uhf.argtypes = [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.myqc_fock_rhf_host.argtypes = [_dp, c_int, _dp, _dp]
+    L.myqc_fock_uhf_host.argtypes = [_dp, c_int, _dp, _dp, _dp, _dp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("myqc_last_error", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
@@ -373,3 +380,85 @@ def make_job(workdir: str, zmat_text: str, inputs_dir: str) -> System:
         shutil.copyfile(os.path.join(inputs_dir, name), os.path.join(workdir, name))
     _parse.parse(workdir)
     return load_system(workdir)
+
+
+# ----------------------------------------------------------------------------------------------
+# G(D) from the packed array (include/myqc_fock.h; RHFI2G.f90:72-95, UHFI2G.f90:71-99)
+# ----------------------------------------------------------------------------------------------
+def fock_rhf(packed: np.ndarray, norb: int, da: np.ndarray) -> np.ndarray:
+    """Guv of RHFI2G.f90:80-90 from the packed unique ERIs (host arrays in, host array out)."""
+    packed = np.ascontiguousarray(packed, dtype=np.float64)
+    da = np.asfortranarray(da, dtype=np.float64)
+    g = np.zeros((norb, norb), dtype=np.float64, order="F")
+    _check(lib().myqc_fock_rhf_host(_d(packed), norb, _d(da), _d(g)))
+    return g
+
+
+def fock_uhf(packed: np.ndarray, norb: int, da: np.ndarray, db: np.ndarray):
+    """(GuvA, GuvB) of UHFI2G.f90:80-93 from the packed unique ERIs."""
+    packed = np.ascontiguousarray(packed, dtype=np.float64)
+    da = np.asfortranarray(da, dtype=np.float64)
+    db = np.asfortranarray(db, dtype=np.float64)
+    ga = np.zeros((norb, norb), dtype=np.float64, order="F")
+    gb = np.zeros((norb, norb), dtype=np.float64, order="F")
+    _check(lib().myqc_fock_uhf_host(_d(packed), norb, _d(da), _d(db), _d(ga), _d(gb)))
+    return ga, gb
+
+
+def fock_rhf_device(d_packed: int, out_offset: int, out_elems: int, norb: int, d_da: int, d_g: int, stream: int = 0):
+    """Device-pointer form (stream ordered): partial G of a slice of whole packed rows."""
+    _check(lib().myqc_fock_rhf(d_packed, out_offset, out_elems, norb, d_da, d_g, stream))
+
+
+def fock_uhf_device(d_packed: int, out_offset: int, out_elems: int, norb: int, d_da: int, d_db: int,
+                    d_ga: int, d_gb: int, stream: int = 0):
+    _check(lib().myqc_fock_uhf(d_packed, out_offset, out_elems, norb, d_da, d_db, d_ga, d_gb, stream))
+
+
+def _read_records(path: str):
+    """Fortran unformatted sequential records (4-byte little-endian markers) as float64 arrays."""
+    raw = open(path, "rb").read()
+    out, pos = [], 0
+    while pos < len(raw):
+        n = int(np.frombuffer(raw, dtype="<i4", count=1, offset=pos)[0])
+        out.append(np.frombuffer(raw, dtype="<f8", count=n // 8, offset=pos + 4).copy())
+        pos += 8 + n
+    return out
+
+
+def _write_records(path: str, arrays):
+    with open(path, "wb") as f:
+        for a in arrays:
+            b = np.asfortranarray(a, dtype="<f8").tobytes(order="F")
+            f.write(np.int32(len(b)).tobytes()); f.write(b); f.write(np.int32(len(b)).tobytes())
+
+
+def pack_dense(xx: np.ndarray) -> np.ndarray:
+    """Packed 8-fold-unique array from a dense XX(n,n,n,n) (the inverse of eri_dense's expansion)."""
+    n = xx.shape[0]
+    ii, jj = np.triu_indices(n)
+    m = xx[ii, jj][:, ii, jj]                 # (npair, npair), row P, column P'
+    r, c = np.triu_indices(len(ii))
+    return np.ascontiguousarray(m[r, c])
+
+
+def rhf_i2g(workdir: str) -> np.ndarray:
+    """PROGRAM RHFI2G (src/I2G/RHFI2G.f90): reads `XX` and `Da`, writes `Guv` in the job directory."""
+    norb = int(open(os.path.join(workdir, "basinfo")).read().split()[1])
+    xx = read_xx(os.path.join(workdir, "XX"), norb)
+    da = _read_records(os.path.join(workdir, "Da"))[0].reshape((norb, norb), order="F")
+    g = fock_rhf(pack_dense(xx), norb, da)
+    _write_records(os.path.join(workdir, "Guv"), [g])
+    return g
+
+
+def uhf_i2g(workdir: str):
+    """PROGRAM UHFI2G (src/I2G/UHFI2G.f90): reads `XX`, `Da` (two records), writes `Guv` (two records)."""
+    norb = int(open(os.path.join(workdir, "basinfo")).read().split()[1])
+    xx = read_xx(os.path.join(workdir, "XX"), norb)
+    recs = _read_records(os.path.join(workdir, "Da"))
+    da = recs[0].reshape((norb, norb), order="F")
+    db = recs[1].reshape((norb, norb), order="F")
+    ga, gb = fock_uhf(pack_dense(xx), norb, da, db)
+    _write_records(os.path.join(workdir, "Guv"), [ga, gb])
+    return ga, gb

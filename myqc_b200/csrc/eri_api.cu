@@ -26,6 +26,7 @@ static int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
+int fock_fail(int code, const std::string& msg) { return fail(code, msg); }  // for fock.cu
 static int cuda_fail(cudaError_t e, const char* what) {
     return fail(MYQC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
@@ -508,6 +509,14 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
         if (e) return cuda_fail((cudaError_t)e, "kernel preparation");
     }
 
+    const bool trace = std::getenv("MYQC_TRACE") != nullptr;
+    auto tprev = std::chrono::steady_clock::now();
+    auto stage = [&](const char* name) {
+        if (!trace) return;
+        const auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[myqc trace]   plan stage %-24s %.1f ms\n", name, std::chrono::duration<double, std::milli>(t - tprev).count());
+        tprev = t;
+    };
     std::unique_ptr<myqc_eri_plan> pl(new myqc_eri_plan());
     pl->device = device;
     CU(cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -520,6 +529,7 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
     if ((rc = build_shells(nnuc, nset, setl, setinfo, ops, basinfo, shells, err))) return fail(rc, err);
     PairList all[3];
     if ((rc = build_pairs(nnuc, xyz, set, setinfo, setl, ops, bas, basinfo, shells, all, err))) return fail(rc, err);
+    stage("shells + pair records");
     {
         // Default: zero the whole slice first (streaming 128-bit stores, 0.95 of HBM peak), class kernels
         // after it.  MYQC_FILL_MODE=screened selects the order-independent screened fill that runs next
@@ -549,6 +559,7 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
         if ((rc = upload(pl.get(), zeros, &pl->d_counters))) return rc;
     }
     if (pl->screened_fill && (rc = build_screen_ranks(pl.get(), all))) return rc;
+    stage("tables");
 
     // ---- sharding: contiguous blocks of packed rows, cut where a shell's functions start -------
     // External shards (one per GPU) are cut first; this plan's shard is then cut again into
@@ -588,6 +599,7 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
     pl->out_offset = packed_row_offset(sub_fn.front(), pl->norb);
     pl->out_elems = packed_row_offset(sub_fn.back(), pl->norb) - pl->out_offset;
 
+    stage("shard cuts");
     const int nsub = (int)sub_fn.size() - 1;
     pl->subs.resize(nsub);
     pl->lists.reserve(6 * nsub);
@@ -634,6 +646,7 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
                 if ((rc = upload_list(pl.get(), sublist(all[t], pl8), pl->lists.back()))) return rc;
             }
         }
+        stage("list upload");
         // launches.  Class (ta,tb), ta <= tb, uniform side = ta, lane side = tb.
         for (int ta = 0; ta < 3; ++ta)
             for (int tb = ta; tb < 3; ++tb) {
@@ -681,6 +694,7 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
     }
     pl->h_rk.clear(); pl->h_rk.shrink_to_fit();
     pl->h_cut.clear(); pl->h_cut.shrink_to_fit();
+    stage("task lists");
     // internal streams and events
     CU(cudaStreamCreateWithFlags(&pl->s_fill, cudaStreamNonBlocking));
     for (auto& st : pl->s_comp) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -693,7 +707,9 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
         for (auto& e : pl->e_fill) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
 
+    stage("streams + events");
     if (nshards == 1) canonical_stats(nnuc, xyz, nset, setl, set, setinfo, pl->nquartets, &pl->model_flops);
+    stage("canonical stats");
     *plan = pl.release();
     return MYQC_OK;
 }

@@ -15,7 +15,7 @@ from oracle import oracle as O
 
 
 def test_library_exports_every_declared_symbol():
-    hdr = open(os.path.join(ROOT, "include", "myqc_eri.h")).read()
+    hdr = open(os.path.join(ROOT, "include", "myqc_eri.h")).read() + open(os.path.join(ROOT, "include", "myqc_fock.h")).read()
     declared = set(re.findall(r"\b(myqc_[a-z0-9_]+)\s*\(", hdr))
     L = Q.lib()
     missing = [n for n in declared if not hasattr(L, n)]
@@ -33,6 +33,9 @@ def test_no_cpu_fallback(tmp_path):
     assert e.value.code == Q.ERR_NO_DEVICE
     with pytest.raises(Q.MyQCError):
         Q.Plan(s)
+    with pytest.raises(Q.MyQCError) as e:
+        Q.fock_rhf(np.zeros(1), 1, np.zeros((1, 1)))
+    assert e.value.code == Q.ERR_NO_DEVICE
 
 
 @pytest.mark.parametrize("name", EXAMPLES + ["h2o_4", "c4h10"])
