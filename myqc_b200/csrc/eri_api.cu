@@ -102,6 +102,11 @@ struct myqc_eri_plan {
     double model_flops = 0.0;
     int nlaunch = 0;
     int64_t h2d_bytes = 0;  // bytes uploaded at plan creation (pair tables, Boys tables, prefixes)
+    // inputs kept for the lazily evaluated work statistics (plan_stats)
+    std::vector<double> in_xyz, in_set;
+    std::vector<int32_t> in_setinfo;
+    int in_nnuc = 0, in_setl = 0;
+    bool stats_done = false, stats_whole = false;
     bool screened_fill = true;
     int32_t *d_rk = nullptr, *d_cut = nullptr;
     std::vector<int32_t> h_rk, h_cut;
@@ -179,57 +184,79 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
         }
     }
     struct TaskN { int4 t; int64_t need; int region; double weight; };
-    std::vector<TaskN> tn;
     std::vector<double> tprim_prefix(T.n + 1, 0.0);  // prefix sums of lane-side primitive counts
     for (int k = 0; k < T.n; ++k) tprim_prefix[k + 1] = tprim_prefix[k] + T.host.nprim[k];
-    for (int u = 0; u < U.n; ++u) {
+    const int nregion = (int)sub.region_end.size();
+    // MYQC_TASK_ORDER=0: plain heaviest-task-first order (23.5 ms on (H2O)_64 against 22.5 ms, profiles/r1_notes.md)
+    static const int task_order = std::getenv("MYQC_TASK_ORDER") ? std::atoi(std::getenv("MYQC_TASK_ORDER")) : 1;
+    auto emit_row = [&](int u, std::vector<TaskN>& dst) {
         const int lo = tri ? u : 0, hi = ntv[u];
-        if (lo >= hi) continue;
+        if (lo >= hi) return;
         size_t si = std::upper_bound(seg.begin(), seg.end(), lo) - seg.begin() - 1;
         for (; si + 1 < seg.size() && seg[si] < hi; ++si) {
             const int b = std::max(seg[si], lo), e = std::min(seg[si + 1], hi);
             if (b < e)
-                tn.push_back({make_int4(u, b, e, 0), need_u[u], 0,
-                              (double)U.host.nprim[u] * (tprim_prefix[e] - tprim_prefix[b])});
+                dst.push_back({make_int4(u, b, e, 0), need_u[u], 0,
+                               (double)U.host.nprim[u] * (tprim_prefix[e] - tprim_prefix[b])});
         }
-    }
-    // region of a task = first fill region that covers everything the task can write; inside a
-    // region the heaviest tasks (most primitive quartets) go first so that launches end on light ones
-    const int nregion = (int)sub.region_end.size();
-    for (TaskN& t : tn) {
-        int r = 0;
-        while (r + 1 < nregion && t.need > sub.region_end[r]) ++r;
-        t.region = r;
-    }
-    // MYQC_TASK_ORDER=0: plain heaviest-task-first order (23.5 ms on (H2O)_64 against 22.5 ms, profiles/r1_notes.md)
-    static const int task_order = std::getenv("MYQC_TASK_ORDER") ? std::atoi(std::getenv("MYQC_TASK_ORDER")) : 1;
-    if (task_order == 1) {
-        // rows heaviest first, the tasks of one row adjacent: everything a launch stores into the packed
-        // rows of one uniform-side pair is stored within a short time, so partial-sector stores of
-        // neighbouring lanes meet in L2
+    };
+    std::vector<TaskN> tn;
+    std::vector<int4> tasks;
+    L.region_task.assign(nregion + 1, 0);
+    if (task_order == 1 && nregion == 1) {
+        // Rows heaviest first, the tasks of one row adjacent (in lane-side order): everything a launch
+        // stores into the packed rows of one uniform-side pair is stored within a short time, so
+        // partial-sector stores of neighbouring lanes meet in L2.  Only the rows are sorted.
         std::vector<double> roww(U.n, 0.0);
-        for (const TaskN& t : tn) roww[t.t.x] += t.weight;
-        std::stable_sort(tn.begin(), tn.end(), [&](const TaskN& x, const TaskN& y) {
-            if (x.region != y.region) return x.region < y.region;
-            if (x.t.x != y.t.x) {
-                if (roww[x.t.x] != roww[y.t.x]) return roww[x.t.x] > roww[y.t.x];
-                return x.t.x < y.t.x;
-            }
-            return x.t.y < y.t.y;
-        });
+        std::vector<int> order;
+        order.reserve(U.n);
+        for (int u = 0; u < U.n; ++u) {
+            const int lo = tri ? u : 0, hi = ntv[u];
+            if (lo >= hi) continue;
+            roww[u] = (double)U.host.nprim[u] * (tprim_prefix[hi] - tprim_prefix[lo]);
+            order.push_back(u);
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return roww[x] > roww[y]; });
+        for (int u : order) {
+            tn.clear();
+            emit_row(u, tn);
+            for (const TaskN& t : tn) { tasks.push_back(t.t); L.weight += t.weight; }
+        }
+        L.region_task[1] = (int)tasks.size();
     } else {
-        std::stable_sort(tn.begin(), tn.end(), [](const TaskN& x, const TaskN& y) {
-            if (x.region != y.region) return x.region < y.region;
-            return x.weight > y.weight;
-        });
-    }
-    std::vector<int4> tasks(tn.size());
-    for (size_t k = 0; k < tn.size(); ++k) { tasks[k] = tn[k].t; L.weight += tn[k].weight; }
-    L.region_task.assign(nregion + 1, (int)tn.size());
-    L.region_task[0] = 0;
-    for (size_t k = 0, r = 0; r < (size_t)nregion; ++r) {
-        while (k < tn.size() && tn[k].region <= (int)r) ++k;
-        L.region_task[r + 1] = (int)k;
+        for (int u = 0; u < U.n; ++u) emit_row(u, tn);
+        // region of a task = first fill region that covers everything the task can write; inside a
+        // region the heaviest tasks (most primitive quartets) go first so that launches end on light ones
+        for (TaskN& t : tn) {
+            int r = 0;
+            while (r + 1 < nregion && t.need > sub.region_end[r]) ++r;
+            t.region = r;
+        }
+        if (task_order == 1) {
+            std::vector<double> roww(U.n, 0.0);
+            for (const TaskN& t : tn) roww[t.t.x] += t.weight;
+            std::stable_sort(tn.begin(), tn.end(), [&](const TaskN& x, const TaskN& y) {
+                if (x.region != y.region) return x.region < y.region;
+                if (x.t.x != y.t.x) {
+                    if (roww[x.t.x] != roww[y.t.x]) return roww[x.t.x] > roww[y.t.x];
+                    return x.t.x < y.t.x;
+                }
+                return x.t.y < y.t.y;
+            });
+        } else {
+            std::stable_sort(tn.begin(), tn.end(), [](const TaskN& x, const TaskN& y) {
+                if (x.region != y.region) return x.region < y.region;
+                return x.weight > y.weight;
+            });
+        }
+        tasks.resize(tn.size());
+        for (size_t k = 0; k < tn.size(); ++k) { tasks[k] = tn[k].t; L.weight += tn[k].weight; }
+        L.region_task.assign(nregion + 1, (int)tn.size());
+        L.region_task[0] = 0;
+        for (size_t k = 0, r = 0; r < (size_t)nregion; ++r) {
+            while (k < tn.size() && tn[k].region <= (int)r) ++k;
+            L.region_task[r + 1] = (int)k;
+        }
     }
     if (tasks.empty()) return MYQC_OK;
     int4* d_tasks = nullptr;
@@ -708,8 +735,12 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
     }
 
     stage("streams + events");
-    if (nshards == 1) canonical_stats(nnuc, xyz, nset, setl, set, setinfo, pl->nquartets, &pl->model_flops);
-    stage("canonical stats");
+    // the canonical work statistics cost ~8 ms of host time: evaluated when plan_stats asks for them
+    pl->stats_whole = (nshards == 1);
+    pl->in_nnuc = nnuc; pl->in_setl = setl;
+    pl->in_xyz.assign(xyz, xyz + 3 * (size_t)nnuc);
+    pl->in_set.assign(set, set + nset);
+    pl->in_setinfo.assign(setinfo, setinfo + 2 + (size_t)setl * nset);
     *plan = pl.release();
     return MYQC_OK;
 }
@@ -922,8 +953,15 @@ int myqc_fp64_peak(int device, double* tflops) {
     return MYQC_OK;
 }
 
-int myqc_eri_plan_stats(const myqc_eri_plan* plan, int64_t* nquartets, double* model_flops, int* nlaunch) {
-    if (!plan) return fail(MYQC_ERR_BAD_ARG, "null plan");
+int myqc_eri_plan_stats(const myqc_eri_plan* plan_c, int64_t* nquartets, double* model_flops, int* nlaunch) {
+    if (!plan_c) return fail(MYQC_ERR_BAD_ARG, "null plan");
+    myqc_eri_plan* plan = const_cast<myqc_eri_plan*>(plan_c);
+    if (!plan->stats_done) {
+        if (plan->stats_whole)
+            canonical_stats(plan->in_nnuc, plan->in_xyz.data(), plan->nset, plan->in_setl, plan->in_set.data(),
+                            plan->in_setinfo.data(), plan->nquartets, &plan->model_flops);
+        plan->stats_done = true;
+    }
     if (nquartets) for (int c = 0; c < 6; ++c) nquartets[c] = plan->nquartets[c];
     if (model_flops) *model_flops = plan->model_flops;
     if (nlaunch) *nlaunch = plan->nlaunch;

@@ -5,9 +5,13 @@
 #include "terms.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <numeric>
+#include <thread>
 
 #include "../../include/myqc_eri.h"
 
@@ -135,9 +139,28 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
             hi[c] = std::max(hi[c], xyz[i + nnuc * c]);
         }
     const double ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
-    std::vector<Tmp> tmp[3];
+    const bool trace = std::getenv("MYQC_TRACE") != nullptr;
+    auto tprev = std::chrono::steady_clock::now();
+    auto stage = [&](const char* name) {
+        if (!trace) return;
+        const auto t = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[myqc trace]     pairs stage %-20s %.1f ms\n", name, std::chrono::duration<double, std::milli>(t - tprev).count());
+        tprev = t;
+    };
     const int ns = (int)shells.size();
-    for (int A = 0; A < ns; ++A) {
+    // normalisation constants per primitive set (gtoD, auxilary.f90:704-726) -- same values as computing
+    // them per term, computed once
+    int nset_all = 0;
+    for (const Shell& sh : shells)
+        for (int a : sh.sets) nset_all = std::max(nset_all, a + 1);
+    std::vector<double> g0(nset_all), g1(nset_all);
+    for (int a = 0; a < nset_all; ++a) { g0[a] = gtoD(0, set[a]); g1[a] = gtoD(1, set[a]); }
+    // shell pairs (A, B >= A) are independent: rows A are dealt to a few host threads, results are
+    // concatenated in A order so that the lists do not depend on the thread count
+    std::vector<std::vector<Tmp>> perA(ns);
+    std::vector<int> rcA(ns, MYQC_OK);
+    auto do_row = [&](int A) {
+        std::vector<Tmp>& outA = perA[A];
         for (int B = A; B < ns; ++B) {
             const Shell& sa = shells[A];
             const Shell& sb = shells[B];
@@ -171,8 +194,13 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
                         d[w][1][1][1] = PA[w] / (2.0 * p) + PB[w] * half;
                         d[w][1][1][2] = half / (2.0 * p);
                     }
-                    const double ga[2] = {gtoD(0, aa), gtoD(1, aa)};
-                    const double gb[2] = {gtoD(0, bb), gtoD(1, bb)};
+                    const double ga[2] = {g0[a], g1[a]};
+                    const double gb[2] = {g0[b], g1[b]};
+                    double ca[4], cb[4];  // contraction coefficients of the four function slots
+                    for (int mu = 0; mu < 4; ++mu) {
+                        ca[mu] = slot_coef(sa, a, mu, setinfo, setl, ops, bas);
+                        cb[mu] = slot_coef(sb, b, mu, setinfo, setl, ops, bas);
+                    }
                     // 2 Pi^2.5 / (p q sqrt(p+q)) is split as scale(p)*scale(q)/sqrt(p+q)
                     const double scale = std::sqrt(2.0) * std::pow(kPiRef, 1.25) / p;
                     auto term = [&](int mu, int nu, int N, int L, int M) -> double {
@@ -183,7 +211,7 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
                         if (std::fabs(cz) < tol || std::fabs(cy) < tol || std::fabs(cx) < tol) return 0.0;
                         double Dk = cx * cy * cz;
                         Dk = Dk * EIJ * ga[mu != 0] * gb[nu != 0];
-                        Dk = Dk * slot_coef(sa, a, mu, setinfo, setl, ops, bas) * slot_coef(sb, b, nu, setinfo, setl, ops, bas);
+                        Dk = Dk * ca[mu] * cb[nu];
                         return Dk * scale;
                     };
                     PrimRec r;
@@ -207,13 +235,34 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
             if (t.prims.empty()) continue;
             std::stable_sort(t.prims.begin(), t.prims.end(), [](const PrimRec& x, const PrimRec& y) { return x.E > y.E; });
             t.nprim = (int)t.prims.size();
-            if (t.nprim > kMaxPrim) { err = "more than 9 primitive pairs per shell pair"; return MYQC_ERR_UNSUPPORTED; }
+            if (t.nprim > kMaxPrim) { rcA[A] = MYQC_ERR_UNSUPPORTED; return; }
             t.bucket = emax_bucket(t.emax);
             for (int c = 0; c < 3; ++c) t.centre[c] = t.prims[0].f[1 + c];  // centre of the dominant primitive
             t.morton = morton3(t.centre, lo, ext);
-            tmp[type].push_back(std::move(t));
+            outA.push_back(std::move(t));
+        }
+    };
+    {
+        int nthr = (int)std::thread::hardware_concurrency();
+        if (const char* e = std::getenv("MYQC_HOST_THREADS")) nthr = std::atoi(e);
+        nthr = std::max(1, std::min(nthr, 8));
+        if (ns < 64) nthr = 1;
+        if (nthr == 1) {
+            for (int A = 0; A < ns; ++A) do_row(A);
+        } else {
+            std::vector<std::thread> th;
+            for (int w = 0; w < nthr; ++w)
+                th.emplace_back([&, w] { for (int A = w; A < ns; A += nthr) do_row(A); });
+            for (auto& x : th) x.join();
         }
     }
+    stage("records");
+    std::vector<Tmp> tmp[3];
+    for (int A = 0; A < ns; ++A) {
+        if (rcA[A] != MYQC_OK) { err = "more than 9 primitive pairs per shell pair"; return rcA[A]; }
+        for (Tmp& t : perA[A]) tmp[t.type].push_back(std::move(t));
+    }
+    stage("merge");
     for (int type = 0; type < 3; ++type) {
         std::vector<Tmp>& v = tmp[type];
         std::stable_sort(v.begin(), v.end(), [](const Tmp& x, const Tmp& y) {
@@ -253,13 +302,19 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
                 pl.pidx[(size_t)k * nf + f] = (int32_t)(i * norb - i * (i - 1) / 2 + (j - i));
             }
             for (int q = 0; q < t.nprim; ++q)
+                std::memcpy(&pl.aos[((size_t)k * kMaxPrim + q) * nfield], t.prims[q].f, sizeof(double) * nfield);
+        }
+        // structure-of-arrays copy: tiles of 32 pairs so that both sides of the transpose stay in cache
+        for (int k0 = 0; k0 < pl.n; k0 += 32) {
+            const int k1 = std::min(pl.n, k0 + 32);
+            for (int q = 0; q < kMaxPrim; ++q)
                 for (int f = 0; f < nfield; ++f) {
-                    const double val = t.prims[q].f[f];
-                    pl.aos[((size_t)k * kMaxPrim + q) * nfield + f] = val;
-                    pl.soa[((size_t)q * nfield + f) * pl.npad + k] = val;
+                    double* dst = &pl.soa[((size_t)q * nfield + f) * pl.npad];
+                    for (int k = k0; k < k1; ++k) dst[k] = pl.aos[((size_t)k * kMaxPrim + q) * nfield + f];
                 }
         }
     }
+    stage("sort + layout");
     return MYQC_OK;
 }
 
