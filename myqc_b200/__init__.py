@@ -38,6 +38,8 @@ EXPORTS = [
     "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard", "myqc_write_xx_ex",
     # include/myqc_fock.h
     "myqc_fock_rhf", "myqc_fock_uhf", "myqc_fock_rhf_host", "myqc_fock_uhf_host",
+    # include/myqc_int1e.h
+    "myqc_int1e", "myqc_int1e_main",
 ]
 
 
@@ -101,6 +103,8 @@ def lib() -> ctypes.CDLL:
     L.myqc_fock_uhf.argtypes = [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.myqc_fock_rhf_host.argtypes = [_dp, c_int, _dp, _dp]
     L.myqc_fock_uhf_host.argtypes = [_dp, c_int, _dp, _dp, _dp, _dp]
+    L.myqc_int1e.argtypes = [c_int, _dp, _ip, c_int, c_int, _dp, _ip, c_int, _dp, _ip, _dp, _dp, _dp]
+    L.myqc_int1e_main.argtypes = [c_char_p]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("myqc_last_error", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
@@ -462,3 +466,28 @@ def uhf_i2g(workdir: str):
     ga, gb = fock_uhf(pack_dense(xx), norb, da, db)
     _write_records(os.path.join(workdir, "Guv"), [ga, gb])
     return ga, gb
+
+
+# ----------------------------------------------------------------------------------------------
+# one-electron integrals (include/myqc_int1e.h; int1e.f90)
+# ----------------------------------------------------------------------------------------------
+def int1e(s: System):
+    """(Suv, Huv) of proc1e (int1e.f90:132-280): overlap and core Hamiltonian, norb x norb."""
+    n = s.norb
+    S = np.zeros((n, n), order="F")
+    H = np.zeros((n, n), order="F")
+    atoms = np.ascontiguousarray(s.atoms, dtype=np.int32)
+    _check(lib().myqc_int1e(s.nnuc, _d(s.xyz), _i(atoms), s.nset, s.setl, _d(s.set), _i(s.setinfo), s.ops,
+                            _d(s.bas), _i(s.basinfo), _d(s.ftab), _d(S), _d(H)))
+    return S, H
+
+
+def int1e_main(workdir: str) -> int:
+    """PROGRAM int1e (int1e.f90:14-131) in `workdir`; returns the library status (0 = ok)."""
+    return lib().myqc_int1e_main(workdir.encode())
+
+
+def read_matrix_text(path: str, norb: int) -> np.ndarray:
+    """READ(u,*) M(:,:) of a list-directed text file (Suv / Huv, scf.f90:140-144)."""
+    toks = open(path).read().replace(",", " ").replace("D", "E").split()
+    return np.array([float(t) for t in toks[:norb * norb]]).reshape((norb, norb), order="F")

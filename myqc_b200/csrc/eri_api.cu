@@ -26,7 +26,23 @@ static int fail(int code, const std::string& msg) {
     g_last_error = msg;
     return code;
 }
-int fock_fail(int code, const std::string& msg) { return fail(code, msg); }  // for fock.cu
+int fock_fail(int code, const std::string& msg) { return fail(code, msg); }  // for fock.cu, int1e.cu
+
+// Boys tables shared by the ERI and the one-electron kernels (boys.cuh): taylor[qi][t][k] =
+// Ft(t, 3 qi + k)/k! for k < 7 (the bytes of the Ftab file), ex[k] = {exp(-k/10), k/10}
+void build_boys_tables(const double* ftab, std::vector<double>& h, std::vector<double>& ex) {
+    h.assign(5 * 121 * 8, 0.0);
+    for (int qi = 0; qi < 5; ++qi)
+        for (int t = 0; t <= 120; ++t) {
+            double fact = 1.0;
+            for (int k = 0; k < 7; ++k) {
+                if (k > 1) fact *= k;
+                h[((size_t)qi * 121 + t) * 8 + k] = ftab[t + 121 * (3 * qi + k)] / fact;
+            }
+        }
+    ex.assign(2 * 608, 0.0);
+    for (int k = 0; k <= 600; ++k) { ex[2 * k] = std::exp(-(k / 10.0)); ex[2 * k + 1] = k / 10.0; }
+}
 static int cuda_fail(cudaError_t e, const char* what) {
     return fail(MYQC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
@@ -568,19 +584,9 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
 
     // Boys tables for the five start orders Q = 0,3,6,9,12: row t = {Ft(t,Q+k)/k!, k<7 ; t/10}
     {
-        std::vector<double> h(5 * 121 * 8);
-        for (int qi = 0; qi < 5; ++qi)
-            for (int t = 0; t <= 120; ++t) {
-                double fact = 1.0;
-                for (int k = 0; k < 7; ++k) {
-                    if (k > 1) fact *= k;
-                    h[((size_t)qi * 121 + t) * 8 + k] = ftab[t + 121 * (3 * qi + k)] / fact;
-                }
-                h[((size_t)qi * 121 + t) * 8 + 7] = 0.0;
-            }
+        std::vector<double> h, ex;
+        build_boys_tables(ftab, h, ex);
         if ((rc = upload(pl.get(), h, &pl->d_ftab))) return rc;
-        std::vector<double> ex(2 * 608, 0.0);
-        for (int k = 0; k <= 600; ++k) { ex[2 * k] = std::exp(-(k / 10.0)); ex[2 * k + 1] = k / 10.0; }
         if ((rc = upload(pl.get(), ex, &pl->d_exptab))) return rc;
         std::vector<int> zeros(kMaxCounters, 0);
         if ((rc = upload(pl.get(), zeros, &pl->d_counters))) return rc;

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/myqc_eri.h"
+#include "../../include/myqc_int1e.h"
 
 namespace myqc {
 extern thread_local std::string g_last_error;
@@ -403,6 +404,70 @@ int myqc_int2e_main(const char* dir, int ngpu) {
         std::printf("\n Two electron integrals constructed on the GPU\n");
     }
     write_fmem(dir, fmem);  // setenv :69
+    return MYQC_OK;
+}
+
+// PROGRAM int1e, src/integrals/int1e.f90:14-131 --------------------------------------------------
+// list-directed dump of a REAL(8) array: three values per line, 17 significant digits (what the
+// consumers read back with READ(u,*), scf.f90:140-144)
+static int write_real_list(const std::string& path, const double* v, size_t n) {
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) return io_fail("cannot write " + path);
+    for (size_t i = 0; i < n; ++i) {
+        std::fprintf(f, "  %24.16E", v[i]);
+        if (i % 3 == 2 || i + 1 == n) std::fputc('\n', f);
+    }
+    std::fclose(f);
+    return MYQC_OK;
+}
+
+int myqc_int1e_main(const char* dir) {
+    std::printf(" int1e called\n");  // int1e.f90:47
+    int nnuc = 0, nA = 0, nB = 0, nopt = 0;
+    double fmem = 0;
+    int rc = myqc_read_env(dir, 0, 0, &nnuc, &nA, &nB, nullptr, nullptr, &fmem, &nopt, nullptr);
+    if (rc) { std::printf(" %s\n", myqc_last_error()); touch_error(dir); return rc; }
+    std::vector<int32_t> atoms(nnuc), options(nopt > 17 ? nopt : 17, 0);
+    std::vector<double> xyz((size_t)3 * nnuc);
+    rc = myqc_read_env(dir, nnuc, (int)options.size(), &nnuc, &nA, &nB, atoms.data(), xyz.data(), &fmem, &nopt, options.data());
+    if (rc) { std::printf(" %s\n", myqc_last_error()); touch_error(dir); return rc; }
+    if (exists(join(dir, "error"))) return MYQC_OK;  // :49-50 (STOP)
+
+    // buildBasis (:58) -- writes basinfo / setinfo, which every later stage reads for norb
+    int nset_cap = 0, norb_cap = 0, maxN = 0, maxL = 0;
+    const std::string mybasis = join(dir, "mybasis");
+    rc = myqc_build_basis(mybasis.c_str(), options[2], nnuc, atoms.data(), &nset_cap, &norb_cap, nullptr, nullptr, nullptr, nullptr, &maxN, &maxL, nullptr);
+    if (rc) { std::printf(" %s\n", myqc_last_error()); touch_error(dir); return rc; }
+    const int OpS = 4, setl = 7;
+    std::vector<double> set(nset_cap), bas((size_t)nset_cap * OpS);
+    std::vector<int32_t> setinfo(2 + (size_t)nset_cap * setl), basinfo(2 + (size_t)5 * norb_cap);
+    rc = myqc_build_basis(mybasis.c_str(), options[2], nnuc, atoms.data(), &nset_cap, &norb_cap, set.data(), setinfo.data(), bas.data(), basinfo.data(), &maxN, &maxL, dir);
+    if (rc) { std::printf(" %s\n", myqc_last_error()); touch_error(dir); return rc; }
+    const int nset = setinfo[0], norb = basinfo[1];
+    long long npri = 0;
+    for (int i = 0; i < norb; ++i) npri += basinfo[1 + i * 5 + 4];
+    std::printf("\n Number of orbitals     %d\n Number of primatives   %lld\n\n", norb, npri);  // :70-75
+    const double temp = 2.0 * norb * norb * 8.0 / 1.0e6;  // :77-78
+    std::printf(" Allocating space for int1e (MB) %8.5f\n", temp);
+    if (fmem - temp < 0.0) {  // :79-82
+        std::printf(" int1e: max memory reached\n");
+        touch_error(dir);
+        return MYQC_ERR_NOMEM;
+    }
+    if (exists(join(dir, "Suv")) && exists(join(dir, "Huv"))) {  // :98-111
+        std::fclose(std::fopen(join(dir, "Sold").c_str(), "a"));
+        std::fclose(std::fopen(join(dir, "Hold").c_str(), "a"));
+        std::printf(" Reading overlap matrix from Suv\n Reading Fock matrix from Huv\n");
+    } else {
+        std::vector<double> ft(121 * 23), S((size_t)norb * norb), H((size_t)norb * norb);
+        rc = myqc_read_ftab(join(dir, "Ftab").c_str(), ft.data());
+        if (!rc) rc = myqc_int1e(nnuc, xyz.data(), atoms.data(), nset, setl, set.data(), setinfo.data(), OpS, bas.data(), basinfo.data(), ft.data(), S.data(), H.data());
+        if (!rc) rc = write_real_list(join(dir, "Suv"), S.data(), S.size());
+        if (!rc) rc = write_real_list(join(dir, "Huv"), H.data(), H.size());
+        if (rc) { std::printf(" int1e: %s\n", myqc_last_error()); touch_error(dir); return rc; }
+        std::printf(" Overlap written to Suv\n One electron integrals written to Huv\n");
+    }
+    write_fmem(dir, fmem);  // the ledger is debited and credited by the same amount (:78,126), setenv :127
     return MYQC_OK;
 }
 

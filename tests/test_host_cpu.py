@@ -15,7 +15,7 @@ from oracle import oracle as O
 
 
 def test_library_exports_every_declared_symbol():
-    hdr = open(os.path.join(ROOT, "include", "myqc_eri.h")).read() + open(os.path.join(ROOT, "include", "myqc_fock.h")).read()
+    hdr = open(os.path.join(ROOT, "include", "myqc_eri.h")).read() + open(os.path.join(ROOT, "include", "myqc_fock.h")).read() + open(os.path.join(ROOT, "include", "myqc_int1e.h")).read()
     declared = set(re.findall(r"\b(myqc_[a-z0-9_]+)\s*\(", hdr))
     L = Q.lib()
     missing = [n for n in declared if not hasattr(L, n)]
