@@ -22,7 +22,8 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmyqc_eri.so")
+# MYQC_LIB: experiments only (tools/build_variants.sh builds kernel variants next to the library)
+LIB_PATH = os.environ.get("MYQC_LIB") or os.path.join(_HERE, "csrc", "libmyqc_eri.so")
 
 MYQC_OK = 0
 ERR_NO_DEVICE, ERR_CUDA, ERR_UNSUPPORTED, ERR_BAD_ARG, ERR_IO, ERR_NOMEM = -1, -2, -3, -4, -5, -6
@@ -40,6 +41,8 @@ EXPORTS = [
     "myqc_fock_rhf", "myqc_fock_uhf", "myqc_fock_rhf_host", "myqc_fock_uhf_host",
     # include/myqc_int1e.h
     "myqc_int1e", "myqc_int1e_main",
+    # include/myqc_ao2mo.h
+    "myqc_ao2mo_transform", "myqc_ao2mo_transform_host", "myqc_pack_dense", "myqc_ao2mo_main", "myqc_ao2mo_flops",
 ]
 
 
@@ -105,10 +108,17 @@ def lib() -> ctypes.CDLL:
     L.myqc_fock_uhf_host.argtypes = [_dp, c_int, _dp, _dp, _dp, _dp]
     L.myqc_int1e.argtypes = [c_int, _dp, _ip, c_int, c_int, _dp, _ip, c_int, _dp, _ip, _dp, _dp, _dp]
     L.myqc_int1e_main.argtypes = [c_char_p]
+    L.myqc_ao2mo_transform.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                                       c_void_p, c_void_p]
+    L.myqc_ao2mo_transform_host.argtypes = [_dp, c_int, _dp, c_int, _dp, c_int, _dp, c_int, _dp, c_int, _dp]
+    L.myqc_pack_dense.argtypes = [_dp, c_int, _dp]
+    L.myqc_ao2mo_main.argtypes = [c_char_p]
+    L.myqc_ao2mo_flops.argtypes = [c_int] * 5
+    L.myqc_ao2mo_flops.restype = ctypes.c_double
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("myqc_last_error", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
-                        "myqc_eri_plan_destroy"):
+                        "myqc_eri_plan_destroy", "myqc_ao2mo_flops"):
             fn.restype = c_int
     _lib = L
     return L
@@ -491,3 +501,58 @@ def read_matrix_text(path: str, norb: int) -> np.ndarray:
     """READ(u,*) M(:,:) of a list-directed text file (Suv / Huv, scf.f90:140-144)."""
     toks = open(path).read().replace(",", " ").replace("D", "E").split()
     return np.array([float(t) for t in toks[:norb * norb]]).reshape((norb, norb), order="F")
+
+
+# ----------------------------------------------------------------------------------------------
+# AO -> MO transformation (include/myqc_ao2mo.h; ao2mo.f90)
+# ----------------------------------------------------------------------------------------------
+def _col_block(c: np.ndarray, norb: int) -> np.ndarray:
+    c = np.asfortranarray(c, dtype=np.float64)
+    assert c.ndim == 2 and c.shape[0] == norb, "coefficient blocks are norb x n_k (the reference's Cm(0:ntot-1, cols))"
+    return c
+
+
+def ao2mo_transform(packed: np.ndarray, norb: int, c1, c2, c3, c4) -> np.ndarray:
+    """O(p,q,r,s) = sum_uvld C1(u,p) C2(v,q) C3(l,r) C4(d,s) (uv|ld): idx1_trans..idx4_trans of
+    ao2mo.f90:1306-1439 composed, from the packed unique ERIs.  Returns O[p,q,r,s] (Fortran order)."""
+    packed = np.ascontiguousarray(packed, dtype=np.float64)
+    cs = [_col_block(c, norb) for c in (c1, c2, c3, c4)]
+    dims = tuple(c.shape[1] for c in cs)
+    out = np.zeros(int(np.prod(dims)))
+    _check(lib().myqc_ao2mo_transform_host(_d(packed), norb, _d(cs[0]), dims[0], _d(cs[1]), dims[1],
+                                           _d(cs[2]), dims[2], _d(cs[3]), dims[3], _d(out)))
+    return out.reshape(dims, order="F")
+
+
+def ao2mo_transform_device(d_packed: int, norb: int, d_c1: int, n1: int, d_c2: int, n2: int, d_c3: int, n3: int,
+                           d_c4: int, n4: int, d_out: int, stream: int = 0):
+    """Device-pointer form (stream ordered, no synchronisation)."""
+    _check(lib().myqc_ao2mo_transform(d_packed, norb, d_c1, n1, d_c2, n2, d_c3, n3, d_c4, n4, d_out, stream))
+
+
+def ao2mo_flops(norb: int, n1: int, n2: int, n3: int, n4: int) -> float:
+    return lib().myqc_ao2mo_flops(norb, n1, n2, n3, n4)
+
+
+def pack_dense_c(xx: np.ndarray) -> np.ndarray:
+    """myqc_pack_dense: the host helper the `ao2mo` program uses on the XX record it reads."""
+    n = xx.shape[0]
+    flat = np.ascontiguousarray(np.asarray(xx).reshape(-1, order="F"))
+    npair = n * (n + 1) // 2
+    out = np.zeros(npair * (npair + 1) // 2)
+    _check(lib().myqc_pack_dense(_d(flat), n, _d(out)))
+    return out
+
+
+def ao2mo_main(workdir: str) -> int:
+    """PROGRAM ao2mo (ao2mo.f90:22-98) in `workdir`; returns the library status (0 = ok)."""
+    return lib().myqc_ao2mo_main(workdir.encode())
+
+
+def write_matrix_text(path: str, mats):
+    """WRITE(u,*) M(:,:) for each matrix (the `Cui` / `eig` files scf.f90 leaves for ao2mo / mp2)."""
+    with open(path, "w") as f:
+        for m in mats:
+            v = np.asarray(m, dtype=np.float64).reshape(-1, order="F")
+            for k in range(0, len(v), 3):
+                f.write("".join("  %24.16E" % x for x in v[k:k + 3]) + "\n")

@@ -1,0 +1,638 @@
+// AO -> MO four-index transformation from the packed unique ERI array, on the device
+// (include/myqc_ao2mo.h).
+//
+// Reference: src/ao2mo/ao2mo.f90 -- idx1_trans..idx4_trans (:1306-1439) are four explicit O(n^5)
+// loop nests over the dense XX(n,n,n,n) array read from disk; slow_ao2mo_MP2_RHF (:465-602),
+// slow_ao2mo_MP2_UHF (:614-904) and slow_ao2mo_CIS_UHF (:919-1227) call them with different
+// coefficient column blocks.  All of them are
+//     O(p,q,r,s) = sum_{u,v,l,d} C1(u,p) C2(v,q) C3(l,r) C4(d,s) (uv|ld).
+//
+// Here (n = norb, NP = n(n+1)/2 pairs, X = the symmetric NP x NP matrix whose upper triangle is
+// the packed array):
+//   stage 1, per panel of BP packed rows P:
+//     unpack   Xsq[P][l][d] = X[P, pair(l,d)]                       (gather, both triangles)
+//     GEMM 1a  T[(P,l)][s]  = sum_d Xsq[(P,l)][d] C4(d,s)           M = BP n, K = n, N = n4
+//     GEMM 1b  H[P][s][r]   = sum_l T[P][l][s]    C3(l,r)           batched over P
+//   stage 2, per chunk of RSB columns rs = s n3 + r of H:
+//     unpack   Gsq[u][v][rs] = H[pair(u,v)][rs]                     (row gather, coalesced)
+//     GEMM 2a  V[u][rs][q]   = sum_v Gsq[u][v][rs] C2(v,q)          batched over u
+//     GEMM 2b  O[p][(rs,q)]  = sum_u C1(u,p) V[u][(rs,q)]           written straight into Om(p,q,r,s)
+// i.e. 2 NP n^2 n4 + 2 NP n n3 n4 + 2 n^2 n2 n3 n4 + 2 n n1 n2 n3 n4 flops instead of the reference's
+// 2 n^4 (n1 + ...) -- the pair symmetry of (uv| and |ld) halves both halves.
+//
+// The GEMM: 128 x 128 x 16 CTA tiles, 8 warps of 64 x 32, FP64 tensor pipe (mma.sync m8n8k4 f64 --
+// FP64 has no tcgen05 form), operands staged through padded shared memory (conflict-free fragment
+// reads), next tile prefetched into registers while the current one is multiplied.  A second,
+// plain-DFMA instantiation of the same tiling (MYQC_AO2MO_GEMM=simt) exists to cross-check the
+// fragment layout in the tests.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/myqc_ao2mo.h"
+#include "../../include/myqc_eri.h"
+
+namespace myqc {
+int fock_fail(int code, const std::string& msg);  // sets myqc_last_error (eri_api.cu)
+}
+
+namespace {
+
+#define CUA(x)                                                                                   \
+    do {                                                                                         \
+        cudaError_t e_ = (x);                                                                    \
+        if (e_ != cudaSuccess)                                                                   \
+            return myqc::fock_fail(MYQC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int BM = 128, BN = 128, BK = 16, GT = 256;
+constexpr int PA_K = BK + 4;   // pitch of A stored [m][k]   (20 = 4 mod 16: fragment reads conflict-free)
+constexpr int PA_M = BM + 4;   // pitch of A stored [k][m]   (132 = 4 mod 16)
+constexpr int PB = BN + 4;     // pitch of B stored [k][n]
+constexpr int A_ELEMS = (BM * PA_K > BK * PA_M) ? BM * PA_K : BK * PA_M;
+constexpr int B_ELEMS = BK * PB;
+constexpr size_t GEMM_SMEM = 2 * (size_t)(A_ELEMS + B_ELEMS) * sizeof(double);
+
+struct GemmArgs {
+    const double* A; int64_t a_sm, a_sk, a_batch;  // A(m,k) at m*a_sm + k*a_sk
+    const double* B; int64_t ldb, b_batch;         // B(k,n) at k*ldb + n
+    double* C; int64_t c_sm, c_sn, c_batch;        // C(m,n) at m*c_sm + n*c_sn
+    int M, N, K;
+};
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// C = A B.  A_KC: A is contiguous along k (loader walks k fastest, tile kept [m][k]); otherwise A is
+// contiguous along m (loader walks m fastest, tile kept [k][m]).  MMA: tensor pipe or plain DFMA.
+template <bool A_KC, bool MMA>
+__global__ void __launch_bounds__(GT) gemm_f64_kernel(const GemmArgs g) {
+    extern __shared__ __align__(16) double gsm[];
+    constexpr int STAGE = A_ELEMS + B_ELEMS;  // stage b: A tile at gsm + b*STAGE, B tile behind it
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const double* A = g.A + (int64_t)blockIdx.z * g.a_batch;
+    const double* B = g.B + (int64_t)blockIdx.z * g.b_batch;
+    double* C = g.C + (int64_t)blockIdx.z * g.c_batch;
+    const int M = g.M, N = g.N, K = g.K;
+
+    auto a_at = [](int m, int k) { return A_KC ? m * PA_K + k : k * PA_M + m; };
+
+    double ra[8], rb[8];
+    auto gload = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = tid + GT * i;
+            const int m = A_KC ? e / BK : e % BM;
+            const int k = A_KC ? e % BK : e / BM;
+            ra[i] = (m0 + m < M && k0 + k < K) ? __ldg(A + (int64_t)(m0 + m) * g.a_sm + (int64_t)(k0 + k) * g.a_sk) : 0.0;
+            const int kb = e / BN, nb = e % BN;
+            rb[i] = (k0 + kb < K && n0 + nb < N) ? __ldg(B + (int64_t)(k0 + kb) * g.ldb + (n0 + nb)) : 0.0;
+        }
+    };
+    auto sstore = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = tid + GT * i;
+            const int m = A_KC ? e / BK : e % BM;
+            const int k = A_KC ? e % BK : e / BM;
+            gsm[buf * STAGE + a_at(m, k)] = ra[i];
+            gsm[buf * STAGE + A_ELEMS + (e / BN) * PB + (e % BN)] = rb[i];
+        }
+    };
+
+    // MMA: warp tile 64 x 32 = 8 x 4 fragments of 8 x 8, two accumulators per lane and fragment.
+    // SIMT: thread tile 8 x 8, rows ty*8 + i, columns tx + 16 j.
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    const int wm = (warp & 1) * 64, wn = (warp >> 1) * 32;
+    const int gq = lane >> 2, tq = lane & 3;  // groupID, threadID_in_group of the PTX fragment layout
+    const int ty = tid >> 4, tx = tid & 15;
+
+    gload(0);
+    sstore(0);
+    __syncthreads();
+    const int nkt = (K + BK - 1) / BK;
+    for (int kt = 0; kt < nkt; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nkt) gload((kt + 1) * BK);
+        const double* a_s = gsm + buf * STAGE;
+        const double* b_s = a_s + A_ELEMS;
+        if constexpr (MMA) {
+#pragma unroll
+            for (int kk = 0; kk < BK; kk += 4) {
+                double af[8], bf[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) af[i] = a_s[a_at(wm + i * 8 + gq, kk + tq)];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = b_s[(kk + tq) * PB + wn + j * 8 + gq];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][2 * j], acc[i][2 * j + 1], af[i], bf[j]);
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < BK; ++kk) {
+                double av[8], bv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) av[i] = a_s[a_at(ty * 8 + i, kk)];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bv[j] = b_s[kk * PB + tx + 16 * j];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+            }
+        }
+        if (kt + 1 < nkt) sstore(buf ^ 1);
+        __syncthreads();
+    }
+
+    if constexpr (MMA) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + wm + i * 8 + gq;
+            if (m >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int n = n0 + wn + j * 8 + 2 * tq + h;
+                    if (n < N) C[(int64_t)m * g.c_sm + (int64_t)n * g.c_sn] = acc[i][2 * j + h];
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + ty * 8 + i;
+            if (m >= M) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int n = n0 + tx + 16 * j;
+                if (n < N) C[(int64_t)m * g.c_sm + (int64_t)n * g.c_sn] = acc[i][j];
+            }
+        }
+    }
+}
+
+bool use_simt() {
+    const char* e = std::getenv("MYQC_AO2MO_GEMM");
+    return e && e[0] == 's';
+}
+
+template <bool A_KC, bool MMA>
+int gemm_launch_t(const GemmArgs& g, int batch, cudaStream_t st) {
+    static bool prepared[64] = {};
+    int dev = 0;
+    CUA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !prepared[dev]) {
+        CUA(cudaFuncSetAttribute(gemm_f64_kernel<A_KC, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        prepared[dev] = true;
+    }
+    if (g.M <= 0 || g.N <= 0 || batch <= 0) return MYQC_OK;
+    // gridDim.y / .z are limited to 65535: split the batch, fold large M into x by swapping roles is
+    // not needed here (M/128 <= 65535 for every panel size this file chooses)
+    const int gx = (g.N + BN - 1) / BN, gy = (g.M + BM - 1) / BM;
+    if (gy > 65535) return myqc::fock_fail(MYQC_ERR_BAD_ARG, "ao2mo GEMM: too many row tiles");
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = std::min(65535, batch - b0);
+        GemmArgs a = g;
+        a.A += (int64_t)b0 * g.a_batch;
+        a.B += (int64_t)b0 * g.b_batch;
+        a.C += (int64_t)b0 * g.c_batch;
+        gemm_f64_kernel<A_KC, MMA><<<dim3(gx, gy, nb), GT, GEMM_SMEM, st>>>(a);
+    }
+    CUA(cudaGetLastError());
+    return MYQC_OK;
+}
+
+int gemm_launch(bool a_kc, const GemmArgs& g, int batch, cudaStream_t st) {
+    const bool simt = use_simt();
+    if (a_kc) return simt ? gemm_launch_t<true, false>(g, batch, st) : gemm_launch_t<true, true>(g, batch, st);
+    return simt ? gemm_launch_t<false, false>(g, batch, st) : gemm_launch_t<false, true>(g, batch, st);
+}
+
+// ---- data movement kernels ---------------------------------------------------------------------
+__device__ __forceinline__ int64_t tri_off(int64_t a, int64_t b, int64_t dim) {  // a <= b
+    return a * dim - ((a * (a - 1)) >> 1) + (b - a);
+}
+
+// Xsq[pp][l][d] = X[P0+pp, pair(l,d)]   grid (BP, n), threads over d
+__global__ void unpack_rows_kernel(const double* __restrict__ packed, int n, int64_t np, int64_t p0, double* __restrict__ xsq) {
+    const int64_t P = p0 + blockIdx.x;
+    const int l = blockIdx.y;
+    double* dst = xsq + ((int64_t)blockIdx.x * n + l) * n;
+    for (int d = threadIdx.x; d < n; d += blockDim.x) {
+        const int a = l < d ? l : d, b = l < d ? d : l;
+        const int64_t Pp = tri_off(a, b, n);
+        const int64_t lo = P < Pp ? P : Pp, hi = P < Pp ? Pp : P;
+        dst[d] = __ldg(packed + tri_off(lo, hi, np));
+    }
+}
+
+// Gsq[u][v][x] = H[pair(u,v)][rs0 + x], x < w   grid (n, n), threads over x
+__global__ void unpack_cols_kernel(const double* __restrict__ h, int n, int64_t nrs, int64_t rs0, int w, double* __restrict__ gsq) {
+    const int u = blockIdx.x, v = blockIdx.y;
+    const int a = u < v ? u : v, b = u < v ? v : u;
+    const double* src = h + tri_off(a, b, n) * nrs + rs0;
+    double* dst = gsq + ((int64_t)u * n + v) * w;
+    for (int x = threadIdx.x; x < w; x += blockDim.x) dst[x] = __ldg(src + x);
+}
+
+// Cr[u][p] = C(u,p)  (column-major block with leading dimension n -> row-major n x nk)
+__global__ void coef_rowmajor_kernel(const double* __restrict__ c, int n, int nk, double* __restrict__ cr) {
+    const int64_t total = (int64_t)n * nk;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int u = (int)(e / nk), p = (int)(e % nk);
+        cr[e] = c[u + (int64_t)n * p];
+    }
+}
+
+int64_t env_i64(const char* name, int64_t dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoll(e) : dflt;
+}
+
+int transform_device(const double* d_packed, int norb, const double* d_c1, int n1, const double* d_c2, int n2,
+                     const double* d_c3, int n3, const double* d_c4, int n4, double* d_out, cudaStream_t st) {
+    if (!d_packed || !d_c1 || !d_c2 || !d_c3 || !d_c4 || !d_out) return myqc::fock_fail(MYQC_ERR_BAD_ARG, "ao2mo: null pointer");
+    if (norb < 1 || n1 < 1 || n2 < 1 || n3 < 1 || n4 < 1 || n1 > norb || n2 > norb || n3 > norb || n4 > norb)
+        return myqc::fock_fail(MYQC_ERR_BAD_ARG, "ao2mo: block sizes must be in 1..norb");
+    const int64_t n = norb, np = n * (n + 1) / 2, nrs = (int64_t)n3 * n4;
+    // panel sizes: scratch of about MYQC_AO2MO_SCRATCH_MB (default 1536 MB) per unpacked panel
+    const int64_t budget = env_i64("MYQC_AO2MO_SCRATCH_MB", 1536) * 1000000 / 8;  // doubles
+    int64_t bp = std::max<int64_t>(1, std::min<int64_t>(np, budget / (n * n)));
+    bp = std::min<int64_t>(bp, (int64_t)65535 * BM / n);  // row tiles of GEMM 1a
+    int64_t rsb = std::max<int64_t>(1, std::min<int64_t>(nrs, budget / (n * n)));
+    const int64_t sz_panel = std::max(bp, rsb) * n * n;               // Xsq / Gsq
+    const int64_t sz_t = std::max(bp * n * n4, n * rsb * n2);         // T / V
+    const int64_t sz_h = np * nrs;
+    const int64_t sz_c = n * ((int64_t)n2 + n3 + n4);
+    double* buf = nullptr;
+    const size_t bytes = sizeof(double) * (size_t)(sz_panel + sz_t + sz_h + sz_c);
+    cudaError_t e = cudaMallocAsync((void**)&buf, bytes, st);
+    if (e != cudaSuccess)
+        return myqc::fock_fail(MYQC_ERR_NOMEM, "ao2mo scratch (" + std::to_string(bytes >> 20) + " MiB): " + cudaGetErrorString(e));
+    double* panel = buf;
+    double* tbuf = panel + sz_panel;
+    double* h = tbuf + sz_t;
+    double* c2r = h + sz_h;
+    double* c3r = c2r + n * n2;
+    double* c4r = c3r + n * n3;
+    coef_rowmajor_kernel<<<64, 256, 0, st>>>(d_c2, norb, n2, c2r);
+    coef_rowmajor_kernel<<<64, 256, 0, st>>>(d_c3, norb, n3, c3r);
+    coef_rowmajor_kernel<<<64, 256, 0, st>>>(d_c4, norb, n4, c4r);
+    int rc = MYQC_OK;
+
+    // ---- stage 1: ket half transformation, H[P][s][r] -------------------------------------------
+    for (int64_t p0 = 0; p0 < np && !rc; p0 += bp) {
+        const int64_t cur = std::min(bp, np - p0);
+        unpack_rows_kernel<<<dim3((unsigned)cur, (unsigned)n), 128, 0, st>>>(d_packed, norb, np, p0, panel);
+        GemmArgs a{};
+        a.A = panel; a.a_sm = n; a.a_sk = 1; a.a_batch = 0;
+        a.B = c4r; a.ldb = n4; a.b_batch = 0;
+        a.C = tbuf; a.c_sm = n4; a.c_sn = 1; a.c_batch = 0;
+        a.M = (int)(cur * n); a.N = n4; a.K = norb;
+        rc = gemm_launch(true, a, 1, st);
+        if (rc) break;
+        GemmArgs b{};
+        b.A = tbuf; b.a_sm = 1; b.a_sk = n4; b.a_batch = n * n4;
+        b.B = c3r; b.ldb = n3; b.b_batch = 0;
+        b.C = h + p0 * nrs; b.c_sm = n3; b.c_sn = 1; b.c_batch = nrs;
+        b.M = n4; b.N = n3; b.K = norb;
+        rc = gemm_launch(false, b, (int)cur, st);
+    }
+    // ---- stage 2: bra half transformation, written into Om(p,q,r,s) -----------------------------
+    for (int64_t rs0 = 0; rs0 < nrs && !rc; rs0 += rsb) {
+        const int64_t w = std::min(rsb, nrs - rs0);
+        unpack_cols_kernel<<<dim3((unsigned)n, (unsigned)n), 128, 0, st>>>(h, norb, nrs, rs0, (int)w, panel);
+        GemmArgs a{};
+        a.A = panel; a.a_sm = 1; a.a_sk = w; a.a_batch = n * w;
+        a.B = c2r; a.ldb = n2; a.b_batch = 0;
+        a.C = tbuf; a.c_sm = n2; a.c_sn = 1; a.c_batch = w * n2;
+        a.M = (int)w; a.N = n2; a.K = norb;
+        rc = gemm_launch(false, a, norb, st);
+        if (rc) break;
+        GemmArgs b{};
+        b.A = d_c1; b.a_sm = n; b.a_sk = 1; b.a_batch = 0;
+        b.B = tbuf; b.ldb = w * n2; b.b_batch = 0;
+        b.C = d_out + rs0 * n2 * n1; b.c_sm = 1; b.c_sn = n1; b.c_batch = 0;
+        b.M = n1; b.N = (int)(w * n2); b.K = norb;
+        rc = gemm_launch(true, b, 1, st);
+    }
+    cudaError_t le = cudaGetLastError();
+    cudaFreeAsync(buf, st);
+    if (rc) return rc;
+    if (le != cudaSuccess) return myqc::fock_fail(MYQC_ERR_CUDA, std::string("ao2mo launch: ") + cudaGetErrorString(le));
+    return MYQC_OK;
+}
+
+// ---- file layer of PROGRAM ao2mo ---------------------------------------------------------------
+std::string joinp(const char* dir, const char* name) {
+    std::string d = (dir && *dir) ? dir : ".";
+    if (d.back() != '/') d += '/';
+    return d + name;
+}
+
+bool read_reals(const std::string& path, std::vector<double>& v) {  // list-directed READ(u,*)
+    std::ifstream f(path);
+    if (!f) return false;
+    std::string line;
+    while (std::getline(f, line)) {
+        for (char& c : line)
+            if (c == ',') c = ' ';
+        std::istringstream ss(line);
+        std::string t;
+        while (ss >> t) {
+            int rep = 1;
+            const size_t star = t.find('*');
+            if (star != std::string::npos && star > 0) {
+                rep = std::atoi(t.substr(0, star).c_str());
+                t = t.substr(star + 1);
+            }
+            for (char& c : t)
+                if (c == 'D' || c == 'd') c = 'E';
+            char* end = nullptr;
+            const double x = std::strtod(t.c_str(), &end);
+            if (end == t.c_str()) return true;  // first non-number ends the data (comment lines)
+            for (int k = 0; k < rep; ++k) v.push_back(x);
+        }
+    }
+    return true;
+}
+
+bool write_record(FILE* f, const double* v, size_t n) {  // WRITE(u) v(0:n-1), unformatted sequential
+    const int32_t len = (int32_t)(n * sizeof(double));
+    return std::fwrite(&len, 4, 1, f) == 1 && (n == 0 || std::fwrite(v, sizeof(double), n, f) == n) &&
+           std::fwrite(&len, 4, 1, f) == 1;
+}
+
+void touch_err(const char* dir) {
+    FILE* f = std::fopen(joinp(dir, "error").c_str(), "a");
+    if (f) std::fclose(f);
+}
+
+struct Job {
+    const char* dir;
+    int n;
+    double* d_packed;
+    double* d_ca;  // device copies of CmA / CmB (column-major n x n)
+    double* d_cb;
+    double* d_out;
+    std::vector<double> host;
+};
+
+// Om(0:n1-1,0:n2-1,0:n3-1,0:n4-1) of the column blocks [o_k, o_k + n_k) of the given spin matrices
+int run_transform(Job& j, const double* c1, int o1, int n1, const double* c2, int o2, int n2, const double* c3, int o3, int n3,
+                  const double* c4, int o4, int n4) {
+    const size_t total = (size_t)n1 * n2 * n3 * n4;
+    j.host.assign(total, 0.0);
+    if (total == 0) return MYQC_OK;
+    const int64_t n = j.n;
+    int rc = transform_device(j.d_packed, j.n, c1 + n * o1, n1, c2 + n * o2, n2, c3 + n * o3, n3, c4 + n * o4, n4, j.d_out, nullptr);
+    if (rc) return rc;
+    CUA(cudaMemcpy(j.host.data(), j.d_out, total * sizeof(double), cudaMemcpyDeviceToHost));
+    return MYQC_OK;
+}
+
+// WRITE(u) Om(i,:,j,:) for the listed (i,j): ao2mo.f90:567-581,719-725,805-811,891-897
+int write_ijab(Job& jb, const char* name, int n1, int n2, int n3, int n4, bool upper_only) {
+    FILE* f = std::fopen(joinp(jb.dir, name).c_str(), "wb");
+    if (!f) return myqc::fock_fail(MYQC_ERR_IO, std::string("cannot write ") + name);
+    std::vector<double> rec((size_t)n2 * n4);
+    bool ok = true;
+    for (int i = 0; i < (upper_only ? n1 - 1 : n1) && ok; ++i)
+        for (int j = (upper_only ? i + 1 : 0); j < n3 && ok; ++j) {
+            for (int b = 0; b < n4; ++b)
+                for (int a = 0; a < n2; ++a)
+                    rec[a + (size_t)n2 * b] = jb.host[i + (size_t)n1 * (a + (size_t)n2 * (j + (size_t)n3 * b))];
+            ok = write_record(f, rec.data(), rec.size());
+        }
+    std::fclose(f);
+    return ok ? MYQC_OK : myqc::fock_fail(MYQC_ERR_IO, std::string("short write to ") + name);
+}
+
+// CIS records (ao2mo.f90:975-989,1044-1058,...): DO j, DO b: vec(i*nv + a) = Om(a,i,j,b) [ajib]
+// or Om(a,b,j,i) [ajbi]; nrec_j x nrec_b records of no*nv values.
+int write_cis(Job& jb, const char* name, bool ajbi, int nv, int no, int nj, int nb) {
+    FILE* f = std::fopen(joinp(jb.dir, name).c_str(), "wb");
+    if (!f) return myqc::fock_fail(MYQC_ERR_IO, std::string("cannot write ") + name);
+    std::vector<double> vec((size_t)no * nv);
+    bool ok = true;
+    for (int j = 0; j < nj && ok; ++j)
+        for (int b = 0; b < nb && ok; ++b) {
+            size_t idx = 0;
+            for (int i = 0; i < no; ++i)
+                for (int a = 0; a < nv; ++a) {
+                    // ajib: Om(0:nv-1,0:no-1,0:nj-1,0:nb-1)(a,i,j,b);  ajbi: Om(0:nv-1,0:nb-1,0:nj-1,0:no-1)(a,b,j,i)
+                    vec[idx++] = ajbi ? jb.host[a + (size_t)nv * (b + (size_t)nb * (j + (size_t)nj * i))]
+                                      : jb.host[a + (size_t)nv * (i + (size_t)no * (j + (size_t)nj * b))];
+                }
+            ok = write_record(f, vec.data(), vec.size());
+        }
+    std::fclose(f);
+    return ok ? MYQC_OK : myqc::fock_fail(MYQC_ERR_IO, std::string("short write to ") + name);
+}
+
+}  // namespace
+
+extern "C" {
+
+double myqc_ao2mo_flops(int norb, int n1, int n2, int n3, int n4) {
+    const double n = norb, np = n * (n + 1) / 2;
+    return 2.0 * np * n * n * n4 + 2.0 * np * n * n3 * n4 + 2.0 * n * n * n2 * n3 * n4 + 2.0 * n * n1 * n2 * n3 * n4;
+}
+
+int myqc_ao2mo_transform(const double* d_packed, int norb, const double* d_c1, int n1, const double* d_c2, int n2,
+                         const double* d_c3, int n3, const double* d_c4, int n4, double* d_out, void* stream) {
+    if (myqc_device_count() == 0) return myqc::fock_fail(MYQC_ERR_NO_DEVICE, "no CUDA device: ao2mo has no CPU fallback");
+    return transform_device(d_packed, norb, d_c1, n1, d_c2, n2, d_c3, n3, d_c4, n4, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int myqc_ao2mo_transform_host(const double* packed, int norb, const double* c1, int n1, const double* c2, int n2,
+                              const double* c3, int n3, const double* c4, int n4, double* out) {
+    if (!packed || !c1 || !c2 || !c3 || !c4 || !out || norb < 1) return myqc::fock_fail(MYQC_ERR_BAD_ARG, "ao2mo: null pointer or bad norb");
+    if (n1 < 1 || n2 < 1 || n3 < 1 || n4 < 1 || n1 > norb || n2 > norb || n3 > norb || n4 > norb)
+        return myqc::fock_fail(MYQC_ERR_BAD_ARG, "ao2mo: block sizes must be in 1..norb");
+    if (myqc_device_count() == 0) return myqc::fock_fail(MYQC_ERR_NO_DEVICE, "no CUDA device: ao2mo has no CPU fallback");
+    const int64_t n = norb, np = n * (n + 1) / 2, total = np * (np + 1) / 2;
+    const size_t nout = (size_t)n1 * n2 * n3 * n4;
+    double *d_p = nullptr, *d_c = nullptr, *d_o = nullptr;
+    CUA(cudaMalloc((void**)&d_p, sizeof(double) * total));
+    cudaError_t e = cudaMalloc((void**)&d_c, sizeof(double) * n * (n1 + n2 + n3 + n4));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_o, sizeof(double) * nout);
+    if (e != cudaSuccess) { cudaFree(d_p); cudaFree(d_c); return myqc::fock_fail(MYQC_ERR_NOMEM, cudaGetErrorString(e)); }
+    double* dc1 = d_c; double* dc2 = dc1 + n * n1; double* dc3 = dc2 + n * n2; double* dc4 = dc3 + n * n3;
+    e = cudaMemcpy(d_p, packed, sizeof(double) * total, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dc1, c1, sizeof(double) * n * n1, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dc2, c2, sizeof(double) * n * n2, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dc3, c3, sizeof(double) * n * n3, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dc4, c4, sizeof(double) * n * n4, cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? MYQC_OK : myqc::fock_fail(MYQC_ERR_CUDA, cudaGetErrorString(e));
+    if (!rc) rc = transform_device(d_p, norb, dc1, n1, dc2, n2, dc3, n3, dc4, n4, d_o, nullptr);
+    if (!rc) {
+        e = cudaMemcpy(out, d_o, sizeof(double) * nout, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = myqc::fock_fail(MYQC_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFree(d_p); cudaFree(d_c); cudaFree(d_o);
+    return rc;
+}
+
+int myqc_pack_dense(const double* xx, int norb, double* packed) {
+    if (!xx || !packed || norb < 1) return myqc::fock_fail(MYQC_ERR_BAD_ARG, "pack_dense: bad arguments");
+    const int64_t n = norb, np = n * (n + 1) / 2;
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t j = i; j < n; ++j) {
+            const int64_t P = i * n - i * (i - 1) / 2 + (j - i);
+            double* row = packed + (P * np - P * (P - 1) / 2) - P;  // row[P'] for P' >= P
+            for (int64_t k = 0; k < n; ++k)
+                for (int64_t l = k; l < n; ++l) {
+                    const int64_t Pp = k * n - k * (k - 1) / 2 + (l - k);
+                    if (Pp >= P) row[Pp] = xx[i + n * (j + n * (k + n * l))];
+                }
+        }
+    return MYQC_OK;
+}
+
+int myqc_ao2mo_main(const char* dir) {
+    // banner: ao2mo.f90:39-45
+    std::printf("\n                 STARTING AO TRANSFORM\n ------------------------------------------------------------\n"
+                " ao2mo called\n\n Starting AO to MO integral transform\n");
+    auto bail = [&](int rc, const char* what) {
+        std::printf(" ao2mo: %s: %s\n", what, myqc_last_error());
+        touch_err(dir);
+        return rc;
+    };
+    int nnuc = 0, nA = 0, nB = 0, nopt = 0;
+    double fmem = 0;
+    int rc = myqc_read_env(dir, 0, 0, &nnuc, &nA, &nB, nullptr, nullptr, &fmem, &nopt, nullptr);
+    if (rc) return bail(rc, "getenv");
+    std::vector<int32_t> atoms(nnuc), options(nopt > 17 ? nopt : 17, 0);
+    std::vector<double> xyz((size_t)3 * nnuc);
+    rc = myqc_read_env(dir, nnuc, (int)options.size(), &nnuc, &nA, &nB, atoms.data(), xyz.data(), &fmem, &nopt, options.data());
+    if (rc) return bail(rc, "getenv");
+    {
+        FILE* f = std::fopen(joinp(dir, "error").c_str(), "rb");  // INQUIRE(file='error'); IF (flag) STOP  (:49-50)
+        if (f) { std::fclose(f); return MYQC_OK; }
+    }
+    std::vector<double> bi;
+    if (!read_reals(joinp(dir, "basinfo"), bi) || bi.size() < 2) {
+        myqc::fock_fail(MYQC_ERR_IO, "cannot read basinfo");
+        return bail(MYQC_ERR_IO, "basinfo");
+    }
+    const int n = (int)bi[1];  // ntot = line(1), :53-55
+    const int noccA = nA, noccB = nB, nvrtA = n - nA, nvrtB = n - nB;
+    const bool mp2 = options[1] == 1, uhf = options[3] == 1, rhf = options[3] == 0;
+    const bool cis = options[13] == 1 && options[1] == 0;
+    // the reference's dispatch and its messages (:62-92)
+    if (mp2 && !(rhf || uhf)) {
+        std::printf(" Sorry, that reference not coded yet\n"); touch_err(dir); return MYQC_ERR_UNSUPPORTED;
+    }
+    if (!mp2 && cis && !uhf) {
+        std::printf(" Sorry, only UHF CIS is coded\n"); touch_err(dir); return MYQC_ERR_UNSUPPORTED;
+    }
+    if (!mp2 && !cis) {
+        std::printf(" Sorry, that transform type has not been coded yet\n"); touch_err(dir); return MYQC_ERR_UNSUPPORTED;
+    }
+    if (myqc_device_count() == 0) {
+        myqc::fock_fail(MYQC_ERR_NO_DEVICE, "no CUDA device: ao2mo has no CPU fallback");
+        return bail(MYQC_ERR_NO_DEVICE, "device");
+    }
+    if (noccA < 0 || noccB < 0 || nvrtA < 0 || nvrtB < 0 || n < 1) {
+        myqc::fock_fail(MYQC_ERR_BAD_ARG, "inconsistent electron / orbital counts");
+        return bail(MYQC_ERR_BAD_ARG, "envdat");
+    }
+
+    const int64_t nn = (int64_t)n * n, np = (int64_t)n * (n + 1) / 2, total = np * (np + 1) / 2;
+    std::vector<double> cui;
+    if (!read_reals(joinp(dir, "Cui"), cui) || (int64_t)cui.size() < (rhf && mp2 ? nn : 2 * nn)) {
+        myqc::fock_fail(MYQC_ERR_IO, "Cui does not hold the MO coefficients");
+        return bail(MYQC_ERR_IO, "Cui");
+    }
+    Job jb{};
+    jb.dir = dir; jb.n = n;
+    {
+        std::vector<double> xx((size_t)(nn * nn)), packed((size_t)total);
+        rc = myqc_read_xx(joinp(dir, "XX").c_str(), xx.data(), n);  // READ(100) Km(:,:,:,:)
+        if (rc) return bail(rc, "XX");
+        myqc_pack_dense(xx.data(), n, packed.data());
+        cudaError_t e = cudaMalloc((void**)&jb.d_packed, sizeof(double) * total);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&jb.d_ca, sizeof(double) * 2 * nn);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&jb.d_out, sizeof(double) * (size_t)(nn * nn));
+        if (e == cudaSuccess) e = cudaMemcpy(jb.d_packed, packed.data(), sizeof(double) * total, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(jb.d_ca, cui.data(), sizeof(double) * nn, cudaMemcpyHostToDevice);
+        jb.d_cb = jb.d_ca + nn;
+        if (e == cudaSuccess)
+            e = cudaMemcpy(jb.d_cb, cui.data() + ((int64_t)cui.size() >= 2 * nn ? nn : 0), sizeof(double) * nn, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            myqc::fock_fail(MYQC_ERR_CUDA, cudaGetErrorString(e));
+            cudaFree(jb.d_packed); cudaFree(jb.d_ca); cudaFree(jb.d_out);
+            return bail(MYQC_ERR_CUDA, "device setup");
+        }
+    }
+    const double *CA = jb.d_ca, *CB = jb.d_cb;
+    if (mp2 && rhf) {  // slow_ao2mo_MP2_RHF, :465-602
+        std::printf("\n Spin Case AB\n Transforming (uv|ld) -> <ij|ab>\n");
+        rc = run_transform(jb, CA, 0, noccA, CA, noccA, nvrtA, CA, 0, noccA, CA, noccA, nvrtA);
+        if (!rc) { std::printf(" Writing to ijab_AA\n"); rc = write_ijab(jb, "ijab_AA", noccA, nvrtA, noccA, nvrtA, true); }
+        if (!rc) { std::printf(" Writing to ijab_AB\n"); rc = write_ijab(jb, "ijab_AB", noccA, nvrtA, noccA, nvrtA, false); }
+    } else if (mp2) {  // slow_ao2mo_MP2_UHF, :614-904
+        std::printf(" Spin Case AA\n");
+        rc = run_transform(jb, CA, 0, noccA, CA, noccA, nvrtA, CA, 0, noccA, CA, noccA, nvrtA);
+        if (!rc) { std::printf(" Writing to ijab_AA\n"); rc = write_ijab(jb, "ijab_AA", noccA, nvrtA, noccA, nvrtA, true); }
+        if (!rc) {
+            std::printf("\n Spin Case BB\n");
+            rc = run_transform(jb, CB, 0, noccB, CB, noccB, nvrtB, CB, 0, noccB, CB, noccB, nvrtB);
+        }
+        if (!rc) { std::printf(" Writing to ijab_BB\n"); rc = write_ijab(jb, "ijab_BB", noccB, nvrtB, noccB, nvrtB, true); }
+        if (!rc) {
+            std::printf("\n Spin Case AB\n");
+            rc = run_transform(jb, CA, 0, noccA, CA, noccA, nvrtA, CB, 0, noccB, CB, noccB, nvrtB);
+        }
+        if (!rc) { std::printf(" Writing to ijab_AB\n"); rc = write_ijab(jb, "ijab_AB", noccA, nvrtA, noccB, nvrtB, false); }
+    } else {  // slow_ao2mo_CIS_UHF, :919-1227
+        std::printf(" Spin Case AA\n Transforming (uv|ld) -> <aj|ib>\n");
+        rc = run_transform(jb, CA, noccA, nvrtA, CA, 0, noccA, CA, 0, noccA, CA, noccA, nvrtA);
+        if (!rc) { std::printf(" Writing to ajib_AA\n"); rc = write_cis(jb, "ajib_AA", false, nvrtA, noccA, noccA, nvrtA); }
+        if (!rc) {
+            std::printf(" Transforming (uv|ld) -> <aj|bi>\n");
+            rc = run_transform(jb, CA, noccA, nvrtA, CA, noccA, nvrtA, CA, 0, noccA, CA, 0, noccA);
+        }
+        if (!rc) { std::printf(" Writing to ajbi_AA\n"); rc = write_cis(jb, "ajbi_AA", true, nvrtA, noccA, noccA, nvrtA); }
+        if (!rc) {
+            std::printf(" Spin Case AB\n Transforming (uv|ld) -> <aj|ib>\n");
+            rc = run_transform(jb, CA, noccA, nvrtA, CA, 0, noccA, CB, 0, noccB, CB, noccB, nvrtB);
+        }
+        if (!rc) { std::printf(" Writing to ajib_AB\n"); rc = write_cis(jb, "ajib_AB", false, nvrtA, noccA, noccB, nvrtB); }
+        if (!rc) {
+            std::printf(" Spin case BB\n Transforming (uv|ld) -> <aj|ib>\n");
+            rc = run_transform(jb, CB, noccB, nvrtB, CB, 0, noccB, CB, 0, noccB, CB, noccB, nvrtB);
+        }
+        if (!rc) { std::printf(" Writing to ajib_BB\n"); rc = write_cis(jb, "ajib_BB", false, nvrtB, noccB, noccB, nvrtB); }
+        if (!rc) {
+            std::printf(" Transforming (uv|ld) -> <aj|bi>\n");
+            rc = run_transform(jb, CB, noccB, nvrtB, CB, noccB, nvrtB, CB, 0, noccB, CB, 0, noccB);
+        }
+        if (!rc) { std::printf(" Writing to ajbi_BB\n"); rc = write_cis(jb, "ajbi_BB", true, nvrtB, noccB, noccB, nvrtB); }
+    }
+    cudaFree(jb.d_packed); cudaFree(jb.d_ca); cudaFree(jb.d_out);
+    if (rc) return bail(rc, "transform");
+    return MYQC_OK;
+}
+
+}  // extern "C"

@@ -47,6 +47,23 @@ namespace {
 
 constexpr double kScreen = 1.0e-14;  // int2e.f90:257
 
+// Store of one integral into the zero-filled packed array.  -DMYQC_STORE_OP=1/2/3 builds the cache-hint
+// variants tools/build_variants.sh measures (st.global.cs / .cg / .wt); the default is a plain store.
+#ifndef MYQC_STORE_OP
+#define MYQC_STORE_OP 0
+#endif
+__device__ __forceinline__ void store_eri(double* p, double v) {
+#if MYQC_STORE_OP == 1
+    __stcs(p, v);
+#elif MYQC_STORE_OP == 2
+    __stcg(p, v);
+#elif MYQC_STORE_OP == 3
+    __stwt(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
 // TMA bulk copy + mbarrier helpers (sm_90+ PTX; SASS: UBLKCP / SYNCS)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -391,7 +408,7 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
                             const int64_t lo = P1[f] < P2[fp] ? P1[f] : P2[fp];
                             const int64_t hi = P1[f] < P2[fp] ? P2[fp] : P1[f];
                             const int64_t idx = lo * np - ((lo * (lo - 1)) >> 1) + (hi - lo) - a.out_offset;
-                            a.out[idx] = OUT_SMEM ? s_out[(f * NFT + fp) * NTHREADS + tid] : out_r[f * NFT + fp];
+                            store_eri(a.out + idx, OUT_SMEM ? s_out[(f * NFT + fp) * NTHREADS + tid] : out_r[f * NFT + fp]);
                         }
                     }
                 }

@@ -45,6 +45,16 @@ def _opt_value(key: str, val: str):
         return 10, int(val)
     if key == "UNITS=":
         return 11, 1 if v.startswith("B") else 0
+    if key == "AO2MO=":  # getao2mo, parser.f90:359-371: every value selects the slow transform
+        return 12, 1
+    if key == "EXCITE=":  # getexcite, parser.f90:375-386 (case-sensitive)
+        return 13, 1 if val in ("CIS", "1") else 0
+    if key == "ROOT_ALG=":  # getroot_alg, parser.f90:390-399
+        return 14, 0
+    if key == "E_NUM=":  # gete_num, parser.f90:403-414
+        return 15, 1 if int(val) < 0 else int(val)
+    if key == "PROP=":  # get_prop, parser.f90:418-431
+        return 16, {"FIRST": 1, "1": 1, "SECOND": 2, "2": 2}.get(val, 0)
     return None
 
 

@@ -351,9 +351,9 @@ def _eigh(F, S):
     return eigh(F, S)  # LAPACK DSYGV itype=1, as scf.f90:851
 
 
-def scf_rhf(S, H, xx, nelec, enr, tol=1e-11, maxit=500):
+def scf_rhf(S, H, xx, nelec, enr, tol=1e-11, maxit=500, orbitals=False):
     """scf.f90 RHF:61-216, RHFiter:720-904, dens.f90:115-124, RHFI2G.f90:80-90.
-    Returns (E_total, eps, iterations)."""
+    Returns (E_total, eps, iterations) [+ (C,) with orbitals=True: the `Cui` / `eig` files]."""
     nocc = nelec // 2
     eps, C = _eigh(H, S)  # initRHF: core guess
     D = 2.0 * C[:, :nocc] @ C[:, :nocc].T
@@ -378,11 +378,13 @@ def scf_rhf(S, H, xx, nelec, enr, tol=1e-11, maxit=500):
     K2 = np.einsum("kl,iljk->ij", D, xx)
     F = H + J - 0.25 * K - 0.25 * K2
     e_tot = 0.5 * np.sum(D * (F + H)) + enr
-    eps, _ = _eigh(F, S)
+    eps, Cf = _eigh(F, S)
+    if orbitals:
+        return float(e_tot), eps, it + 1, Cf
     return float(e_tot), eps, it + 1
 
 
-def scf_uhf(S, H, xx, nA, nB, enr, tol=1e-9, maxit=2000):
+def scf_uhf(S, H, xx, nA, nB, enr, tol=1e-9, maxit=2000, orbitals=False):
     """scf.f90 UHF:221-395, UHFiter:909-1117, dens.f90:213-228, UHFI2G.f90:80-93."""
     _, C = _eigh(H, S)
     Ca, Cb = C.copy(), C.copy()
@@ -408,8 +410,10 @@ def scf_uhf(S, H, xx, nA, nB, enr, tol=1e-9, maxit=2000):
     Fa = H + J - np.einsum("kl,ikjl->ij", Da, xx)
     Fb = H + J - np.einsum("kl,ikjl->ij", Db, xx)
     e_tot = 0.5 * (np.sum(Da * (Fa + H)) + np.sum(Db * (Fb + H))) + enr
-    ea, _ = _eigh(Fa, S)
-    eb, _ = _eigh(Fb, S)
+    ea, Caf = _eigh(Fa, S)
+    eb, Cbf = _eigh(Fb, S)
+    if orbitals:
+        return float(e_tot), ea, eb, it + 1, Caf, Cbf
     return float(e_tot), ea, eb, it + 1
 
 
@@ -422,3 +426,115 @@ def electrons(mol: Molecule):
     nB = (nelc - unpr) // 2
     nA = nB + unpr
     return nA, nB
+
+
+# ----------------------------------------------------------------------------------------------
+# ao2mo (src/ao2mo/ao2mo.f90) and the MP2 energies that consume its files (src/mp2/mp2.f90):
+# numpy restatement used to check the device transformation (tests only)
+# ----------------------------------------------------------------------------------------------
+def ao2mo_idx_trans(xx, c1, c2, c3, c4):
+    """idx1_trans .. idx4_trans (ao2mo.f90:1306-1439) in the reference's order:
+    B(p,q,r,s) = sum_t A(t,q,r,s) x(t,p); then index 2, 3, 4."""
+    L = np.einsum("tqrs,tp->pqrs", xx, c1)   # idx1_trans :1306-1328
+    M = np.einsum("ptrs,tq->pqrs", L, c2)    # idx2_trans :1343-1365
+    N = np.einsum("pqts,tr->pqrs", M, c3)    # idx3_trans :1380-1402
+    return np.einsum("pqrt,ts->pqrs", N, c4)  # idx4_trans :1417-1439
+
+
+def ao2mo_files(kind, xx, CA, CB, nA, nB):
+    """The unformatted records the reference's `ao2mo` writes, as {file name: [records]}.
+    kind = "mp2_rhf" (ao2mo.f90:465-602), "mp2_uhf" (:614-904), "cis_uhf" (:919-1227)."""
+    n = xx.shape[0]
+    oA, vA, oB, vB = CA[:, :nA], CA[:, nA:], CB[:, :nB], CB[:, nB:]
+    out = {}
+
+    def ijab(Om, upper):
+        n1, _, n3, _ = Om.shape
+        if upper:  # DO i=0,nocc-2; DO j=i+1,nocc-1; WRITE Om(i,:,j,:)
+            return [Om[i, :, j, :].reshape(-1, order="F") for i in range(n1 - 1) for j in range(i + 1, n3)]
+        return [Om[i, :, j, :].reshape(-1, order="F") for i in range(n1) for j in range(n3)]
+
+    if kind == "mp2_rhf":
+        Om = ao2mo_idx_trans(xx, oA, vA, oA, vA)
+        out["ijab_AA"] = ijab(Om, True)
+        out["ijab_AB"] = ijab(Om, False)
+    elif kind == "mp2_uhf":
+        out["ijab_AA"] = ijab(ao2mo_idx_trans(xx, oA, vA, oA, vA), True)
+        out["ijab_BB"] = ijab(ao2mo_idx_trans(xx, oB, vB, oB, vB), True)
+        out["ijab_AB"] = ijab(ao2mo_idx_trans(xx, oA, vA, oB, vB), False)
+    elif kind == "cis_uhf":
+        def ajib(Om):  # DO j; DO b; vec(idx(i,a)) = Om(a,i,j,b), idx runs a fastest
+            nv, no, nj, nb = Om.shape
+            return [np.array([Om[a, i, j, b] for i in range(no) for a in range(nv)]) for j in range(nj) for b in range(nb)]
+
+        def ajbi(Om):  # vec(idx(i,a)) = Om(a,b,j,i)
+            nv, nb, nj, no = Om.shape
+            return [np.array([Om[a, b, j, i] for i in range(no) for a in range(nv)]) for j in range(nj) for b in range(nb)]
+
+        out["ajib_AA"] = ajib(ao2mo_idx_trans(xx, vA, oA, oA, vA))
+        out["ajbi_AA"] = ajbi(ao2mo_idx_trans(xx, vA, vA, oA, oA))
+        out["ajib_AB"] = ajib(ao2mo_idx_trans(xx, vA, oA, oB, vB))
+        out["ajib_BB"] = ajib(ao2mo_idx_trans(xx, vB, oB, oB, vB))
+        out["ajbi_BB"] = ajbi(ao2mo_idx_trans(xx, vB, vB, oB, oB))
+    else:
+        raise ValueError(kind)
+    return out
+
+
+def mp2_rhf_energy(records_ab, eig, nocc, nvrt):
+    """mp2_rhf (mp2.f90:79-150), literally: consumes the ijab_AB records in file order.
+    Returns (E(AA) = sum1, E(AB) = sum2, E(MBPT2) = 2 sum1 + sum2)."""
+    ntot = nocc + nvrt
+    it = iter(records_ab)
+    sum1 = sum2 = 0.0
+    for i in range(nocc - 1):
+        for j in range(i + 1):
+            m = next(it).reshape((nvrt, nvrt), order="F")
+            for a in range(nvrt):
+                for b in range(nvrt):
+                    sum2 += m[a, b] ** 2 / (eig[i] + eig[j] - eig[a + nocc] - eig[b + nocc])
+        for j in range(i + 1, nocc):
+            m = next(it).reshape((nvrt, nvrt), order="F")
+            for a in range(nvrt - 1):
+                for b in range(a + 1):
+                    sum2 += m[a, b] ** 2 / (eig[i] + eig[j] - eig[a + nocc] - eig[b + nocc])
+                for b in range(a + 1, nvrt):
+                    d = eig[i] + eig[j] - eig[a + nocc] - eig[b + nocc]
+                    sum2 += m[a, b] ** 2 / d
+                    sum1 += (m[a, b] - m[b, a]) ** 2 / d
+            for b in range(nvrt):
+                sum2 += m[nvrt - 1, b] ** 2 / (eig[i] + eig[j] - eig[ntot - 1] - eig[b + nocc])
+    for j in range(nocc):
+        m = next(it).reshape((nvrt, nvrt), order="F")
+        for a in range(nvrt):
+            for b in range(nvrt):
+                sum2 += m[a, b] ** 2 / (eig[nocc - 1] + eig[j] - eig[a + nocc] - eig[b + nocc])
+    return sum1, sum2, 2 * sum1 + sum2
+
+
+def mp2_uhf_energy(files, eigA, eigB, nA, nB, ntot):
+    """mp2_uhf (mp2.f90:154-237): (E(AA), E(BB), E(AB), E(MBPT2))."""
+    vA, vB = ntot - nA, ntot - nB
+    s1 = s2 = s3 = 0.0
+    it = iter(files["ijab_AA"])
+    for i in range(nA - 1):
+        for j in range(i + 1, nA):
+            m = next(it).reshape((vA, vA), order="F")
+            for a in range(vA - 1):
+                for b in range(a + 1, vA):
+                    s1 += (m[a, b] - m[b, a]) ** 2 / (eigA[i] + eigA[j] - eigA[a + nA] - eigA[b + nA])
+    it = iter(files["ijab_BB"])
+    for i in range(nB - 1):
+        for j in range(i + 1, nB):
+            m = next(it).reshape((vB, vB), order="F")
+            for a in range(vB - 1):
+                for b in range(a + 1, vB):
+                    s2 += (m[a, b] - m[b, a]) ** 2 / (eigB[i] + eigB[j] - eigB[a + nB] - eigB[b + nB])
+    it = iter(files["ijab_AB"])
+    for i in range(nA):
+        for j in range(nB):
+            m = next(it).reshape((vA, vB), order="F")
+            for a in range(vA):
+                for b in range(vB):
+                    s3 += m[a, b] ** 2 / (eigA[i] + eigB[j] - eigA[a + nA] - eigB[b + nB])
+    return s1, s2, s3, s1 + s2 + s3

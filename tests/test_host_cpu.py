@@ -15,7 +15,8 @@ from oracle import oracle as O
 
 
 def test_library_exports_every_declared_symbol():
-    hdr = open(os.path.join(ROOT, "include", "myqc_eri.h")).read() + open(os.path.join(ROOT, "include", "myqc_fock.h")).read() + open(os.path.join(ROOT, "include", "myqc_int1e.h")).read()
+    import glob
+    hdr = "".join(open(h).read() for h in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))))
     declared = set(re.findall(r"\b(myqc_[a-z0-9_]+)\s*\(", hdr))
     L = Q.lib()
     missing = [n for n in declared if not hasattr(L, n)]
@@ -35,6 +36,9 @@ def test_no_cpu_fallback(tmp_path):
         Q.Plan(s)
     with pytest.raises(Q.MyQCError) as e:
         Q.fock_rhf(np.zeros(1), 1, np.zeros((1, 1)))
+    assert e.value.code == Q.ERR_NO_DEVICE
+    with pytest.raises(Q.MyQCError) as e:
+        Q.ao2mo_transform(np.zeros(1), 1, *[np.ones((1, 1))] * 4)
     assert e.value.code == Q.ERR_NO_DEVICE
 
 
@@ -163,3 +167,26 @@ def test_synthetic_geometries(tmp_path):
     assert (atoms == 6).sum() == 20 and (atoms == 1).sum() == 42
     cc = np.linalg.norm(xyz[1] - xyz[0]) / parse.A2B
     assert abs(cc - 1.54) < 1e-6
+
+
+def test_pack_dense_helper_matches_the_numpy_packing():
+    """myqc_pack_dense (what `ao2mo` applies to the XX record it reads) == the numpy triangle gather."""
+    rng = np.random.default_rng(4)
+    n = 5
+    a = rng.standard_normal((n, n, n, n))
+    xx = a + a.transpose(1, 0, 2, 3)
+    xx = xx + xx.transpose(0, 1, 3, 2)
+    xx = xx + xx.transpose(2, 3, 0, 1)
+    assert np.array_equal(Q.pack_dense_c(xx), Q.pack_dense(xx))
+    assert np.array_equal(Q.pack_dense_c(xx), O.packed_from_dense(xx))
+
+
+def test_ao2mo_program_without_a_device_touches_error(tmp_path):
+    """PROGRAM ao2mo has no CPU fallback either: with the inputs in place but no GPU it reports and
+    leaves the `error` sentinel the driver tests (myQC.f90:74-78)."""
+    if Q.device_count() > 0:
+        pytest.skip("a GPU is present")
+    zm = example_zmat("H2").replace("CALC= SCF", "CALC= MP2")
+    Q.make_job(str(tmp_path), zm, INPUTS)
+    open(tmp_path / "basinfo", "w").write(" 4 2\n")
+    assert Q.ao2mo_main(str(tmp_path)) == Q.ERR_NO_DEVICE and (tmp_path / "error").exists()

@@ -115,3 +115,34 @@ def test_boys_regimes(oracle_inputs):
     F = O.boys(0, 40.0, ft)
     assert abs(F[0] - 0.5 * np.sqrt(float(np.float32(np.pi)) / 40.0)) < 1e-16
     assert abs(F[0] - 0.5 * np.sqrt(np.pi / 40.0)) > 1e-10
+
+
+def test_ao2mo_restatement_against_brute_force():
+    """idx1..4_trans restatement == the one-shot four-index contraction."""
+    rng = np.random.default_rng(2)
+    n = 6
+    xx = rng.standard_normal((n, n, n, n))
+    c = [rng.standard_normal((n, k)) for k in (3, 2, 4, 5)]
+    ref = np.einsum("uvld,up,vq,lr,ds->pqrs", xx, *c)
+    assert np.abs(O.ao2mo_idx_trans(xx, *c) - ref).max() < 1e-12
+
+
+def test_mp2_energy_of_co2_against_the_cfour_output_the_reference_ships(oracle_inputs):
+    """examples/CO2/cfour/out: E2(AA) = -0.011001822459, E2(AB) = -0.067863676761,
+    E2(TOT) = -0.089867321680.  Pins the ao2mo file layout + mp2.f90 restatement used by the GPU
+    tests; the reference's float32 pi accounts for the 1e-6 difference."""
+    from conftest import oracle_system
+    mol, b, ft = oracle_system("CO2", oracle_inputs)
+    xx = np.array(O.int2e_dense(mol, b, ft)[0])
+    S, H = O.int1e(mol, b, ft)
+    nA, nB = O.electrons(mol)
+    _, eps, _, C = O.scf_rhf(S, H, xx, nA + nB, O.nuclear_repulsion(mol), orbitals=True)
+    f = O.ao2mo_files("mp2_rhf", xx, C, C, nA, nB)
+    assert len(f["ijab_AA"]) == nA * (nA - 1) // 2 and len(f["ijab_AB"]) == nA * nA
+    e_aa, e_ab, e2 = O.mp2_rhf_energy(f["ijab_AB"], eps, nA, b.norb - nA)
+    assert abs(e_aa - (-0.011001822459)) < 1e-6 and abs(e_ab - (-0.067863676761)) < 2e-6
+    assert abs(e2 - (-0.089867321680)) < 3e-6
+    # the UHF route on the same closed shell gives the same numbers (mp2.f90:154-237)
+    fu = O.ao2mo_files("mp2_uhf", xx, C, C, nA, nB)
+    s1, s2, s3, tot = O.mp2_uhf_energy(fu, eps, eps, nA, nB, b.norb)
+    assert abs(s1 - e_aa) < 1e-12 and abs(s2 - e_aa) < 1e-12 and abs(s3 - e_ab) < 1e-12 and abs(tot - e2) < 1e-12
