@@ -58,6 +58,10 @@ int myqc_ao2mo_main(const char *dir);
  * 2 n n3 n4 npair + 2 n^2 n2 n3 n4 + 2 n n1 n2 n3 n4.                                              */
 double myqc_ao2mo_flops(int norb, int n1, int n2, int n3, int n4);
 
+/* Measured throughput of the FP64 tensor pipe of `device` in TFLOP/s (register-resident DMMA m8n8k4
+ * microbenchmark): the roofline denominator of the GEMM stages, next to myqc_fp64_peak (DFMA).       */
+int myqc_dmma_peak(int device, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

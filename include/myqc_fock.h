@@ -38,6 +38,22 @@ int myqc_fock_rhf(const double *d_packed, int64_t out_offset, int64_t out_elems,
 int myqc_fock_uhf(const double *d_packed, int64_t out_offset, int64_t out_elems, int norb,
                   const double *d_da, const double *d_db, double *d_ga, double *d_gb, void *stream);
 
+/* Optional sparsity mask.  The reference's screen leaves most of a large molecule's integrals exactly
+ * zero; an SCF calls the G build 10-30 times on the same array.  myqc_fock_mask_build scans the slice once
+ * (one streaming pass) and sets bit k of row P = (i,j) iff some (ij|kl), l >= k, is nonzero; the *_masked
+ * builds then skip every all-zero (row, k) block without reading it.  Results are identical to the
+ * unmasked calls (skipped blocks contribute exactly nothing).  d_mask: DEVICE pointer to
+ * myqc_fock_mask_words(norb) uint32 words, indexed by the absolute packed row, so the shards of one
+ * array can share one buffer; build fills only the rows of the slice it is given.                 */
+int64_t myqc_fock_mask_words(int norb);
+int myqc_fock_mask_build(const double *d_packed, int64_t out_offset, int64_t out_elems, int norb,
+                         uint32_t *d_mask, void *stream);
+int myqc_fock_rhf_masked(const double *d_packed, int64_t out_offset, int64_t out_elems, int norb,
+                         const double *d_da, const uint32_t *d_mask, double *d_g, void *stream);
+int myqc_fock_uhf_masked(const double *d_packed, int64_t out_offset, int64_t out_elems, int norb,
+                         const double *d_da, const double *d_db, const uint32_t *d_mask,
+                         double *d_ga, double *d_gb, void *stream);
+
 /* Host-buffer convenience calls (everything copied in and out; packed is the whole array). */
 int myqc_fock_rhf_host(const double *packed, int norb, const double *da, double *g);
 int myqc_fock_uhf_host(const double *packed, int norb, const double *da, const double *db,

@@ -39,10 +39,11 @@ EXPORTS = [
     "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard", "myqc_write_xx_ex",
     # include/myqc_fock.h
     "myqc_fock_rhf", "myqc_fock_uhf", "myqc_fock_rhf_host", "myqc_fock_uhf_host",
+    "myqc_fock_mask_words", "myqc_fock_mask_build", "myqc_fock_rhf_masked", "myqc_fock_uhf_masked",
     # include/myqc_int1e.h
     "myqc_int1e", "myqc_int1e_main",
     # include/myqc_ao2mo.h
-    "myqc_ao2mo_transform", "myqc_ao2mo_transform_host", "myqc_pack_dense", "myqc_ao2mo_main", "myqc_ao2mo_flops",
+    "myqc_ao2mo_transform", "myqc_ao2mo_transform_host", "myqc_pack_dense", "myqc_ao2mo_main", "myqc_ao2mo_flops", "myqc_dmma_peak",
 ]
 
 
@@ -104,6 +105,11 @@ def lib() -> ctypes.CDLL:
     c_i64 = ctypes.c_int64
     L.myqc_fock_rhf.argtypes = [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p]
     L.myqc_fock_uhf.argtypes = [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.myqc_fock_mask_words.argtypes = [c_int]
+    L.myqc_fock_mask_words.restype = c_i64
+    L.myqc_fock_mask_build.argtypes = [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p]
+    L.myqc_fock_rhf_masked.argtypes = [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.myqc_fock_uhf_masked.argtypes = [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.myqc_fock_rhf_host.argtypes = [_dp, c_int, _dp, _dp]
     L.myqc_fock_uhf_host.argtypes = [_dp, c_int, _dp, _dp, _dp, _dp]
     L.myqc_int1e.argtypes = [c_int, _dp, _ip, c_int, c_int, _dp, _ip, c_int, _dp, _ip, _dp, _dp, _dp]
@@ -113,12 +119,13 @@ def lib() -> ctypes.CDLL:
     L.myqc_ao2mo_transform_host.argtypes = [_dp, c_int, _dp, c_int, _dp, c_int, _dp, c_int, _dp, c_int, _dp]
     L.myqc_pack_dense.argtypes = [_dp, c_int, _dp]
     L.myqc_ao2mo_main.argtypes = [c_char_p]
+    L.myqc_dmma_peak.argtypes = [c_int, _dp]
     L.myqc_ao2mo_flops.argtypes = [c_int] * 5
     L.myqc_ao2mo_flops.restype = ctypes.c_double
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("myqc_last_error", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
-                        "myqc_eri_plan_destroy", "myqc_ao2mo_flops"):
+                        "myqc_eri_plan_destroy", "myqc_ao2mo_flops", "myqc_fock_mask_words"):
             fn.restype = c_int
     _lib = L
     return L
@@ -429,6 +436,26 @@ def fock_uhf_device(d_packed: int, out_offset: int, out_elems: int, norb: int, d
     _check(lib().myqc_fock_uhf(d_packed, out_offset, out_elems, norb, d_da, d_db, d_ga, d_gb, stream))
 
 
+def fock_mask_words(norb: int) -> int:
+    """uint32 words of the sparsity mask of a norb-function packed array (myqc_fock.h)."""
+    return int(lib().myqc_fock_mask_words(norb))
+
+
+def fock_mask_build(d_packed: int, out_offset: int, out_elems: int, norb: int, d_mask: int, stream: int = 0):
+    """One streaming pass over the slice: bit k of row P set iff (P | k, .) holds a nonzero integral."""
+    _check(lib().myqc_fock_mask_build(d_packed, out_offset, out_elems, norb, d_mask, stream))
+
+
+def fock_rhf_masked_device(d_packed: int, out_offset: int, out_elems: int, norb: int, d_da: int, d_mask: int, d_g: int,
+                           stream: int = 0):
+    _check(lib().myqc_fock_rhf_masked(d_packed, out_offset, out_elems, norb, d_da, d_mask, d_g, stream))
+
+
+def fock_uhf_masked_device(d_packed: int, out_offset: int, out_elems: int, norb: int, d_da: int, d_db: int, d_mask: int,
+                           d_ga: int, d_gb: int, stream: int = 0):
+    _check(lib().myqc_fock_uhf_masked(d_packed, out_offset, out_elems, norb, d_da, d_db, d_mask, d_ga, d_gb, stream))
+
+
 def _read_records(path: str):
     """Fortran unformatted sequential records (4-byte little-endian markers) as float64 arrays."""
     raw = open(path, "rb").read()
@@ -528,6 +555,13 @@ def ao2mo_transform_device(d_packed: int, norb: int, d_c1: int, n1: int, d_c2: i
                            d_c4: int, n4: int, d_out: int, stream: int = 0):
     """Device-pointer form (stream ordered, no synchronisation)."""
     _check(lib().myqc_ao2mo_transform(d_packed, norb, d_c1, n1, d_c2, n2, d_c3, n3, d_c4, n4, d_out, stream))
+
+
+def dmma_peak(device: int = 0) -> float:
+    """Measured FP64 tensor-pipe (DMMA m8n8k4) peak of `device` in TFLOP/s."""
+    v = ctypes.c_double()
+    _check(lib().myqc_dmma_peak(device, ctypes.byref(v)))
+    return v.value
 
 
 def ao2mo_flops(norb: int, n1: int, n2: int, n3: int, n4: int) -> float:

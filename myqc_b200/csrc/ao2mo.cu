@@ -88,17 +88,31 @@ __global__ void __launch_bounds__(GT) gemm_f64_kernel(const GemmArgs g) {
 
     auto a_at = [](int m, int k) { return A_KC ? m * PA_K + k : k * PA_M + m; };
 
+    // Element e = tid + 256 i of a tile: the eight elements a thread moves per operand differ by a
+    // uniform step, so one base pointer per operand and loop-invariant row/column masks are enough.
+    //   A, k-contiguous: m = tid/16 + 16 i, k = tid%16      A, m-contiguous: m = tid%128, k = tid/128 + 2 i
+    //   B:               k = tid/128 + 2 i, n = tid%128
+    const int am = A_KC ? tid / BK : tid % BM, ak = A_KC ? tid % BK : tid / BM;
+    const int bk = tid / BN, bn = tid % BN;
+    const double* pa = A + (int64_t)(m0 + am) * g.a_sm + (int64_t)ak * g.a_sk;
+    const double* pb = B + (int64_t)bk * g.ldb + (n0 + bn);
+    const int64_t a_step = A_KC ? 16 * g.a_sm : 2 * g.a_sk;   // between the eight elements
+    const int64_t b_step = 2 * g.ldb;
+    const int64_t a_tile = (int64_t)BK * g.a_sk, b_tile = (int64_t)BK * g.ldb;  // between k tiles
+    unsigned a_ok = 0;  // A_KC: bit i = row m0 + am + 16 i exists; else: the one row m0 + am exists
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a_ok |= ((m0 + am + (A_KC ? 16 * i : 0)) < M ? 1u : 0u) << i;
+    const bool b_ok = n0 + bn < N;
     double ra[8], rb[8];
     auto gload = [&](int k0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int e = tid + GT * i;
-            const int m = A_KC ? e / BK : e % BM;
-            const int k = A_KC ? e % BK : e / BM;
-            ra[i] = (m0 + m < M && k0 + k < K) ? __ldg(A + (int64_t)(m0 + m) * g.a_sm + (int64_t)(k0 + k) * g.a_sk) : 0.0;
-            const int kb = e / BN, nb = e % BN;
-            rb[i] = (k0 + kb < K && n0 + nb < N) ? __ldg(B + (int64_t)(k0 + kb) * g.ldb + (n0 + nb)) : 0.0;
+            const bool kin = A_KC ? (k0 + ak < K) : (k0 + ak + 2 * i < K);
+            ra[i] = (kin && ((a_ok >> i) & 1u)) ? __ldg(pa + i * a_step) : 0.0;
+            rb[i] = (b_ok && k0 + bk + 2 * i < K) ? __ldg(pb + i * b_step) : 0.0;
         }
+        pa += a_tile;
+        pb += b_tile;
     };
     auto sstore = [&](int buf) {
 #pragma unroll
@@ -190,6 +204,23 @@ __global__ void __launch_bounds__(GT) gemm_f64_kernel(const GemmArgs g) {
     }
 }
 
+// FP64 tensor-pipe roofline denominator: eight independent DMMA accumulator pairs per warp
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b) {
+    double c[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) c[k] = threadIdx.x + k;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dmma884(c[2 * k], c[2 * k + 1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += c[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 bool use_simt() {
     const char* e = std::getenv("MYQC_AO2MO_GEMM");
     return e && e[0] == 's';
@@ -263,6 +294,48 @@ __global__ void coef_rowmajor_kernel(const double* __restrict__ c, int n, int nk
     }
 }
 
+// MYQC_AO2MO_TRACE=1: CUDA-event time of every stage, summed over panels, on stderr (synchronises)
+struct StageTrace {
+    bool on = false;
+    cudaStream_t st = nullptr;
+    std::vector<cudaEvent_t> ev;  // pairs
+    std::vector<int> stage;
+    void begin(int s) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+        stage.push_back(s);
+    }
+    void end() {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        ev.push_back(e);
+    }
+    void report(const double* flops) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        static const char* names[6] = {"unpack rows", "GEMM 1a", "GEMM 1b", "unpack cols", "GEMM 2a", "GEMM 2b"};
+        double ms[6] = {0, 0, 0, 0, 0, 0};
+        for (size_t k = 0; k < stage.size(); ++k) {
+            float t = 0;
+            cudaEventElapsedTime(&t, ev[2 * k], ev[2 * k + 1]);
+            ms[stage[k]] += t;
+        }
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        for (int k = 0; k < 6; ++k)
+            std::fprintf(stderr, "[myqc ao2mo trace] %-12s %9.3f ms%s", names[k], ms[k],
+                         flops[k] > 0 ? "" : "\n");
+        std::fprintf(stderr, "\n");
+        for (int k = 0; k < 6; ++k)
+            if (flops[k] > 0)
+                std::fprintf(stderr, "[myqc ao2mo trace] %-12s %7.2f TFLOP/s\n", names[k], flops[k] / (ms[k] * 1e-3 + 1e-30) / 1e12);
+    }
+};
+
 int64_t env_i64(const char* name, int64_t dflt) {
     const char* e = std::getenv(name);
     return e ? std::atoll(e) : dflt;
@@ -298,42 +371,63 @@ int transform_device(const double* d_packed, int norb, const double* d_c1, int n
     coef_rowmajor_kernel<<<64, 256, 0, st>>>(d_c3, norb, n3, c3r);
     coef_rowmajor_kernel<<<64, 256, 0, st>>>(d_c4, norb, n4, c4r);
     int rc = MYQC_OK;
+    StageTrace tr;
+    tr.on = std::getenv("MYQC_AO2MO_TRACE") != nullptr;
+    tr.st = st;
 
     // ---- stage 1: ket half transformation, H[P][s][r] -------------------------------------------
     for (int64_t p0 = 0; p0 < np && !rc; p0 += bp) {
         const int64_t cur = std::min(bp, np - p0);
+        tr.begin(0);
         unpack_rows_kernel<<<dim3((unsigned)cur, (unsigned)n), 128, 0, st>>>(d_packed, norb, np, p0, panel);
+        tr.end();
         GemmArgs a{};
         a.A = panel; a.a_sm = n; a.a_sk = 1; a.a_batch = 0;
         a.B = c4r; a.ldb = n4; a.b_batch = 0;
         a.C = tbuf; a.c_sm = n4; a.c_sn = 1; a.c_batch = 0;
         a.M = (int)(cur * n); a.N = n4; a.K = norb;
+        tr.begin(1);
         rc = gemm_launch(true, a, 1, st);
+        tr.end();
         if (rc) break;
         GemmArgs b{};
         b.A = tbuf; b.a_sm = 1; b.a_sk = n4; b.a_batch = n * n4;
         b.B = c3r; b.ldb = n3; b.b_batch = 0;
         b.C = h + p0 * nrs; b.c_sm = n3; b.c_sn = 1; b.c_batch = nrs;
         b.M = n4; b.N = n3; b.K = norb;
+        tr.begin(2);
         rc = gemm_launch(false, b, (int)cur, st);
+        tr.end();
     }
     // ---- stage 2: bra half transformation, written into Om(p,q,r,s) -----------------------------
     for (int64_t rs0 = 0; rs0 < nrs && !rc; rs0 += rsb) {
         const int64_t w = std::min(rsb, nrs - rs0);
+        tr.begin(3);
         unpack_cols_kernel<<<dim3((unsigned)n, (unsigned)n), 128, 0, st>>>(h, norb, nrs, rs0, (int)w, panel);
+        tr.end();
         GemmArgs a{};
         a.A = panel; a.a_sm = 1; a.a_sk = w; a.a_batch = n * w;
         a.B = c2r; a.ldb = n2; a.b_batch = 0;
         a.C = tbuf; a.c_sm = n2; a.c_sn = 1; a.c_batch = w * n2;
         a.M = (int)w; a.N = n2; a.K = norb;
+        tr.begin(4);
         rc = gemm_launch(false, a, norb, st);
+        tr.end();
         if (rc) break;
         GemmArgs b{};
         b.A = d_c1; b.a_sm = n; b.a_sk = 1; b.a_batch = 0;
         b.B = tbuf; b.ldb = w * n2; b.b_batch = 0;
         b.C = d_out + rs0 * n2 * n1; b.c_sm = 1; b.c_sn = n1; b.c_batch = 0;
         b.M = n1; b.N = (int)(w * n2); b.K = norb;
+        tr.begin(5);
         rc = gemm_launch(true, b, 1, st);
+        tr.end();
+    }
+    {
+        const double dn = (double)n, dnp = (double)np;
+        const double fl[6] = {0.0, 2.0 * dnp * dn * dn * n4, 2.0 * dnp * dn * n3 * n4, 0.0,
+                              2.0 * dn * dn * n2 * (double)nrs, 2.0 * dn * n1 * n2 * (double)nrs};
+        tr.report(fl);
     }
     cudaError_t le = cudaGetLastError();
     cudaFreeAsync(buf, st);
@@ -452,6 +546,39 @@ int write_cis(Job& jb, const char* name, bool ajbi, int nv, int no, int nj, int 
 }  // namespace
 
 extern "C" {
+
+int myqc_dmma_peak(int device, double* tflops) {
+    if (!tflops) return myqc::fock_fail(MYQC_ERR_BAD_ARG, "null result");
+    if (myqc_device_count() == 0) return myqc::fock_fail(MYQC_ERR_NO_DEVICE, "no CUDA device");
+    CUA(cudaSetDevice(device));
+    int sms = 0;
+    CUA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int grid = sms * 4, iters = 2048;
+    double* d = nullptr;
+    CUA(cudaMalloc((void**)&d, (size_t)grid * 256 * sizeof(double)));
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0); cudaEventCreate(&t1);
+    double best = 0.0;
+    cudaError_t e = cudaSuccess;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(t0);
+        dmma_peak_kernel<<<grid, 256>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(t1);
+        e = cudaEventSynchronize(t1);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1);
+        // one m8n8k4 DMMA = 8*8*4 FMA = 512 flop per warp
+        const double flops = 512.0 * 32 * (double)iters * 8.0 * grid;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    cudaFree(d);
+    *tflops = best;
+    if (e != cudaSuccess) return myqc::fock_fail(MYQC_ERR_CUDA, cudaGetErrorString(e));
+    return MYQC_OK;
+}
 
 double myqc_ao2mo_flops(int norb, int n1, int n2, int n3, int n4) {
     const double n = norb, np = n * (n + 1) / 2;

@@ -46,6 +46,8 @@ struct FockArgs {
     double* k0;         // [n*n] K accumulator (first four images; the finalize kernel adds the transpose)
     double* k1;
     int* counter;
+    const uint32_t* mask;  // optional [npair][mask_words]: bit k of row P set iff (P | k, .) holds a nonzero
+    int mask_words;
 };
 
 __global__ void pair_table_kernel(int n, int2* ij) {
@@ -82,10 +84,23 @@ __global__ void __launch_bounds__(NW * 32) fock_rows_kernel(const FockArgs a) {
     for (int x = tid; x < nk; x += kThreads) sK[x] = 0.0;
 
     for (;;) {
-        if (tid == 0) s_row = atomicAdd(a.counter, 1);
+        if (tid == 0) {
+            // with a mask, rows without a single nonzero integral are skipped by the claiming thread
+            int r;
+            for (;;) {
+                r = atomicAdd(a.counter, 1);
+                if (!a.mask || a.row_lo + r >= a.row_hi) break;
+                const uint32_t* mw = a.mask + (a.row_lo + r) * a.mask_words;
+                uint32_t bits = 0;
+                for (int w = 0; w < a.mask_words; ++w) bits |= __ldg(mw + w);
+                if (bits) break;
+            }
+            s_row = r;
+        }
         __syncthreads();
         const int64_t P = a.row_lo + s_row;
         if (P >= a.row_hi) break;
+        const uint32_t* mrow = a.mask ? a.mask + P * a.mask_words : nullptr;
         const int2 pij = a.ij[P];
         const int i = pij.x, j = pij.y;
         for (int x = tid; x < n; x += kThreads) {
@@ -105,6 +120,7 @@ __global__ void __launch_bounds__(NW * 32) fock_rows_kernel(const FockArgs a) {
         double* myK0 = sK + (size_t)(0 * NWARPS + warp) * 2 * n;
         double* myK1 = sK + (size_t)(1 * NWARPS + warp) * 2 * n;  // only touched when NSPIN == 2
         for (int k = i + warp; k < n; k += NWARPS) {
+            if (mrow && !((__ldg(mrow + (k >> 5)) >> (k & 31)) & 1u)) continue;  // (P | k, .) is all zero
             const int64_t Pk = (int64_t)k * n - (int64_t)k * (k - 1) / 2 - k;  // P'(k,l) = Pk + l
             const int l0 = (k == i) ? j : k;
             const double d0_ik = sD[k], d0_jk = sD[n + k];
@@ -195,6 +211,35 @@ __global__ void __launch_bounds__(NW * 32) fock_rows_kernel(const FockArgs a) {
     }
 }
 
+// Sparsity mask of the packed array: bit k of row P = (i,j) is set iff some (ij|kl), l >= k, is nonzero.
+// Built once per integral evaluation (one streaming pass), reused by every G build of the SCF.
+__global__ void __launch_bounds__(256) fock_mask_kernel(const double* __restrict__ packed, int64_t out_offset, int64_t row_lo,
+                                                        int64_t row_hi, int n, int64_t npair, const int2* __restrict__ ij,
+                                                        uint32_t* __restrict__ mask, int mask_words) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t P = row_lo + blockIdx.x; P < row_hi; P += gridDim.x) {
+        const int2 pij = ij[P];
+        const int i = pij.x, j = pij.y;
+        const double* row = packed + ((P * npair - ((P * (P - 1)) >> 1)) - out_offset) - P;
+        for (int k = i + warp; k < n; k += 8) {
+            const int64_t Pk = (int64_t)k * n - (int64_t)k * (k - 1) / 2 - k;
+            const int l0 = (k == i) ? j : k;
+            bool nz = false;
+            for (int lb = l0 + lane; lb < n; lb += 32 * 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int l = lb + 32 * u;
+                    v[u] = l < n ? __ldcs(row + Pk + l) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) nz |= (v[u] != 0.0);
+            }
+            if (__any_sync(0xffffffffu, nz) && lane == 0) atomicOr(mask + P * mask_words + (k >> 5), 1u << (k & 31));
+        }
+    }
+}
+
 // G = J - fac (K + K^T)
 __global__ void fock_finalize_kernel(int n, const double* jp, const double* k, double fac, double* g) {
     const int b = blockIdx.x;
@@ -212,7 +257,7 @@ __global__ void fock_finalize_kernel(int n, const double* jp, const double* k, d
     } while (0)
 
 int fock_build(const double* d_packed, int64_t out_offset, int64_t out_elems, int norb, const double* d_da,
-               const double* d_db, double* d_ga, double* d_gb, cudaStream_t st) {
+               const double* d_db, double* d_ga, double* d_gb, cudaStream_t st, const uint32_t* d_mask = nullptr) {
     const bool uhf = d_db != nullptr;
     if (!d_packed || !d_da || !d_ga || norb < 1 || (uhf && !d_gb)) return myqc::fock_fail(MYQC_ERR_BAD_ARG, "null pointer or bad norb");
     const int64_t n = norb, npair = n * (n + 1) / 2;
@@ -266,6 +311,7 @@ int fock_build(const double* d_packed, int64_t out_offset, int64_t out_elems, in
     a.packed = d_packed; a.out_offset = out_offset; a.row_lo = row_lo; a.row_hi = row_hi;
     a.n = norb; a.npair = npair; a.ij = ij; a.dp2 = dp2; a.dk0 = dk0; a.dk1 = dk1;
     a.jp = jp; a.k0 = k0; a.k1 = k1; a.counter = counter;
+    a.mask = d_mask; a.mask_words = (norb + 31) / 32;
     int occ = 1;
     if (uhf) {
         CUF(cudaFuncSetAttribute(fock_rows_kernel<2, NW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -327,6 +373,54 @@ int myqc_fock_uhf(const double* d_packed, int64_t out_offset, int64_t out_elems,
                   const double* d_db, double* d_ga, double* d_gb, void* stream) {
     if (!d_db) return myqc::fock_fail(MYQC_ERR_BAD_ARG, "null beta density");
     return fock_build(d_packed, out_offset, out_elems, norb, d_da, d_db, d_ga, d_gb, static_cast<cudaStream_t>(stream));
+}
+
+int64_t myqc_fock_mask_words(int norb) {
+    const int64_t n = norb;
+    return norb < 1 ? 0 : (n * (n + 1) / 2) * ((n + 31) / 32);
+}
+
+int myqc_fock_mask_build(const double* d_packed, int64_t out_offset, int64_t out_elems, int norb, uint32_t* d_mask, void* stream) {
+    if (!d_packed || !d_mask || norb < 1) return myqc::fock_fail(MYQC_ERR_BAD_ARG, "null pointer or bad norb");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t n = norb, npair = n * (n + 1) / 2;
+    auto off = [&](int64_t P) { return P * npair - P * (P - 1) / 2; };
+    auto row_of = [&](int64_t o) {
+        int64_t lo = 0, hi = npair;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) / 2;
+            if (off(mid) < o) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    const int64_t row_lo = row_of(out_offset), row_hi = row_of(out_offset + out_elems);
+    if (off(row_lo) != out_offset || off(row_hi) != out_offset + out_elems)
+        return myqc::fock_fail(MYQC_ERR_BAD_ARG, "the packed slice does not consist of whole rows");
+    const int mw = (norb + 31) / 32;
+    int dev = 0, sms = 0;
+    CUF(cudaGetDevice(&dev));
+    CUF(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int2* ij = nullptr;
+    CUF(cudaMallocAsync((void**)&ij, sizeof(int2) * npair, st));
+    pair_table_kernel<<<norb, 128, 0, st>>>(norb, ij);
+    CUF(cudaMemsetAsync(d_mask + row_lo * mw, 0, sizeof(uint32_t) * (size_t)((row_hi - row_lo) * mw), st));
+    int64_t grid = (int64_t)sms * 8;
+    if (grid > row_hi - row_lo) grid = row_hi - row_lo;
+    if (grid > 0) fock_mask_kernel<<<(int)grid, 256, 0, st>>>(d_packed, out_offset, row_lo, row_hi, norb, npair, ij, d_mask, mw);
+    CUF(cudaGetLastError());
+    CUF(cudaFreeAsync(ij, st));
+    return MYQC_OK;
+}
+
+int myqc_fock_rhf_masked(const double* d_packed, int64_t out_offset, int64_t out_elems, int norb, const double* d_da,
+                         const uint32_t* d_mask, double* d_g, void* stream) {
+    return fock_build(d_packed, out_offset, out_elems, norb, d_da, nullptr, d_g, nullptr, static_cast<cudaStream_t>(stream), d_mask);
+}
+
+int myqc_fock_uhf_masked(const double* d_packed, int64_t out_offset, int64_t out_elems, int norb, const double* d_da,
+                         const double* d_db, const uint32_t* d_mask, double* d_ga, double* d_gb, void* stream) {
+    if (!d_db) return myqc::fock_fail(MYQC_ERR_BAD_ARG, "null beta density");
+    return fock_build(d_packed, out_offset, out_elems, norb, d_da, d_db, d_ga, d_gb, static_cast<cudaStream_t>(stream), d_mask);
 }
 
 int myqc_fock_rhf_host(const double* packed, int norb, const double* da, double* g) {

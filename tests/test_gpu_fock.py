@@ -155,3 +155,41 @@ def test_rhfi2g_file_mirror(tmp_path, oracle_inputs):
     mol, b, ft = oracle_system("HF", oracle_inputs)
     xx = np.array(O.int2e_dense(mol, b, ft)[0])
     assert np.abs(guv - ref_rhf(xx, d)).max() < TOL and np.array_equal(guv, g)
+
+
+@pytest.mark.parametrize("name", ["CO2", "h2o_8", "c4h10"])
+def test_masked_builds_are_identical_to_unmasked(name, tmp_path):
+    """The sparsity mask (myqc_fock_mask_build) only skips all-zero (row, k) blocks: RHF and UHF results
+    equal the unmasked builds; every set bit has a nonzero behind it and every clear bit has none."""
+    import torch
+    s = product_system(name, tmp_path)
+    n = s.norb
+    packed_h = Q.eri_packed(s)
+    packed = torch.from_numpy(packed_h).cuda()
+    d1 = torch.from_numpy(np.asfortranarray(sym_density(n, 3)).ravel(order="F").copy()).cuda()
+    d2 = torch.from_numpy(np.asfortranarray(sym_density(n, 4)).ravel(order="F").copy()).cuda()
+    mask = torch.full((Q.fock_mask_words(n),), -1, dtype=torch.int32, device="cuda")
+    Q.fock_mask_build(packed.data_ptr(), 0, packed.numel(), n, mask.data_ptr())
+    g0, g1 = torch.empty(n * n, dtype=torch.float64, device="cuda"), torch.empty(n * n, dtype=torch.float64, device="cuda")
+    Q.fock_rhf_device(packed.data_ptr(), 0, packed.numel(), n, d1.data_ptr(), g0.data_ptr())
+    Q.fock_rhf_masked_device(packed.data_ptr(), 0, packed.numel(), n, d1.data_ptr(), mask.data_ptr(), g1.data_ptr())
+    torch.cuda.synchronize()
+    assert float((g0 - g1).abs().max()) < 1e-12
+    ga0, gb0, ga1, gb1 = (torch.empty(n * n, dtype=torch.float64, device="cuda") for _ in range(4))
+    Q.fock_uhf_device(packed.data_ptr(), 0, packed.numel(), n, d1.data_ptr(), d2.data_ptr(), ga0.data_ptr(), gb0.data_ptr())
+    Q.fock_uhf_masked_device(packed.data_ptr(), 0, packed.numel(), n, d1.data_ptr(), d2.data_ptr(), mask.data_ptr(),
+                             ga1.data_ptr(), gb1.data_ptr())
+    torch.cuda.synchronize()
+    assert float((ga0 - ga1).abs().max()) < 1e-12 and float((gb0 - gb1).abs().max()) < 1e-12
+    # the mask itself against numpy
+    mw = (n + 31) // 32
+    m = mask.cpu().numpy().view(np.uint32).reshape(-1, mw)
+    npair = n * (n + 1) // 2
+    kk = np.repeat(np.arange(n), np.arange(n, 0, -1))
+    pos = 0
+    for P in range(npair):
+        row = packed_h[pos:pos + npair - P] != 0
+        pos += npair - P
+        cnt = np.bincount(kk[P:], weights=row, minlength=n) > 0
+        bits = np.array([(m[P, k >> 5] >> (k & 31)) & 1 for k in range(n)], dtype=bool)
+        assert np.array_equal(bits, cnt), P

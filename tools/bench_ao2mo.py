@@ -12,6 +12,8 @@ from myqc_b200 import molecules
 INP = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "inputs")
 names = sys.argv[1:] or ["h2o_16", "h2o_32", "h2o_64"]
 peak = Q.fp64_peak(0)
+dmma = Q.dmma_peak(0)
+print(json.dumps({"fp64_dfma_peak_tflops": peak, "fp64_dmma_peak_tflops": dmma}), flush=True)
 st = torch.cuda.current_stream().cuda_stream
 for name in names:
     with tempfile.TemporaryDirectory() as d:
@@ -30,11 +32,12 @@ for name in names:
     co, cv = c.data_ptr(), c.data_ptr() + 8 * n * nocc          # Cm(:,0:nocc-1), Cm(:,nocc:ntot-1)
     out = torch.empty(nocc * nvrt * nocc * nvrt, dtype=torch.float64, device="cuda")
     flops = Q.ao2mo_flops(n, nocc, nvrt, nocc, nvrt)
-    for kind in (["mma", "simt"] if name != "h2o_64" else ["mma"]):
+    kinds = os.environ.get("AO2MO_BENCH_KINDS", "mma,simt" if name != "h2o_64" else "mma").split(",")
+    for kind in kinds:
         os.environ["MYQC_AO2MO_GEMM"] = kind
         fn = lambda: Q.ao2mo_transform_device(packed.data_ptr(), n, co, nocc, cv, nvrt, co, nocc, cv, nvrt, out.data_ptr(), st)
         fn(); torch.cuda.synchronize()
-        reps = 3 if name != "h2o_64" else 2
+        reps = int(os.environ.get("AO2MO_BENCH_REPS", "3" if name != "h2o_64" else "2"))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
@@ -45,7 +48,7 @@ for name in names:
         o4 = out.view(nvrt, nocc, nvrt, nocc)  # C-order view of the Fortran (p,q,r,s) array: [s][r][q][p]
         sym = float((o4 - o4.permute(2, 3, 0, 1)).abs().max())
         print(json.dumps({"workload": name, "tiles": kind, "norb": n, "nocc": nocc, "nvrt": nvrt, "ms": ms,
-                          "flops": flops, "tflops": flops / (ms * 1e-3) / 1e12, "fp64_peak_tflops_measured": peak,
+                          "flops": flops, "tflops": flops / (ms * 1e-3) / 1e12, "fp64_peak_tflops_measured": peak, "dmma_peak_tflops_measured": dmma,
                           "frac": flops / (ms * 1e-3) / 1e12 / peak, "max_asymmetry": sym,
                           "out_gb": 8e-9 * out.numel()}), flush=True)
     del packed, out
