@@ -39,6 +39,16 @@ int myqc_ao2mo_transform(const double *d_packed, int norb, const double *d_c1, i
                          const double *d_c2, int n2, const double *d_c3, int n3,
                          const double *d_c4, int n4, double *d_out, void *stream);
 
+/* Same with caller-provided scratch (at least myqc_ao2mo_workspace_bytes(...) bytes of device memory,
+ * 16-byte aligned): nothing is allocated inside, so repeated calls (one per spin case / file) reuse the
+ * buffer and the call can be captured in a CUDA graph.  The dominant part is the half-transformed
+ * array H, npair * n3 * n4 doubles.                                                                 */
+int64_t myqc_ao2mo_workspace_bytes(int norb, int n1, int n2, int n3, int n4);
+int myqc_ao2mo_transform_ws(const double *d_packed, int norb, const double *d_c1, int n1,
+                            const double *d_c2, int n2, const double *d_c3, int n3,
+                            const double *d_c4, int n4, double *d_out, void *d_workspace,
+                            int64_t workspace_bytes, void *stream);
+
 /* Host buffers in and out (device 0).                                                             */
 int myqc_ao2mo_transform_host(const double *packed, int norb, const double *c1, int n1,
                               const double *c2, int n2, const double *c3, int n3,

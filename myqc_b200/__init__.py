@@ -44,6 +44,7 @@ EXPORTS = [
     "myqc_int1e", "myqc_int1e_main",
     # include/myqc_ao2mo.h
     "myqc_ao2mo_transform", "myqc_ao2mo_transform_host", "myqc_pack_dense", "myqc_ao2mo_main", "myqc_ao2mo_flops", "myqc_dmma_peak",
+    "myqc_ao2mo_workspace_bytes", "myqc_ao2mo_transform_ws",
 ]
 
 
@@ -120,12 +121,16 @@ def lib() -> ctypes.CDLL:
     L.myqc_pack_dense.argtypes = [_dp, c_int, _dp]
     L.myqc_ao2mo_main.argtypes = [c_char_p]
     L.myqc_dmma_peak.argtypes = [c_int, _dp]
+    L.myqc_ao2mo_workspace_bytes.argtypes = [c_int] * 5
+    L.myqc_ao2mo_workspace_bytes.restype = ctypes.c_int64
+    L.myqc_ao2mo_transform_ws.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
+                                          c_void_p, c_void_p, ctypes.c_int64, c_void_p]
     L.myqc_ao2mo_flops.argtypes = [c_int] * 5
     L.myqc_ao2mo_flops.restype = ctypes.c_double
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("myqc_last_error", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
-                        "myqc_eri_plan_destroy", "myqc_ao2mo_flops", "myqc_fock_mask_words"):
+                        "myqc_eri_plan_destroy", "myqc_ao2mo_flops", "myqc_fock_mask_words", "myqc_ao2mo_workspace_bytes"):
             fn.restype = c_int
     _lib = L
     return L
@@ -562,6 +567,16 @@ def dmma_peak(device: int = 0) -> float:
     v = ctypes.c_double()
     _check(lib().myqc_dmma_peak(device, ctypes.byref(v)))
     return v.value
+
+
+def ao2mo_workspace_bytes(norb: int, n1: int, n2: int, n3: int, n4: int) -> int:
+    return int(lib().myqc_ao2mo_workspace_bytes(norb, n1, n2, n3, n4))
+
+
+def ao2mo_transform_ws(d_packed: int, norb: int, d_c1: int, n1: int, d_c2: int, n2: int, d_c3: int, n3: int,
+                       d_c4: int, n4: int, d_out: int, d_ws: int, ws_bytes: int, stream: int = 0):
+    """Device-pointer form with caller-provided scratch: no allocation, no synchronisation."""
+    _check(lib().myqc_ao2mo_transform_ws(d_packed, norb, d_c1, n1, d_c2, n2, d_c3, n3, d_c4, n4, d_out, d_ws, ws_bytes, stream))
 
 
 def ao2mo_flops(norb: int, n1: int, n2: int, n3: int, n4: int) -> float:

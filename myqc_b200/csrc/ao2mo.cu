@@ -65,6 +65,7 @@ struct GemmArgs {
     const double* B; int64_t ldb, b_batch;         // B(k,n) at k*ldb + n
     double* C; int64_t c_sm, c_sn, c_batch;        // C(m,n) at m*c_sm + n*c_sn
     int M, N, K;
+    int g_n, g_np;  // A mode 2: A(m = pp*g_n + l, k = d) = A[pp*g_np + pair(min(l,d), max(l,d))]
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -73,10 +74,13 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// C = A B.  A_KC: A is contiguous along k (loader walks k fastest, tile kept [m][k]); otherwise A is
-// contiguous along m (loader walks m fastest, tile kept [k][m]).  MMA: tensor pipe or plain DFMA.
-template <bool A_KC, bool MMA>
+// C = A B.  AMODE 1: A is contiguous along k (loader walks k fastest, tile kept [m][k]); 0: A is
+// contiguous along m (loader walks m fastest, tile kept [k][m]); 2: row m = (pp, l) of A is row l of
+// the symmetric n x n matrix whose upper triangle is the packed row pp of a panel (both triangles
+// gathered from the one stored, thread mapping and tile as mode 1).  MMA: tensor pipe or plain DFMA.
+template <int AMODE, bool MMA>
 __global__ void __launch_bounds__(GT) gemm_f64_kernel(const GemmArgs g) {
+    constexpr bool A_KC = AMODE != 0;
     extern __shared__ __align__(16) double gsm[];
     constexpr int STAGE = A_ELEMS + B_ELEMS;  // stage b: A tile at gsm + b*STAGE, B tile behind it
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(GT) gemm_f64_kernel(const GemmArgs g) {
     //   B:               k = tid/128 + 2 i, n = tid%128
     const int am = A_KC ? tid / BK : tid % BM, ak = A_KC ? tid % BK : tid / BM;
     const int bk = tid / BN, bn = tid % BN;
-    const double* pa = A + (int64_t)(m0 + am) * g.a_sm + (int64_t)ak * g.a_sk;
+    const double* pa = A + (AMODE == 2 ? 0 : (int64_t)(m0 + am) * g.a_sm + (int64_t)ak * g.a_sk);
     const double* pb = B + (int64_t)bk * g.ldb + (n0 + bn);
     const int64_t a_step = A_KC ? 16 * g.a_sm : 2 * g.a_sk;   // between the eight elements
     const int64_t b_step = 2 * g.ldb;
@@ -103,15 +107,39 @@ __global__ void __launch_bounds__(GT) gemm_f64_kernel(const GemmArgs g) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) a_ok |= ((m0 + am + (A_KC ? 16 * i : 0)) < M ? 1u : 0u) << i;
     const bool b_ok = n0 + bn < N;
+    // mode 2: first row of this thread as (panel row pp, AO index l); the other seven follow by +16
+    const int gn = g.g_n, gnp = g.g_np;
+    int g_l0 = 0, g_rb0 = 0;
+    if (AMODE == 2) {
+        const int pp = (m0 + am) / gn;
+        g_l0 = (m0 + am) - pp * gn;
+        g_rb0 = pp * gnp;
+    }
     double ra[8], rb[8];
     auto gload = [&](int k0) {
+        if constexpr (AMODE == 2) {
+            const int d = k0 + ak;
+            const int td = d * gn - ((d * (d - 1)) >> 1) - d;  // pair(d, l) = td + l for l >= d
+            const bool kin = d < K;
+            int l = g_l0, rbase = g_rb0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int tl = l * gn - ((l * (l - 1)) >> 1) - l;  // pair(l, d) = tl + d for d >= l
+                const int off = rbase + (d >= l ? tl + d : td + l);
+                ra[i] = (kin && ((a_ok >> i) & 1u)) ? __ldg(pa + off) : 0.0;
+                l += 16;
+                while (l >= gn) { l -= gn; rbase += gnp; }
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const bool kin = A_KC ? (k0 + ak < K) : (k0 + ak + 2 * i < K);
-            ra[i] = (kin && ((a_ok >> i) & 1u)) ? __ldg(pa + i * a_step) : 0.0;
+            if constexpr (AMODE != 2) {
+                const bool kin = A_KC ? (k0 + ak < K) : (k0 + ak + 2 * i < K);
+                ra[i] = (kin && ((a_ok >> i) & 1u)) ? __ldg(pa + i * a_step) : 0.0;
+            }
             rb[i] = (b_ok && k0 + bk + 2 * i < K) ? __ldg(pb + i * b_step) : 0.0;
         }
-        pa += a_tile;
+        if constexpr (AMODE != 2) pa += a_tile;
         pb += b_tile;
     };
     auto sstore = [&](int buf) {
@@ -226,13 +254,13 @@ bool use_simt() {
     return e && e[0] == 's';
 }
 
-template <bool A_KC, bool MMA>
+template <int AMODE, bool MMA>
 int gemm_launch_t(const GemmArgs& g, int batch, cudaStream_t st) {
     static bool prepared[64] = {};
     int dev = 0;
     CUA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !prepared[dev]) {
-        CUA(cudaFuncSetAttribute(gemm_f64_kernel<A_KC, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+        CUA(cudaFuncSetAttribute(gemm_f64_kernel<AMODE, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
         prepared[dev] = true;
     }
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return MYQC_OK;
@@ -246,16 +274,17 @@ int gemm_launch_t(const GemmArgs& g, int batch, cudaStream_t st) {
         a.A += (int64_t)b0 * g.a_batch;
         a.B += (int64_t)b0 * g.b_batch;
         a.C += (int64_t)b0 * g.c_batch;
-        gemm_f64_kernel<A_KC, MMA><<<dim3(gx, gy, nb), GT, GEMM_SMEM, st>>>(a);
+        gemm_f64_kernel<AMODE, MMA><<<dim3(gx, gy, nb), GT, GEMM_SMEM, st>>>(a);
     }
     CUA(cudaGetLastError());
     return MYQC_OK;
 }
 
-int gemm_launch(bool a_kc, const GemmArgs& g, int batch, cudaStream_t st) {
+int gemm_launch(int amode, const GemmArgs& g, int batch, cudaStream_t st) {
     const bool simt = use_simt();
-    if (a_kc) return simt ? gemm_launch_t<true, false>(g, batch, st) : gemm_launch_t<true, true>(g, batch, st);
-    return simt ? gemm_launch_t<false, false>(g, batch, st) : gemm_launch_t<false, true>(g, batch, st);
+    if (amode == 2) return simt ? gemm_launch_t<2, false>(g, batch, st) : gemm_launch_t<2, true>(g, batch, st);
+    if (amode == 1) return simt ? gemm_launch_t<1, false>(g, batch, st) : gemm_launch_t<1, true>(g, batch, st);
+    return simt ? gemm_launch_t<0, false>(g, batch, st) : gemm_launch_t<0, true>(g, batch, st);
 }
 
 // ---- data movement kernels ---------------------------------------------------------------------
@@ -263,16 +292,43 @@ __device__ __forceinline__ int64_t tri_off(int64_t a, int64_t b, int64_t dim) { 
     return a * dim - ((a * (a - 1)) >> 1) + (b - a);
 }
 
-// Xsq[pp][l][d] = X[P0+pp, pair(l,d)]   grid (BP, n), threads over d
-__global__ void unpack_rows_kernel(const double* __restrict__ packed, int n, int64_t np, int64_t p0, double* __restrict__ xsq) {
+// Row panel of the symmetric pair matrix: Xrow[pp][P'] = X[P0+pp, P'] for all NP columns.
+// Columns P' >= P0 (the stored part of the rows, plus the small triangle inside the panel's own
+// diagonal block): one pass along the rows, coalesced.     grid (BP, chunks of 1024 columns)
+__global__ void __launch_bounds__(256) panel_upper_kernel(const double* __restrict__ packed, int64_t np, int64_t p0,
+                                                          double* __restrict__ xrow) {
     const int64_t P = p0 + blockIdx.x;
-    const int l = blockIdx.y;
-    double* dst = xsq + ((int64_t)blockIdx.x * n + l) * n;
-    for (int d = threadIdx.x; d < n; d += blockDim.x) {
-        const int a = l < d ? l : d, b = l < d ? d : l;
-        const int64_t Pp = tri_off(a, b, n);
-        const int64_t lo = P < Pp ? P : Pp, hi = P < Pp ? Pp : P;
-        dst[d] = __ldg(packed + tri_off(lo, hi, np));
+    double* dst = xrow + (int64_t)blockIdx.x * np;
+    const int64_t c0 = p0 + (int64_t)blockIdx.y * 1024;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t Pp = c0 + j * 256 + threadIdx.x;
+        if (Pp < np) {
+            const int64_t lo = P < Pp ? P : Pp, hi = P < Pp ? Pp : P;
+            dst[Pp] = __ldg(packed + tri_off(lo, hi, np));
+        }
+    }
+}
+
+// Columns P' < P0 live in the rows P' of the packed array, at columns P0 .. P0+BP-1 (contiguous):
+// 32 x 32 tiles transposed through shared memory, coalesced on both sides.  grid (BP/32, P0/32), block (32, 8)
+__global__ void __launch_bounds__(256) panel_lower_kernel(const double* __restrict__ packed, int64_t np, int64_t p0, int bp,
+                                                          double* __restrict__ xrow) {
+    __shared__ double tile[32][33];
+    const int pp0 = blockIdx.x * 32;
+    const int64_t q0 = (int64_t)blockIdx.y * 32;  // first P' of the tile
+#pragma unroll
+    for (int y = threadIdx.y; y < 32; y += 8) {
+        const int64_t Pp = q0 + y;
+        const int pp = pp0 + threadIdx.x;
+        if (Pp < p0 && pp < bp) tile[y][threadIdx.x] = __ldg(packed + tri_off(Pp, p0 + pp, np));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int y = threadIdx.y; y < 32; y += 8) {
+        const int pp = pp0 + y;
+        const int64_t Pp = q0 + threadIdx.x;
+        if (Pp < p0 && pp < bp) xrow[(int64_t)pp * np + Pp] = tile[threadIdx.x][y];
     }
 }
 
@@ -318,7 +374,7 @@ struct StageTrace {
     void report(const double* flops) {
         if (!on) return;
         cudaStreamSynchronize(st);
-        static const char* names[6] = {"unpack rows", "GEMM 1a", "GEMM 1b", "unpack cols", "GEMM 2a", "GEMM 2b"};
+        static const char* names[6] = {"row panel", "GEMM 1a", "GEMM 1b", "unpack cols", "GEMM 2a", "GEMM 2b"};
         double ms[6] = {0, 0, 0, 0, 0, 0};
         for (size_t k = 0; k < stage.size(); ++k) {
             float t = 0;
@@ -341,30 +397,49 @@ int64_t env_i64(const char* name, int64_t dflt) {
     return e ? std::atoll(e) : dflt;
 }
 
+// Scratch layout of one transformation (doubles): [panel | T/V | H | C2r C3r C4r]
+struct Sizes {
+    int64_t n, np, nrs, bp, rsb, panel, t, h, c;
+    int64_t total() const { return panel + t + h + c; }
+};
+
+Sizes plan_sizes(int norb, int n1, int n2, int n3, int n4) {
+    Sizes z{};
+    z.n = norb; z.np = z.n * (z.n + 1) / 2; z.nrs = (int64_t)n3 * n4;
+    // panel sizes: about MYQC_AO2MO_SCRATCH_MB (default 1536 MB) per panel
+    const int64_t budget = std::min<int64_t>(env_i64("MYQC_AO2MO_SCRATCH_MB", 1536) * 1000000 / 8, (int64_t)2000000000);  // doubles, < 2^31
+    z.bp = std::max<int64_t>(1, std::min<int64_t>(z.np, budget / z.np));          // rows of Xrow[bp][np]
+    z.bp = std::min<int64_t>(z.bp, (int64_t)65535 * BM / z.n);                     // row tiles of GEMM 1a
+    z.rsb = std::max<int64_t>(1, std::min<int64_t>(z.nrs, budget / (z.n * z.n)));  // columns of Gsq[n][n][rsb]
+    z.panel = std::max(z.bp * z.np, z.rsb * z.n * z.n);
+    z.t = std::max(z.bp * z.n * n4, z.n * z.rsb * n2);
+    z.h = z.np * z.nrs;
+    z.c = z.n * ((int64_t)n2 + n3 + n4);
+    (void)n1;
+    return z;
+}
+
 int transform_device(const double* d_packed, int norb, const double* d_c1, int n1, const double* d_c2, int n2,
-                     const double* d_c3, int n3, const double* d_c4, int n4, double* d_out, cudaStream_t st) {
+                     const double* d_c3, int n3, const double* d_c4, int n4, double* d_out, cudaStream_t st,
+                     double* ws = nullptr, int64_t ws_bytes = 0) {
     if (!d_packed || !d_c1 || !d_c2 || !d_c3 || !d_c4 || !d_out) return myqc::fock_fail(MYQC_ERR_BAD_ARG, "ao2mo: null pointer");
     if (norb < 1 || n1 < 1 || n2 < 1 || n3 < 1 || n4 < 1 || n1 > norb || n2 > norb || n3 > norb || n4 > norb)
         return myqc::fock_fail(MYQC_ERR_BAD_ARG, "ao2mo: block sizes must be in 1..norb");
-    const int64_t n = norb, np = n * (n + 1) / 2, nrs = (int64_t)n3 * n4;
-    // panel sizes: scratch of about MYQC_AO2MO_SCRATCH_MB (default 1536 MB) per unpacked panel
-    const int64_t budget = env_i64("MYQC_AO2MO_SCRATCH_MB", 1536) * 1000000 / 8;  // doubles
-    int64_t bp = std::max<int64_t>(1, std::min<int64_t>(np, budget / (n * n)));
-    bp = std::min<int64_t>(bp, (int64_t)65535 * BM / n);  // row tiles of GEMM 1a
-    int64_t rsb = std::max<int64_t>(1, std::min<int64_t>(nrs, budget / (n * n)));
-    const int64_t sz_panel = std::max(bp, rsb) * n * n;               // Xsq / Gsq
-    const int64_t sz_t = std::max(bp * n * n4, n * rsb * n2);         // T / V
-    const int64_t sz_h = np * nrs;
-    const int64_t sz_c = n * ((int64_t)n2 + n3 + n4);
-    double* buf = nullptr;
-    const size_t bytes = sizeof(double) * (size_t)(sz_panel + sz_t + sz_h + sz_c);
-    cudaError_t e = cudaMallocAsync((void**)&buf, bytes, st);
-    if (e != cudaSuccess)
-        return myqc::fock_fail(MYQC_ERR_NOMEM, "ao2mo scratch (" + std::to_string(bytes >> 20) + " MiB): " + cudaGetErrorString(e));
+    const Sizes z = plan_sizes(norb, n1, n2, n3, n4);
+    const int64_t n = z.n, np = z.np, nrs = z.nrs, bp = z.bp, rsb = z.rsb;
+    double* buf = ws;
+    const size_t bytes = sizeof(double) * (size_t)z.total();
+    if (ws) {
+        if ((size_t)ws_bytes < bytes) return myqc::fock_fail(MYQC_ERR_BAD_ARG, "ao2mo: workspace smaller than myqc_ao2mo_workspace_bytes()");
+    } else {
+        cudaError_t e = cudaMallocAsync((void**)&buf, bytes, st);
+        if (e != cudaSuccess)
+            return myqc::fock_fail(MYQC_ERR_NOMEM, "ao2mo scratch (" + std::to_string(bytes >> 20) + " MiB): " + cudaGetErrorString(e));
+    }
     double* panel = buf;
-    double* tbuf = panel + sz_panel;
-    double* h = tbuf + sz_t;
-    double* c2r = h + sz_h;
+    double* tbuf = panel + z.panel;
+    double* h = tbuf + z.t;
+    double* c2r = h + z.h;
     double* c3r = c2r + n * n2;
     double* c4r = c3r + n * n3;
     coef_rowmajor_kernel<<<64, 256, 0, st>>>(d_c2, norb, n2, c2r);
@@ -379,15 +454,17 @@ int transform_device(const double* d_packed, int norb, const double* d_c1, int n
     for (int64_t p0 = 0; p0 < np && !rc; p0 += bp) {
         const int64_t cur = std::min(bp, np - p0);
         tr.begin(0);
-        unpack_rows_kernel<<<dim3((unsigned)cur, (unsigned)n), 128, 0, st>>>(d_packed, norb, np, p0, panel);
+        panel_upper_kernel<<<dim3((unsigned)cur, (unsigned)((np - p0 + 1023) / 1024)), 256, 0, st>>>(d_packed, np, p0, panel);
+        if (p0 > 0)
+            panel_lower_kernel<<<dim3((unsigned)((cur + 31) / 32), (unsigned)((p0 + 31) / 32)), dim3(32, 8), 0, st>>>(d_packed, np, p0, (int)cur, panel);
         tr.end();
         GemmArgs a{};
-        a.A = panel; a.a_sm = n; a.a_sk = 1; a.a_batch = 0;
+        a.A = panel; a.a_sm = 0; a.a_sk = 0; a.a_batch = 0; a.g_n = norb; a.g_np = (int)np;
         a.B = c4r; a.ldb = n4; a.b_batch = 0;
         a.C = tbuf; a.c_sm = n4; a.c_sn = 1; a.c_batch = 0;
         a.M = (int)(cur * n); a.N = n4; a.K = norb;
         tr.begin(1);
-        rc = gemm_launch(true, a, 1, st);
+        rc = gemm_launch(2, a, 1, st);
         tr.end();
         if (rc) break;
         GemmArgs b{};
@@ -396,7 +473,7 @@ int transform_device(const double* d_packed, int norb, const double* d_c1, int n
         b.C = h + p0 * nrs; b.c_sm = n3; b.c_sn = 1; b.c_batch = nrs;
         b.M = n4; b.N = n3; b.K = norb;
         tr.begin(2);
-        rc = gemm_launch(false, b, (int)cur, st);
+        rc = gemm_launch(0, b, (int)cur, st);
         tr.end();
     }
     // ---- stage 2: bra half transformation, written into Om(p,q,r,s) -----------------------------
@@ -411,7 +488,7 @@ int transform_device(const double* d_packed, int norb, const double* d_c1, int n
         a.C = tbuf; a.c_sm = n2; a.c_sn = 1; a.c_batch = w * n2;
         a.M = (int)w; a.N = n2; a.K = norb;
         tr.begin(4);
-        rc = gemm_launch(false, a, norb, st);
+        rc = gemm_launch(0, a, norb, st);
         tr.end();
         if (rc) break;
         GemmArgs b{};
@@ -420,7 +497,7 @@ int transform_device(const double* d_packed, int norb, const double* d_c1, int n
         b.C = d_out + rs0 * n2 * n1; b.c_sm = 1; b.c_sn = n1; b.c_batch = 0;
         b.M = n1; b.N = (int)(w * n2); b.K = norb;
         tr.begin(5);
-        rc = gemm_launch(true, b, 1, st);
+        rc = gemm_launch(1, b, 1, st);
         tr.end();
     }
     {
@@ -430,7 +507,7 @@ int transform_device(const double* d_packed, int norb, const double* d_c1, int n
         tr.report(fl);
     }
     cudaError_t le = cudaGetLastError();
-    cudaFreeAsync(buf, st);
+    if (!ws) cudaFreeAsync(buf, st);
     if (rc) return rc;
     if (le != cudaSuccess) return myqc::fock_fail(MYQC_ERR_CUDA, std::string("ao2mo launch: ") + cudaGetErrorString(le));
     return MYQC_OK;
@@ -589,6 +666,20 @@ int myqc_ao2mo_transform(const double* d_packed, int norb, const double* d_c1, i
                          const double* d_c3, int n3, const double* d_c4, int n4, double* d_out, void* stream) {
     if (myqc_device_count() == 0) return myqc::fock_fail(MYQC_ERR_NO_DEVICE, "no CUDA device: ao2mo has no CPU fallback");
     return transform_device(d_packed, norb, d_c1, n1, d_c2, n2, d_c3, n3, d_c4, n4, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int64_t myqc_ao2mo_workspace_bytes(int norb, int n1, int n2, int n3, int n4) {
+    if (norb < 1 || n1 < 1 || n2 < 1 || n3 < 1 || n4 < 1) return 0;
+    return (int64_t)sizeof(double) * plan_sizes(norb, n1, n2, n3, n4).total();
+}
+
+int myqc_ao2mo_transform_ws(const double* d_packed, int norb, const double* d_c1, int n1, const double* d_c2, int n2,
+                            const double* d_c3, int n3, const double* d_c4, int n4, double* d_out, void* d_workspace,
+                            int64_t workspace_bytes, void* stream) {
+    if (myqc_device_count() == 0) return myqc::fock_fail(MYQC_ERR_NO_DEVICE, "no CUDA device: ao2mo has no CPU fallback");
+    if (!d_workspace) return myqc::fock_fail(MYQC_ERR_BAD_ARG, "ao2mo: null workspace");
+    return transform_device(d_packed, norb, d_c1, n1, d_c2, n2, d_c3, n3, d_c4, n4, d_out, static_cast<cudaStream_t>(stream),
+                            static_cast<double*>(d_workspace), workspace_bytes);
 }
 
 int myqc_ao2mo_transform_host(const double* packed, int norb, const double* c1, int n1, const double* c2, int n2,

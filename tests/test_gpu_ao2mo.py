@@ -68,6 +68,29 @@ def test_many_panels_and_column_chunks(tmp_path, oracle_inputs, monkeypatch):
     assert np.abs(got - O.ao2mo_idx_trans(xx, *c)).max() < TOL * 10
 
 
+def test_caller_workspace_form_matches(tmp_path):
+    """myqc_ao2mo_transform_ws (no allocation inside) == the allocating call; too small a workspace is refused."""
+    import torch
+    s = product_system("h2o_4", tmp_path)
+    n = s.norb
+    packed_h = Q.eri_packed(s)
+    c = blocks(n, (20, 8, 20, 8), 9)
+    ref = Q.ao2mo_transform(packed_h, n, *c)
+    packed = torch.from_numpy(packed_h).cuda()
+    dc = [torch.from_numpy(x.ravel(order="F").copy()).cuda() for x in c]
+    out = torch.empty(ref.size, dtype=torch.float64, device="cuda")
+    nbytes = Q.ao2mo_workspace_bytes(n, 20, 8, 20, 8)
+    ws = torch.empty(nbytes // 8 + 1, dtype=torch.float64, device="cuda")
+    for _ in range(2):  # the buffer is reusable
+        Q.ao2mo_transform_ws(packed.data_ptr(), n, dc[0].data_ptr(), 20, dc[1].data_ptr(), 8, dc[2].data_ptr(), 20,
+                             dc[3].data_ptr(), 8, out.data_ptr(), ws.data_ptr(), nbytes)
+        torch.cuda.synchronize()
+        assert np.abs(out.cpu().numpy().reshape(ref.shape, order="F") - ref).max() < 1e-12
+    with pytest.raises(Q.MyQCError):
+        Q.ao2mo_transform_ws(packed.data_ptr(), n, dc[0].data_ptr(), 20, dc[1].data_ptr(), 8, dc[2].data_ptr(), 20,
+                             dc[3].data_ptr(), 8, out.data_ptr(), ws.data_ptr(), nbytes - 8)
+
+
 def _scf_files(name, tmp_path, oracle_inputs, uhf):
     """int2e through the product, SCF through the oracle: leaves XX, basinfo, Cui in the job directory."""
     s = product_system(name, tmp_path)

@@ -32,10 +32,13 @@ for name in names:
     co, cv = c.data_ptr(), c.data_ptr() + 8 * n * nocc          # Cm(:,0:nocc-1), Cm(:,nocc:ntot-1)
     out = torch.empty(nocc * nvrt * nocc * nvrt, dtype=torch.float64, device="cuda")
     flops = Q.ao2mo_flops(n, nocc, nvrt, nocc, nvrt)
+    ws_bytes = Q.ao2mo_workspace_bytes(n, nocc, nvrt, nocc, nvrt)
+    ws = torch.empty(ws_bytes // 8 + 2, dtype=torch.float64, device="cuda")
     kinds = os.environ.get("AO2MO_BENCH_KINDS", "mma,simt" if name != "h2o_64" else "mma").split(",")
     for kind in kinds:
         os.environ["MYQC_AO2MO_GEMM"] = kind
-        fn = lambda: Q.ao2mo_transform_device(packed.data_ptr(), n, co, nocc, cv, nvrt, co, nocc, cv, nvrt, out.data_ptr(), st)
+        fn = lambda: Q.ao2mo_transform_ws(packed.data_ptr(), n, co, nocc, cv, nvrt, co, nocc, cv, nvrt, out.data_ptr(),
+                                          ws.data_ptr(), ws_bytes, st)
         fn(); torch.cuda.synchronize()
         reps = int(os.environ.get("AO2MO_BENCH_REPS", "3" if name != "h2o_64" else "2"))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -50,6 +53,6 @@ for name in names:
         print(json.dumps({"workload": name, "tiles": kind, "norb": n, "nocc": nocc, "nvrt": nvrt, "ms": ms,
                           "flops": flops, "tflops": flops / (ms * 1e-3) / 1e12, "fp64_peak_tflops_measured": peak, "dmma_peak_tflops_measured": dmma,
                           "frac": flops / (ms * 1e-3) / 1e12 / peak, "max_asymmetry": sym,
-                          "out_gb": 8e-9 * out.numel()}), flush=True)
-    del packed, out
+                          "out_gb": 8e-9 * out.numel(), "workspace_gb": 1e-9 * ws_bytes}), flush=True)
+    del packed, out, ws
     torch.cuda.empty_cache()
