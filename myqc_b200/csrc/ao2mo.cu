@@ -109,11 +109,12 @@ __global__ void __launch_bounds__(GT) gemm_f64_kernel(const GemmArgs g) {
     const bool b_ok = n0 + bn < N;
     // mode 2: first row of this thread as (panel row pp, AO index l); the other seven follow by +16
     const int gn = g.g_n, gnp = g.g_np;
-    int g_l0 = 0, g_rb0 = 0;
+    int g_l0 = 0, g_rb0 = 0, g_w = 8;  // g_w: first i whose row has wrapped into the next panel row (n >= 128)
     if (AMODE == 2) {
         const int pp = (m0 + am) / gn;
         g_l0 = (m0 + am) - pp * gn;
         g_rb0 = pp * gnp;
+        g_w = (gn - g_l0 + 15) >> 4;
     }
     double ra[8], rb[8];
     auto gload = [&](int k0) {
@@ -121,14 +122,26 @@ __global__ void __launch_bounds__(GT) gemm_f64_kernel(const GemmArgs g) {
             const int d = k0 + ak;
             const int td = d * gn - ((d * (d - 1)) >> 1) - d;  // pair(d, l) = td + l for l >= d
             const bool kin = d < K;
-            int l = g_l0, rbase = g_rb0;
+            if (gn >= 128) {  // at most one wrap inside the 8 x 16 rows of a thread: no dependent chain
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int tl = l * gn - ((l * (l - 1)) >> 1) - l;  // pair(l, d) = tl + d for d >= l
-                const int off = rbase + (d >= l ? tl + d : td + l);
-                ra[i] = (kin && ((a_ok >> i) & 1u)) ? __ldg(pa + off) : 0.0;
-                l += 16;
-                while (l >= gn) { l -= gn; rbase += gnp; }
+                for (int i = 0; i < 8; ++i) {
+                    const bool wr = i >= g_w;
+                    const int l = g_l0 + 16 * i - (wr ? gn : 0);
+                    const int rbase = g_rb0 + (wr ? gnp : 0);
+                    const int tl = l * gn - ((l * (l - 1)) >> 1) - l;  // pair(l, d) = tl + d for d >= l
+                    const int off = rbase + (d >= l ? tl + d : td + l);
+                    ra[i] = (kin && ((a_ok >> i) & 1u)) ? __ldg(pa + off) : 0.0;
+                }
+            } else {
+                int l = g_l0, rbase = g_rb0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int tl = l * gn - ((l * (l - 1)) >> 1) - l;
+                    const int off = rbase + (d >= l ? tl + d : td + l);
+                    ra[i] = (kin && ((a_ok >> i) & 1u)) ? __ldg(pa + off) : 0.0;
+                    l += 16;
+                    while (l >= gn) { l -= gn; rbase += gnp; }
+                }
             }
         }
 #pragma unroll
@@ -411,6 +424,7 @@ Sizes plan_sizes(int norb, int n1, int n2, int n3, int n4) {
     z.bp = std::max<int64_t>(1, std::min<int64_t>(z.np, budget / z.np));          // rows of Xrow[bp][np]
     z.bp = std::min<int64_t>(z.bp, (int64_t)65535 * BM / z.n);                     // row tiles of GEMM 1a
     z.rsb = std::max<int64_t>(1, std::min<int64_t>(z.nrs, budget / (z.n * z.n)));  // columns of Gsq[n][n][rsb]
+    if (z.rsb < z.nrs && z.rsb > BM) z.rsb -= z.rsb % BM;                          // whole row tiles of GEMM 2a
     z.panel = std::max(z.bp * z.np, z.rsb * z.n * z.n);
     z.t = std::max(z.bp * z.n * n4, z.n * z.rsb * n2);
     z.h = z.np * z.nrs;
