@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1027,19 +1028,81 @@ int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const
     rc = myqc_eri_plan_execute(pl, d_out, nullptr);
     if (trace) cudaDeviceSynchronize();
     const auto t3 = now();
+    const char* xfer_kind = "cudaMemcpy";
+    double xfer_frac = 1.0;
     if (!rc && n > 0) {
-        // pinned destinations run at PCIe speed; pageable ones are staged by the driver
-        cudaError_t e = cudaMemcpy(packed_slice, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = cuda_fail(e, "copy packed slice to host");
+        // Destination in device-accessible (pinned) host memory and a slice worth the trouble: sparse
+        // transfer.  ~90 % of a large molecule's integrals are exact zeros, so only the chunks that hold a
+        // nonzero cross PCIe (stored by the GPU straight into the host buffer) while host threads write the
+        // zeros of the other chunks locally.  Everything else: one cudaMemcpy (pinned destinations run at
+        // PCIe speed; pageable ones are staged by the driver).  MYQC_SPARSE_D2H=0 forces the plain copy.
+        cudaPointerAttributes pa{};
+        const char* envs = std::getenv("MYQC_SPARSE_D2H");
+        const bool want = !(envs && envs[0] == '0') && n >= (int64_t)(1 << 22);
+        bool sparse = want && cudaPointerGetAttributes(&pa, packed_slice) == cudaSuccess &&
+                      pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr;
+        cudaGetLastError();  // an unregistered pointer may leave a sticky-free error code behind
+        if (sparse) {
+            const int64_t nchunk = (n + myqc::kXferChunk - 1) / myqc::kXferChunk;
+            unsigned char* d_flags = nullptr;
+            unsigned char* h_flags = nullptr;
+            cudaEvent_t ev_flags = nullptr;
+            int sms = 0;
+            cudaError_t e = cudaMalloc((void**)&d_flags, (size_t)nchunk);
+            if (e == cudaSuccess) e = cudaMallocHost((void**)&h_flags, (size_t)nchunk);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_flags, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+            if (e == cudaSuccess) e = (cudaError_t)myqc::launch_chunk_flags(d_out, n, d_flags, sms, nullptr);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(h_flags, d_flags, (size_t)nchunk, cudaMemcpyDeviceToHost, nullptr);
+            if (e == cudaSuccess) e = cudaEventRecord(ev_flags, nullptr);
+            if (e == cudaSuccess)
+                e = (cudaError_t)myqc::launch_chunk_push(d_out, n, d_flags, static_cast<double*>(pa.devicePointer), sms, nullptr);
+            if (e == cudaSuccess) e = cudaEventSynchronize(ev_flags);
+            if (e == cudaSuccess) {
+                // zeros of the unflagged chunks, written by host threads while the push kernel runs
+                int nthr = (int)std::thread::hardware_concurrency();
+                if (const char* et = std::getenv("MYQC_HOST_THREADS")) nthr = std::atoi(et);
+                nthr = std::max(1, std::min(nthr / std::max(1, nshards), 32));
+                std::atomic<int64_t> sent{0};
+                auto zero_range = [&](int64_t c0, int64_t c1) {
+                    int64_t mine = 0, c = c0;
+                    while (c < c1) {
+                        if (h_flags[c]) { ++mine; ++c; continue; }
+                        int64_t r = c;
+                        while (r < c1 && !h_flags[r]) ++r;
+                        const int64_t e0 = c * myqc::kXferChunk, e1 = std::min<int64_t>(n, r * myqc::kXferChunk);
+                        std::memset(packed_slice + e0, 0, (size_t)(e1 - e0) * sizeof(double));
+                        c = r;
+                    }
+                    sent += mine;
+                };
+                std::vector<std::thread> th;
+                const int64_t per = (nchunk + nthr - 1) / nthr;
+                for (int t = 1; t < nthr; ++t)
+                    if (t * per < nchunk) th.emplace_back(zero_range, t * per, std::min<int64_t>(nchunk, (t + 1) * per));
+                zero_range(0, std::min<int64_t>(nchunk, per));
+                for (auto& t : th) t.join();
+                xfer_frac = (double)sent.load() / (double)nchunk;
+                xfer_kind = "sparse push";
+                e = cudaStreamSynchronize(nullptr);
+            }
+            if (ev_flags) cudaEventDestroy(ev_flags);
+            cudaFree(d_flags);
+            if (h_flags) cudaFreeHost(h_flags);
+            if (e != cudaSuccess) rc = cuda_fail(e, "sparse transfer of the packed slice to the host");
+        } else {
+            cudaError_t e = cudaMemcpy(packed_slice, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) rc = cuda_fail(e, "copy packed slice to host");
+        }
     }
     const auto t4 = now();
     cudaFree(d_out);
     myqc_eri_plan_destroy(pl);
     const auto t5 = now();
     if (trace)
-        std::fprintf(stderr, "[myqc trace] shard %d/%d: plan %.1f ms, cudaMalloc %.1f ms, execute %.1f ms, D2H %.1f ms (%.2f GB, %.1f GB/s), free %.1f ms\n",
+        std::fprintf(stderr, "[myqc trace] shard %d/%d: plan %.1f ms, cudaMalloc %.1f ms, execute %.1f ms, D2H %.1f ms (%.2f GB, %.1f GB/s effective, %s, %.1f %% of the chunks sent), free %.1f ms\n",
                      shard, nshards, ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), 8e-9 * (double)n,
-                     8e-9 * (double)n / (ms(t3, t4) * 1e-3 + 1e-12), ms(t4, t5));
+                     8e-9 * (double)n / (ms(t3, t4) * 1e-3 + 1e-12), xfer_kind, 100.0 * xfer_frac, ms(t4, t5));
     return rc;
 }
 

@@ -579,6 +579,59 @@ __global__ void expand_dense_kernel(const double* __restrict__ packed, int norb,
 }
 
 // ------------------------------------------------------------------------------------------
+// Sparse transfer to the host.  A warp owns a chunk of kXferChunk consecutive elements of the slice.
+__global__ void __launch_bounds__(256) chunk_flags_kernel(const double* __restrict__ out, int64_t n, unsigned char* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nchunk = (n + kXferChunk - 1) / kXferChunk;
+    const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nchunk; c += nwarp) {
+        const int64_t base = c * kXferChunk;
+        long long bits = 0;
+#pragma unroll
+        for (int j = 0; j < kXferChunk / 32; ++j) {
+            const int64_t e = base + j * 32 + lane;
+            if (e < n) bits |= __double_as_longlong(__ldcs(out + e));
+        }
+        const bool any = __any_sync(0xffffffffu, bits != 0);
+        if (lane == 0) flags[c] = any ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) chunk_push_kernel(const double* __restrict__ out, int64_t n, const unsigned char* __restrict__ flags,
+                                                         double* __restrict__ host) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nchunk = (n + kXferChunk - 1) / kXferChunk;
+    const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nchunk; c += nwarp) {
+        if (!flags[c]) continue;
+        const int64_t base = c * kXferChunk;
+        double v[kXferChunk / 32];
+#pragma unroll
+        for (int j = 0; j < kXferChunk / 32; ++j) {
+            const int64_t e = base + j * 32 + lane;
+            v[j] = e < n ? __ldcs(out + e) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < kXferChunk / 32; ++j) {
+            const int64_t e = base + j * 32 + lane;
+            if (e < n) host[e] = v[j];  // 256 contiguous bytes per warp store, posted over PCIe
+        }
+    }
+}
+
+int launch_chunk_flags(const double* out, int64_t n, unsigned char* flags, int num_sms, void* stream) {
+    if (n <= 0) return 0;
+    chunk_flags_kernel<<<num_sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, flags);
+    return (int)cudaGetLastError();
+}
+
+int launch_chunk_push(const double* out, int64_t n, const unsigned char* flags, double* host, int num_sms, void* stream) {
+    if (n <= 0) return 0;
+    chunk_push_kernel<<<num_sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, flags, host);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // Kernels that are meant to share SMs (the class kernels and the screened fill) must ask for the
 // same L1/shared split; with the default fill mode the split of every kernel is left to the driver
 // (a larger L1 is worth ~2 % on the small classes).

@@ -86,4 +86,11 @@ int measure_dfma_peak(int num_sms, double* tflops);
 int launch_fill_zero(double* out, int64_t n, int* counters, int ncounters, int num_sms, void* stream);
 int launch_expand_dense(const double* packed, int norb, double* xx, int num_sms, void* stream);
 
+// Sparse device -> host transfer of a packed slice (most of a large molecule's integrals are exact zeros):
+// chunks of kXferChunk doubles; flags[c] = 1 iff chunk c holds a nonzero bit pattern; the push kernel
+// stores the flagged chunks straight into device-accessible (pinned) host memory.
+constexpr int kXferChunk = 256;
+int launch_chunk_flags(const double* out, int64_t n, unsigned char* flags, int num_sms, void* stream);
+int launch_chunk_push(const double* out, int64_t n, const unsigned char* flags, double* host, int num_sms, void* stream);
+
 }  // namespace myqc

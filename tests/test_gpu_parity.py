@@ -203,3 +203,26 @@ def test_permuting_atoms_permutes_integrals(tmp_path, oracle_inputs):
     x1, x2 = Q.eri_dense(s1), Q.eri_dense(s2)
     p = np.concatenate([np.arange(7, 14), np.arange(0, 7)])
     assert np.abs(x1 - x2[np.ix_(p, p, p, p)]).max() < 1e-12
+
+
+@pytest.mark.parametrize("nsh,shift", [(1, 0), (2, 1)])
+def test_sparse_host_transfer_is_bit_identical(nsh, shift, tmp_path, monkeypatch):
+    """Pinned destination: only the chunks that hold a nonzero cross PCIe (stored by the GPU into the host
+    buffer), host threads write the zeros.  Same bytes as the plain cudaMemcpy path, for whole arrays and
+    shards, at odd element offsets of the destination, and with a poisoned destination (every element
+    must be written by one side or the other)."""
+    import torch
+    s = product_system("h2o_16", tmp_path)
+    off = Q.shard_layout(s, nsh)
+    for sh in range(nsh):
+        nloc = int(off[sh + 1] - off[sh])
+        assert nloc >= 1 << 22  # large enough for the sparse path
+        monkeypatch.setenv("MYQC_SPARSE_D2H", "0")
+        plain = np.empty(nloc)
+        Q.eri_packed_shard(s, plain, shard=sh, nshards=nsh)
+        monkeypatch.delenv("MYQC_SPARSE_D2H")
+        pinned = torch.full((nloc + 2,), float("nan"), dtype=torch.float64).pin_memory()
+        dst = pinned.numpy()[shift:shift + nloc]
+        Q.eri_packed_shard(s, dst, shard=sh, nshards=nsh)
+        assert np.array_equal(dst.view(np.int64), plain.view(np.int64))
+        assert np.isnan(pinned.numpy()[shift + nloc])  # nothing written past the slice
