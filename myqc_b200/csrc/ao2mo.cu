@@ -395,13 +395,13 @@ struct StageTrace {
             ms[stage[k]] += t;
         }
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
-        for (int k = 0; k < 6; ++k)
-            std::fprintf(stderr, "[myqc ao2mo trace] %-12s %9.3f ms%s", names[k], ms[k],
-                         flops[k] > 0 ? "" : "\n");
-        std::fprintf(stderr, "\n");
-        for (int k = 0; k < 6; ++k)
+        for (int k = 0; k < 6; ++k) {
             if (flops[k] > 0)
-                std::fprintf(stderr, "[myqc ao2mo trace] %-12s %7.2f TFLOP/s\n", names[k], flops[k] / (ms[k] * 1e-3 + 1e-30) / 1e12);
+                std::fprintf(stderr, "[myqc ao2mo trace] %-12s %9.3f ms  %6.2f TFLOP/s\n", names[k], ms[k],
+                             flops[k] / (ms[k] * 1e-3 + 1e-30) / 1e12);
+            else
+                std::fprintf(stderr, "[myqc ao2mo trace] %-12s %9.3f ms\n", names[k], ms[k]);
+        }
     }
 };
 

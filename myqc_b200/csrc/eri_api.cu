@@ -1060,9 +1060,11 @@ int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const
             if (e == cudaSuccess) e = cudaEventSynchronize(ev_flags);
             if (e == cudaSuccess) {
                 // zeros of the unflagged chunks, written by host threads while the push kernel runs
-                int nthr = (int)std::thread::hardware_concurrency();
+                // half the hardware threads, shared between the shards of one box, at most 8: measured on the
+                // 16-vCPU host of the B200 boxes, more writers only fight the PCIe stream for host memory
+                int nthr = std::min(8, (int)std::thread::hardware_concurrency() / 2 / std::max(1, nshards));
                 if (const char* et = std::getenv("MYQC_HOST_THREADS")) nthr = std::atoi(et);
-                nthr = std::max(1, std::min(nthr / std::max(1, nshards), 32));
+                nthr = std::max(1, std::min(nthr, 64));
                 std::atomic<int64_t> sent{0};
                 auto zero_range = [&](int64_t c0, int64_t c1) {
                     int64_t mine = 0, c = c0;

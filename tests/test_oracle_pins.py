@@ -140,8 +140,18 @@ def test_mp2_energy_of_co2_against_the_cfour_output_the_reference_ships(oracle_i
     f = O.ao2mo_files("mp2_rhf", xx, C, C, nA, nB)
     assert len(f["ijab_AA"]) == nA * (nA - 1) // 2 and len(f["ijab_AB"]) == nA * nA
     e_aa, e_ab, e2 = O.mp2_rhf_energy(f["ijab_AB"], eps, nA, b.norb - nA)
-    assert abs(e_aa - (-0.011001822459)) < 1e-6 and abs(e_ab - (-0.067863676761)) < 2e-6
-    assert abs(e2 - (-0.089867321680)) < 3e-6
+    cf = json.load(open(os.path.join(GOLDEN, "cfour_mp2.json")))  # parsed from examples/CO2/cfour/out by tools/make_golden.py
+    assert abs(e_aa - cf["E2(AA)"]) < 1e-6 and abs(e_ab - cf["E2(AB)"]) < 2e-6
+    assert abs(e2 - cf["E2(TOT)"]) < 3e-6
+    # committed fixture of the same quantities (tests/golden/ao2mo_CO2.npz): the GPU tests compare against it
+    g = np.load(os.path.join(GOLDEN, "ao2mo_CO2.npz"))
+    assert abs(float(g["e2"]) - e2) < 1e-12 and abs(float(g["e2_aa"]) - e_aa) < 1e-12
+    om = O.ao2mo_idx_trans(xx, C[:, :nA], C[:, nA:], C[:, :nA], C[:, nA:])
+    # eigenvectors are defined up to a sign (and rotations inside the degenerate pi pairs): compare through
+    # the fixture's own orbitals
+    Cg = g["C"]
+    om_g = O.ao2mo_idx_trans(xx, Cg[:, :nA], Cg[:, nA:], Cg[:, :nA], Cg[:, nA:])
+    assert np.abs(om_g - g["iajb"]).max() < 1e-12 and om.shape == om_g.shape
     # the UHF route on the same closed shell gives the same numbers (mp2.f90:154-237)
     fu = O.ao2mo_files("mp2_uhf", xx, C, C, nA, nB)
     s1, s2, s3, tot = O.mp2_uhf_energy(fu, eps, eps, nA, nB, b.norb)

@@ -9,6 +9,9 @@ box has no /root/reference).
   tests/golden/oracle_anchors.json  SCF energies / (00|00) values of the oracle, to be compared with
                               BASELINE.md section 2 (recorded there from the survey session)
   tests/golden/packed_<mol>.npy    oracle packed ERIs of the small examples (GPU parity fixtures)
+  tests/golden/cfour_mp2.json      MP2 energies of the CFOUR output the reference ships (examples/CO2/cfour/out)
+  tests/golden/ao2mo_CO2.npz       Cui / eig of the oracle's CO2 SCF and its (ia|jb) block: the ao2mo fixture
+                                   (`python tools/make_golden.py ao2mo` regenerates only these two)
 """
 import hashlib, json, os, re, shutil, sys
 import numpy as np
@@ -70,5 +73,29 @@ def main():
     json.dump(anchors, open(os.path.join(G, "oracle_anchors.json"), "w"), indent=1)
 
 
+def ao2mo_golden():
+    out = open(os.path.join(REF, "examples", "CO2", "cfour", "out")).read()
+    vals = {k: float(re.search(re.escape(k) + r"\s*=\s*(-?\d+\.\d+)", out).group(1))
+            for k in ("E(SCF)", "E2(AA)", "E2(AB)", "E2(TOT)")}
+    vals["source"] = "examples/CO2/cfour/out (CFOUR, true pi; myQC's float32 pi moves E2 by 1e-6)"
+    json.dump(vals, open(os.path.join(G, "cfour_mp2.json"), "w"), indent=1)
+    ft = O.read_ftab(os.path.join(INP, "Ftab"))
+    mb = open(os.path.join(INP, "mybasis")).read()
+    mol = O.parse_zmat(open(os.path.join(INP, "CO2", "ZMAT")).read())
+    b = O.build_basis(mb, mol.atoms)
+    xx, _ = O.int2e_dense(mol, b, ft)
+    S, H = O.int1e(mol, b, ft)
+    nA, nB = O.electrons(mol)
+    E, eps, _, C = O.scf_rhf(S, H, xx, nA + nB, O.nuclear_repulsion(mol), orbitals=True)
+    om = O.ao2mo_idx_trans(xx, C[:, :nA], C[:, nA:], C[:, :nA], C[:, nA:])
+    e_aa, e_ab, e2 = O.mp2_rhf_energy(O.ao2mo_files("mp2_rhf", xx, C, C, nA, nB)["ijab_AB"], eps, nA, b.norb - nA)
+    np.savez(os.path.join(G, "ao2mo_CO2.npz"), C=C, eig=eps, iajb=om, nocc=nA, e_scf=E, e2_aa=e_aa, e2_ab=e_ab, e2=e2)
+    print(vals, E, e_aa, e_ab, e2)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "ao2mo":
+        ao2mo_golden()
+    else:
+        main()
+        ao2mo_golden()
