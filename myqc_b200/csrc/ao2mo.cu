@@ -187,6 +187,9 @@ __global__ void __launch_bounds__(GT) gemm_f64_kernel(const GemmArgs g) {
         const double* a_s = gsm + buf * STAGE;
         const double* b_s = a_s + A_ELEMS;
         if constexpr (MMA) {
+            // a warp whose 64 x 32 tile lies entirely outside C (ragged last tiles: 320 = 2 x 128 + 64) issues
+            // no DMMA and leaves the tensor pipe of its SM sub-partition to the warp that shares it
+            if (m0 + wm < M && n0 + wn < N) {
 #pragma unroll
             for (int kk = 0; kk < BK; kk += 4) {
                 double af[8], bf[4];
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(GT) gemm_f64_kernel(const GemmArgs g) {
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dmma884(acc[i][2 * j], acc[i][2 * j + 1], af[i], bf[j]);
+            }
             }
         } else {
 #pragma unroll
