@@ -128,11 +128,6 @@ struct Cfg {
     static constexpr size_t OFF_U = OFF_EXP + 608 * 16;
     static constexpr size_t OFF_BAR = OFF_U + (size_t)NWARPS * 2 * U_BYTES;
     static constexpr bool LANE_AOS = (UT >= 1);  // measured: pays for {1,1},{1,2},{2,2}, costs for {0,x}
-    // deferred near/mid Boys pass: only where the Boys evaluation outweighs the R table + contraction
-#ifndef MYQC_DEFER_NEAR
-#define MYQC_DEFER_NEAR 0
-#endif
-    static constexpr bool DEFER_NEAR = (MYQC_DEFER_NEAR >= 1) && (LT <= MYQC_DEFER_NEAR);
     static constexpr int TASKP = class_task_pairs(UT, TT);                 // lane-side pairs per task
     static constexpr size_t OFF_SORT = OFF_BAR + (size_t)NWARPS * 2 * 8;   // per warp: TASKP idx + 64 bins (int)
     static constexpr size_t OFF_OUT = OFF_SORT + (size_t)NWARPS * (TASKP + 64) * 4;
@@ -332,31 +327,6 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
 #pragma unroll
                         for (int h = 0; h < NHT; ++h) K[f][h] = 0.0;
 
-                    // step A for one primitive quartet: K[f][H'] += D_k * R[H_k + H']
-                    auto contract = [&](const double* up, const double (&G)[LT + 1], double X, double Y, double Z) {
-                        double R[NR];
-                        build_R<LT>(G, X, Y, Z, R);
-                        static_for<0, NTU>([&](auto kc) {
-                            constexpr int k = decltype(kc)::value;
-                            constexpr int f = term_fn(UT, k);
-                            if constexpr (USL < 0 || f / 4 == USL) {
-                                constexpr int lf = (USL >= 0) ? (f % 4) : f;
-                                constexpr int hk = term_h(UT, k);
-                                const double cu = up[kRecCoef + k];
-                                static_for<0, NHT>([&](auto hc) {
-                                    constexpr int hp = decltype(hc)::value;
-                                    constexpr int ri = h_add(hk, hp);
-                                    K[lf][hp] = fma(cu, R[ri], K[lf][hp]);
-                                });
-                            }
-                        });
-                    };
-                    // Light classes (MYQC_DEFER_NEAR): a lane whose quartet needs the Taylor / Boys2 path only
-                    // notes the uniform-side primitive and moves on; the noted ones are done afterwards, when
-                    // every active lane is on that path.  The expensive branch then runs max-over-lanes times
-                    // instead of once per primitive in which any lane needs it.  (Per lane the same quartets
-                    // are evaluated by the same arithmetic; only the order of the K sums changes.)
-                    unsigned near_mask = 0;
                     for (int ku = 0; ku < npu; ++ku) {
                         const double* up = s_u + ku * FU;
                         if (up[4] * et < kScreen) break;  // IF (EGH*EIJ .LT. 1.0D-14) CYCLE  (int2e.f90:257)
@@ -380,32 +350,27 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
                                 G[j] = g;
                             }
                         } else {
-                            if constexpr (C::DEFER_NEAR) {
-                                near_mask |= 1u << ku;
-                                continue;
+                            const double rs = rsqrt_pos(s);
+                            const double alpha = pq * (rs * rs);
+                            boys_near_mid<Q, LT>(alpha * R2, alpha, rs, G, s_ft, s_exp);
+                        }
+                        double R[NR];
+                        build_R<LT>(G, X, Y, Z, R);
+                        // step A: K[f][H'] += D_k * R[H_k + H']
+                        static_for<0, NTU>([&](auto kc) {
+                            constexpr int k = decltype(kc)::value;
+                            constexpr int f = term_fn(UT, k);
+                            if constexpr (USL < 0 || f / 4 == USL) {
+                                constexpr int lf = (USL >= 0) ? (f % 4) : f;
+                                constexpr int hk = term_h(UT, k);
+                                const double cu = up[kRecCoef + k];
+                                static_for<0, NHT>([&](auto hc) {
+                                    constexpr int hp = decltype(hc)::value;
+                                    constexpr int ri = h_add(hk, hp);
+                                    K[lf][hp] = fma(cu, R[ri], K[lf][hp]);
+                                });
                             }
-                            const double rs = rsqrt_pos(s);
-                            const double alpha = pq * (rs * rs);
-                            boys_near_mid<Q, LT>(alpha * R2, alpha, rs, G, s_ft, s_exp);
-                        }
-                        contract(up, G, X, Y, Z);
-                    }
-                    if constexpr (C::DEFER_NEAR) {
-                        while (near_mask) {
-                            const int ku = __ffs(near_mask) - 1;
-                            near_mask &= near_mask - 1;
-                            const double* up = s_u + ku * FU;
-                            const double p = up[0];
-                            const double X = up[1] - Qx, Y = up[2] - Qy, Z = up[3] - Qz;
-                            const double R2 = fma(X, X, fma(Y, Y, Z * Z));
-                            const double s = p + q;
-                            const double pq = p * q;
-                            const double rs = rsqrt_pos(s);
-                            const double alpha = pq * (rs * rs);
-                            double G[LT + 1];
-                            boys_near_mid<Q, LT>(alpha * R2, alpha, rs, G, s_ft, s_exp);
-                            contract(up, G, X, Y, Z);
-                        }
+                        });
                     }
                     // step B: out[f][f'] += (-1)^{|H'|} D'_k' K[f][H'_k']
                     static_for<0, NTT>([&](auto kc) {
