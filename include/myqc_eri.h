@@ -77,6 +77,13 @@ int myqc_eri_packed_shard(int nnuc, const double *xyz, int nset, int setl, const
                           const double *ftab, double *packed_slice, int device, int shard, int nshards,
                           int64_t *h2d_bytes);
 
+/* Bytes that crossed the device -> host link in this thread's last myqc_eri_packed_shard call.  A
+ * pinned (device-accessible) destination of at least 4 Mi elements takes the sparse route: the slice
+ * is cut into 2 KB chunks, the GPU stores the chunks that hold a nonzero straight into the host buffer
+ * and host threads write the zeros of the others (MYQC_SPARSE_D2H=0 turns it off, MYQC_HOST_THREADS
+ * sets the number of zeroing threads); any other destination gets one cudaMemcpy of the slice.      */
+int64_t myqc_eri_last_d2h_bytes(void);
+
 /* ---- plan API: device-resident execution, one plan per (GPU, shard) -------------------------
  * A plan holds the shell-pair tables of one shard of the canonical quartet space on one device.
  * Shard s of nshards owns a contiguous block of rows of the packed array (rows = bra pair index

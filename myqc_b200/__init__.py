@@ -36,7 +36,7 @@ EXPORTS = [
     "myqc_eri_expand_dense", "myqc_read_env", "myqc_build_basis", "myqc_read_ftab",
     "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main", "myqc_eri_shard_layout",
     "myqc_eri_canonical_stats", "myqc_eri_plan_launch_count", "myqc_eri_plan_launch_info",
-    "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard", "myqc_write_xx_ex",
+    "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard", "myqc_write_xx_ex", "myqc_eri_last_d2h_bytes",
     # include/myqc_fock.h
     "myqc_fock_rhf", "myqc_fock_uhf", "myqc_fock_rhf_host", "myqc_fock_uhf_host",
     "myqc_fock_mask_words", "myqc_fock_mask_build", "myqc_fock_rhf_masked", "myqc_fock_uhf_masked",
@@ -103,6 +103,8 @@ def lib() -> ctypes.CDLL:
     L.myqc_eri_plan_execute_timed.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ctypes.c_float)]
     L.myqc_fp64_peak.argtypes = [c_int, _dp]
     L.myqc_eri_packed_shard.argtypes = common + [_dp, c_int, c_int, c_int, _i64p]
+    L.myqc_eri_last_d2h_bytes.argtypes = []
+    L.myqc_eri_last_d2h_bytes.restype = ctypes.c_int64
     c_i64 = ctypes.c_int64
     L.myqc_fock_rhf.argtypes = [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p]
     L.myqc_fock_uhf.argtypes = [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
@@ -130,7 +132,7 @@ def lib() -> ctypes.CDLL:
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("myqc_last_error", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
-                        "myqc_eri_plan_destroy", "myqc_ao2mo_flops", "myqc_fock_mask_words", "myqc_ao2mo_workspace_bytes"):
+                        "myqc_eri_plan_destroy", "myqc_eri_last_d2h_bytes", "myqc_ao2mo_flops", "myqc_fock_mask_words", "myqc_ao2mo_workspace_bytes"):
             fn.restype = c_int
     _lib = L
     return L
@@ -284,6 +286,11 @@ def eri_packed_shard(s: System, out: np.ndarray, device: int = 0, shard: int = 0
     _check(lib().myqc_eri_packed_shard(*s._common(), _d(out), device, shard, nshards, ctypes.byref(h2d)))
     _last_h2d_bytes = h2d.value
     return out
+
+
+def last_d2h_bytes() -> int:
+    """Bytes that crossed the device -> host link in the last eri_packed_shard call of this thread."""
+    return int(lib().myqc_eri_last_d2h_bytes())
 
 
 def plan_h2d_bytes(s: System) -> int:

@@ -22,6 +22,7 @@
 namespace myqc {
 
 thread_local std::string g_last_error;
+thread_local int64_t g_last_d2h_bytes = 0;
 
 static int fail(int code, const std::string& msg) {
     g_last_error = msg;
@@ -529,6 +530,7 @@ static int check_args(int nnuc, const double* xyz, int nset, int setl, const dou
 extern "C" {
 
 const char* myqc_last_error(void) { return g_last_error.c_str(); }
+int64_t myqc_eri_last_d2h_bytes(void) { return myqc::g_last_d2h_bytes; }
 
 int myqc_device_count(void) {
     int n = 0;
@@ -1085,6 +1087,7 @@ int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const
                 zero_range(0, std::min<int64_t>(nchunk, per));
                 for (auto& t : th) t.join();
                 xfer_frac = (double)sent.load() / (double)nchunk;
+                myqc::g_last_d2h_bytes = sent.load() * myqc::kXferChunk * (int64_t)sizeof(double) + nchunk;
                 xfer_kind = "sparse push";
                 e = cudaStreamSynchronize(nullptr);
             }
@@ -1095,6 +1098,7 @@ int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const
         } else {
             cudaError_t e = cudaMemcpy(packed_slice, d_out, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) rc = cuda_fail(e, "copy packed slice to host");
+            myqc::g_last_d2h_bytes = n * (int64_t)sizeof(double);
         }
     }
     const auto t4 = now();
