@@ -340,9 +340,9 @@ def run_ours(args):
         k["frac"] = k["achieved"] / k["peak"] if k["peak"] else None
     dom = max(kernels, key=lambda k: k["ms"])
     # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this
-    # same workload (profiles/r1b_h2o64_dram_traffic_bytes.json); null for other workloads / shard counts
+    # same workload (profiles/r1c_h2o64_dram_traffic_bytes.json); null for other workloads / shard counts
     traffic = None
-    tfile = os.path.join(ROOT, "profiles", "r1b_h2o64_dram_traffic_bytes.json")
+    tfile = os.path.join(ROOT, "profiles", "r1c_h2o64_dram_traffic_bytes.json")
     if args.workload == "h2o_64" and world == 1 and os.path.exists(tfile):
         tmap = json.load(open(tfile))
         key = {"fill_zero": "fill_zero_kernel"}.get(dom["kernel"])
@@ -354,7 +354,7 @@ def run_ours(args):
             traffic = float(sum(hits))
     roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
                 "unit": dom["unit"], "frac": dom["frac"], "traffic": traffic,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1b_h2o64_ncu_full.json",
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r1c_h2o64_ncu_full.json",
                 "peak_source": peak_src if dom["bound"] == "hbm" else "measured DFMA microbenchmark in this run (myqc_fp64_peak)",
                 "share_of_step": dom["ms"] / float(acc.sum()) if acc.sum() > 0 else None}
     whole = {"fp64_tflops_model": model_flops / (ms * 1e-3) / 1e12 / 1.0,
