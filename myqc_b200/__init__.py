@@ -42,6 +42,8 @@ EXPORTS = [
     "myqc_fock_mask_words", "myqc_fock_mask_build", "myqc_fock_rhf_masked", "myqc_fock_uhf_masked",
     # include/myqc_int1e.h
     "myqc_int1e", "myqc_int1e_main",
+    # include/myqc_parse.h
+    "myqc_parse_zmat", "myqc_parse_main",
     # include/myqc_ao2mo.h
     "myqc_ao2mo_transform", "myqc_ao2mo_transform_host", "myqc_pack_dense", "myqc_ao2mo_main", "myqc_ao2mo_flops", "myqc_dmma_peak",
     "myqc_ao2mo_workspace_bytes", "myqc_ao2mo_transform_ws",
@@ -117,6 +119,9 @@ def lib() -> ctypes.CDLL:
     L.myqc_fock_uhf_host.argtypes = [_dp, c_int, _dp, _dp, _dp, _dp]
     L.myqc_int1e.argtypes = [c_int, _dp, _ip, c_int, c_int, _dp, _ip, c_int, _dp, _ip, _dp, _dp, _dp]
     L.myqc_int1e_main.argtypes = [c_char_p]
+    L.myqc_parse_zmat.argtypes = [c_char_p, c_int, ctypes.POINTER(c_int), _ip, _dp, _ip, ctypes.POINTER(c_int),
+                                  ctypes.POINTER(c_int), ctypes.POINTER(c_int)]
+    L.myqc_parse_main.argtypes = [c_char_p]
     L.myqc_ao2mo_transform.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int,
                                        c_void_p, c_void_p]
     L.myqc_ao2mo_transform_host.argtypes = [_dp, c_int, _dp, c_int, _dp, c_int, _dp, c_int, _dp, c_int, _dp]
@@ -401,17 +406,17 @@ def pair_index(i: int, j: int, norb: int) -> int:
 # ---- job helpers ----------------------------------------------------------------------------
 def make_job(workdir: str, zmat_text: str, inputs_dir: str) -> System:
     """Create a myQC job directory (ZMAT + mybasis + Ftab), run the `parse` stage
-    (myqc_b200.parse) and load what int2e would read."""
+    (myqc_parse_main, include/myqc_parse.h) and load what int2e would read."""
     import shutil
-
-    from . import parse as _parse
 
     os.makedirs(workdir, exist_ok=True)
     with open(os.path.join(workdir, "ZMAT"), "w") as f:
         f.write(zmat_text)
     for name in ("mybasis", "Ftab"):
         shutil.copyfile(os.path.join(inputs_dir, name), os.path.join(workdir, name))
-    _parse.parse(workdir)
+    rc = parse_main(workdir)
+    if rc != MYQC_OK:
+        raise MyQCError(rc, lib().myqc_last_error().decode())
     return load_system(workdir)
 
 
@@ -529,6 +534,26 @@ def int1e(s: System):
     _check(lib().myqc_int1e(s.nnuc, _d(s.xyz), _i(atoms), s.nset, s.setl, _d(s.set), _i(s.setinfo), s.ops,
                             _d(s.bas), _i(s.basinfo), _d(s.ftab), _d(S), _d(H)))
     return S, H
+
+
+def parse_zmat(zmat_text: str):
+    """myqc_parse_zmat (PROGRAM parser's arithmetic, parser.f90): returns
+    (atoms int32[n], xyz float64[n,3] bohr, options int32[17], nelcA, nelcB, problems bit mask)."""
+    L = lib()
+    n, na, nb, pr = (ctypes.c_int() for _ in range(4))
+    opts = np.zeros(17, dtype=np.int32)
+    _check(L.myqc_parse_zmat(zmat_text.encode(), 0, n, None, None, _i(opts), na, nb, pr))
+    atoms = np.zeros(n.value, dtype=np.int32)
+    xyz = np.zeros(3 * n.value)
+    _check(L.myqc_parse_zmat(zmat_text.encode(), n.value, n, _i(atoms), _d(xyz), _i(opts), na, nb, pr))
+    return atoms, xyz.reshape(-1, 3), opts, na.value, nb.value, pr.value
+
+
+def parse_main(workdir: str) -> int:
+    """PROGRAM parser (parser.f90:22-108) in `workdir`: ZMAT -> nucpos, envdat, fmem; returns the status."""
+    import sys
+    sys.stdout.flush()
+    return lib().myqc_parse_main(workdir.encode())
 
 
 def int1e_main(workdir: str) -> int:

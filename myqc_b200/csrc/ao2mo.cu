@@ -745,7 +745,13 @@ int myqc_pack_dense(const double* xx, int norb, double* packed) {
     return MYQC_OK;
 }
 
+static int ao2mo_main_impl(const char* dir);
 int myqc_ao2mo_main(const char* dir) {
+    const int rc = ao2mo_main_impl(dir);
+    std::fflush(stdout);  // see myqc_parse_main
+    return rc;
+}
+static int ao2mo_main_impl(const char* dir) {
     // banner: ao2mo.f90:39-45
     std::printf("\n                 STARTING AO TRANSFORM\n ------------------------------------------------------------\n"
                 " ao2mo called\n\n Starting AO to MO integral transform\n");

@@ -327,7 +327,13 @@ static void write_fmem(const char* dir, double fmem) {  // nmem / setenv, env.f9
     std::fclose(f);
 }
 
+static int int2e_main_impl(const char* dir, int ngpu);
 int myqc_int2e_main(const char* dir, int ngpu) {
+    const int rc = int2e_main_impl(dir, ngpu);
+    std::fflush(stdout);  // see myqc_parse_main
+    return rc;
+}
+static int int2e_main_impl(const char* dir, int ngpu) {
     std::printf("\n int2e called\n");  // int2e.f90:48-49
     int nnuc = 0, nA = 0, nB = 0, nopt = 0;
     double fmem = 0;
@@ -421,7 +427,13 @@ static int write_real_list(const std::string& path, const double* v, size_t n) {
     return MYQC_OK;
 }
 
+static int int1e_main_impl(const char* dir);
 int myqc_int1e_main(const char* dir) {
+    const int rc = int1e_main_impl(dir);
+    std::fflush(stdout);
+    return rc;
+}
+static int int1e_main_impl(const char* dir) {
     std::printf(" int1e called\n");  // int1e.f90:47
     int nnuc = 0, nA = 0, nB = 0, nopt = 0;
     double fmem = 0;

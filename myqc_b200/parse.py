@@ -21,33 +21,43 @@ DEFAULTS = [0, 0, 0, 0, 0, 1, 1000, 1, 7, 0, 1, 0, 1, 0, 0, 0, 0]
 
 
 def _opt_value(key: str, val: str):
-    """(index, value) for the keys read_options understands (parser.f90:683-735)."""
-    v = val.upper()
+    """(index, value) for the keys read_options understands (parser.f90:683-735) with the value tables of
+    getcalc .. get_prop (:147-431); keys and values are case-sensitive, as in the reference."""
     if key == "CALC=":
-        return 1, {"SCF": 0, "MP2": 1}.get(v, 0)
+        if val in ("SCF", "HF"):
+            return 1, 0
+        if val in ("MP2", "CIS"):
+            return 1, {"MP2": 1, "CIS": 2}[val]
+        raise ValueError("Sorry, that method has not been implimented. Exiting...")
     if key == "BASIS=":
-        return 2, {"STO-3G": 0, "tester1": 1, "tester2": 2, "tester3": 3}.get(val, 0)
+        if val not in ("STO-3G", "tester1", "tester2", "tester3"):
+            raise ValueError("Sorry, that basis has not been implimented. Exiting...")
+        return 2, {"STO-3G": 0, "tester1": 1, "tester2": 2, "tester3": 3}[val]
     if key == "REF=":
-        return 3, {"RHF": 0, "UHF": 1, "ROHF": 2}.get(v, 0)
+        if val not in ("RHF", "UHF", "ROHF"):
+            raise ValueError("Sorry, that reference has not been implimented. Exiting...")
+        return 3, {"RHF": 0, "UHF": 1, "ROHF": 2}[val]
     if key == "PAR=":
-        return 4, {"NONE": 0, "OMP": 1, "MPI": 2}.get(v, 0)
+        return 4, {"OMP": 2, "MPI": 3}.get(val, 1)
     if key == "NODES=":
-        return 5, int(val)
+        return 5, 1
     if key == "MEMORY=":
-        return 6, int(val)
+        return 6, 1000 if int(val) < 0 else int(val)
     if key == "VERB=":
-        return 7, int(val)
+        return 7, {"1": 1, "2": 2, "3": 3}.get(val, 0)
     if key == "SCF_Conv=":
         return 8, int(val)
     if key == "CHARGE=":
         return 9, int(val.replace("+", ""))
     if key == "MULTI=":
+        if int(val) <= 0:
+            raise ValueError("bad value for multiplicity, exiting.")
         return 10, int(val)
     if key == "UNITS=":
-        return 11, 1 if v.startswith("B") else 0
+        return 11, 1 if val == "Bohr" else 0
     if key == "AO2MO=":  # getao2mo, parser.f90:359-371: every value selects the slow transform
         return 12, 1
-    if key == "EXCITE=":  # getexcite, parser.f90:375-386 (case-sensitive)
+    if key == "EXCITE=":  # getexcite, parser.f90:375-386
         return 13, 1 if val in ("CIS", "1") else 0
     if key == "ROOT_ALG=":  # getroot_alg, parser.f90:390-399
         return 14, 0
@@ -60,19 +70,28 @@ def _opt_value(key: str, val: str):
 
 def parse_zmat(text: str):
     """Returns (atoms int32[n], xyz float64[n,3] in bohr after the COM shift, options int32[17])."""
-    rows = [ln.split() for ln in text.splitlines() if ln.strip()]
-    if not rows or rows[0][0] != "CARTESIAN":
-        raise ValueError("Sorry, that input style not supported yet (parser.f90:77-85)")
-    atoms, coords = [], []
-    k = 1
-    while k < len(rows) and rows[k][0] != "END":
-        atoms.append(ELEMENTS.index(rows[k][0]) + 1)
-        coords.append([float(x) for x in rows[k][1:4]])
+    lines = [ln.replace(",", " ").split() for ln in text.splitlines()]
+    k = 0
+    while k < len(lines) and not lines[k]:
         k += 1
-    if k == len(rows):
+    if k == len(lines) or lines[k][0] not in ("CARTESIAN", "INTERNAL"):
+        raise ValueError("Bad system type input. Exiting...")  # getsys, parser.f90:147-162
+    if lines[k][0] != "CARTESIAN":
+        raise ValueError("Sorry, that input style not supported yet")  # parser.f90:81-84
+    atoms, coords = [], []
+    k += 1
+    while k < len(lines) and (not lines[k] or lines[k][0] != "END"):
+        if lines[k]:  # list-directed reads skip blank records
+            atoms.append(ELEMENTS.index(lines[k][0]) + 1)
+            coords.append([float(x.replace("D", "E").replace("d", "E")) for x in lines[k][1:4]])
+        k += 1
+    if k == len(lines):
         raise ValueError("You need to put 'END' marker in ZMAT")
+    if not atoms:
+        raise ValueError("No atoms in system")
     options = list(DEFAULTS)
-    for r in rows[k + 1:]:
+    # read_options (parser.f90:683-735): `READ(1,*)` skips one record after END, then KEY= VALUE records
+    for r in lines[k + 2:]:
         if len(r) >= 2:
             kv = _opt_value(r[0], r[1])
             if kv is not None:

@@ -186,7 +186,56 @@ def test_ao2mo_program_without_a_device_touches_error(tmp_path):
     leaves the `error` sentinel the driver tests (myQC.f90:74-78)."""
     if Q.device_count() > 0:
         pytest.skip("a GPU is present")
-    zm = example_zmat("H2").replace("CALC= SCF", "CALC= MP2")
-    Q.make_job(str(tmp_path), zm, INPUTS)
-    open(tmp_path / "basinfo", "w").write(" 4 2\n")
+    Q.make_job(str(tmp_path), example_zmat("Be"), INPUTS)  # CALC= MP2, REF= RHF
+    open(tmp_path / "basinfo", "w").write(" 4 5\n")
     assert Q.ao2mo_main(str(tmp_path)) == Q.ERR_NO_DEVICE and (tmp_path / "error").exists()
+
+
+# ---- N3: the `parse` stage in C++ (include/myqc_parse.h) ----------------------------------------
+@pytest.mark.parametrize("name", EXAMPLES + ["O_triplet", "h2o_16", "c20h42", "h2o_64"])
+def test_cpp_parser_matches_python_mirror_and_oracle(name):
+    """myqc_parse_zmat == myqc_b200.parse == the oracle's restatement of parser.f90: atoms, the
+    centre-of-mass / unit-converted geometry bit for bit, all 17 options, electron counts."""
+    zm = example_zmat(name)
+    a, x, o, na, nb, problems = Q.parse_zmat(zm)
+    a2, x2, o2 = parse.parse_zmat(zm)
+    m = O.parse_zmat(zm)
+    assert np.array_equal(a, a2) and np.array_equal(x, x2) and np.array_equal(o, o2)
+    assert np.array_equal(x, m.xyz) and np.array_equal(a, m.atoms)
+    assert (na, nb) == parse.electron_counts(a2, o2) == tuple(O.electrons(m)) and problems == 0
+
+
+def test_parse_program_files_and_error_sentinel(tmp_path):
+    """PROGRAM parser at the process boundary: nucpos / envdat / fmem token for token as the Python mirror
+    writes them; `error` in the cases the reference touches it (parser.f90:81-84, 640-644, 513-524, 94-99)."""
+    def run(zm, sub):
+        d = tmp_path / sub
+        d.mkdir()
+        (d / "ZMAT").write_text(zm)
+        return d, Q.parse_main(str(d))
+
+    zm = example_zmat("OH")
+    d, rc = run(zm, "ok")
+    assert rc == 0 and not (d / "error").exists()
+    ref = tmp_path / "ref"
+    parse.write_job_files(str(ref), *parse.parse_zmat(zm))
+    for f in ("nucpos", "envdat", "fmem"):
+        assert (d / f).read_text().split() == (ref / f).read_text().split(), f
+    atoms, xyz, na, nb, fmem, opts = Q.read_env(str(d))
+    assert (na, nb) == (5, 4) and fmem == 1000.0 and opts[13] == 1 and opts[15] == 4  # EXCITE= CIS, E_NUM= 4
+    # the record right after END is skipped by read_options' bare READ(1,*) -- also when it is an option line
+    d, rc = run(zm.replace("END\n\n", "END\n"), "skipped")
+    assert rc == 0 and Q.read_env(str(d))[5][1] == 0 and parse.parse_zmat(zm.replace("END\n\n", "END\n"))[2][1] == 0
+    d, rc = run(zm.replace("CARTESIAN", "INTERNAL"), "internal")
+    assert rc != 0 and (d / "error").exists() and not (d / "nucpos").exists()
+    d, rc = run(zm.replace("END", ""), "noend")
+    assert rc != 0 and (d / "error").exists()
+    d, rc = run(zm.replace("REF= UHF", "REF= RHF"), "rhf_open_shell")  # files are written, error is touched
+    assert (d / "error").exists() and (d / "envdat").exists()
+    d, rc = run(example_zmat("H2").replace("0.50", "0.10"), "close")
+    assert (d / "error").exists()
+    d, rc = run(example_zmat("CO2").replace("CALC= MP2", "CALC= MP2\nEXCITE= CIS"), "bad_options")
+    assert rc != 0 and (d / "error").exists()
+    d, rc = run(example_zmat("HF") + "FOO= 1\n", "unknown_key")  # reported, ignored
+    assert rc == 0 and not (d / "error").exists()
+    assert Q.parse_main(str(tmp_path / "nowhere")) == Q.ERR_IO
