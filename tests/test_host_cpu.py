@@ -259,3 +259,20 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["metric"] == "unique_eris_per_s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["config"]["workload"] == "CO2"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_bench_reference_arm_under_torchrun_only_rank0_prints():
+    """The driver launches the reference arm like ours (torchrun, N ranks): rank 0 prints the line, the others
+    exit 0 without output."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--workload", "CO2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1, out.stdout[:2000]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2
