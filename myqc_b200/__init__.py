@@ -37,6 +37,7 @@ EXPORTS = [
     "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main", "myqc_eri_shard_layout",
     "myqc_eri_canonical_stats", "myqc_eri_plan_launch_count", "myqc_eri_plan_launch_info",
     "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard", "myqc_write_xx_ex", "myqc_eri_last_d2h_bytes",
+    "myqc_eri_plan_launch_quartets", "myqc_eri_plan_check", "myqc_eri_release_cache",
     # include/myqc_fock.h
     "myqc_fock_rhf", "myqc_fock_uhf", "myqc_fock_rhf_host", "myqc_fock_uhf_host",
     "myqc_fock_mask_words", "myqc_fock_mask_build", "myqc_fock_rhf_masked", "myqc_fock_uhf_masked",
@@ -101,7 +102,11 @@ def lib() -> ctypes.CDLL:
     L.myqc_eri_shard_layout.argtypes = common[:-1] + [c_int, _i64p]
     L.myqc_eri_canonical_stats.argtypes = [c_int, _dp, c_int, c_int, _dp, _ip, _i64p, _dp]
     L.myqc_eri_plan_launch_count.argtypes = [c_void_p]
-    L.myqc_eri_plan_launch_info.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), _i64p]
+    L.myqc_eri_plan_launch_info.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int), _i64p]
+    L.myqc_eri_plan_launch_quartets.argtypes = [c_void_p, _i64p]
+    L.myqc_eri_plan_check.argtypes = [c_int, _dp, c_int, c_int, _dp, _ip, c_int, _dp, _ip, c_int, c_int, _i64p]
+    L.myqc_eri_release_cache.argtypes = []
+    L.myqc_eri_release_cache.restype = None
     L.myqc_eri_plan_execute_timed.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ctypes.c_float)]
     L.myqc_fp64_peak.argtypes = [c_int, _dp]
     L.myqc_eri_packed_shard.argtypes = common + [_dp, c_int, c_int, c_int, _i64p]
@@ -137,7 +142,8 @@ def lib() -> ctypes.CDLL:
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("myqc_last_error", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
-                        "myqc_eri_plan_destroy", "myqc_eri_last_d2h_bytes", "myqc_ao2mo_flops", "myqc_fock_mask_words", "myqc_ao2mo_workspace_bytes"):
+                        "myqc_eri_plan_destroy", "myqc_eri_last_d2h_bytes", "myqc_ao2mo_flops", "myqc_fock_mask_words", "myqc_ao2mo_workspace_bytes",
+                        "myqc_eri_release_cache"):
             fn.restype = c_int
     _lib = L
     return L
@@ -298,6 +304,19 @@ def last_d2h_bytes() -> int:
     return int(lib().myqc_eri_last_d2h_bytes())
 
 
+def plan_check(s: System, shard: int = 0, nshards: int = 1) -> dict:
+    """Host-only coverage check of one shard's plan (no device needed): replays what the kernels write."""
+    r = (ctypes.c_int64 * 6)()
+    c = s._common()
+    _check(lib().myqc_eri_plan_check(*c[:9], shard, nshards, r))
+    return {"errors": r[0], "slice_elems": r[1], "zero_filled": r[2], "stored": r[3], "expected": r[4], "tasks": r[5]}
+
+
+def release_cache():
+    """Drop the plan / device slice the one-shot calls keep per device."""
+    lib().myqc_eri_release_cache()
+
+
 def plan_h2d_bytes(s: System) -> int:
     """Bytes of pair/Boys tables the last eri_packed_shard call uploaded."""
     return _last_h2d_bytes
@@ -338,13 +357,20 @@ class Plan:
         _check(lib().myqc_eri_plan_execute(self._h, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(stream)))
 
     def launches(self):
-        """[(class id or -1 for the zero fill, tri flag, rows)] in launch order."""
+        """[(owner kind ut, partner-first-shell kind tc, slice, tasks)] in launch order."""
         out = []
         for k in range(lib().myqc_eri_plan_launch_count(self._h)):
-            c, t, r = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
-            _check(lib().myqc_eri_plan_launch_info(self._h, k, ctypes.byref(c), ctypes.byref(t), ctypes.byref(r)))
-            out.append((c.value, t.value, r.value))
+            u, t, sl, r = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+            _check(lib().myqc_eri_plan_launch_info(self._h, k, ctypes.byref(u), ctypes.byref(t), ctypes.byref(sl), ctypes.byref(r)))
+            out.append((u.value, t.value, sl.value, r.value))
         return out
+
+    def launch_quartets(self):
+        """After an execute: per launch, primitive quartets evaluated against partners with an S / an SP second shell."""
+        n = lib().myqc_eri_plan_launch_count(self._h)
+        nq = (ctypes.c_int64 * (2 * n))()
+        _check(lib().myqc_eri_plan_launch_quartets(self._h, nq))
+        return [(nq[2 * k], nq[2 * k + 1]) for k in range(n)]
 
     def execute_timed(self, d_out_ptr: int, stream: int = 0):
         """Like execute(), but synchronises and returns per-launch milliseconds (CUDA events)."""
@@ -374,6 +400,12 @@ class Plan:
 
 CLASS_NAMES = ["{0,0}", "{0,1}", "{0,2}", "{1,1}", "{1,2}", "{2,2}"]
 CLASS_W = [60.0, 99.0, 228.0, 228.0, 693.0, 2691.0]  # model flop per canonical primitive quartet
+
+
+def class_id(la: int, lb: int) -> int:
+    """Index into CLASS_NAMES / CLASS_W of the quartet class with la and lb SP sets in its two pairs."""
+    la, lb = min(la, lb), max(la, lb)
+    return [[0, 1, 2], [1, 3, 4], [2, 4, 5]][la][lb]
 
 
 def shard_layout(s: System, nshards: int) -> np.ndarray:

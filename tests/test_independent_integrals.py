@@ -1,0 +1,220 @@
+"""An independent witness for the oracle (and, through the golden vectors, for the CUDA path).
+
+The oracle, the golden fixtures and the kernels all evaluate the integrals the way the reference does:
+McMurchie-Davidson (Hermite expansion coefficients, R_NLM recursion, int2e.f90:618-726, auxilary.f90:22-80,
+349-633).  This file evaluates a sample of two- and three-centre integrals by a DIFFERENT algorithm -- the
+Obara-Saika vertical recurrence on primitive Cartesian Gaussians, in 40-digit mpmath arithmetic -- and shares
+with the reference only what DEFINES its numbers and is not an algorithmic choice:
+  * float32 pi in the prefactor 2 pi^2.5/(p q sqrt(p+q)), in the normalisation and in F0 for T >= 12,
+  * Boys values from the bytes of the `Ftab` file with the reference's three regimes, started at order
+    Q = 3 x (number of SP sets) (T2, T3, T5; auxilary.f90:85-215,265-285, restated here from the Fortran),
+  * the primitive screen EIJ*EGH < 1e-14 (T4, int2e.f90:257).
+If the Hermite machinery of the oracle had a flaw (a wrong sign, a missing term, a wrong term list), these
+numbers would differ at the 1e-3..1e-8 level; they agree to ~1e-13."""
+import itertools
+import os
+import struct
+
+import mpmath as mp
+import numpy as np
+import pytest
+
+import myqc_b200 as Q
+from conftest import GOLDEN, INPUTS, product_system
+
+mp.mp.dps = 40
+PI32 = mp.mpf(float(np.float32(3.1415926535897931)))  # REAL(KIND=8),PARAMETER :: Pi = 3.1415926535897931 (no D0)
+
+
+def read_ftab():
+    raw = open(os.path.join(INPUTS, "Ftab"), "rb").read()
+    n = struct.unpack("<i", raw[:4])[0]
+    assert n == 22264
+    return np.frombuffer(raw[4:4 + n], dtype="<f8").reshape((121, 23), order="F")  # Ft(t, j)
+
+
+def boys_reference(ft, qmax, T):
+    """F_0..F_qmax(T) as auxilary.f90:85-215 defines them (values, not rounding order)."""
+    T = mp.mpf(T)
+    F = [mp.mpf(0)] * (qmax + 1)
+    if T < 12:
+        tk = int(mp.floor(T * 10 + mp.mpf("0.5")))  # NINT, half away from zero (T >= 0)
+        d = mp.mpf(tk) / 10 - T
+        F[qmax] = sum(mp.mpf(float(ft[tk, qmax + k])) * d ** k / mp.factorial(k) for k in range(7))
+        for j in range(qmax - 1, -1, -1):
+            F[j] = (2 * T * F[j + 1] + mp.exp(-T)) / (2 * j + 1)
+    elif T < 2 * qmax + 36:
+        if T < 15:
+            g = mp.mpf("0.4999489092") - mp.mpf("0.2473631686") / T + mp.mpf("0.321180909") / T ** 2 - mp.mpf("0.3811559346") / T ** 3
+        elif T < 18:
+            g = mp.mpf("0.4998436875") - mp.mpf("0.24249438") / T + mp.mpf("0.24642845") / T ** 2
+        elif T < 24:
+            g = mp.mpf("0.499093162") - mp.mpf("0.2152832") / T
+        else:
+            g = mp.mpf("0.490")  # the reference leaves T >= 30 undefined (T5); the term it scales is < 3e-15
+        F[0] = mp.sqrt(PI32) / 2 / mp.sqrt(T) - mp.exp(-T) * g / T
+        for j in range(1, qmax + 1):
+            F[j] = ((2 * (j - 1) + 1) * F[j - 1] - mp.exp(-T)) / (2 * T)
+    else:
+        F[0] = mp.sqrt(PI32) / 2 / mp.sqrt(T)
+        for j in range(1, qmax + 1):
+            F[j] = (2 * (j - 1) + 1) * F[j - 1] / (2 * T)
+    return F
+
+
+def orbitals(s):
+    """Per orbital: centre, l, direction, and its primitives (set id, exponent, coefficient, set max l)."""
+    setl = int(s.setinfo[1])
+    orbs = [dict(prims=[]) for _ in range(s.norb)]
+    for o in range(s.norb):
+        n, l, ori, npr, cen = (int(x) for x in s.basinfo[2 + 5 * o: 7 + 5 * o])
+        orbs[o].update(l=l, ori=ori, centre=cen)
+    for st in range(s.nset):
+        info = s.setinfo[2 + setl * st: 2 + setl * (st + 1)]
+        no, maxl, cen = int(info[0]), int(info[1]), int(info[2])
+        for k in range(no):
+            o = int(info[3 + k])
+            assert orbs[o]["centre"] == cen
+            orbs[o]["prims"].append((st, float(s.set[st]), float(s.bas[s.ops * st + k]), maxl))
+    xyz = np.array(s.xyz).reshape(3, s.nnuc).T
+    return orbs, xyz
+
+
+def norm(l, a):
+    a = mp.mpf(a)
+    return (2 * a / PI32) ** mp.mpf("0.75") if l == 0 else (128 * a ** 5 / PI32 ** 3) ** mp.mpf("0.25")
+
+
+def os_primitive(A, B, C, D, a, b, c, d, la, lb, lc, ld, boys):
+    """[ab|cd] over unnormalised primitive Cartesian Gaussians with angular vectors la..ld (tuples), by the
+    Obara-Saika recurrence; boys(m) = F_m(T).  pi is the reference's."""
+    A, B, C, D = (mp.matrix([mp.mpf(float(x)) for x in v]) for v in (A, B, C, D))
+    a, b, c, d = (mp.mpf(x) for x in (a, b, c, d))
+    p, q = a + b, c + d
+    P, Qc = (a * A + b * B) / p, (c * C + d * D) / q
+    W = (p * P + q * Qc) / (p + q)
+    rho = p * q / (p + q)
+    ab2 = sum((A[i] - B[i]) ** 2 for i in range(3))
+    cd2 = sum((C[i] - D[i]) ** 2 for i in range(3))
+    pref = 2 * PI32 ** mp.mpf("2.5") / (p * q * mp.sqrt(p + q)) * mp.exp(-a * b / p * ab2) * mp.exp(-c * d / q * cd2)
+    cen = (A, B, C, D)
+    memo = {}
+
+    def I(ls, m):
+        key = (ls, m)
+        if key in memo:
+            return memo[key]
+        if all(x == 0 for v in ls for x in v):
+            r = pref * boys(m)
+        else:
+            # lower the first centre that carries angular momentum
+            k = next(i for i in range(4) if any(ls[i]))
+            ax = next(i for i in range(3) if ls[k][i])
+            low = [list(v) for v in ls]
+            low[k][ax] -= 1
+            lowt = tuple(tuple(v) for v in low)
+            bra = k < 2
+            z, PQ = (p, P) if bra else (q, Qc)
+            r = (PQ[ax] - cen[k][ax]) * I(lowt, m) + (W[ax] - PQ[ax]) * I(lowt, m + 1)
+            for k2 in range(4):
+                n = low[k2][ax]
+                if n == 0:
+                    continue
+                l2 = [list(v) for v in low]
+                l2[k2][ax] -= 1
+                l2t = tuple(tuple(v) for v in l2)
+                if (k2 < 2) == bra:
+                    r += n / (2 * z) * (I(l2t, m) - rho / z * I(l2t, m + 1))
+                else:
+                    r += n / (2 * (p + q)) * I(l2t, m + 1)
+        memo[key] = r
+        return r
+
+    return I((tuple(la), tuple(lb), tuple(lc), tuple(ld)), 0)
+
+
+def eri_independent(s, ft, i, j, k, l):
+    orbs, xyz = orbitals(s)
+    oo = [orbs[x] for x in (i, j, k, l)]
+    ang = []
+    for o in oo:
+        v = [0, 0, 0]
+        if o["l"] == 1:
+            v[o["ori"]] = 1
+        ang.append(tuple(v))
+    cen = [xyz[o["centre"]] for o in oo]
+    total = mp.mpf(0)
+    for pa, pb, pc, pd in itertools.product(*(o["prims"] for o in oo)):
+        a, b, c, d = pa[1], pb[1], pc[1], pd[1]
+        ab2 = float(((cen[0] - cen[1]) ** 2).sum())
+        cd2 = float(((cen[2] - cen[3]) ** 2).sum())
+        eij = np.exp(-a * b * ab2 / (a + b))
+        egh = np.exp(-c * d * cd2 / (c + d))
+        if egh * eij < 1.0e-14:  # int2e.f90:257
+            continue
+        qmax = 3 * (pa[3] + pb[3] + pc[3] + pd[3])  # Nmax = Lmax = Mmax = la+lb+lc+ld of the SETS (T3)
+        p, q = mp.mpf(a) + mp.mpf(b), mp.mpf(c) + mp.mpf(d)
+        P = (mp.mpf(a) * mp.matrix(cen[0].tolist()) + mp.mpf(b) * mp.matrix(cen[1].tolist())) / p
+        Qc = (mp.mpf(c) * mp.matrix(cen[2].tolist()) + mp.mpf(d) * mp.matrix(cen[3].tolist())) / q
+        T = p * q / (p + q) * sum((P[x] - Qc[x]) ** 2 for x in range(3))
+        F = boys_reference(ft, qmax, T)
+        val = os_primitive(cen[0], cen[1], cen[2], cen[3], a, b, c, d, *ang, lambda m: F[m])
+        w = mp.mpf(1)
+        for o, pr in zip(oo, (pa, pb, pc, pd)):
+            w *= norm(o["l"], pr[1]) * mp.mpf(pr[2])
+        total += w * val
+    return total
+
+
+def packed_index(i, j, k, l, n):
+    i, j = min(i, j), max(i, j)
+    k, l = min(k, l), max(k, l)
+    P, Pp = Q.pair_index(i, j, n), Q.pair_index(k, l, n)
+    P, Pp = min(P, Pp), max(P, Pp)
+    npair = n * (n + 1) // 2
+    return P * npair - P * (P - 1) // 2 + (Pp - P)
+
+
+# orbital order per heavy atom: 1s 2s 2px 2py 2pz; H: 1s.  The samples cover (ss|ss), (sp|ss), (sp|sp), (pp|pp),
+# 2s functions (SP sets: start order 12 even for an all-s quartet), one- to three-centre quartets, and all Boys regimes.
+SAMPLES = {
+    "OH": [(0, 0, 5, 5), (0, 5, 0, 5), (1, 5, 1, 5), (4, 5, 4, 5), (2, 2, 5, 5), (1, 4, 5, 5), (4, 4, 4, 4), (2, 4, 2, 4)],
+    "NO": [(0, 5, 0, 5), (0, 0, 5, 5), (1, 6, 1, 6), (4, 9, 4, 9), (2, 7, 3, 8), (4, 4, 9, 9), (2, 9, 2, 9), (1, 9, 4, 6),
+           (0, 9, 4, 5), (3, 3, 8, 8)],
+    "CO2": [(0, 5, 10, 10), (4, 9, 4, 14), (9, 14, 9, 14), (1, 6, 11, 14), (2, 7, 2, 12), (4, 4, 9, 14), (5, 10, 5, 10)],
+}
+
+
+@pytest.mark.parametrize("name", sorted(SAMPLES))
+def test_obara_saika_witness_agrees_with_golden_vectors_and_oracle(name, tmp_path, capfd, oracle_inputs):
+    from conftest import oracle_system
+    from oracle import oracle as O
+    s = product_system(name, tmp_path)
+    ft = read_ftab()
+    gold = np.load(os.path.join(GOLDEN, f"packed_{name}.npy"))
+    mol, b, ftab = oracle_system(name, oracle_inputs)
+    ref = O.int2e_packed(mol, b, ftab)
+    worst = 0.0
+    for (i, j, k, l) in SAMPLES[name]:
+        v = float(eri_independent(s, ft, i, j, k, l))
+        e = packed_index(i, j, k, l, s.norb)
+        worst = max(worst, abs(v - gold[e]), abs(v - ref[e]))
+        assert abs(v - gold[e]) < 1e-10 and abs(v - ref[e]) < 1e-10, (name, (i, j, k, l), v, gold[e], ref[e])
+    assert worst < 1e-12  # in practice ~1e-14: two algorithms, one definition
+
+
+def test_witness_discriminates(tmp_path, capfd):
+    """With the true pi instead of the reference's float32 pi the same witness misses the golden vector by ~1e-8."""
+    global PI32
+    s = product_system("NO", tmp_path)
+    ft = read_ftab()
+    gold = np.load(os.path.join(GOLDEN, "packed_NO.npy"))
+    i, j, k, l = 0, 0, 5, 5
+    e = packed_index(i, j, k, l, s.norb)
+    keep = PI32
+    try:
+        PI32 = mp.pi
+        v = float(eri_independent(s, ft, i, j, k, l))
+    finally:
+        PI32 = keep
+    assert 1e-9 < abs(v - gold[e]) < 1e-6
