@@ -87,9 +87,9 @@ struct HostPlan {
     std::vector<int32_t> clist[2];  // shells of type 0 / 1, ascending
     // shell classes (same type and exponents) and the partner segments (eri_kernels.cuh)
     int ncls = 0;
-    std::vector<int32_t> sh_class, cls_list, seg_start;
+    std::vector<int32_t> sh_class, cls_kind, seg_start;
     std::vector<unsigned short> seg_d;
-    std::vector<double> seg_emax;
+    std::vector<double> seg_eprof;  // [entries][4]
     std::vector<double> shell_cost; // estimated seconds of one warp for everything first shell A owns
     // shard
     int A0 = 0, A1 = 0;             // owner first shells [A0, A1)
@@ -136,6 +136,16 @@ struct CostModel {
             for (int tc = 0; tc < 2; ++tc)
                 for (int A = hp.ns - 1; A >= 0; --A) cnt_ge[k][tc][A] += cnt_ge[k][tc][A + 1];
         }
+    }
+    // estimated number of kind-k partners (first-shell type tc, first shell >= A) that pass the bound against emax_u
+    double partners(double emax_u, int A, int k, int tc) const {
+        if (ntot[k] == 0 || !(emax_u > 0.0)) return 0.0;
+        size_t lo = 0, hi = emax[k].size();
+        while (lo < hi) {
+            const size_t mid = (lo + hi) / 2;
+            if (emax_u * emax[k][mid] < 1.0e-14) hi = mid; else lo = mid + 1;
+        }
+        return (double)lo * (double)cnt_ge[k][tc][A] / (double)ntot[k];
     }
     // estimated primitive quartets of owner (emax_u, nprim_u, first shell A) against the kind-k partners whose
     // first shell is of type tc: the partners that pass the bound, taken as an unbiased sample of first shells
@@ -187,31 +197,19 @@ static int build_host_tables(int nnuc, const double* xyz, int nset, int setl, co
             double& bm = hp.blk_emax[(size_t)A * hp.nblk + B / kBlockShells];
             bm = std::max(bm, hp.lists[k].emax[i]);
         }
-    // shell classes: shells of one type with the same exponents (the lanes of a chunk then run the same
-    // primitives); the first three classes of a type get a pending list each, the others share the fourth
+    // shell classes: one per shell type (S, SP): a segment lists the partners of one kind of a (C, block).
+    // (The survival bins of the kernel, not the class, make the lanes of a chunk alike.)
     {
-        std::vector<std::vector<double>> keys;
-        std::vector<int> ktype;
         hp.sh_class.assign(ns, 0);
-        for (int s = 0; s < ns; ++s) {
-            std::vector<double> key;
-            for (int a : hp.shells[s].sets) key.push_back(set[a]);
-            int c = -1;
-            for (size_t q = 0; q < keys.size() && c < 0; ++q)
-                if (ktype[q] == hp.shells[s].type && keys[q] == key) c = (int)q;
-            if (c < 0) { keys.push_back(key); ktype.push_back(hp.shells[s].type); c = (int)keys.size() - 1; }
-            hp.sh_class[s] = c;
-        }
-        hp.ncls = (int)keys.size();
-        hp.cls_list.assign(hp.ncls, 0);
-        int seen[2] = {0, 0};
-        for (int c = 0; c < hp.ncls; ++c) hp.cls_list[c] = 4 * ktype[c] + std::min(3, seen[ktype[c]]++);
+        for (int s = 0; s < ns; ++s) hp.sh_class[s] = hp.shells[s].type;
+        hp.ncls = 2;
+        hp.cls_kind = {0, 1};
     }
     // partner segments: (C, block, class) -> the D >= C of that class in that block with a live pair, by decreasing emax
     {
         const int nblk = hp.nblk, ncls = hp.ncls;
         hp.seg_start.assign((size_t)ns * nblk * ncls + 1, 0);
-        hp.seg_d.clear(); hp.seg_emax.clear();
+        hp.seg_d.clear(); hp.seg_eprof.clear();
         std::vector<std::vector<std::pair<double, int>>> bucket(ncls);
         for (int C = 0; C < ns; ++C)
             for (int b = 0; b < nblk; ++b) {
@@ -221,7 +219,16 @@ static int build_host_tables(int nnuc, const double* xyz, int nset, int setl, co
                 for (int c = 0; c < ncls; ++c) {
                     std::stable_sort(bucket[c].begin(), bucket[c].end(), [](const std::pair<double, int>& x, const std::pair<double, int>& y) { return x.first > y.first; });
                     hp.seg_start[((size_t)C * nblk + b) * ncls + c] = (int32_t)hp.seg_d.size();
-                    for (const auto& e : bucket[c]) { hp.seg_d.push_back((unsigned short)e.second); hp.seg_emax.push_back(e.first); }
+                    for (const auto& e : bucket[c]) {
+                        hp.seg_d.push_back((unsigned short)e.second);
+                        // prefactors of ranks 1, 3, 5, 7 (the primitives of a record are sorted by E, descending)
+                        const int kind = hp.sh_type[C] + hp.sh_type[e.second];
+                        const int rec = hp.pair_rec[(size_t)C * ns + e.second];
+                        const PairList& L = hp.lists[kind];
+                        const int nfield = pt_nfield(kind);
+                        for (int r = 0; r < 8; r += 2)
+                            hp.seg_eprof.push_back(r < L.nprim[rec] ? L.aos[((size_t)rec * kMaxPrim + r) * nfield + 4] : 0.0);
+                    }
                 }
             }
         hp.seg_start.back() = (int32_t)hp.seg_d.size();
@@ -295,13 +302,13 @@ static std::vector<int> split_shells(const std::vector<double>& w, int m) {
 // have to be written), against every partner first shell C >= A, cut into pieces of bounded cost
 static void build_tasks(HostPlan& hp, const CostModel& cm) {
     const int ns = hp.ns, nblk = hp.nblk;
-    double total = 0.0;
-    for (int A = hp.A0; A < hp.A1; ++A) total += hp.shell_cost[A];
-    // A task should hold several chunks of 32 quartets per partner kind (the last chunk of a kind is partly
-    // empty) and still be a small fraction of a launch: ~400 microseconds of the work model, less when the
-    // whole shard is small (at least ~8 tasks per resident warp), never below ~100 microseconds.
-    double tmax = std::min(400e-6, std::max(100e-6, total / (2400.0 * 8.0)));
-    if (const char* e = std::getenv("MYQC_TASK_US")) tmax = 1e-6 * std::atof(e);
+    // A task is one warp's unit of work.  Its quartets are evaluated 32 at a time per pending list (partner kind x
+    // survival bin), and the last chunk of every list is partly empty, so a task must hold many quartets: the
+    // targets below are partners per task (estimated from the sorted prefactors).  Tasks with few partners
+    // are mostly zero fill and are bounded by the bytes they write instead.
+    const double kItemsLight = std::getenv("MYQC_TASK_ITEMS") ? std::atof(std::getenv("MYQC_TASK_ITEMS")) : 1024.0;
+    const double kItemsHeavy = std::getenv("MYQC_TASK_ITEMS_HEAVY") ? std::atof(std::getenv("MYQC_TASK_ITEMS_HEAVY")) : 320.0;
+    const double kTaskBytes = 4.0e6;
     for (int UT = 0; UT < 3; ++UT)
         for (int tc = 0; tc < 2; ++tc) {
             LaunchH& L = hp.launches[UT * 2 + tc];
@@ -317,8 +324,14 @@ static void build_tasks(HostPlan& hp, const CostModel& cm) {
                 const int nc = (int)cl.size() - c0;
                 if (nc <= 0) continue;
                 std::vector<int4>& tasks = hp.launches[UT * 2 + tc].tasks;
-                const double cost = owner_cost(hp, cm, A, B, tc, nullptr);
-                int npiece = (int)std::ceil(cost / tmax);
+                double bytes = 0.0;
+                owner_cost(hp, cm, A, B, tc, &bytes);
+                const int rec = hp.pair_rec[(size_t)A * ns + B];
+                double items = 0.0;
+                if (rec >= 0)
+                    for (int td = 0; td < 2; ++td) items += cm.partners(hp.lists[UT].emax[rec], A, tc + td, tc);
+                const bool heavy = (UT + tc >= 2) && !(UT == 0);  // launches whose second partner kind has 64 integrals per quartet
+                int npiece = (int)std::max(std::floor(items / (heavy ? kItemsHeavy : kItemsLight)), std::ceil(bytes / kTaskBytes));
                 npiece = std::max(1, npiece);
                 const int ab = A | (B << 16);
                 if (npiece <= nc) {
@@ -528,9 +541,11 @@ static void check_plan(const HostPlan& hp, CheckResult& cr) {
                     for (int e = hp.seg_start[si]; e < hp.seg_start[si + 1]; ++e) {
                         const int Ds = hp.seg_d[e];
                         if (Ds < Cs || Ds / kBlockShells != b || hp.sh_class[Ds] != c) ++cr.errors;
-                        if (hp.seg_emax[e] != hp.pair_emax[(size_t)Cs * ns + Ds] || hp.pair_rec[(size_t)Cs * ns + Ds] < 0) ++cr.errors;
-                        if (e > hp.seg_start[si] && hp.seg_emax[e] > hp.seg_emax[e - 1]) ++cr.errors;
-                        if ((hp.cls_list[c] >> 2) != hp.sh_type[Ds]) ++cr.errors;
+                        if (hp.seg_eprof[4 * (size_t)e] != hp.pair_emax[(size_t)Cs * ns + Ds] || hp.pair_rec[(size_t)Cs * ns + Ds] < 0) ++cr.errors;
+                        if (e > hp.seg_start[si] && hp.seg_eprof[4 * (size_t)e] > hp.seg_eprof[4 * (size_t)(e - 1)]) ++cr.errors;
+                        for (int r = 1; r < 4; ++r)
+                            if (hp.seg_eprof[4 * (size_t)e + r] > hp.seg_eprof[4 * (size_t)e + r - 1]) ++cr.errors;
+                        if (hp.cls_kind[c] != hp.sh_type[Ds]) ++cr.errors;
                         ++seen[(size_t)Cs * ns + Ds];
                     }
                 }
@@ -681,13 +696,13 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
     if ((rc = upload(pl.get(), hp.blk_emax, &d_blk_emax))) return rc;
     for (int t = 0; t < 2; ++t)
         if ((rc = upload(pl.get(), hp.clist[t], &d_clist[t]))) return rc;
-    int32_t *d_seg_start = nullptr, *d_cls_list = nullptr;
+    int32_t *d_seg_start = nullptr, *d_cls_kind = nullptr;
     unsigned short* d_seg_d = nullptr;
-    double* d_seg_emax = nullptr;
+    double* d_seg_eprof = nullptr;
     if ((rc = upload(pl.get(), hp.seg_start, &d_seg_start))) return rc;
     if ((rc = upload(pl.get(), hp.seg_d, &d_seg_d))) return rc;
-    if ((rc = upload(pl.get(), hp.seg_emax, &d_seg_emax))) return rc;
-    if ((rc = upload(pl.get(), hp.cls_list, &d_cls_list))) return rc;
+    if ((rc = upload(pl.get(), hp.seg_eprof, &d_seg_eprof))) return rc;
+    if ((rc = upload(pl.get(), hp.cls_kind, &d_cls_kind))) return rc;
     double* d_aos[3] = {nullptr, nullptr, nullptr};
     int32_t* d_nprim[3] = {nullptr, nullptr, nullptr};
     for (int k = 0; k < 3; ++k) {
@@ -720,8 +735,8 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
             a.ns = hp.ns; a.nblk = hp.nblk; a.norb = hp.norb;
             a.npair = hp.npair;
             a.pair_rec = d_pair_rec; a.pair_emax = d_pair_emax; a.blk_emax = d_blk_emax;
-            a.seg_start = d_seg_start; a.seg_d = d_seg_d; a.seg_emax = d_seg_emax;
-            a.cls_list = d_cls_list; a.ncls = hp.ncls;
+            a.seg_start = d_seg_start; a.seg_d = d_seg_d; a.seg_eprof = reinterpret_cast<const double2*>(d_seg_eprof);
+            a.cls_kind = d_cls_kind; a.ncls = hp.ncls;
             a.clist = d_clist[L.TC];
             a.u_aos = d_aos[L.UT]; a.u_nprim = d_nprim[L.UT];
             for (int td = 0; td < 2; ++td) {

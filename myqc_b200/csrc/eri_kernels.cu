@@ -105,7 +105,8 @@ struct SCfg {
     static constexpr int NBUF = (UT == 2) ? 1 : 2;   // owner-record buffers per warp (TMA prefetch of the next task)
     static constexpr bool FT_SMEM = (UT < 2);        // Taylor tables in shared memory (else read through L1)
     static constexpr int DESC = 36;                  // ints per chunk descriptor: 32 items, kind|count, result offset
-    static constexpr int NLIST = 8;                  // pending lists: 0..3 partners with an S second shell, 4..7 with an SP one
+    static constexpr int NLIST = 8;                  // pending lists: partner kind (second shell S / SP) x 4 bins of surviving primitives
+    static constexpr bool BINS = !HEAVY;             // the heavy launches see too few quartets per task to afford four lists per kind
     // shared memory: [Taylor tables] | exp table | per warp: owner records, mbarriers, rows, pending, descriptors, results
     static constexpr size_t OFF_EXP = FT_SMEM ? 2 * 121 * 8 * 8 : 0;
     static constexpr size_t OFF_WARP = OFF_EXP + 608 * 16;
@@ -419,14 +420,14 @@ __global__ void __launch_bounds__(SCfg<UT, TC, USL>::NTHREADS, SCfg<UT, TC, USL>
         // live pair with C are listed by decreasing emax(C,D) (same exponents: by increasing distance), so the
         // partners that pass the bound emax_u*emax_v >= 1e-14 are a prefix of the segment, and the 32 quartets a
         // chunk evaluates have the same partner exponents and similar distances (same primitive survival, same
-        // Boys regime).  pc = eight pending counts, one byte each (always < 64).
+        // Boys regime).  pc = eight pending counts (two kinds x four survival bins), one byte each (always < 64).
         int zci = c_lo, zb = b_lo;
         int nch = 0, used = 0;
         unsigned long long pc = 0ull;
         unsigned tq0 = 0, tq1 = 0;
         long long span = 0;
         int ci = c_lo - 1, Cs = 0, b = 0, bfirst_c = 0, bend = 0, cls = a.ncls;
-        int sbase = 0, send = 0, slist = 0;
+        int sbase = 0, send = 0, skind = 0;
         bool blk_live = false;
         int pci = c_lo, pb = b_lo - 1;  // last block whose partners have all been listed
         int fci = c_lo, fb = b_lo - 1;  // newest block a parked chunk holds integrals of: a flush must reach it
@@ -530,14 +531,31 @@ __global__ void __launch_bounds__(SCfg<UT, TC, USL>::NTHREADS, SCfg<UT, TC, USL>
                 continue;
             }
             if (sbase < send) {
-                // ---- up to 32 partners of the current segment: those that pass the pair-level bound (a prefix)
+                // ---- up to 32 partners of the current segment: those that pass the pair-level bound (a prefix).
+                // Each goes to the pending list of its kind and of the number of its primitives that survive
+                // against this owner (1-2, 3-4, 5-6, 7-9): the lanes of a chunk then run about the same number of
+                // primitive quartets.  ep = {E(1) = emax, E(3), E(5), E(7)} of the partner's sorted prefactors.
                 const int e = sbase + lane;
-                const bool ok = (e < send) && (eu_max * __ldg(a.seg_emax + e) >= kScreen);
+                double2 ep01 = make_double2(0.0, 0.0), ep23 = make_double2(0.0, 0.0);
+                if (e < send) {
+                    ep01 = __ldg(a.seg_eprof + 2 * (size_t)e);
+                    ep23 = __ldg(a.seg_eprof + 2 * (size_t)e + 1);
+                }
+                const bool ok = eu_max * ep01.x >= kScreen;
+                const int bin = C::BINS ? (eu_max * ep01.y >= kScreen ? 1 : 0) + (eu_max * ep23.x >= kScreen ? 1 : 0) + (eu_max * ep23.y >= kScreen ? 1 : 0) : 0;
                 const unsigned mk = __ballot_sync(0xffffffffu, ok);
                 const int cnt = __popc(mk);
-                const int pn = (int)((pc >> (8 * slist)) & 0xffull);
-                if (ok) m.pend[slist * 64 + pn + lane] = (Cs << 16) | (int)__ldg(a.seg_d + e);
-                pc += (unsigned long long)cnt << (8 * slist);
+                const unsigned lt = (1u << lane) - 1u;
+                int item = 0;
+                if (ok) item = (Cs << 16) | (int)__ldg(a.seg_d + e);
+#pragma unroll
+                for (int j = 0; j < (C::BINS ? 4 : 1); ++j) {
+                    const unsigned mj = __ballot_sync(0xffffffffu, ok && bin == j);
+                    const int L2 = skind * 4 + j;
+                    const int pn = (int)((pc >> (8 * L2)) & 0xffull);
+                    if (ok && bin == j) m.pend[L2 * 64 + pn + __popc(mj & lt)] = item;
+                    pc += (unsigned long long)__popc(mj) << (8 * L2);
+                }
                 sbase = (cnt == 32) ? sbase + 32 : send;
                 __syncwarp();
                 continue;
@@ -548,7 +566,7 @@ __global__ void __launch_bounds__(SCfg<UT, TC, USL>::NTHREADS, SCfg<UT, TC, USL>
                 const size_t sidx = ((size_t)Cs * nblk + b) * a.ncls + cls;
                 sbase = __ldg(a.seg_start + sidx);
                 send = __ldg(a.seg_start + sidx + 1);
-                slist = __ldg(a.cls_list + cls);
+                skind = __ldg(a.cls_kind + cls);
                 continue;
             }
             if (ci >= c_lo && b >= bfirst_c && b < bend) { pci = ci; pb = b; }  // block (ci,b) has been enumerated

@@ -26,8 +26,8 @@ struct StripArgs {
     // by decreasing emax(C,D): entries seg_start[(C*nblk + b)*ncls + c] .. seg_start[.. + 1]
     const int32_t* seg_start;
     const unsigned short* seg_d;
-    const double* seg_emax;
-    const int32_t* cls_list;   // [ncls] pending list of a class: 0..3 for S shells, 4..7 for SP shells
+    const double2* seg_eprof;  // per entry two double2: {E(1) = emax, E(3)}, {E(5), E(7)}: the pair's primitive prefactors by rank (0 past the last)
+    const int32_t* cls_kind;   // [ncls] 0: shells of the class are S shells, 1: SP shells
     int ncls;
     // first shells C this launch handles: the shells of type TC in ascending order
     const int32_t* clist;
