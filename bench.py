@@ -6,8 +6,7 @@
    collective on the data path; only the timing barrier / max-over-ranks use NCCL.)
 
 A "step" is one full evaluation of this rank's shard of the packed 8-fold-unique ERI array of the
-workload molecule: the owner-row strip kernels, each writing its runs of the array once (zeros and
-integrals; there is no separate fill launch), inputs (shell-pair tables, Boys table, task lists)
+workload molecule: zero fill + six quartet-class kernels, inputs (shell-pair tables, Boys table)
 already resident in HBM.  `value` = unique ERIs of the whole molecule / max-over-ranks step time.
 `e2e` is the same metric through the host-buffer C-ABI call a user makes (plan build, H2D of the
 pair tables, kernels, D2H of the packed slice into pinned host memory inside the timed region).
@@ -35,8 +34,6 @@ sys.path.insert(0, ROOT)
 INPUTS = os.path.join(ROOT, "tests", "golden", "inputs")
 METRIC = "unique_eris_per_s"
 UNIT = "ERI/s"
-# nominal dense FP64 (non-tensor DFMA) peak of a B200: 148 SMs x 64 DFMA/clk x 2 flop x 1.965 GHz
-FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
 
 
 def log(*a):
@@ -286,7 +283,6 @@ def run_ours(args):
             scratch.zero_()
         acc += np.array(plan.execute_timed(out.data_ptr(), stream))
     acc /= nrep
-    lq = plan.launch_quartets()  # device counters of the last execute: primitive quartets per launch and partner kind
     barrier()
     checksum = float(out[:plan.out_elems].sum().item()) if plan.out_elems else 0.0
     checksum = allsum(checksum)
@@ -324,53 +320,63 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- per-launch breakdown and the rooflines of the step ----------------------------------------
-    # One execute() = the strip kernels (owner kind ut, partner-first-shell kind tc[, slice]); each writes its
-    # own runs of the packed array (zeros and integrals), so there is no separate fill launch.  Model flops of a
-    # launch = primitive quartets it evaluated (device counters) x W(class).
-    kernels = []
-    for (ut, tc, sl, ntask), t, (q0, q1) in zip(launches, acc, lq):
-        fl = Q.CLASS_W[Q.class_id(ut, tc)] * q0 + Q.CLASS_W[Q.class_id(ut, tc + 1)] * q1
-        kernels.append({"kernel": f"eri_strip<ut={ut},tc={tc}" + (f",slice={sl}>" if ut == 2 and tc == 1 else ">"),
-                        "classes": [Q.CLASS_NAMES[Q.class_id(ut, tc)], Q.CLASS_NAMES[Q.class_id(ut, tc + 1)]],
-                        "tasks": int(ntask), "ms": float(t), "prim_quartets": [int(q0), int(q1)],
-                        "fp64_tflops_model": fl / (t * 1e-3) / 1e12 if t > 0 else 0.0,
-                        "fp64_frac": fl / (t * 1e-3) / 1e12 / fp64_peak if t > 0 and fp64_peak else None})
+    # ---- per-kernel breakdown and the rooflines of the step ------------------------------------------
+    # One execute() = the zero fill + the six quartet-class kernels ((SP SP|SP SP) as four mu-slices).  Times are
+    # CUDA events around every launch of a serialised pass; launches of one kernel family are added up.
+    per_class_ms = {}
+    fill_elems = 0
+    for (cls, tri, rows), t in zip(launches, acc):
+        per_class_ms[cls] = per_class_ms.get(cls, 0.0) + float(t)
+        if cls < 0:
+            fill_elems += int(rows)
     serial_ms = float(acc.sum())
-    flops_exec = sum(k["fp64_tflops_model"] * k["ms"] for k in kernels) * 1e9  # model flops of the quartets evaluated
-    # the (pp|pp)-type launches the north star singles out: SP.SP owners against SP first shells ({1,2} and {2,2} quartets)
-    pp = [k for k in kernels if k["kernel"].startswith("eri_strip<ut=2,tc=1")]
-    pp_ms = sum(k["ms"] for k in pp)
-    pp_fl = sum(k["fp64_tflops_model"] * k["ms"] for k in pp) * 1e9
-    bytes_alg = 8.0 * plan.out_elems            # algorithmic bytes of this rank's step: every unique ERI written once
-    hbm_t = bytes_alg / (hbm_peak * 1e9)        # seconds the HBM roofline allows
+    kernels = []
+    for cls, t in sorted(per_class_ms.items()):
+        if cls < 0:
+            gb = 8.0 * fill_elems / 1e9
+            kernels.append({"kernel": "fill_zero", "zeros_written": fill_elems, "ms": t, "bound": "hbm", "share_of_step": t / serial_ms,
+                            "achieved": gb / (t * 1e-3) if t > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s"})
+        else:
+            # canonical primitive quartets of the class x W(class); for a shard the class counts of the whole molecule
+            # are scaled by this rank's share of the model flops (the plan cuts shards by that weight)
+            fl = Q.CLASS_W[cls] * float(nq[cls]) / world
+            kernels.append({"kernel": "eri_class" + Q.CLASS_NAMES[cls], "ms": t, "bound": "fp64", "share_of_step": t / serial_ms,
+                            "achieved": fl / (t * 1e-3) / 1e12 if t > 0 else 0.0, "peak": fp64_peak, "unit": "TFLOP/s",
+                            "frac_of_nominal_peak": fl / (t * 1e-3) / 1e12 / Q.FP64_NOMINAL_TFLOPS if t > 0 else None})
+    for k in kernels:
+        k["frac"] = k["achieved"] / k["peak"] if k["peak"] else None
+    cls_ms = sum(k["ms"] for k in kernels if k["bound"] == "fp64")
+    family = {"kernel": "eri_class_kernel family (all class launches of one step)", "ms": cls_ms, "share_of_step": cls_ms / serial_ms,
+              "fp64_tflops_model": (model_flops / world) / (cls_ms * 1e-3) / 1e12 if cls_ms > 0 else 0.0}
+    family["frac"] = family["fp64_tflops_model"] / fp64_peak if fp64_peak else None
+    family["frac_of_nominal_peak"] = family["fp64_tflops_model"] / Q.FP64_NOMINAL_TFLOPS
+    # The roofline object is the STEP against its binding roofline (the larger of the two roofline times), with both
+    # fractions spelled out; `dominant_family` is the kernel family with the largest share of the step.
+    bytes_alg = 8.0 * plan.out_elems
+    hbm_t = bytes_alg / (hbm_peak * 1e9)
     fp_t = (model_flops / world) / (fp64_peak * 1e12) if fp64_peak else 0.0
     bound = "hbm" if hbm_t >= fp_t else "fp64"
-    ms_rank0 = ms_local
     if bound == "hbm":
-        achieved, peak, unit = bytes_alg / 1e9 / (ms_rank0 * 1e-3), hbm_peak, "GB/s"
+        achieved, peak, unit = bytes_alg / 1e9 / (ms_local * 1e-3), hbm_peak, "GB/s"
     else:
-        achieved, peak, unit = (model_flops / world) / (ms_rank0 * 1e-3) / 1e12, fp64_peak, "TFLOP/s"
+        achieved, peak, unit = (model_flops / world) / (ms_local * 1e-3) / 1e12, fp64_peak, "TFLOP/s"
     traffic = None
     tfile = os.path.join(ROOT, "profiles", "r2_h2o64_dram_traffic_bytes.json")
     if args.workload == "h2o_64" and world == 1 and os.path.exists(tfile):
         traffic = float(sum(json.load(open(tfile)).values()))
-    roofline = {"kernel": "step (all eri_strip launches of one execute)", "bound": bound, "achieved": achieved, "peak": peak,
+    roofline = {"kernel": "step (zero fill + all class launches of one execute)", "bound": bound, "achieved": achieved, "peak": peak,
                 "unit": unit, "frac": achieved / peak if peak else None, "traffic": traffic,
-                "traffic_source": "sum over the step's launches of dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full (profiles/r2_h2o64_ncu_full.json)",
+                "traffic_source": "sum over the step's launches of dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r2_h2o64_ncu_full.json)",
                 "peak_source": peak_src if bound == "hbm" else "measured DFMA microbenchmark in this run (myqc_fp64_peak)",
                 "algorithmic_bytes": bytes_alg, "model_flops": model_flops / world,
-                "hbm_frac": bytes_alg / 1e9 / (ms_rank0 * 1e-3) / hbm_peak,
-                "fp64_frac_measured_peak": (model_flops / world) / (ms_rank0 * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
-                "fp64_frac_nominal_peak": (model_flops / world) / (ms_rank0 * 1e-3) / 1e12 / FP64_NOMINAL_TFLOPS,
-                "fp64_peak_nominal_tflops": FP64_NOMINAL_TFLOPS,
-                "pp_launches": {"kernels": "eri_strip<ut=2,tc=1,slice=0..3>", "ms": pp_ms,
-                                "fp64_frac_measured_peak": pp_fl / (pp_ms * 1e-3) / 1e12 / fp64_peak if pp_ms > 0 and fp64_peak else None},
-                "serialised_launch_sum_ms": serial_ms}
+                "hbm_frac": bytes_alg / 1e9 / (ms_local * 1e-3) / hbm_peak,
+                "fp64_frac_measured_peak": (model_flops / world) / (ms_local * 1e-3) / 1e12 / fp64_peak if fp64_peak else None,
+                "fp64_frac_nominal_peak": (model_flops / world) / (ms_local * 1e-3) / 1e12 / Q.FP64_NOMINAL_TFLOPS,
+                "fp64_peak_nominal_tflops": Q.FP64_NOMINAL_TFLOPS,
+                "dominant_family": family, "serialised_launch_sum_ms": serial_ms}
     whole = {"fp64_tflops_model": model_flops / (ms * 1e-3) / 1e12 / 1.0,
              "fp64_frac_of_measured_dfma_peak": model_flops / (ms * 1e-3) / 1e12 / (fp64_peak * world) if fp64_peak else None,
-             "fp64_frac_of_nominal_peak": model_flops / (ms * 1e-3) / 1e12 / (FP64_NOMINAL_TFLOPS * world),
-             "executed_over_canonical_model_flops": flops_exec / (model_flops / world) if model_flops else None,
+             "fp64_frac_of_nominal_peak": model_flops / (ms * 1e-3) / 1e12 / (Q.FP64_NOMINAL_TFLOPS * world),
              "hbm_gbs_algorithmic": 8.0 * s.nunique / 1e9 / (ms * 1e-3),
              "hbm_frac": 8.0 * s.nunique / 1e9 / (ms * 1e-3) / (hbm_peak * world)}
 

@@ -20,7 +20,7 @@
  *     (int2e.f90:118,161-163).  Never regenerated from a formula.
  *   - caller owns all pointers; the library copies inputs and owns all device memory (plans own their
  *     device buffers until destroyed; the one-shot calls keep the last plan and device slice per device
- *     until myqc_eri_release_cache()).
+ *     until myqc_eri_release_cache(), see below).
  *   - return 0 on success, negative MYQC_ERR_* otherwise; the library never exits the process.
  *     The shim maps non-zero to `touch error` (int2e.f90:174-178).
  *   - there is NO CPU fallback: without a CUDA device every compute entry returns
@@ -61,7 +61,9 @@ int myqc_device_count(void);
  *         offset of (i,j,g,h) = i + n*(j + n*(g + n*h)), all 8 symmetry images filled
  *         (what fillsym leaves, int2e.f90:290-304,540-554).
  * packed: out, caller-allocated npair(npair+1)/2 doubles, layout above.
- * ngpu:   number of devices to shard over (1..myqc_device_count()); 0 = all visible.      */
+ * ngpu:   number of devices to shard over (1..myqc_device_count()); 0 = all visible.  myqc_eri_dense with
+ *         ngpu > 1: every device computes its shard of the packed array, then expands the slab XX(:,:,:,h)
+ *         of its range of h from the whole packed array (no device holds more than packed + XX/ngpu).  */
 int myqc_eri_dense(int nnuc, const double *xyz, int nset, int setl, const double *set,
                    const int32_t *setinfo, int ops, const double *bas, const int32_t *basinfo,
                    const double *ftab, double *xx, int ngpu);
@@ -85,12 +87,17 @@ int myqc_eri_packed_shard(int nnuc, const double *xyz, int nset, int setl, const
  * sets the number of zeroing threads); any other destination gets one cudaMemcpy of the slice.      */
 int64_t myqc_eri_last_d2h_bytes(void);
 
+/* The one-shot calls (myqc_eri_packed, myqc_eri_packed_shard, multi-device myqc_eri_dense) keep the plan (pair
+ * tables, task lists) and the device slice of the last call per device, keyed on the bytes of every input, so a
+ * caller that asks for the same integrals again pays for them once (MYQC_NO_CACHE=1 turns this off).  This
+ * releases what is kept.                                                                                  */
+void myqc_eri_release_cache(void);
+
 /* ---- plan API: device-resident execution, one plan per (GPU, shard) -------------------------
- * A plan holds the shell-pair tables and the task lists of one shard of the canonical quartet space on
- * one device.  Shard s of nshards owns a contiguous block of rows of the packed array (rows = bra pair
- * index P), cut where a shell's orbitals start and balanced by a work model (model flops + bytes
- * written); every quartet is evaluated by the shard that owns its rows, so shards are independent
- * (no collective) and compute exactly what the unsharded plan computes.  nshards=1 is the whole problem. */
+ * A plan holds the shell-pair tables of one shard of the canonical quartet space on one device.
+ * Shard s of nshards owns a contiguous block of rows of the packed array (rows = bra pair index
+ * P), cut at shell boundaries and balanced by model flops; shards are independent (no
+ * collective).  nshards=1 is the whole problem.                                               */
 typedef struct myqc_eri_plan myqc_eri_plan;
 
 int myqc_eri_plan_create(int nnuc, const double *xyz, int nset, int setl, const double *set,
@@ -129,28 +136,13 @@ int myqc_eri_shard_layout(int nnuc, const double *xyz, int nset, int setl, const
 int myqc_eri_canonical_stats(int nnuc, const double *xyz, int nset, int setl, const double *set,
                               const int32_t *setinfo, int64_t *nquartets, double *model_flops);
 
-/* Measurement hooks (bench.py).  One execute() enqueues launch_count kernels; launch k is the strip kernel of
- * owner kind ut (0 S.S, 1 S.SP, 2 SP.SP) against partner first shells of kind tc (0 S, 1 SP), slice = first
- * function of an SP.SP owner (0 otherwise), with ntasks tasks.  execute_timed brackets every launch with CUDA
- * events on `stream`, synchronises, and returns the per-launch milliseconds in ms[launch_count].
- * launch_quartets (after an execute; synchronises the device): nq[2k + td] = primitive quartets launch k
- * evaluated against partners whose second shell is S (td = 0) / SP (td = 1), i.e. of class {ut, tc + td}. */
+/* Measurement hooks (bench.py): launches of one execute() = 1 zero fill + the class kernels.
+ * launch_info: cls = -1 for the zero fill, else the class id 0..5 in the order of nquartets[];
+ * rows = elements filled / uniform-side rows.  execute_timed brackets every launch with CUDA
+ * events on `stream`, synchronises, and returns the per-launch milliseconds in ms[launch_count]. */
 int myqc_eri_plan_launch_count(const myqc_eri_plan *plan);
-int myqc_eri_plan_launch_info(const myqc_eri_plan *plan, int k, int *ut, int *tc, int *slice, int64_t *ntasks);
-int myqc_eri_plan_launch_quartets(myqc_eri_plan *plan, int64_t *nq);
+int myqc_eri_plan_launch_info(const myqc_eri_plan *plan, int k, int *cls, int *tri, int64_t *rows);
 int myqc_eri_plan_execute_timed(myqc_eri_plan *plan, double *d_out, void *stream, float *ms);
-
-/* Host-only coverage check of the plan of one shard: replays what its kernels write with the kernels' own
- * index arithmetic.  result[0] = violations (elements zero-filled or stored more or less than once, integrals
- * missing), [1] = elements of the slice, [2] = elements zero-filled, [3] = integrals stored, [4] = integrals
- * expected (-1 if the slice is too large to enumerate), [5] = tasks.                                  */
-int myqc_eri_plan_check(int nnuc, const double *xyz, int nset, int setl, const double *set,
-                        const int32_t *setinfo, int ops, const double *bas, const int32_t *basinfo,
-                        int shard, int nshards, int64_t *result);
-
-/* The one-shot calls keep the plan and the device slice of the last call per device (keyed on the bytes of
- * every input; MYQC_NO_CACHE=1 turns it off); this releases them.                                    */
-void myqc_eri_release_cache(void);
 
 /* Register-resident DFMA microbenchmark: the FP64 (non-tensor) roofline denominator, measured
  * on the device the plan runs on (MEASURED_PEAKS.json has no FP64 figure).                    */

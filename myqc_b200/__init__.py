@@ -37,7 +37,7 @@ EXPORTS = [
     "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main", "myqc_eri_shard_layout",
     "myqc_eri_canonical_stats", "myqc_eri_plan_launch_count", "myqc_eri_plan_launch_info",
     "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard", "myqc_write_xx_ex", "myqc_eri_last_d2h_bytes",
-    "myqc_eri_plan_launch_quartets", "myqc_eri_plan_check", "myqc_eri_release_cache",
+    "myqc_eri_release_cache",
     # include/myqc_fock.h
     "myqc_fock_rhf", "myqc_fock_uhf", "myqc_fock_rhf_host", "myqc_fock_uhf_host",
     "myqc_fock_mask_words", "myqc_fock_mask_build", "myqc_fock_rhf_masked", "myqc_fock_uhf_masked",
@@ -102,16 +102,14 @@ def lib() -> ctypes.CDLL:
     L.myqc_eri_shard_layout.argtypes = common[:-1] + [c_int, _i64p]
     L.myqc_eri_canonical_stats.argtypes = [c_int, _dp, c_int, c_int, _dp, _ip, _i64p, _dp]
     L.myqc_eri_plan_launch_count.argtypes = [c_void_p]
-    L.myqc_eri_plan_launch_info.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int), _i64p]
-    L.myqc_eri_plan_launch_quartets.argtypes = [c_void_p, _i64p]
-    L.myqc_eri_plan_check.argtypes = [c_int, _dp, c_int, c_int, _dp, _ip, c_int, _dp, _ip, c_int, c_int, _i64p]
-    L.myqc_eri_release_cache.argtypes = []
-    L.myqc_eri_release_cache.restype = None
+    L.myqc_eri_plan_launch_info.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), _i64p]
     L.myqc_eri_plan_execute_timed.argtypes = [c_void_p, c_void_p, c_void_p, ctypes.POINTER(ctypes.c_float)]
     L.myqc_fp64_peak.argtypes = [c_int, _dp]
     L.myqc_eri_packed_shard.argtypes = common + [_dp, c_int, c_int, c_int, _i64p]
     L.myqc_eri_last_d2h_bytes.argtypes = []
     L.myqc_eri_last_d2h_bytes.restype = ctypes.c_int64
+    L.myqc_eri_release_cache.argtypes = []
+    L.myqc_eri_release_cache.restype = None
     c_i64 = ctypes.c_int64
     L.myqc_fock_rhf.argtypes = [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p]
     L.myqc_fock_uhf.argtypes = [c_void_p, c_i64, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
@@ -304,14 +302,6 @@ def last_d2h_bytes() -> int:
     return int(lib().myqc_eri_last_d2h_bytes())
 
 
-def plan_check(s: System, shard: int = 0, nshards: int = 1) -> dict:
-    """Host-only coverage check of one shard's plan (no device needed): replays what the kernels write."""
-    r = (ctypes.c_int64 * 6)()
-    c = s._common()
-    _check(lib().myqc_eri_plan_check(*c[:9], shard, nshards, r))
-    return {"errors": r[0], "slice_elems": r[1], "zero_filled": r[2], "stored": r[3], "expected": r[4], "tasks": r[5]}
-
-
 def release_cache():
     """Drop the plan / device slice the one-shot calls keep per device."""
     lib().myqc_eri_release_cache()
@@ -357,20 +347,13 @@ class Plan:
         _check(lib().myqc_eri_plan_execute(self._h, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(stream)))
 
     def launches(self):
-        """[(owner kind ut, partner-first-shell kind tc, slice, tasks)] in launch order."""
+        """[(class id or -1 for the zero fill, tri flag, rows)] in launch order."""
         out = []
         for k in range(lib().myqc_eri_plan_launch_count(self._h)):
-            u, t, sl, r = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
-            _check(lib().myqc_eri_plan_launch_info(self._h, k, ctypes.byref(u), ctypes.byref(t), ctypes.byref(sl), ctypes.byref(r)))
-            out.append((u.value, t.value, sl.value, r.value))
+            c, t, r = ctypes.c_int(), ctypes.c_int(), ctypes.c_int64()
+            _check(lib().myqc_eri_plan_launch_info(self._h, k, ctypes.byref(c), ctypes.byref(t), ctypes.byref(r)))
+            out.append((c.value, t.value, r.value))
         return out
-
-    def launch_quartets(self):
-        """After an execute: per launch, primitive quartets evaluated against partners with an S / an SP second shell."""
-        n = lib().myqc_eri_plan_launch_count(self._h)
-        nq = (ctypes.c_int64 * (2 * n))()
-        _check(lib().myqc_eri_plan_launch_quartets(self._h, nq))
-        return [(nq[2 * k], nq[2 * k + 1]) for k in range(n)]
 
     def execute_timed(self, d_out_ptr: int, stream: int = 0):
         """Like execute(), but synchronises and returns per-launch milliseconds (CUDA events)."""
@@ -400,12 +383,8 @@ class Plan:
 
 CLASS_NAMES = ["{0,0}", "{0,1}", "{0,2}", "{1,1}", "{1,2}", "{2,2}"]
 CLASS_W = [60.0, 99.0, 228.0, 228.0, 693.0, 2691.0]  # model flop per canonical primitive quartet
-
-
-def class_id(la: int, lb: int) -> int:
-    """Index into CLASS_NAMES / CLASS_W of the quartet class with la and lb SP sets in its two pairs."""
-    la, lb = min(la, lb), max(la, lb)
-    return [[0, 1, 2], [1, 3, 4], [2, 4, 5]][la][lb]
+# nominal dense FP64 (non-tensor DFMA) peak of a B200: 148 SMs x 64 DFMA/clk x 2 flop x 1.965 GHz
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12
 
 
 def shard_layout(s: System, nshards: int) -> np.ndarray:

@@ -1,14 +1,13 @@
-// C-ABI of the ERI engine (include/myqc_eri.h): planner (owner-row strips, tasks, shards), plans,
-// one-shot host-buffer calls.
+// C-ABI of the ERI engine (include/myqc_eri.h): plans, one-shot host-buffer calls.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <atomic>
-#include <chrono>
-#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
+#include <climits>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -20,7 +19,6 @@
 #include "../../include/myqc_eri.h"
 #include "eri_kernels.cuh"
 #include "pairs.hpp"
-#include "strip_geom.hpp"
 
 namespace myqc {
 
@@ -65,315 +63,100 @@ static int class_id(int la, int lb) {
     return id[la][lb];
 }
 
-// ---------------------------------------------------------------------------------------------
-// The host plan: everything the kernels read, as host vectors.  Pure host arithmetic (no device): the
-// shard layout and the coverage check use it without a GPU.
-struct LaunchH {
-    int UT = 0, TC = 0;
-    std::vector<int4> tasks;
+struct DevList {  // device copy of a PairList
+    int type = 0, n = 0, npad = 0;
+    double *aos = nullptr, *soa = nullptr;
+    int32_t *nprim = nullptr, *pidx = nullptr;
+    PairList host;  // host copy (without the bulky record arrays) for the prefix computation
 };
 
-struct HostPlan {
-    int ns = 0, norb = 0, nblk = 0;
+struct Launch {
+    int UT, TT;
+    ClassArgs args;                // args.tasks/ntasks describe the whole need-sorted task array
+    std::vector<int> region_task;  // [nregion+1] task ranges: region r = tasks whose writes end inside fill region r
+    double weight = 0.0;           // sum over tasks of (primitives of the row) x (primitives of the lane-side range)
+};
+
+constexpr int kMaxCounters = 1024;
+
+}  // namespace myqc
+
+using namespace myqc;
+
+struct Sub {  // one virtual sub-shard: a contiguous piece of the plan's slice with its own launches
+    int64_t out_offset = 0, out_elems = 0;  // absolute packed offsets
+    std::vector<Launch> launches;
+    int counter_base = 0, ncounters = 0;
+    // Fill regions: the slice is zero-filled in nregion consecutive pieces; the tasks of every
+    // class kernel are sorted by the end of the last packed row they can write to, so the tasks
+    // of region r only touch memory that pieces 0..r have already zeroed and can run while the
+    // later pieces are still being filled (no extra lists, no extra arithmetic: same tasks).
+    std::vector<int64_t> region_end;  // [nregion] offsets relative to the sub-shard's slice
+    // screened fill (default): one launch that writes the zeros of exactly those elements no class
+    // kernel writes, so it needs no ordering against them
+    FillArgs fill;
+    int64_t fill_zero_elems = 0;  // zeros the screened fill writes (slice elements minus screened-in ones)
+};
+
+struct myqc_eri_plan {
+    int device = 0, num_sms = 0;
+    int norb = 0, nset = 0;
     int64_t npair = 0;
-    std::vector<Shell> shells;
-    PairList lists[3];
-    std::vector<int32_t> sh_fn;     // [ns][4]
-    std::vector<int32_t> sh_first;  // [ns+1]
-    std::vector<signed char> sh_type;
-    std::vector<int32_t> pair_rec;  // [ns*ns]
-    std::vector<double> pair_emax;  // [ns*ns]
-    std::vector<double> blk_emax;   // [ns*nblk]
-    std::vector<int32_t> clist[2];  // shells of type 0 / 1, ascending
-    // shell classes (same type and exponents) and the partner segments (eri_kernels.cuh)
-    int ncls = 0;
-    std::vector<int32_t> sh_class, cls_kind, seg_start;
-    std::vector<unsigned short> seg_d;
-    std::vector<double> seg_eprof;  // [entries][4]
-    std::vector<double> shell_cost; // estimated seconds of one warp for everything first shell A owns
-    // shard
-    int A0 = 0, A1 = 0;             // owner first shells [A0, A1)
     int64_t out_offset = 0, out_elems = 0;
-    LaunchH launches[6];            // (UT,TC) = (0,0) (0,1) (1,0) (1,1) (2,0) (2,1)
+    std::vector<void*> dev_allocs;
+    std::vector<DevList> lists;
+    std::vector<Sub> subs;
+    double* d_ftab = nullptr;    // [5][121][8]
+    double* d_exptab = nullptr;  // [601][2] {exp(-k/10), k/10}
+    int* d_counters = nullptr;   // one row counter per class-kernel launch
+    int ncounters = 0;
+    // internal streams: the zero fill of sub-shard k+1 overlaps the FP64 kernels of sub-shard k,
+    // and class kernels of one sub-shard overlap each other's tails
+    static constexpr int kNumCompute = 4;
+    cudaStream_t s_fill = nullptr, s_comp[kNumCompute] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t e_start = nullptr, e_done[kNumCompute + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> e_fill;
+    // stats (canonical primitive-quartet counts of the whole shard)
+    int64_t nquartets[6] = {0, 0, 0, 0, 0, 0};
+    double model_flops = 0.0;
+    int nlaunch = 0;
+    int64_t h2d_bytes = 0;  // bytes uploaded at plan creation (pair tables, Boys tables, prefixes)
+    // inputs kept for the lazily evaluated work statistics (plan_stats)
+    std::vector<double> in_xyz, in_set;
+    std::vector<int32_t> in_setinfo;
+    int in_nnuc = 0, in_setl = 0;
+    bool stats_done = false, stats_whole = false;
+    bool screened_fill = true;
+    int32_t *d_rk = nullptr, *d_cut = nullptr;
+    std::vector<int32_t> h_rk, h_cut;
+    int nrank = 0;
 };
 
-// packed index of the first element of the first row whose leading orbital is `fn`
-static int64_t packed_row_offset(int64_t fn, int64_t norb) {
-    const int64_t np = norb * (norb + 1) / 2;
-    if (fn >= norb) return np * (np + 1) / 2;
-    const int64_t P = fn * norb - fn * (fn - 1) / 2;  // P(fn,fn)
-    return P * np - P * (P - 1) / 2;
+namespace myqc {
+
+template <class T>
+static int upload(myqc_eri_plan* pl, const std::vector<T>& h, T** d) {
+    *d = nullptr;
+    if (h.empty()) return MYQC_OK;
+    CU(cudaMalloc((void**)d, h.size() * sizeof(T)));
+    pl->dev_allocs.push_back(*d);
+    CU(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    pl->h2d_bytes += (int64_t)(h.size() * sizeof(T));
+    return MYQC_OK;
 }
 
-// Work model behind the task sizes and the shard cuts.  One warp runs a task; a task should take
-// a small fraction of the launch.  Rates are per warp, for a GPU running ~2400 warps: the same
-// constants on every rank (the shard layout is pure host arithmetic), and only ratios matter.
-constexpr double kWarpFlops = 3.5e9;   // model flops per second and warp
-constexpr double kWarpBytes = 2.0e9;   // packed-array bytes written per second and warp
-
-struct CostModel {
-    // partner kind k (0..2), first-shell type tc: emax of the pairs sorted descending, with prefix sums of
-    // their primitive counts; cnt_ge[k][tc][A] = number of kind-k pairs whose first shell is >= A and of type tc
-    std::vector<double> emax[3];
-    std::vector<double> primsum[3];
-    std::vector<int32_t> cnt_ge[3][2];
-    int ntot[3] = {0, 0, 0};
-    void build(const HostPlan& hp) {
-        for (int k = 0; k < 3; ++k) {
-            const PairList& L = hp.lists[k];
-            std::vector<int> order(L.n);
-            for (int i = 0; i < L.n; ++i) order[i] = i;
-            std::sort(order.begin(), order.end(), [&](int x, int y) { return L.emax[x] > L.emax[y]; });
-            emax[k].resize(L.n);
-            primsum[k].assign(L.n + 1, 0.0);
-            for (int i = 0; i < L.n; ++i) {
-                emax[k][i] = L.emax[order[i]];
-                primsum[k][i + 1] = primsum[k][i] + L.nprim[order[i]];
-            }
-            ntot[k] = L.n;
-            for (int tc = 0; tc < 2; ++tc) cnt_ge[k][tc].assign(hp.ns + 1, 0);
-            for (int i = 0; i < L.n; ++i) cnt_ge[k][hp.sh_type[L.shA[i]]][L.shA[i]] += 1;
-            for (int tc = 0; tc < 2; ++tc)
-                for (int A = hp.ns - 1; A >= 0; --A) cnt_ge[k][tc][A] += cnt_ge[k][tc][A + 1];
-        }
-    }
-    // estimated number of kind-k partners (first-shell type tc, first shell >= A) that pass the bound against emax_u
-    double partners(double emax_u, int A, int k, int tc) const {
-        if (ntot[k] == 0 || !(emax_u > 0.0)) return 0.0;
-        size_t lo = 0, hi = emax[k].size();
-        while (lo < hi) {
-            const size_t mid = (lo + hi) / 2;
-            if (emax_u * emax[k][mid] < 1.0e-14) hi = mid; else lo = mid + 1;
-        }
-        return (double)lo * (double)cnt_ge[k][tc][A] / (double)ntot[k];
-    }
-    // estimated primitive quartets of owner (emax_u, nprim_u, first shell A) against the kind-k partners whose
-    // first shell is of type tc: the partners that pass the bound, taken as an unbiased sample of first shells
-    double quartets(double emax_u, int nprim_u, int A, int k, int tc) const {
-        if (ntot[k] == 0 || !(emax_u > 0.0)) return 0.0;
-        size_t lo = 0, hi = emax[k].size();
-        while (lo < hi) {  // first index with emax_u*emax < 1e-14
-            const size_t mid = (lo + hi) / 2;
-            if (emax_u * emax[k][mid] < 1.0e-14) hi = mid; else lo = mid + 1;
-        }
-        return (double)nprim_u * primsum[k][lo] * (double)cnt_ge[k][tc][A] / (double)ntot[k];
-    }
-};
-
-static int build_host_tables(int nnuc, const double* xyz, int nset, int setl, const double* set,
-                             const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
-                             HostPlan& hp, std::string& err) {
+static int upload_list(myqc_eri_plan* pl, const PairList& src, DevList& d) {
+    d.type = src.type; d.n = src.n; d.npad = src.npad;
+    d.host.type = src.type; d.host.n = src.n; d.host.emax = src.emax; d.host.bucket = src.bucket; d.host.pidx = src.pidx; d.host.nprim = src.nprim;
     int rc;
-    if ((rc = build_shells(nnuc, nset, setl, setinfo, ops, basinfo, hp.shells, err))) return rc;
-    hp.ns = (int)hp.shells.size();
-    hp.norb = basinfo[1];
-    hp.npair = (int64_t)hp.norb * (hp.norb + 1) / 2;
-    if (hp.ns >= 32768 || hp.norb >= 32768) { err = "more than 32767 shells or orbitals"; return MYQC_ERR_UNSUPPORTED; }
-    {
-        int covered = 0;
-        for (const Shell& sh : hp.shells) covered += sh.end_fn - sh.first_fn;
-        if (covered != hp.norb) { err = "the sets do not cover orbitals 0..norb-1 exactly once"; return MYQC_ERR_BAD_ARG; }
-    }
-    if ((rc = build_pairs(nnuc, xyz, set, setinfo, setl, ops, bas, basinfo, hp.shells, hp.lists, err))) return rc;
-    const int ns = hp.ns;
-    hp.nblk = (ns + kBlockShells - 1) / kBlockShells;
-    hp.sh_fn.assign((size_t)ns * 4, -1);
-    hp.sh_first.assign(ns + 1, hp.norb);
-    hp.sh_type.assign(ns, 0);
-    for (int s = 0; s < ns; ++s) {
-        for (int k = 0; k < 4; ++k) hp.sh_fn[(size_t)s * 4 + k] = hp.shells[s].fn[k];
-        hp.sh_first[s] = hp.shells[s].first_fn;
-        hp.sh_type[s] = (signed char)hp.shells[s].type;
-        hp.clist[hp.shells[s].type].push_back(s);
-    }
-    hp.pair_rec.assign((size_t)ns * ns, -1);
-    hp.pair_emax.assign((size_t)ns * ns, 0.0);
-    hp.blk_emax.assign((size_t)ns * hp.nblk, 0.0);
-    for (int k = 0; k < 3; ++k)
-        for (int i = 0; i < hp.lists[k].n; ++i) {
-            const int A = hp.lists[k].shA[i], B = hp.lists[k].shB[i];
-            hp.pair_rec[(size_t)A * ns + B] = i;
-            hp.pair_emax[(size_t)A * ns + B] = hp.lists[k].emax[i];
-            double& bm = hp.blk_emax[(size_t)A * hp.nblk + B / kBlockShells];
-            bm = std::max(bm, hp.lists[k].emax[i]);
-        }
-    // shell classes: one per shell type (S, SP): a segment lists the partners of one kind of a (C, block).
-    // (The survival bins of the kernel, not the class, make the lanes of a chunk alike.)
-    {
-        hp.sh_class.assign(ns, 0);
-        for (int s = 0; s < ns; ++s) hp.sh_class[s] = hp.shells[s].type;
-        hp.ncls = 2;
-        hp.cls_kind = {0, 1};
-    }
-    // partner segments: (C, block, class) -> the D >= C of that class in that block with a live pair, by decreasing emax
-    {
-        const int nblk = hp.nblk, ncls = hp.ncls;
-        hp.seg_start.assign((size_t)ns * nblk * ncls + 1, 0);
-        hp.seg_d.clear(); hp.seg_eprof.clear();
-        std::vector<std::vector<std::pair<double, int>>> bucket(ncls);
-        for (int C = 0; C < ns; ++C)
-            for (int b = 0; b < nblk; ++b) {
-                for (auto& v : bucket) v.clear();
-                for (int D = std::max(C, b * kBlockShells); D < std::min(ns, (b + 1) * kBlockShells); ++D)
-                    if (hp.pair_rec[(size_t)C * ns + D] >= 0) bucket[hp.sh_class[D]].push_back({hp.pair_emax[(size_t)C * ns + D], D});
-                for (int c = 0; c < ncls; ++c) {
-                    std::stable_sort(bucket[c].begin(), bucket[c].end(), [](const std::pair<double, int>& x, const std::pair<double, int>& y) { return x.first > y.first; });
-                    hp.seg_start[((size_t)C * nblk + b) * ncls + c] = (int32_t)hp.seg_d.size();
-                    for (const auto& e : bucket[c]) {
-                        hp.seg_d.push_back((unsigned short)e.second);
-                        // prefactors of ranks 1, 3, 5, 7 (the primitives of a record are sorted by E, descending)
-                        const int kind = hp.sh_type[C] + hp.sh_type[e.second];
-                        const int rec = hp.pair_rec[(size_t)C * ns + e.second];
-                        const PairList& L = hp.lists[kind];
-                        const int nfield = pt_nfield(kind);
-                        for (int r = 0; r < 8; r += 2)
-                            hp.seg_eprof.push_back(r < L.nprim[rec] ? L.aos[((size_t)rec * kMaxPrim + r) * nfield + 4] : 0.0);
-                    }
-                }
-            }
-        hp.seg_start.back() = (int32_t)hp.seg_d.size();
-    }
+    if ((rc = upload(pl, src.aos, &d.aos))) return rc;
+    if ((rc = upload(pl, src.soa, &d.soa))) return rc;
+    if ((rc = upload(pl, src.nprim, &d.nprim))) return rc;
+    if ((rc = upload(pl, src.pidx, &d.pidx))) return rc;
     return MYQC_OK;
 }
 
-// seconds of one warp for owner pair (A,B) against the partner first shells of type tc (launch (UT,tc))
-static double owner_cost(const HostPlan& hp, const CostModel& cm, int A, int B, int tc, double* bytes_out) {
-    const int ns = hp.ns;
-    const int UT = hp.sh_type[A] + hp.sh_type[B];
-    const int rec = hp.pair_rec[(size_t)A * ns + B];
-    // rows of the owner
-    int nrows = 0;
-    for (int mu = 0; mu < 4; ++mu)
-        for (int nu = 0; nu < 4; ++nu) {
-            const int i = hp.sh_fn[(size_t)A * 4 + mu], j = hp.sh_fn[(size_t)B * 4 + nu];
-            if (i < 0 || j < 0 || (A == B && i > j)) continue;
-            ++nrows;
-        }
-    // columns whose first index lies in a type-tc shell C >= A (upper bound: the runs l >= k)
-    double cols = 0.0;
-    {
-        const std::vector<int32_t>& cl = hp.clist[tc];
-        const size_t c0 = std::lower_bound(cl.begin(), cl.end(), A) - cl.begin();
-        for (size_t c = c0; c < cl.size(); ++c)
-            for (int kc = 0; kc < 4; ++kc) {
-                const int k = hp.sh_fn[(size_t)cl[c] * 4 + kc];
-                if (k >= 0) cols += hp.norb - k;
-            }
-    }
-    const double bytes = 8.0 * nrows * cols;
-    if (bytes_out) *bytes_out = bytes;
-    double flops = 0.0;
-    if (rec >= 0) {
-        const PairList& L = hp.lists[UT];
-        for (int td = 0; td < 2; ++td) {
-            const int k = tc + td;
-            flops += kW[class_id(UT, k)] * cm.quartets(L.emax[rec], L.nprim[rec], A, k, tc);
-        }
-    }
-    return flops / kWarpFlops + bytes / kWarpBytes;
-}
-
-static void build_shell_costs(HostPlan& hp, const CostModel& cm) {
-    hp.shell_cost.assign(hp.ns, 0.0);
-    for (int A = 0; A < hp.ns; ++A)
-        for (int B = A; B < hp.ns; ++B)
-            for (int tc = 0; tc < 2; ++tc) hp.shell_cost[A] += owner_cost(hp, cm, A, B, tc, nullptr);
-}
-
-// cut [0, ns) into m contiguous ranges of first shells of ~equal cost; returns m+1 shell indices
-static std::vector<int> split_shells(const std::vector<double>& w, int m) {
-    const int n = (int)w.size();
-    std::vector<int> bound(m + 1, n);
-    bound[0] = 0;
-    double tot = 0;
-    for (double x : w) tot += x;
-    double acc = 0;
-    int sidx = 1;
-    for (int c = 0; c < n && sidx < m; ++c) {
-        acc += w[c];
-        while (sidx < m && acc >= tot * sidx / m) bound[sidx++] = c + 1;
-    }
-    for (int k = 1; k <= m; ++k) bound[k] = std::max(bound[k], bound[k - 1]);
-    bound[m] = n;
-    return bound;
-}
-
-// tasks of the shard [A0, A1): every owner pair (dead ones included: their rows are zeros that still
-// have to be written), against every partner first shell C >= A, cut into pieces of bounded cost
-static void build_tasks(HostPlan& hp, const CostModel& cm) {
-    const int ns = hp.ns, nblk = hp.nblk;
-    // A task is one warp's unit of work.  Its quartets are evaluated 32 at a time per pending list (partner kind x
-    // survival bin), and the last chunk of every list is partly empty, so a task must hold many quartets: the
-    // targets below are partners per task (estimated from the sorted prefactors).  Tasks with few partners
-    // are mostly zero fill and are bounded by the bytes they write instead.
-    const double kItemsLight = std::getenv("MYQC_TASK_ITEMS") ? std::atof(std::getenv("MYQC_TASK_ITEMS")) : 1024.0;
-    const double kItemsHeavy = std::getenv("MYQC_TASK_ITEMS_HEAVY") ? std::atof(std::getenv("MYQC_TASK_ITEMS_HEAVY")) : 320.0;
-    const double kTaskBytes = 4.0e6;
-    for (int UT = 0; UT < 3; ++UT)
-        for (int tc = 0; tc < 2; ++tc) {
-            LaunchH& L = hp.launches[UT * 2 + tc];
-            L.UT = UT; L.TC = tc;
-            L.tasks.clear();
-        }
-    for (int A = hp.A0; A < hp.A1; ++A)
-        for (int B = A; B < ns; ++B) {
-            const int UT = hp.sh_type[A] + hp.sh_type[B];
-            for (int tc = 0; tc < 2; ++tc) {
-                const std::vector<int32_t>& cl = hp.clist[tc];
-                const int c0 = (int)(std::lower_bound(cl.begin(), cl.end(), A) - cl.begin());
-                const int nc = (int)cl.size() - c0;
-                if (nc <= 0) continue;
-                std::vector<int4>& tasks = hp.launches[UT * 2 + tc].tasks;
-                double bytes = 0.0;
-                owner_cost(hp, cm, A, B, tc, &bytes);
-                const int rec = hp.pair_rec[(size_t)A * ns + B];
-                double items = 0.0;
-                if (rec >= 0)
-                    for (int td = 0; td < 2; ++td) items += cm.partners(hp.lists[UT].emax[rec], A, tc + td, tc);
-                const bool heavy = (UT + tc >= 2) && !(UT == 0);  // launches whose second partner kind has 64 integrals per quartet
-                int npiece = (int)std::max(std::floor(items / (heavy ? kItemsHeavy : kItemsLight)), std::ceil(bytes / kTaskBytes));
-                npiece = std::max(1, npiece);
-                const int ab = A | (B << 16);
-                if (npiece <= nc) {
-                    for (int p = 0; p < npiece; ++p) {
-                        const int lo = c0 + (int)((int64_t)nc * p / npiece), hi = c0 + (int)((int64_t)nc * (p + 1) / npiece);
-                        if (hi > lo) tasks.push_back(make_int4(ab, lo, hi, (cl[lo] / kBlockShells) | (nblk << 16)));
-                    }
-                } else {
-                    // more pieces than first shells: cut the partner blocks of each C too
-                    const int per_c = (npiece + nc - 1) / nc;
-                    for (int c = c0; c < c0 + nc; ++c) {
-                        const int bfirst = cl[c] / kBlockShells, nb = nblk - bfirst;
-                        const int np = std::min(per_c, nb);
-                        for (int p = 0; p < np; ++p) {
-                            const int lo = bfirst + (int)((int64_t)nb * p / np), hi = bfirst + (int)((int64_t)nb * (p + 1) / np);
-                            if (hi > lo) tasks.push_back(make_int4(ab, c, c + 1, lo | (hi << 16)));
-                        }
-                    }
-                }
-            }
-        }
-}
-
-static int build_host_plan(int nnuc, const double* xyz, int nset, int setl, const double* set,
-                           const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
-                           int shard, int nshards, HostPlan& hp, std::string& err) {
-    int rc = build_host_tables(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, hp, err);
-    if (rc) return rc;
-    CostModel cm;
-    cm.build(hp);
-    build_shell_costs(hp, cm);
-    const std::vector<int> cuts = split_shells(hp.shell_cost, nshards);
-    hp.A0 = cuts[shard];
-    hp.A1 = cuts[shard + 1];
-    hp.out_offset = packed_row_offset(hp.sh_first[hp.A0], hp.norb);
-    hp.out_elems = packed_row_offset(hp.sh_first[hp.A1], hp.norb) - hp.out_offset;
-    build_tasks(hp, cm);
-    return MYQC_OK;
-}
-
-// canonical primitive-quartet statistics (SURVEY.md 8d): unordered primitive pairs {a<=b},
-// unordered pairs of pairs, kept iff EIJ*EGH >= 1e-14.
+// number of lane-side pairs v with emax_u*emax_v >= 1e-14 (lane list sorted descending)
 static std::vector<int32_t> prefix_counts(const std::vector<double>& eu, const std::vector<double>& et) {
     std::vector<int32_t> out(eu.size());
     for (size_t u = 0; u < eu.size(); ++u) {
@@ -388,6 +171,219 @@ static std::vector<int32_t> prefix_counts(const std::vector<double>& eu, const s
     return out;
 }
 
+static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
+    const DevList& U = pl->lists[ui];
+    const DevList& T = pl->lists[ti];
+    if (U.n == 0 || T.n == 0) return MYQC_OK;
+    Launch L;
+    L.UT = U.type; L.TT = T.type;
+    ClassArgs& a = L.args;
+    std::memset(&a, 0, sizeof(a));
+    a.u_aos = U.aos; a.u_nprim = U.nprim; a.u_pidx = U.pidx; a.nU = U.n;
+    const std::vector<int32_t> ntv = row_prefix(U.host, T.host);
+    // segments of the lane-side list: at most kTaskPairs pairs, cut at group boundaries once a
+    // segment holds >= 64 pairs, so that a task holds pairs of (mostly) one kind
+    const int maxpairs = class_task_pairs(U.type, T.type);
+    const int mingroup = std::min(64, maxpairs);
+    std::vector<int> seg;  // segment start offsets, terminated by T.n
+    seg.push_back(0);
+    for (int k = 1; k < T.n; ++k) {
+        const int len = k - seg.back();
+        if (len >= maxpairs || (len >= mingroup && T.host.bucket[k] != T.host.bucket[k - 1])) seg.push_back(k);
+    }
+    seg.push_back(T.n);
+    // last packed element a row u can write to: end of packed row max_f P(u,f)
+    std::vector<int64_t> need_u(U.n, 0);
+    {
+        const int nfu = pt_nf(U.type);
+        for (int u = 0; u < U.n; ++u) {
+            int64_t pmax = -1;
+            for (int f = 0; f < nfu; ++f) pmax = std::max<int64_t>(pmax, U.host.pidx[(size_t)u * nfu + f]);
+            need_u[u] = pmax < 0 ? 0 : (pmax + 1) * pl->npair - (pmax + 1) * pmax / 2 - sub.out_offset;  // row end, slice-relative
+        }
+    }
+    struct TaskN { int4 t; int64_t need; int region; double weight; };
+    std::vector<double> tprim_prefix(T.n + 1, 0.0);  // prefix sums of lane-side primitive counts
+    for (int k = 0; k < T.n; ++k) tprim_prefix[k + 1] = tprim_prefix[k] + T.host.nprim[k];
+    const int nregion = (int)sub.region_end.size();
+    // MYQC_TASK_ORDER=0: plain heaviest-task-first order (23.5 ms on (H2O)_64 against 22.5 ms, profiles/r1_notes.md)
+    static const int task_order = std::getenv("MYQC_TASK_ORDER") ? std::atoi(std::getenv("MYQC_TASK_ORDER")) : 1;
+    auto emit_row = [&](int u, std::vector<TaskN>& dst) {
+        const int lo = tri ? u : 0, hi = ntv[u];
+        if (lo >= hi) return;
+        size_t si = std::upper_bound(seg.begin(), seg.end(), lo) - seg.begin() - 1;
+        for (; si + 1 < seg.size() && seg[si] < hi; ++si) {
+            const int b = std::max(seg[si], lo), e = std::min(seg[si + 1], hi);
+            if (b < e)
+                dst.push_back({make_int4(u, b, e, 0), need_u[u], 0,
+                               (double)U.host.nprim[u] * (tprim_prefix[e] - tprim_prefix[b])});
+        }
+    };
+    std::vector<TaskN> tn;
+    std::vector<int4> tasks;
+    L.region_task.assign(nregion + 1, 0);
+    if (task_order == 1 && nregion == 1) {
+        // Rows heaviest first, the tasks of one row adjacent (in lane-side order): everything a launch
+        // stores into the packed rows of one uniform-side pair is stored within a short time, so
+        // partial-sector stores of neighbouring lanes meet in L2.  Only the rows are sorted.
+        std::vector<double> roww(U.n, 0.0);
+        std::vector<int> order;
+        order.reserve(U.n);
+        for (int u = 0; u < U.n; ++u) {
+            const int lo = tri ? u : 0, hi = ntv[u];
+            if (lo >= hi) continue;
+            roww[u] = (double)U.host.nprim[u] * (tprim_prefix[hi] - tprim_prefix[lo]);
+            order.push_back(u);
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return roww[x] > roww[y]; });
+        for (int u : order) {
+            tn.clear();
+            emit_row(u, tn);
+            for (const TaskN& t : tn) { tasks.push_back(t.t); L.weight += t.weight; }
+        }
+        L.region_task[1] = (int)tasks.size();
+    } else {
+        for (int u = 0; u < U.n; ++u) emit_row(u, tn);
+        // region of a task = first fill region that covers everything the task can write; inside a
+        // region the heaviest tasks (most primitive quartets) go first so that launches end on light ones
+        for (TaskN& t : tn) {
+            int r = 0;
+            while (r + 1 < nregion && t.need > sub.region_end[r]) ++r;
+            t.region = r;
+        }
+        if (task_order == 1) {
+            std::vector<double> roww(U.n, 0.0);
+            for (const TaskN& t : tn) roww[t.t.x] += t.weight;
+            std::stable_sort(tn.begin(), tn.end(), [&](const TaskN& x, const TaskN& y) {
+                if (x.region != y.region) return x.region < y.region;
+                if (x.t.x != y.t.x) {
+                    if (roww[x.t.x] != roww[y.t.x]) return roww[x.t.x] > roww[y.t.x];
+                    return x.t.x < y.t.x;
+                }
+                return x.t.y < y.t.y;
+            });
+        } else {
+            std::stable_sort(tn.begin(), tn.end(), [](const TaskN& x, const TaskN& y) {
+                if (x.region != y.region) return x.region < y.region;
+                return x.weight > y.weight;
+            });
+        }
+        tasks.resize(tn.size());
+        for (size_t k = 0; k < tn.size(); ++k) { tasks[k] = tn[k].t; L.weight += tn[k].weight; }
+        L.region_task.assign(nregion + 1, (int)tn.size());
+        L.region_task[0] = 0;
+        for (size_t k = 0, r = 0; r < (size_t)nregion; ++r) {
+            while (k < tn.size() && tn[k].region <= (int)r) ++k;
+            L.region_task[r + 1] = (int)k;
+        }
+    }
+    if (tasks.empty()) return MYQC_OK;
+    int4* d_tasks = nullptr;
+    int rc = upload(pl, tasks, &d_tasks);
+    if (rc) return rc;
+    a.tasks = d_tasks;
+    a.ntasks = (int)tasks.size();
+    a.t_soa = T.soa; a.t_aos = T.aos; a.t_nprim = T.nprim; a.t_pidx = T.pidx;
+    a.t_npad = T.npad; a.nT = T.n; a.tri = tri ? 1 : 0;
+    a.ftab_q = pl->d_ftab + (size_t)(U.type + T.type) * 121 * 8;
+    a.exptab = reinterpret_cast<const double2*>(pl->d_exptab);
+    const int ncnt = class_nlaunch(L.UT, L.TT) * nregion;  // one task counter per launch and region
+    if (pl->ncounters + ncnt > kMaxCounters) return fail(MYQC_ERR_UNSUPPORTED, "too many launches in one plan");
+    a.row_counter = pl->d_counters + pl->ncounters;
+    pl->ncounters += ncnt;
+    sub.ncounters += ncnt;
+    a.out = nullptr;
+    a.out_offset = sub.out_offset;
+    a.npair = pl->npair;
+    sub.launches.push_back(L);
+    pl->nlaunch += class_nlaunch(L.UT, L.TT) * nregion;
+    return MYQC_OK;
+}
+
+// Rank / cut arrays of the screened fill (see fill_screened_kernel).  all[] are the complete pair
+// lists of the molecule: every function pair P belongs to exactly one shell pair.
+static int build_screen_ranks(myqc_eri_plan* pl, const PairList all[3]) {
+    std::vector<double> E;
+    for (int t = 0; t < 3; ++t) E.insert(E.end(), all[t].emax.begin(), all[t].emax.end());
+    std::sort(E.begin(), E.end(), std::greater<double>());
+    pl->nrank = (int)E.size();
+    pl->h_rk.assign((size_t)pl->npair, INT32_MAX);
+    pl->h_cut.assign((size_t)pl->npair, 0);
+    for (int t = 0; t < 3; ++t) {
+        const int nf = pt_nf(t);
+        for (int q = 0; q < all[t].n; ++q) {
+            const double e = all[t].emax[q];
+            // first occurrence of e in the descending list
+            const int32_t rank = (int32_t)(std::lower_bound(E.begin(), E.end(), e, std::greater<double>()) - E.begin());
+            size_t lo = 0, hi = E.size();
+            while (lo < hi) {  // first index whose product with e fails the reference's test
+                const size_t mid = (lo + hi) / 2;
+                if (e * E[mid] < 1.0e-14) hi = mid; else lo = mid + 1;
+            }
+            for (int f = 0; f < nf; ++f) {
+                const int32_t P = all[t].pidx[(size_t)q * nf + f];
+                if (P < 0) continue;
+                pl->h_rk[P] = rank;
+                pl->h_cut[P] = (int32_t)lo;
+            }
+        }
+    }
+    int rc;
+    if ((rc = upload(pl, pl->h_rk, &pl->d_rk))) return rc;
+    if ((rc = upload(pl, pl->h_cut, &pl->d_cut))) return rc;
+    return MYQC_OK;
+}
+
+static int build_sub_fill(myqc_eri_plan* pl, Sub& sub, int64_t row_lo, int64_t row_hi) {
+    FillArgs& f = sub.fill;
+    std::memset(&f, 0, sizeof(f));
+    f.out_offset = sub.out_offset;
+    f.npair = pl->npair;
+    f.row_lo = row_lo; f.row_hi = row_hi;
+    f.rk = pl->d_rk; f.cut = pl->d_cut;
+    f.all = std::getenv("MYQC_FILL_ALL") ? 1 : 0;
+    f.sleep_ns = std::getenv("MYQC_FILL_SLEEP_NS") ? std::atoi(std::getenv("MYQC_FILL_SLEEP_NS")) : 0;
+    sub.fill_zero_elems = 0;
+    if (row_hi <= row_lo) return MYQC_OK;
+    const int64_t ncb_all = (pl->npair + kFillCols - 1) / kFillCols;
+    f.cb0 = (int)(row_lo / kFillCols);
+    f.ncb = (int)(ncb_all - f.cb0);
+    std::vector<int32_t> ucb(f.ncb + 1, 0);
+    for (int k = 0; k < f.ncb; ++k) {
+        const int64_t cend = std::min<int64_t>(((int64_t)f.cb0 + k + 1) * kFillCols, pl->npair);  // one past the last column
+        const int64_t rows = std::min(row_hi, cend) - row_lo;                                    // rows r <= last column
+        const int64_t nrb = rows > 0 ? (rows + kFillRows - 1) / kFillRows : 0;
+        if ((int64_t)ucb[k] + nrb > INT32_MAX) return fail(MYQC_ERR_UNSUPPORTED, "too many fill units");
+        ucb[k + 1] = ucb[k] + (int32_t)nrb;
+    }
+    f.nunits = ucb[f.ncb];
+    int32_t* d_ucb = nullptr;
+    int rc = upload(pl, ucb, &d_ucb);
+    if (rc) return rc;
+    f.ucb = d_ucb;
+    if (pl->ncounters + 1 > kMaxCounters) return fail(MYQC_ERR_UNSUPPORTED, "too many launches in one plan");
+    f.counter = pl->d_counters + pl->ncounters;
+    pl->ncounters += 1;
+    // zeros written = elements of the rows minus the screened-in ones: count pairs (P <= P') with
+    // rk[P'] < cut[P] with a Fenwick tree over the ranks
+    std::vector<int32_t> bit((size_t)pl->nrank + 1, 0);
+    int64_t touched = 0;
+    for (int64_t P = pl->npair - 1; P >= row_lo; --P) {
+        const int32_t r = pl->h_rk[P];
+        if (r < pl->nrank)
+            for (int i = r + 1; i <= pl->nrank; i += i & (-i)) ++bit[i];
+        if (P < row_hi) {
+            int64_t c = 0;
+            for (int i = pl->h_cut[P]; i > 0; i -= i & (-i)) c += bit[i];
+            touched += c;
+        }
+    }
+    sub.fill_zero_elems = sub.out_elems - touched;
+    return MYQC_OK;
+}
+
+// canonical primitive-quartet statistics (SURVEY.md 8d): unordered primitive pairs {a<=b},
+// unordered pairs of pairs, kept iff EIJ*EGH >= 1e-14; restricted to the shard by `owner`.
 static void canonical_stats(int nnuc, const double* xyz, int nset, int setl, const double* set,
                             const int32_t* setinfo, int64_t nq[6], double* flops) {
     std::vector<double> E[3];
@@ -419,6 +415,102 @@ static void canonical_stats(int nnuc, const double* xyz, int nset, int setl, con
     for (int c = 0; c < 6; ++c) *flops += kW[c] * (double)nq[c];
 }
 
+// packed index of the first element of the first row whose leading orbital is `fn`
+static int64_t packed_row_offset(int64_t fn, int64_t norb) {
+    const int64_t np = norb * (norb + 1) / 2;
+    if (fn >= norb) return np * (np + 1) / 2;
+    const int64_t P = fn * norb - fn * (fn - 1) / 2;  // P(fn,fn)
+    return P * np - P * (P - 1) / 2;
+}
+
+// Ownership rule (multi-GPU): a shell quartet belongs to the shard that owns the
+// smallest first-orbital id among its four shells; all its canonical integrals then lie in packed
+// rows whose leading orbital is inside that shell.  Shards are contiguous blocks of such rows.
+// Pure host arithmetic: every rank computes the same answer independently.
+struct CutTable {
+    std::vector<int> cuts;   // candidate cut points: first orbital of each shell, ascending
+    std::vector<double> w;   // estimated model flops owned by [cuts[c], cuts[c+1])
+};
+
+static int build_cut_table(const std::vector<Shell>& shells, const PairList all[3], CutTable& ct, std::string& err) {
+    for (const Shell& sh : shells) {  // row blocks are closed only for contiguous orbital ranges
+        int cnt = 0, mx = -1;
+        for (int k = 0; k < 4; ++k) if (sh.fn[k] >= 0) { ++cnt; mx = std::max(mx, sh.fn[k]); }
+        if (mx - sh.first_fn + 1 != cnt) { err = "sharding needs contiguous orbital ids per shell"; return MYQC_ERR_UNSUPPORTED; }
+    }
+    std::vector<int>& cuts = ct.cuts;
+    cuts.clear();
+    for (const Shell& sh : shells) cuts.push_back(sh.first_fn);
+    std::sort(cuts.begin(), cuts.end());
+    cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+    const int nc = (int)cuts.size();
+    auto cut_of = [&](int fn) { return (int)(std::upper_bound(cuts.begin(), cuts.end(), fn) - cuts.begin()) - 1; };
+    // weight of block c ~ model flops of the quartets it owns.  A row u of class (ta,tb) has
+    // cnt[u] partners (the emax prefix); the prefix is treated as an unbiased sample of owners, so
+    // the row's weight is split between cut(u) (partners with cut >= cut(u)) and the lower cuts
+    // in proportion to the partner histogram.
+    ct.w.assign(nc, 0.0);
+    for (int ta = 0; ta < 3; ++ta)
+        for (int tb = ta; tb < 3; ++tb) {
+            const PairList& A = all[ta];
+            const PairList& B = all[tb];
+            if (A.n == 0 || B.n == 0) continue;
+            const std::vector<int32_t> cnt = row_prefix(A, B);
+            std::vector<double> hist(nc + 1, 0.0), ge(nc + 2, 0.0);
+            double mean_prim = 0.0;
+            for (int k = 0; k < B.n; ++k) {
+                hist[cut_of(B.owner_fn[k])] += 1.0;
+                mean_prim += B.nprim[k];
+            }
+            mean_prim /= B.n;
+            for (int c = nc - 1; c >= 0; --c) ge[c] = ge[c + 1] + hist[c];
+            // seconds per primitive quartet: model flops / (measured class efficiency x DFMA peak);
+            // efficiencies from profiles/r1_notes.md ((H2O)_64, one B200)
+            static const double kEff[6] = {0.34, 0.31, 0.23, 0.23, 0.20, 0.12};
+            const int cid = class_id(ta, tb);
+            const double wq = kW[cid] / (kEff[cid] * 34.2e12) * mean_prim / B.n;
+            for (int u = 0; u < A.n; ++u) {
+                double nrow = cnt[u];
+                if (ta == tb) nrow = std::max(0.0, nrow - u);
+                const double wr = wq * nrow * (double)A.nprim[u];
+                const int cu = cut_of(A.owner_fn[u]);
+                ct.w[cu] += wr * ge[cu];
+                for (int c = 0; c < cu; ++c) ct.w[c] += wr * hist[c];
+            }
+        }
+    // plus the zero fill of the rows the block owns (HBM bound, ~6.2 TB/s)
+    {
+        int norb = 0;
+        for (const Shell& sh : shells)
+            for (int k = 0; k < 4; ++k) norb = std::max(norb, sh.fn[k] + 1);
+        for (int c = 0; c < nc; ++c) {
+            const int64_t b = packed_row_offset(c == 0 ? 0 : cuts[c], norb);
+            const int64_t e = packed_row_offset(c + 1 < nc ? cuts[c + 1] : norb, norb);
+            ct.w[c] += 8.0 * (double)(e - b) / 6.2e12;
+        }
+    }
+    return MYQC_OK;
+}
+
+// cut the candidate range [c_lo, c_hi) into m contiguous parts of ~equal weight; returns m+1 indices
+static std::vector<int> split_range(const CutTable& ct, int c_lo, int c_hi, int m) {
+    std::vector<int> bound(m + 1, c_hi);
+    bound[0] = c_lo;
+    double tot = 0;
+    for (int c = c_lo; c < c_hi; ++c) tot += ct.w[c];
+    double acc = 0;
+    int sidx = 1;
+    for (int c = c_lo; c < c_hi && sidx < m; ++c) {
+        acc += ct.w[c];
+        while (sidx < m && acc >= tot * sidx / m) bound[sidx++] = c + 1;
+    }
+    for (int k = 1; k <= m; ++k) bound[k] = std::max(bound[k], bound[k - 1]);
+    bound[m] = c_hi;
+    return bound;
+}
+
+static int cut_to_fn(const CutTable& ct, int c, int norb) { return c < (int)ct.cuts.size() ? (c == 0 ? 0 : ct.cuts[c]) : norb; }
+
 static int check_args(int nnuc, const double* xyz, int nset, int setl, const double* set,
                       const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
                       const double* ftab) {
@@ -431,197 +523,6 @@ static int check_args(int nnuc, const double* xyz, int nset, int setl, const dou
         if (c < 0 || c >= nnuc) return fail(MYQC_ERR_BAD_ARG, "set centre out of range");
         if (!(set[s] > 0.0)) return fail(MYQC_ERR_BAD_ARG, "non-positive exponent");
     }
-    return MYQC_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Coverage check of a host plan (no device): replays what the kernels write -- the zero-filled spans of
-// every task, cut at pseudo-random flush points, and the integrals of every partner that passes the
-// pair-level bound -- with the same index arithmetic (strip_geom.hpp), and verifies that every element of
-// the shard's slice is zero-filled exactly once, that every integral lands inside its own task's span,
-// and that every integral that should exist is stored exactly once.
-struct CheckResult { int64_t zero_elems = 0, value_elems = 0, expected_values = 0, errors = 0; };
-
-static void check_plan(const HostPlan& hp, CheckResult& cr) {
-    const int ns = hp.ns, nblk = hp.nblk, norb = hp.norb;
-    std::vector<unsigned char> z((size_t)hp.out_elems, 0), val((size_t)hp.out_elems, 0);
-    uint32_t rng = 12345u;
-    auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
-    for (int li = 0; li < 6; ++li) {
-        const LaunchH& L = hp.launches[li];
-        const std::vector<int32_t>& cl = hp.clist[L.TC];
-        const int nslice = (L.UT == 2 && L.TC == 1) ? 4 : 1;
-        for (int slice_i = 0; slice_i < nslice; ++slice_i) {
-            const int USL = nslice == 4 ? slice_i : -1;
-            const int NFU = USL >= 0 ? 4 : pt_nf(L.UT);
-            for (const int4& t : L.tasks) {
-                const int A = t.x & 0xffff, B = t.x >> 16, c_lo = t.y, c_hi = t.z, b_lo = t.w & 0xffff, b_hi = t.w >> 16;
-                const int* fa = &hp.sh_fn[(size_t)A * 4];
-                const int* fb = &hp.sh_fn[(size_t)B * 4];
-                const bool a_is_sp = (L.UT == 1) && hp.sh_type[A] == 1;
-                const double eu = hp.pair_emax[(size_t)A * ns + B];
-                // spans: consecutive positions (ci, b), cut at random places like the kernel's flushes
-                int zci = c_lo, zb = b_lo;
-                auto zero_span = [&](int pci, int pb) {
-                    for (int f = 0; f < NFU; ++f) {
-                        int i, j;
-                        if (!owner_row(L.UT, USL, a_is_sp, A == B, fa, fb, f, &i, &j)) continue;
-                        const int64_t P1 = pair_index64(i, j, norb);
-                        const int64_t rb = row_start64(P1, hp.npair) - P1 - hp.out_offset;
-                        for (int c2 = zci; c2 <= pci; ++c2) {
-                            const int C2 = cl[c2];
-                            const int bfirst = C2 / kBlockShells;
-                            const int blo = (c2 == zci && zb >= 0) ? zb : bfirst;
-                            const int bhi = (c2 == pci) ? pb : nblk - 1;
-                            if (blo > bhi) continue;
-                            const int llo = (blo == bfirst) ? 0 : hp.sh_first[blo * kBlockShells];
-                            const int lhi = (bhi == nblk - 1) ? norb : hp.sh_first[(bhi + 1) * kBlockShells];
-                            for (int kc = 0; kc < (L.TC ? 4 : 1); ++kc) {
-                                const int k = hp.sh_fn[(size_t)C2 * 4 + kc];
-                                if (k < 0) continue;
-                                int l0;
-                                const int n = row_piece(i, j, k, llo, lhi, &l0);
-                                const int64_t addr = rb + col_base64(k, norb) + l0;
-                                for (int x = 0; x < n; ++x) {
-                                    if (addr + x < 0 || addr + x >= hp.out_elems) { ++cr.errors; continue; }
-                                    if (z[(size_t)(addr + x)]++) ++cr.errors;
-                                    ++cr.zero_elems;
-                                }
-                            }
-                        }
-                    }
-                    if (pb >= nblk - 1) { zci = pci + 1; zb = -1; } else { zci = pci; zb = pb + 1; }
-                };
-                for (int ci = c_lo; ci < c_hi; ++ci) {
-                    const int Cs = cl[ci];
-                    const int bmin = (ci == c_lo) ? b_lo : Cs / kBlockShells;
-                    const int bend = (ci == c_hi - 1) ? b_hi : nblk;
-                    for (int b = bmin; b < bend; ++b) {
-                        // partners of this block
-                        for (int Ds = std::max(b * kBlockShells, Cs); Ds < std::min(ns, (b + 1) * kBlockShells); ++Ds) {
-                            if (hp.pair_rec[(size_t)Cs * ns + Ds] < 0) continue;
-                            if (!(eu * hp.pair_emax[(size_t)Cs * ns + Ds] >= 1.0e-14)) continue;
-                            if (eu * hp.blk_emax[(size_t)Cs * nblk + b] < 1.0e-14) ++cr.errors;  // block bound must not hide it
-                            const int TD = hp.sh_type[Ds];
-                            const int* fc = &hp.sh_fn[(size_t)Cs * 4];
-                            const int* fd = &hp.sh_fn[(size_t)Ds * 4];
-                            for (int f = 0; f < NFU; ++f) {
-                                int i, j;
-                                if (!owner_row(L.UT, USL, a_is_sp, A == B, fa, fb, f, &i, &j)) continue;
-                                const int64_t P1 = pair_index64(i, j, norb);
-                                const int64_t rb = row_start64(P1, hp.npair) - P1 - hp.out_offset;
-                                for (int kc = 0; kc < (L.TC ? 4 : 1); ++kc)
-                                    for (int ld = 0; ld < (TD ? 4 : 1); ++ld) {
-                                        const int k = fc[kc], l = fd[ld];
-                                        if (k < 0 || l < 0 || k > l || k < i || (k == i && l < j)) continue;
-                                        const int64_t addr = rb + col_base64(k, norb) + l;
-                                        if (addr < 0 || addr >= hp.out_elems) { ++cr.errors; continue; }
-                                        if (val[(size_t)addr]++) ++cr.errors;
-                                        ++cr.value_elems;
-                                    }
-                            }
-                        }
-                        if (rnd() % 5 == 0) zero_span(ci, b);
-                    }
-                    if (rnd() % 3 == 0 && bend == nblk) zero_span(ci, nblk - 1);
-                }
-                zero_span(c_hi - 1, b_hi - 1);
-            }
-        }
-    }
-    for (int64_t e = 0; e < hp.out_elems; ++e)
-        if (z[(size_t)e] != 1) ++cr.errors;
-    // the partner segments list every live pair (C,D), D >= C, exactly once, in its block and class, by decreasing emax
-    {
-        std::vector<int> seen((size_t)ns * ns, 0);
-        for (int Cs = 0; Cs < ns; ++Cs)
-            for (int b = 0; b < nblk; ++b)
-                for (int c = 0; c < hp.ncls; ++c) {
-                    const size_t si = ((size_t)Cs * nblk + b) * hp.ncls + c;
-                    for (int e = hp.seg_start[si]; e < hp.seg_start[si + 1]; ++e) {
-                        const int Ds = hp.seg_d[e];
-                        if (Ds < Cs || Ds / kBlockShells != b || hp.sh_class[Ds] != c) ++cr.errors;
-                        if (hp.seg_eprof[4 * (size_t)e] != hp.pair_emax[(size_t)Cs * ns + Ds] || hp.pair_rec[(size_t)Cs * ns + Ds] < 0) ++cr.errors;
-                        if (e > hp.seg_start[si] && hp.seg_eprof[4 * (size_t)e] > hp.seg_eprof[4 * (size_t)(e - 1)]) ++cr.errors;
-                        for (int r = 1; r < 4; ++r)
-                            if (hp.seg_eprof[4 * (size_t)e + r] > hp.seg_eprof[4 * (size_t)e + r - 1]) ++cr.errors;
-                        if (hp.cls_kind[c] != hp.sh_type[Ds]) ++cr.errors;
-                        ++seen[(size_t)Cs * ns + Ds];
-                    }
-                }
-        for (int Cs = 0; Cs < ns; ++Cs)
-            for (int Ds = Cs; Ds < ns; ++Ds)
-                if (seen[(size_t)Cs * ns + Ds] != (hp.pair_rec[(size_t)Cs * ns + Ds] >= 0 ? 1 : 0)) ++cr.errors;
-    }
-    // expected: every element (P1 <= P2) of the slice whose shell pairs pass the bound
-    std::vector<int> fn_shell(norb, -1);
-    for (int s = 0; s < ns; ++s)
-        for (int k = 0; k < 4; ++k)
-            if (hp.sh_fn[(size_t)s * 4 + k] >= 0) fn_shell[hp.sh_fn[(size_t)s * 4 + k]] = s;
-    if (hp.out_elems <= (int64_t)40000000) {
-        for (int i = 0; i < norb; ++i)
-            for (int j = i; j < norb; ++j) {
-                const int64_t P1 = pair_index64(i, j, norb);
-                const int64_t row0 = row_start64(P1, hp.npair) - hp.out_offset;
-                if (row0 < 0 || row0 >= hp.out_elems) continue;
-                const double eu = hp.pair_emax[(size_t)fn_shell[i] * ns + fn_shell[j]];
-                for (int k = i; k < norb; ++k)
-                    for (int l = (k == i ? j : k); l < norb; ++l) {
-                        const double ev = hp.pair_emax[(size_t)fn_shell[k] * ns + fn_shell[l]];
-                        const bool want = eu > 0.0 && ev > 0.0 && eu * ev >= 1.0e-14;
-                        const int64_t addr = row0 + (pair_index64(k, l, norb) - P1);
-                        if (want) ++cr.expected_values;
-                        if ((val[(size_t)addr] != 0) != want) ++cr.errors;
-                    }
-            }
-    } else {
-        cr.expected_values = -1;
-    }
-}
-
-}  // namespace myqc
-
-using namespace myqc;
-
-struct LaunchD {
-    int UT = 0, TC = 0, slice = 0;
-    StripArgs args;
-};
-
-struct myqc_eri_plan {
-    int device = 0, num_sms = 0;
-    int norb = 0, nset = 0;
-    int64_t npair = 0;
-    int64_t out_offset = 0, out_elems = 0;
-    std::vector<void*> dev_allocs;
-    std::vector<LaunchD> launches;  // one per kernel launch of an execute()
-    int* d_counters = nullptr;                 // one task counter per launch
-    unsigned long long* d_stats = nullptr;     // two counters per launch: primitive quartets evaluated, TD = 0 / 1
-    // internal streams: launches are independent (disjoint runs of the array), their tails overlap
-    static constexpr int kNumCompute = 4;
-    cudaStream_t s_comp[kNumCompute] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t e_start = nullptr, e_done[kNumCompute] = {nullptr, nullptr, nullptr, nullptr};
-    // stats (canonical primitive-quartet counts of the whole molecule, lazily evaluated)
-    int64_t nquartets[6] = {0, 0, 0, 0, 0, 0};
-    double model_flops = 0.0;
-    int64_t h2d_bytes = 0;  // bytes uploaded at plan creation
-    int64_t ntasks = 0;
-    std::vector<double> in_xyz, in_set;
-    std::vector<int32_t> in_setinfo;
-    int in_nnuc = 0, in_setl = 0;
-    bool stats_done = false, stats_whole = false;
-};
-
-namespace myqc {
-
-template <class T>
-static int upload(myqc_eri_plan* pl, const std::vector<T>& h, T** d) {
-    *d = nullptr;
-    if (h.empty()) return MYQC_OK;
-    CU(cudaMalloc((void**)d, h.size() * sizeof(T)));
-    pl->dev_allocs.push_back(*d);
-    CU(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
-    pl->h2d_bytes += (int64_t)(h.size() * sizeof(T));
     return MYQC_OK;
 }
 
@@ -671,98 +572,180 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
     pl->npair = (int64_t)pl->norb * (pl->norb + 1) / 2;
 
     std::string err;
-    HostPlan hp;
-    if ((rc = build_host_plan(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, shard, nshards, hp, err))) return fail(rc, err);
-    stage("host plan (pairs, tasks)");
-    pl->out_offset = hp.out_offset;
-    pl->out_elems = hp.out_elems;
+    std::vector<Shell> shells;
+    if ((rc = build_shells(nnuc, nset, setl, setinfo, ops, basinfo, shells, err))) return fail(rc, err);
+    PairList all[3];
+    if ((rc = build_pairs(nnuc, xyz, set, setinfo, setl, ops, bas, basinfo, shells, all, err))) return fail(rc, err);
+    stage("shells + pair records");
+    {
+        // Default: zero the whole slice first (streaming 128-bit stores, 0.95 of HBM peak), class kernels
+        // after it.  MYQC_FILL_MODE=screened selects the order-independent screened fill that runs next
+        // to the class kernels; measured on (H2O)_64 it does not pay (profiles/r1_notes.md): the class
+        // kernels' scattered stores and the fill compete for DRAM, the co-run takes the sum of both.
+        const char* fm = std::getenv("MYQC_FILL_MODE");
+        pl->screened_fill = (fm && std::strcmp(fm, "screened") == 0);
+    }
 
-    // ---- upload ----------------------------------------------------------------------------------
-    double *d_ftab = nullptr, *d_exptab = nullptr;
+    // Boys tables for the five start orders Q = 0,3,6,9,12: row t = {Ft(t,Q+k)/k!, k<7 ; t/10}
     {
         std::vector<double> h, ex;
         build_boys_tables(ftab, h, ex);
-        if ((rc = upload(pl.get(), h, &d_ftab))) return rc;
-        if ((rc = upload(pl.get(), ex, &d_exptab))) return rc;
+        if ((rc = upload(pl.get(), h, &pl->d_ftab))) return rc;
+        if ((rc = upload(pl.get(), ex, &pl->d_exptab))) return rc;
+        std::vector<int> zeros(kMaxCounters, 0);
+        if ((rc = upload(pl.get(), zeros, &pl->d_counters))) return rc;
     }
-    int32_t *d_sh_fn = nullptr, *d_sh_first = nullptr, *d_pair_rec = nullptr, *d_clist[2] = {nullptr, nullptr};
-    signed char* d_sh_type = nullptr;
-    double *d_pair_emax = nullptr, *d_blk_emax = nullptr;
-    if ((rc = upload(pl.get(), hp.sh_fn, &d_sh_fn))) return rc;
-    if ((rc = upload(pl.get(), hp.sh_first, &d_sh_first))) return rc;
-    if ((rc = upload(pl.get(), hp.sh_type, &d_sh_type))) return rc;
-    if ((rc = upload(pl.get(), hp.pair_rec, &d_pair_rec))) return rc;
-    if ((rc = upload(pl.get(), hp.pair_emax, &d_pair_emax))) return rc;
-    if ((rc = upload(pl.get(), hp.blk_emax, &d_blk_emax))) return rc;
-    for (int t = 0; t < 2; ++t)
-        if ((rc = upload(pl.get(), hp.clist[t], &d_clist[t]))) return rc;
-    int32_t *d_seg_start = nullptr, *d_cls_kind = nullptr;
-    unsigned short* d_seg_d = nullptr;
-    double* d_seg_eprof = nullptr;
-    if ((rc = upload(pl.get(), hp.seg_start, &d_seg_start))) return rc;
-    if ((rc = upload(pl.get(), hp.seg_d, &d_seg_d))) return rc;
-    if ((rc = upload(pl.get(), hp.seg_eprof, &d_seg_eprof))) return rc;
-    if ((rc = upload(pl.get(), hp.cls_kind, &d_cls_kind))) return rc;
-    double* d_aos[3] = {nullptr, nullptr, nullptr};
-    int32_t* d_nprim[3] = {nullptr, nullptr, nullptr};
-    for (int k = 0; k < 3; ++k) {
-        if ((rc = upload(pl.get(), hp.lists[k].aos, &d_aos[k]))) return rc;
-        if ((rc = upload(pl.get(), hp.lists[k].nprim, &d_nprim[k]))) return rc;
-    }
-    stage("table upload");
-    constexpr int kMaxLaunch = 16;
+    if (pl->screened_fill && (rc = build_screen_ranks(pl.get(), all))) return rc;
+    stage("tables");
+
+    // ---- sharding: contiguous blocks of packed rows, cut where a shell's functions start -------
+    // External shards (one per GPU) are cut first; this plan's shard is then cut again into
+    // virtual sub-shards so that the zero fill of piece k+1 overlaps the FP64 kernels of piece k.
+    CutTable ct;
+    ct.cuts.push_back(0);
+    ct.w.push_back(1.0);
+    int nvs = 1;
     {
-        std::vector<int> zc(kMaxLaunch, 0);
-        std::vector<unsigned long long> zs(2 * kMaxLaunch, 0ull);
-        if ((rc = upload(pl.get(), zc, &pl->d_counters))) return rc;
-        if ((rc = upload(pl.get(), zs, &pl->d_stats))) return rc;
+        const char* env = std::getenv("MYQC_VSHARDS");
+        const int64_t total = pl->npair * (pl->npair + 1) / 2;
+        // Measured on (H2O)_64 (profiles/r1_notes.md): cutting one GPU's shard into pieces overlaps the
+        // zero fill with the FP64 kernels but costs more in extra launches, shorter task lists and
+        // duplicated "later" lists than it wins (23.5 / 25.0 / 26.6 / 32.4 ms for 1 / 2 / 4 / 8 pieces),
+        // so the default is one piece; MYQC_VSHARDS overrides it for experiments.
+        (void)total;
+        nvs = env ? std::atoi(env) : 1;
+        if (nvs < 1) nvs = 1;
+        if (nvs > 16) nvs = 16;
     }
-    // launches: the long tasks first (SP.SP owners), so that the launches that end on many short tasks come last
-    static const int order[6] = {5, 4, 3, 2, 1, 0};
-    for (int oi = 0; oi < 6; ++oi) {
-        const LaunchH& L = hp.launches[order[oi]];
-        if (L.tasks.empty()) continue;
-        int4* d_tasks = nullptr;
-        if ((rc = upload(pl.get(), L.tasks, &d_tasks))) return rc;
-        for (int slice = 0; slice < strip_nslices(L.UT, L.TC); ++slice) {
-            LaunchD D;
-            D.UT = L.UT; D.TC = L.TC; D.slice = slice;
-            StripArgs& a = D.args;
-            std::memset(&a, 0, sizeof(a));
-            a.sh_fn = reinterpret_cast<const int4*>(d_sh_fn);
-            a.sh_type = d_sh_type;
-            a.sh_first = d_sh_first;
-            a.ns = hp.ns; a.nblk = hp.nblk; a.norb = hp.norb;
-            a.npair = hp.npair;
-            a.pair_rec = d_pair_rec; a.pair_emax = d_pair_emax; a.blk_emax = d_blk_emax;
-            a.seg_start = d_seg_start; a.seg_d = d_seg_d; a.seg_eprof = reinterpret_cast<const double2*>(d_seg_eprof);
-            a.cls_kind = d_cls_kind; a.ncls = hp.ncls;
-            a.clist = d_clist[L.TC];
-            a.u_aos = d_aos[L.UT]; a.u_nprim = d_nprim[L.UT];
-            for (int td = 0; td < 2; ++td) {
-                const int k = L.TC + td;
-                a.t_aos[td] = d_aos[k]; a.t_nprim[td] = d_nprim[k];
-                a.ftab_q[td] = d_ftab + (size_t)(L.UT + k) * 121 * 8;
+    std::vector<int> sub_fn(2, 0);
+    sub_fn[1] = pl->norb;
+    if (nshards > 1 || nvs > 1) {
+        if ((rc = build_cut_table(shells, all, ct, err))) return fail(rc, err);
+        const int nc = (int)ct.cuts.size();
+        const std::vector<int> ext = split_range(ct, 0, nc, nshards);
+        const std::vector<int> sub = split_range(ct, ext[shard], ext[shard + 1], nvs);
+        sub_fn.clear();
+        for (int c : sub) sub_fn.push_back(cut_to_fn(ct, c, pl->norb));
+        // drop empty pieces
+        std::vector<int> keep;
+        for (size_t k = 0; k < sub_fn.size(); ++k)
+            if (k == 0 || sub_fn[k] > keep.back()) keep.push_back(sub_fn[k]);
+        if (keep.size() < 2) keep.push_back(keep.back());
+        sub_fn = keep;
+    }
+    pl->out_offset = packed_row_offset(sub_fn.front(), pl->norb);
+    pl->out_elems = packed_row_offset(sub_fn.back(), pl->norb) - pl->out_offset;
+
+    stage("shard cuts");
+    const int nsub = (int)sub_fn.size() - 1;
+    pl->subs.resize(nsub);
+    pl->lists.reserve(6 * nsub);
+    for (int k = 0; k < nsub; ++k) {
+        Sub& sub = pl->subs[k];
+        const int fn_lo = sub_fn[k], fn_hi = sub_fn[k + 1];
+        sub.out_offset = packed_row_offset(fn_lo, pl->norb);
+        sub.out_elems = packed_row_offset(fn_hi, pl->norb) - sub.out_offset;
+        sub.counter_base = pl->ncounters;
+        {
+            const char* envr = std::getenv("MYQC_FILL_REGIONS");
+            // Default 1: on (H2O)_64 the fill of region r+1 and the kernels of region r do not co-run
+            // well (persistent grids starve each other): 23.2 / 24.2 / 24.8 ms for 1 / 2 / 4 regions
+            // (profiles/r1_notes.md).  MYQC_FILL_REGIONS overrides it for experiments.
+            int nreg = envr ? std::atoi(envr) : 1;
+            if (nreg < 1 || pl->screened_fill) nreg = 1;
+            if (nreg > 16) nreg = 16;
+            sub.region_end.resize(nreg);
+            for (int r = 0; r < nreg; ++r) {
+                int64_t e = sub.out_elems * (r + 1) / nreg;
+                e = (e + 1) & ~(int64_t)1;  // keep 16-byte aligned pieces
+                sub.region_end[r] = std::min(e, sub.out_elems);
             }
-            a.exptab = reinterpret_cast<const double2*>(d_exptab);
-            a.tasks = d_tasks;
-            a.ntasks = (int)L.tasks.size();
-            const int li = (int)pl->launches.size();
-            if (li >= kMaxLaunch) return fail(MYQC_ERR_UNSUPPORTED, "too many launches in one plan");
-            a.counter = pl->d_counters + li;
-            a.stats = pl->d_stats + 2 * li;
-            a.out = nullptr;
-            a.out_offset = hp.out_offset;
-            pl->launches.push_back(D);
-            pl->ntasks += a.ntasks;
+            sub.region_end[nreg - 1] = sub.out_elems;
+        }
+        // lists: "mine" (owner key in [fn_lo,fn_hi)) and "later" (owner key >= fn_hi)
+        int mine_id[3], later_id[3];
+        const bool whole = (fn_lo == 0 && fn_hi >= pl->norb);
+        for (int t = 0; t < 3; ++t) {
+            std::vector<char> pm(all[t].n), pl8(all[t].n);
+            bool any_later = false;
+            for (int q = 0; q < all[t].n; ++q) {
+                pm[q] = (all[t].owner_fn[q] >= fn_lo && all[t].owner_fn[q] < fn_hi);
+                pl8[q] = (all[t].owner_fn[q] >= fn_hi);
+                any_later = any_later || pl8[q];
+            }
+            pl->lists.emplace_back();
+            mine_id[t] = (int)pl->lists.size() - 1;
+            if ((rc = upload_list(pl.get(), whole ? all[t] : sublist(all[t], pm), pl->lists.back()))) return rc;
+            later_id[t] = -1;
+            if (any_later) {
+                pl->lists.emplace_back();
+                later_id[t] = (int)pl->lists.size() - 1;
+                if ((rc = upload_list(pl.get(), sublist(all[t], pl8), pl->lists.back()))) return rc;
+            }
+        }
+        stage("list upload");
+        // launches.  Class (ta,tb), ta <= tb, uniform side = ta, lane side = tb.
+        for (int ta = 0; ta < 3; ++ta)
+            for (int tb = ta; tb < 3; ++tb) {
+                if (ta == tb) {
+                    if ((rc = add_launch(pl.get(), sub, mine_id[ta], mine_id[ta], true))) return rc;
+                    if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), sub, mine_id[ta], later_id[ta], false))) return rc;
+                } else {
+                    if ((rc = add_launch(pl.get(), sub, mine_id[ta], mine_id[tb], false))) return rc;
+                    if (later_id[tb] >= 0 && (rc = add_launch(pl.get(), sub, mine_id[ta], later_id[tb], false))) return rc;
+                    if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), sub, later_id[ta], mine_id[tb], false))) return rc;
+                }
+            }
+        pl->nlaunch += (int)sub.region_end.size();  // zero fills of this piece
+        if (pl->screened_fill) {
+            // pacing table: one entry per class-kernel task counter, weighted by the launch's estimated
+            // duration (upper bound of its primitive quartets x measured time per quartet of its class)
+            static const double kPsPerQuartet[6] = {5.1, 9.8, 29.0, 31.0, 107.0, 640.0};  // (H2O)_64, profiles/r1_notes.md
+            std::vector<int32_t> pidx, pn;
+            std::vector<float> pw;
+            double wsum = 0.0;
+            for (const Launch& L : sub.launches) {
+                const int ns = class_nlaunch(L.UT, L.TT);
+                const double w = L.weight * kPsPerQuartet[class_id(L.UT, L.TT)] / ns;
+                for (int k = 0; k < ns; ++k) {
+                    pidx.push_back((int32_t)(L.args.row_counter - pl->d_counters) + k);
+                    pn.push_back(L.args.ntasks);
+                    pw.push_back((float)w);
+                    wsum += w;
+                }
+            }
+            for (float& w : pw) w = (float)(w / (wsum > 0 ? wsum : 1.0));
+            int32_t *d_pidx = nullptr, *d_pn = nullptr;
+            float* d_pw = nullptr;
+            if ((rc = upload(pl.get(), pidx, &d_pidx))) return rc;
+            if ((rc = upload(pl.get(), pn, &d_pn))) return rc;
+            if ((rc = upload(pl.get(), pw, &d_pw))) return rc;
+            const int64_t n = pl->norb;
+            const int64_t row_lo = (int64_t)fn_lo * n - (int64_t)fn_lo * (fn_lo - 1) / 2;
+            const int64_t row_hi = (int64_t)fn_hi * n - (int64_t)fn_hi * (fn_hi - 1) / 2;
+            if ((rc = build_sub_fill(pl.get(), sub, row_lo, row_hi))) return rc;
+            sub.fill.counters = pl->d_counters;
+            sub.fill.prog_idx = d_pidx; sub.fill.prog_n = d_pn; sub.fill.prog_w = d_pw;
+            sub.fill.nprog = (int)pidx.size();
         }
     }
-    stage("task upload");
+    pl->h_rk.clear(); pl->h_rk.shrink_to_fit();
+    pl->h_cut.clear(); pl->h_cut.shrink_to_fit();
+    stage("task lists");
+    // internal streams and events
+    CU(cudaStreamCreateWithFlags(&pl->s_fill, cudaStreamNonBlocking));
     for (auto& st : pl->s_comp) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&pl->e_start, cudaEventDisableTiming));
     for (auto& e : pl->e_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    {
+        size_t nfill = 0;
+        for (const Sub& sub : pl->subs) nfill += sub.region_end.size();
+        pl->e_fill.resize(nfill);
+        for (auto& e : pl->e_fill) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+
     stage("streams + events");
-    // the canonical work statistics cost a few ms of host time: evaluated when plan_stats asks for them
+    // the canonical work statistics cost ~8 ms of host time: evaluated when plan_stats asks for them
     pl->stats_whole = (nshards == 1);
     pl->in_nnuc = nnuc; pl->in_setl = setl;
     pl->in_xyz.assign(xyz, xyz + 3 * (size_t)nnuc);
@@ -788,86 +771,152 @@ int myqc_eri_shard_layout(int nnuc, const double* xyz, int nset, int setl, const
     if (rc) return rc;
     if (nshards < 1 || !offsets) return fail(MYQC_ERR_BAD_ARG, "bad nshards/offsets");
     std::string err;
-    HostPlan hp;
-    if ((rc = build_host_tables(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, hp, err))) return fail(rc, err);
-    CostModel cm;
-    cm.build(hp);
-    build_shell_costs(hp, cm);
-    const std::vector<int> cuts = split_shells(hp.shell_cost, nshards);
-    for (int k = 0; k <= nshards; ++k) offsets[k] = packed_row_offset(hp.sh_first[cuts[k]], hp.norb);
-    return MYQC_OK;
-}
-
-int myqc_eri_plan_check(int nnuc, const double* xyz, int nset, int setl, const double* set,
-                        const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
-                        int shard, int nshards, int64_t* result) {
-    // host only: builds the plan of one shard and replays what its kernels would write
-    static const double dummy_ft[1] = {0.0};
-    int rc = check_args(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, dummy_ft);
-    if (rc) return rc;
-    if (nshards < 1 || shard < 0 || shard >= nshards || !result) return fail(MYQC_ERR_BAD_ARG, "bad shard/nshards/result");
-    std::string err;
-    HostPlan hp;
-    if ((rc = build_host_plan(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, shard, nshards, hp, err))) return fail(rc, err);
-    if (hp.out_elems > (int64_t)2000000000) return fail(MYQC_ERR_UNSUPPORTED, "slice too large for the host-side coverage check");
-    CheckResult cr;
-    check_plan(hp, cr);
-    int64_t ntasks = 0;
-    for (const LaunchH& L : hp.launches) ntasks += (int64_t)L.tasks.size() * strip_nslices(L.UT, L.TC);
-    result[0] = cr.errors; result[1] = hp.out_elems; result[2] = cr.zero_elems; result[3] = cr.value_elems;
-    result[4] = cr.expected_values; result[5] = ntasks;
+    std::vector<Shell> shells;
+    if ((rc = build_shells(nnuc, nset, setl, setinfo, ops, basinfo, shells, err))) return fail(rc, err);
+    PairList all[3];
+    if ((rc = build_pairs(nnuc, xyz, set, setinfo, setl, ops, bas, basinfo, shells, all, err))) return fail(rc, err);
+    CutTable ct;
+    if (nshards == 1) { offsets[0] = 0; offsets[1] = packed_row_offset(basinfo[1], basinfo[1]); return MYQC_OK; }
+    if ((rc = build_cut_table(shells, all, ct, err))) return fail(rc, err);
+    const std::vector<int> ext = split_range(ct, 0, (int)ct.cuts.size(), nshards);
+    for (int k = 0; k <= nshards; ++k) offsets[k] = packed_row_offset(cut_to_fn(ct, ext[k], basinfo[1]), basinfo[1]);
     return MYQC_OK;
 }
 
 int64_t myqc_eri_plan_out_offset(const myqc_eri_plan* plan) { return plan ? plan->out_offset : -1; }
 int64_t myqc_eri_plan_out_elems(const myqc_eri_plan* plan) { return plan ? plan->out_elems : -1; }
 
+// serial order of launches: for each sub-shard and fill region: its zero fill, then the class
+// kernels restricted to the tasks of that region
+static int plan_launch_total(const myqc_eri_plan* plan) {
+    int n = 0;
+    for (const Sub& sub : plan->subs) n += (int)sub.region_end.size() * (1 + (int)sub.launches.size());
+    return n;
+}
+
+// launch the tasks of fill region r of one class launch (its own task counter per region)
+static int launch_region(myqc_eri_plan* plan, Sub& sub, Launch& L, int r, int slice, double* d_sub_out, cudaStream_t st) {
+    const int t0 = L.region_task[r], t1 = L.region_task[r + 1];
+    if (t1 <= t0) return 0;
+    ClassArgs a = L.args;
+    a.out = d_sub_out;
+    a.tasks = L.args.tasks + t0;
+    a.ntasks = t1 - t0;
+    a.row_counter = L.args.row_counter + r * class_nlaunch(L.UT, L.TT);
+    return launch_class(L.UT, L.TT, slice, a, plan->num_sms, st);
+}
+
+static int fill_region(myqc_eri_plan* plan, Sub& sub, int r, double* d_sub_out, cudaStream_t st, bool paced = false) {
+    if (plan->screened_fill) {
+        FillArgs f = sub.fill;
+        f.out = d_sub_out;
+        static const bool no_pace = std::getenv("MYQC_FILL_NOPACE") != nullptr;
+        if (!paced || no_pace) f.nprog = 0;
+        return launch_fill_screened(f, plan->num_sms, st);
+    }
+    const int64_t b = r == 0 ? 0 : sub.region_end[r - 1], e = sub.region_end[r];
+    // the first fill of a sub-shard also resets all of its task counters
+    return launch_fill_zero(d_sub_out + b, e - b, plan->d_counters + sub.counter_base, r == 0 ? sub.ncounters : 0,
+                            plan->num_sms, st);
+}
+
 int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
     if (!plan || (!d_out && plan->out_elems > 0)) return fail(MYQC_ERR_BAD_ARG, "null plan or output");
     CU(cudaSetDevice(plan->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int nl = (int)plan->launches.size();
-    if (nl == 0) return MYQC_OK;
-    CU(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)nl, st));
-    CU(cudaMemsetAsync(plan->d_stats, 0, sizeof(unsigned long long) * 2 * (size_t)nl, st));
+    // MYQC_TIMELINE=1: completion time of every launch on its internal stream, printed on stderr
+    // (a debugging aid: it synchronises the device at the end of the call)
+    static const bool timeline = std::getenv("MYQC_TIMELINE") != nullptr;
+    std::vector<std::pair<std::string, cudaEvent_t>> tl;
+    auto mark = [&](const std::string& name, cudaStream_t s) {
+        if (!timeline) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        tl.emplace_back(name, e);
+    };
+    if (plan->screened_fill) CU(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)plan->ncounters, st));
+    mark("start", st);
     // fork: internal streams start after whatever is already queued on the caller's stream
     CU(cudaEventRecord(plan->e_start, st));
+    CU(cudaStreamWaitEvent(plan->s_fill, plan->e_start, 0));
     for (auto& sc : plan->s_comp) CU(cudaStreamWaitEvent(sc, plan->e_start, 0));
-    for (int k = 0; k < nl; ++k) {
-        LaunchD& L = plan->launches[k];
-        StripArgs a = L.args;
-        a.out = d_out;
-        const int e = launch_strip(L.UT, L.TC, L.slice, a, plan->num_sms, plan->s_comp[k % myqc_eri_plan::kNumCompute]);
-        if (e) return cuda_fail((cudaError_t)e, "strip kernel launch");
+    int ef = 0;
+    for (Sub& sub : plan->subs) {
+        double* d_sub = d_out + (sub.out_offset - plan->out_offset);
+        for (int r = 0; r < (int)sub.region_end.size(); ++r) {
+            int e = fill_region(plan, sub, r, d_sub, plan->s_fill, true);
+            if (e) return cuda_fail((cudaError_t)e, "fill launch");
+            CU(cudaEventRecord(plan->e_fill[ef++], plan->s_fill));
+            mark("fill", plan->s_fill);
+        }
     }
+    int rr = 0;
+    ef = 0;
+    for (Sub& sub : plan->subs) {
+        double* d_sub = d_out + (sub.out_offset - plan->out_offset);
+        for (int r = 0; r < (int)sub.region_end.size(); ++r, ++ef) {
+            bool waited[myqc_eri_plan::kNumCompute] = {false, false, false, false};
+            for (Launch& L : sub.launches) {
+                if (L.region_task[r + 1] <= L.region_task[r]) continue;
+                // the mu-slices of (SP SP|SP SP) are independent launches: one internal stream each
+                for (int slice = 0; slice < class_nlaunch(L.UT, L.TT); ++slice) {
+                    const int si = rr++ % myqc_eri_plan::kNumCompute;
+                    // plain fill: the slice must be zeroed before a class kernel stores into it; the
+                    // screened fill writes a disjoint set of elements and needs no ordering
+                    if (!waited[si] && !plan->screened_fill) { CU(cudaStreamWaitEvent(plan->s_comp[si], plan->e_fill[ef], 0)); waited[si] = true; }
+                    int e = launch_region(plan, sub, L, r, slice, d_sub, plan->s_comp[si]);
+                    if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+                    mark("class{" + std::to_string(L.UT) + "," + std::to_string(L.TT) + "} on stream " + std::to_string(si), plan->s_comp[si]);
+                }
+            }
+        }
+    }
+    // join
     for (int i = 0; i < myqc_eri_plan::kNumCompute; ++i) {
         CU(cudaEventRecord(plan->e_done[i], plan->s_comp[i]));
         CU(cudaStreamWaitEvent(st, plan->e_done[i], 0));
     }
+    CU(cudaEventRecord(plan->e_done[myqc_eri_plan::kNumCompute], plan->s_fill));
+    CU(cudaStreamWaitEvent(st, plan->e_done[myqc_eri_plan::kNumCompute], 0));
+    if (timeline) {
+        mark("join", st);
+        cudaDeviceSynchronize();
+        for (size_t k = 1; k < tl.size(); ++k) {
+            float t = 0;
+            cudaEventElapsedTime(&t, tl[0].second, tl[k].second);
+            std::fprintf(stderr, "[myqc timeline] %-28s done at %8.3f ms\n", tl[k].first.c_str(), t);
+        }
+        for (auto& x : tl) cudaEventDestroy(x.second);
+    }
     return MYQC_OK;
 }
 
-int myqc_eri_plan_launch_count(const myqc_eri_plan* plan) { return plan ? (int)plan->launches.size() : 0; }
-
-int myqc_eri_plan_launch_info(const myqc_eri_plan* plan, int k, int* ut, int* tc, int* slice, int64_t* ntasks) {
-    if (!plan || k < 0 || k >= (int)plan->launches.size()) return fail(MYQC_ERR_BAD_ARG, "bad launch index");
-    const LaunchD& L = plan->launches[k];
-    if (ut) *ut = L.UT;
-    if (tc) *tc = L.TC;
-    if (slice) *slice = L.slice;
-    if (ntasks) *ntasks = L.args.ntasks;
-    return MYQC_OK;
+int myqc_eri_plan_launch_count(const myqc_eri_plan* plan) {
+    if (!plan) return 0;
+    return plan_launch_total(plan);
 }
 
-int myqc_eri_plan_launch_quartets(myqc_eri_plan* plan, int64_t* nq) {
-    if (!plan || !nq) return fail(MYQC_ERR_BAD_ARG, "null plan/output");
-    CU(cudaSetDevice(plan->device));
-    const size_t n = 2 * plan->launches.size();
-    std::vector<unsigned long long> h(n);
-    CU(cudaDeviceSynchronize());
-    if (n) CU(cudaMemcpy(h.data(), plan->d_stats, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < n; ++i) nq[i] = (int64_t)h[i];
-    return MYQC_OK;
+int myqc_eri_plan_launch_info(const myqc_eri_plan* plan, int k, int* cls, int* tri, int64_t* rows) {
+    if (!plan || k < 0 || k >= plan_launch_total(plan)) return fail(MYQC_ERR_BAD_ARG, "bad launch index");
+    for (const Sub& sub : plan->subs) {
+        for (int r = 0; r < (int)sub.region_end.size(); ++r) {
+            const int n = 1 + (int)sub.launches.size();
+            if (k >= n) { k -= n; continue; }
+            if (k == 0) {  // the zero fill of this region
+                if (cls) *cls = -1;
+                if (tri) *tri = 0;
+                if (rows) *rows = plan->screened_fill ? sub.fill_zero_elems : sub.region_end[r] - (r == 0 ? 0 : sub.region_end[r - 1]);
+                return MYQC_OK;
+            }
+            const Launch& L = sub.launches[k - 1];
+            if (cls) *cls = class_id(L.UT, L.TT);
+            if (tri) *tri = L.args.tri;
+            if (rows) *rows = L.region_task[r + 1] - L.region_task[r];
+            return MYQC_OK;
+        }
+    }
+    return fail(MYQC_ERR_BAD_ARG, "bad launch index");
 }
 
 // Serialised pass on the caller's stream with CUDA events around every launch: the per-kernel
@@ -876,20 +925,24 @@ int myqc_eri_plan_execute_timed(myqc_eri_plan* plan, double* d_out, void* stream
     if (!plan || !ms || (!d_out && plan->out_elems > 0)) return fail(MYQC_ERR_BAD_ARG, "null plan/output/ms");
     CU(cudaSetDevice(plan->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int n = (int)plan->launches.size();
-    if (n == 0) return MYQC_OK;
+    const int n = plan_launch_total(plan);
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) CU(cudaEventCreate(&e));
-    CU(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)n, st));
-    CU(cudaMemsetAsync(plan->d_stats, 0, sizeof(unsigned long long) * 2 * (size_t)n, st));
+    if (plan->screened_fill) CU(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)plan->ncounters, st));
     CU(cudaEventRecord(ev[0], st));
-    for (int k = 0; k < n; ++k) {
-        LaunchD& L = plan->launches[k];
-        StripArgs a = L.args;
-        a.out = d_out;
-        const int e = launch_strip(L.UT, L.TC, L.slice, a, plan->num_sms, st);
-        if (e) return cuda_fail((cudaError_t)e, "strip kernel launch");
-        CU(cudaEventRecord(ev[k + 1], st));
+    int idx = 0;
+    for (Sub& sub : plan->subs) {
+        double* d_sub = d_out + (sub.out_offset - plan->out_offset);
+        for (int r = 0; r < (int)sub.region_end.size(); ++r) {
+            int e = fill_region(plan, sub, r, d_sub, st);
+            if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
+            CU(cudaEventRecord(ev[++idx], st));
+            for (Launch& L : sub.launches) {
+                for (int slice = 0; slice < class_nlaunch(L.UT, L.TT) && !e; ++slice) e = launch_region(plan, sub, L, r, slice, d_sub, st);
+                if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+                CU(cudaEventRecord(ev[++idx], st));
+            }
+        }
     }
     CU(cudaEventSynchronize(ev[n]));
     for (int k = 0; k < n; ++k) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
@@ -921,16 +974,18 @@ int myqc_eri_plan_stats(const myqc_eri_plan* plan_c, int64_t* nquartets, double*
     }
     if (nquartets) for (int c = 0; c < 6; ++c) nquartets[c] = plan->nquartets[c];
     if (model_flops) *model_flops = plan->model_flops;
-    if (nlaunch) *nlaunch = (int)plan->launches.size();
+    if (nlaunch) *nlaunch = plan->nlaunch;
     return MYQC_OK;
 }
 
 void myqc_eri_plan_destroy(myqc_eri_plan* plan) {
     if (!plan) return;
     cudaSetDevice(plan->device);
+    if (plan->s_fill) { cudaStreamSynchronize(plan->s_fill); cudaStreamDestroy(plan->s_fill); }
     for (auto& st : plan->s_comp) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     if (plan->e_start) cudaEventDestroy(plan->e_start);
     for (auto& e : plan->e_done) if (e) cudaEventDestroy(e);
+    for (auto& e : plan->e_fill) if (e) cudaEventDestroy(e);
     for (void* p : plan->dev_allocs) cudaFree(p);
     delete plan;
 }
@@ -951,7 +1006,7 @@ int myqc_eri_expand_dense(const double* d_packed, int norb, double* d_xx, void* 
 // One-shot calls with host buffers.  The plan and the device slice of the last call are kept per device
 // (keyed on the bytes of every input): an SCF driver that asks for the same integrals again, or a
 // benchmark loop, pays for the pair tables, the task lists and a 40 GB cudaMalloc/cudaFree once.
-// myqc_eri_release_cache() drops them.
+// myqc_eri_release_cache() drops them; MYQC_NO_CACHE=1 turns the cache off.
 namespace myqc {
 
 struct CacheEntry {
@@ -1026,7 +1081,7 @@ int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const
     std::lock_guard<std::mutex> dev_lock(g_dev_mu[device]);
     CacheEntry local;
     CacheEntry& ce = no_cache ? local : g_cache[device];
-    bool hit = (ce.plan != nullptr && ce.key == key);
+    const bool hit = (ce.plan != nullptr && ce.key == key);
     if (!hit) {
         if (ce.plan) { cudaSetDevice(device); myqc_eri_plan_destroy(ce.plan); ce.plan = nullptr; ce.key = 0; }
         rc = myqc_eri_plan_create(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab, device, shard, nshards, &ce.plan);
@@ -1038,7 +1093,7 @@ int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const
     const auto t1 = now();
     if (h2d_bytes) *h2d_bytes = hit ? 0 : pl->h2d_bytes;
     const int64_t n = pl->out_elems;
-    if (n > 0 && !packed_slice) return fail(MYQC_ERR_BAD_ARG, "null output");
+    if (n > 0 && !packed_slice) { if (no_cache) drop_entry(local); return fail(MYQC_ERR_BAD_ARG, "null output"); }
     if (n > ce.out_cap) {
         if (ce.d_out) { cudaFree(ce.d_out); ce.d_out = nullptr; ce.out_cap = 0; }
         cudaError_t e = cudaMalloc((void**)&ce.d_out, (size_t)n * sizeof(double));
@@ -1179,9 +1234,10 @@ int myqc_eri_packed(int nnuc, const double* xyz, int nset, int setl, const doubl
     return run_packed_host(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab, packed, ngpu);
 }
 
-// Dense XX on `ngpu` devices: every device computes its shard of the packed array; the slices are
-// exchanged through the host so that every device holds the whole packed array, and device g expands
-// the slab XX(:,:,:,h) of its range of h (the 8n^4-byte stream is produced once, in parallel).
+// Dense XX on `ngpu` devices.  One device: packed array and XX both on it.  Several: every device computes
+// its shard of the packed array into a host copy; every device then takes the whole packed array and expands
+// the slab XX(:,:,:,h) of its range of h, so the 8n^4-byte stream is produced once, in parallel, and no device
+// needs more than the packed array plus 1/ngpu of XX.
 int myqc_eri_dense(int nnuc, const double* xyz, int nset, int setl, const double* set,
                    const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
                    const double* ftab, double* xx, int ngpu) {

@@ -1,4 +1,4 @@
-// Owner-row strip kernels for the two-electron integrals on sm_100a (B200).
+// Quartet-class ERI kernels for sm_100a (B200).
 //
 // What is computed (reference: src/integrals/int2e.f90:618-726 clmnew, auxilary.f90:22-215):
 // for every canonical contracted shell quartet (u | v) that passes the reference's
@@ -9,31 +9,28 @@
 // downwards (Boys1); F0 = sqrt(pi)/2/sqrt(T) - exp(-T) g(T)/T with upward recursion for
 // 12 <= T < 2Q+36 (Boys2); the bare asymptotic form above (Boys3).
 //
-// How the work follows the output (the reference writes every element of XX once, int2e.f90:290-307):
-//   * In the packed 8-fold-unique array the integrals of a shell quartet (AB|CD) all lie in the rows
-//     of the shell pair whose first shell is smaller.  That pair is the quartet's OWNER u; the other
-//     pair v = (C,D) is its partner.  (If A = C both pairs own some of the elements; the quartet is
-//     then evaluated from both sides and each side keeps the elements of its own rows.)
-//   * A task = (owner pair u; a range of partner first shells C).  For a fixed first index k the
-//     columns (k,l) of a packed row are one contiguous run over l, so the task's part of u's rows is
-//     a few contiguous runs per row.  One warp runs the task: it walks C and, for each C, the
-//     partner second shells D >= C in blocks of 32 (one D per lane), keeps the (C,D) that pass the
-//     pair-level bound emax_u*emax_v >= 1e-14, and evaluates them 32 at a time per partner kind
-//     (D an S shell / D an SP shell), one quartet per lane.
-//   * Results are parked in a per-warp shared-memory buffer.  When the buffer is full (or the task
-//     ends) the warp FLUSHES: it writes zeros over the whole span of the packed rows it has walked
-//     since the last flush (128-bit coalesced stores) and then stores the parked integrals into it.
-//     Both happen within microseconds, so the 8-byte stores merge in L2 into sectors that are
-//     already resident and fully written; every sector reaches DRAM once, whole.  There is no
-//     separate zero-fill pass and no read-modify-write of evicted sectors.
-//   * Kernel variants by (owner kind UT, partner-first-shell kind TC) keep the register budget of a
-//     launch at what its two quartet classes need; tasks of different launches write disjoint
-//     runs of the array, so the launches are independent.
-//   * Per quartet (unchanged arithmetic): the owner's primitive records are staged into shared memory
-//     by TMA bulk copy (cp.async.bulk + mbarrier) and read as warp-uniform broadcasts; K[f][H'] is
-//     accumulated over the owner primitives (step A), the partner coefficients are folded once per
-//     partner primitive (step B); far-field quartets (T >= 2Q+36) need one reciprocal square root
-//     and no exponential; the Boys Taylor tables and an exp(-k/10) table live in shared memory.
+// Mapping onto the B200:
+//   * one kernel instantiation per quartet class (UT, TT) = (#SP sets in the uniform-side pair,
+//     #SP sets in the lane-side pair); all loops over Hermite terms are unrolled at compile time
+//     (static_for), so the K-, R- and output accumulators live in registers and the inner loop is
+//     straight-line DFMA code (FP64 pipe bound; no tensor cores: this is not a dense contraction).
+//   * warps are autonomous: each warp pulls rows u of the quartet space from a global counter,
+//     stages the row's primitive-pair record block (<= 3.7 KB) into its own shared-memory double
+//     buffer with a TMA bulk copy (cp.async.bulk + mbarrier) while it still works on the previous
+//     row, and reads it back as warp-uniform broadcasts.  No CTA-wide barrier in the main loop.
+//   * each lane owns one lane-side pair v (coalesced SoA loads).  Pair lists are ordered by
+//     prefactor bucket and Morton code of the pair centre, so the 32 pairs of a warp are spatially
+//     close: they sit in the same Boys regime and lose the same primitives to the screen.
+//   * for each lane-side primitive, K[f][H'] is accumulated over the uniform-side primitives
+//     (step A: |terms_U| x |H_T| DFMA per primitive quartet); the lane-side coefficients are folded
+//     once afterwards (step B) -- the second half-contraction is hoisted out of the inner loop.
+//   * far-field quartets (T >= 2Q+36, the bulk of a large molecule) need one reciprocal square
+//     root and no exponential: G_j = sqrt(pi)/2 /sqrt(p q) (2j-1)!! (-1)^j / R^(2j+1).
+//   * the Boys Taylor table of the class (121 x 8 doubles, pre-divided by k!) and an exp(-k/10)
+//     table live in shared memory; exp(-T) = exp(-k/10) * exp(k/10 - T) with a 9-term series.
+//   * (SP SP|SP SP) is split into four mu-slices of the uniform side so that 40 K- and 64 output
+//     accumulators fit; outputs of the two big classes are kept in lane-private shared memory
+//     between lane-side primitives.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -41,7 +38,6 @@
 #include <type_traits>
 
 #include "eri_kernels.cuh"
-#include "strip_geom.hpp"
 #include "terms.hpp"
 #include "boys.cuh"
 
@@ -50,6 +46,23 @@ namespace myqc {
 namespace {
 
 constexpr double kScreen = 1.0e-14;  // int2e.f90:257
+
+// Store of one integral into the zero-filled packed array.  -DMYQC_STORE_OP=1/2/3 builds the cache-hint
+// variants tools/build_variants.sh measures (st.global.cs / .cg / .wt); the default is a plain store.
+#ifndef MYQC_STORE_OP
+#define MYQC_STORE_OP 0
+#endif
+__device__ __forceinline__ void store_eri(double* p, double v) {
+#if MYQC_STORE_OP == 1
+    __stcs(p, v);
+#elif MYQC_STORE_OP == 2
+    __stcg(p, v);
+#elif MYQC_STORE_OP == 3
+    __stwt(p, v);
+#else
+    *p = v;
+#endif
+}
 
 // ------------------------------------------------------------------------------------------
 // TMA bulk copy + mbarrier helpers (sm_90+ PTX; SASS: UBLKCP / SYNCS)
@@ -87,526 +100,545 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-// ------------------------------------------------------------------------------------------
-template <int UT, int TC, int USL>
-struct SCfg {
-    static constexpr int NFU = (USL >= 0) ? 4 : tt_nf(UT);  // packed rows of the owner this launch writes
-    static constexpr int NK = TC ? 4 : 1;                   // first indices k of a partner first shell
-    static constexpr int FU = tt_nfield(UT);
-    static constexpr uint32_t U_BYTES = 9 * FU * 8;
-    static constexpr int NOUT0 = NFU * tt_nf(TC), NOUT1 = NFU * tt_nf(TC + 1);  // integrals per quartet, TD = 0 / 1
-    static constexpr bool HEAVY = (NOUT1 > 16);
-    // result buffer (doubles per warp) and the most quartet chunks it is cut into
-    static constexpr int RES_CAP = HEAVY ? 3584 : (NOUT1 == 16 ? 1024 : 512);
-    static constexpr int MAXCH = HEAVY ? 7 : (NOUT1 == 16 ? 8 : 16);
-    static constexpr int NWARPS = HEAVY ? 6 : (NOUT1 == 16 ? 6 : 8);
-    static constexpr int NTHREADS = 32 * NWARPS;
-    static constexpr int MINB = HEAVY ? 1 : 2;
-    static constexpr int NBUF = (UT == 2) ? 1 : 2;   // owner-record buffers per warp (TMA prefetch of the next task)
-    static constexpr bool FT_SMEM = (UT < 2);        // Taylor tables in shared memory (else read through L1)
-    static constexpr int DESC = 36;                  // ints per chunk descriptor: 32 items, kind|count, result offset
-    static constexpr int NLIST = 8;                  // pending lists: partner kind (second shell S / SP) x 4 bins of surviving primitives
-    static constexpr bool BINS = !HEAVY;             // the heavy launches see too few quartets per task to afford four lists per kind
-    // shared memory: [Taylor tables] | exp table | per warp: owner records, mbarriers, rows, pending, descriptors, results
-    static constexpr size_t OFF_EXP = FT_SMEM ? 2 * 121 * 8 * 8 : 0;
-    static constexpr size_t OFF_WARP = OFF_EXP + 608 * 16;
-    static constexpr size_t W_BAR = (size_t)NBUF * U_BYTES;
-    static constexpr size_t W_ROW = W_BAR + 16;                 // int rowi[16], rowj[16]; int64 rbase[16]
-    static constexpr size_t W_PEND = W_ROW + 16 * 4 * 2 + 16 * 8;
-    static constexpr size_t W_DESC = W_PEND + (size_t)NLIST * 64 * 4;
-    static constexpr size_t W_RES = W_DESC + (size_t)MAXCH * DESC * 4;
-    static constexpr size_t W_BYTES = (W_RES + (size_t)RES_CAP * 8 + 15) / 16 * 16;
-    static constexpr size_t SMEM = OFF_WARP + (size_t)NWARPS * W_BYTES;
-    static_assert(W_RES % 16 == 0 && W_BAR % 16 == 0 && OFF_WARP % 16 == 0, "alignment of the per-warp areas");
-    static_assert(SMEM <= 232448, "shared memory per CTA");
-};
-
-// partner function pair fp -> (index of k in C's slots, index of l in D's slots)
-template <int TC, int TD>
-__device__ __forceinline__ constexpr int fp_kc(int fp) { return (TC + TD == 0) ? 0 : (TC + TD == 1) ? (TC ? fp : 0) : (fp >> 2); }
-template <int TC, int TD>
-__device__ __forceinline__ constexpr int fp_ld(int fp) { return (TC + TD == 0) ? 0 : (TC + TD == 1) ? (TC ? 0 : fp) : (fp & 3); }
-
-__device__ __forceinline__ int slot_of(const int4& f, int s) { return s == 0 ? f.x : (s == 1 ? f.y : (s == 2 ? f.z : f.w)); }
-
-// ------------------------------------------------------------------------------------------
-// One quartet (u | v) per lane: u = the warp's owner pair (records in shared memory), v = record `v`
-// of the partner kind TT.  The NOUT integrals go to res[o*32], o = f*NFT + fp.  Returns the number
-// of primitive quartets that passed the reference's screen.
 template <int UT, int TT, int USL>
-__device__ __forceinline__ unsigned quartet_lane(const double* __restrict__ s_u, int npu, double eu_max,
-                                                 const double* __restrict__ trec, int npt, const double* __restrict__ ft,
-                                                 const double2* __restrict__ s_exp, double* __restrict__ res) {
-    constexpr int LT = UT + TT, Q = 3 * LT;  // Boys start order, int2e.f90:654-658,668
-    constexpr int NR = h_count(LT), NHT = tt_nh(TT);
-    constexpr int NFU = (USL >= 0) ? 4 : tt_nf(UT), NFT = tt_nf(TT);
-    constexpr int NTU = tt_nterm(UT), NTT = tt_nterm(TT), FU = tt_nfield(UT), FT = tt_nfield(TT);
-    constexpr int NOUT = NFU * NFT;
-    constexpr bool OUT_SMEM = (NOUT > 16);
-
-    double out_r[OUT_SMEM ? 1 : NOUT];
-    if constexpr (OUT_SMEM) {
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) res[o * 32] = 0.0;
-    } else {
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) out_r[o] = 0.0;
-    }
-    unsigned nquart = 0;
-    // Partner records: the lane reads its own contiguous [9][FT] block (one base pointer, compile-time offsets;
-    // every 32-byte sector it touches is used in full), and the next primitive's lines are prefetched into L1
-    // while this one is contracted.
-    for (int kt = 0; kt < npt; ++kt) {
-        const double* tp = trec + kt * FT;
-        const double2 t45 = __ldg(reinterpret_cast<const double2*>(tp) + 2);
-        const double et = t45.x;
-        if (eu_max * et < kScreen) break;  // primitives are sorted by E, descending
-        const double2 t01 = __ldg(reinterpret_cast<const double2*>(tp));
-        const double2 t23 = __ldg(reinterpret_cast<const double2*>(tp) + 1);
-        if (kt + 1 < npt) {
-#pragma unroll
-            for (int b = 0; b < FT * 8; b += 128)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(tp + FT) + b));
-        }
-        const double q = t01.x, Qx = t01.y, Qy = t23.x, Qz = t23.y;
-        const double cfar = kHalfSqrtPi * t45.y;  // sqrt(pi)/2 / sqrt(q)
-        double K[NFU][NHT];
-#pragma unroll
-        for (int f = 0; f < NFU; ++f)
-#pragma unroll
-            for (int h = 0; h < NHT; ++h) K[f][h] = 0.0;
-
-        for (int ku = 0; ku < npu; ++ku) {
-            const double* up = s_u + ku * FU;
-            if (up[4] * et < kScreen) break;  // IF (EGH*EIJ .LT. 1.0D-14) CYCLE  (int2e.f90:257)
-            ++nquart;
-            const double p = up[0];
-            const double X = up[1] - Qx, Y = up[2] - Qy, Z = up[3] - Qz;
-            const double R2 = fma(X, X, fma(Y, Y, Z * Z));
-            const double s = p + q;
-            const double pq = p * q;
-            const double w = pq * R2;  // T*(p+q)
-            double G[LT + 1];
-            if (w >= (double)(2 * Q + 36) * s) {
-                // Boys3 (auxilary.f90:194-215): G_j = sqrt(pi)/2 /sqrt(pq) (2j-1)!! (-1)^j R^-(2j+1)
-                const double rinv = rsqrt_pos(R2);
-                const double m = -(rinv * rinv);
-                double g = cfar * up[5] * rinv;
-                G[0] = g;
-#pragma unroll
-                for (int j = 1; j <= LT; ++j) {
-                    g *= (double)(2 * j - 1) * m;
-                    G[j] = g;
-                }
-            } else {
-                const double rs = rsqrt_pos(s);
-                const double alpha = pq * (rs * rs);
-                boys_near_mid<Q, LT>(alpha * R2, alpha, rs, G, ft, s_exp);
-            }
-            double R[NR];
-            build_R<LT>(G, X, Y, Z, R);
-            // step A: K[f][H'] += D_k * R[H_k + H']
-            static_for<0, NTU>([&](auto kc) {
-                constexpr int k = decltype(kc)::value;
-                constexpr int f = term_fn(UT, k);
-                if constexpr (USL < 0 || f / 4 == USL) {
-                    constexpr int lf = (USL >= 0) ? (f % 4) : f;
-                    constexpr int hk = term_h(UT, k);
-                    const double cu = up[kRecCoef + k];
-                    static_for<0, NHT>([&](auto hc) {
-                        constexpr int hp = decltype(hc)::value;
-                        constexpr int ri = h_add(hk, hp);
-                        K[lf][hp] = fma(cu, R[ri], K[lf][hp]);
-                    });
-                }
-            });
-        }
-        // step B: out[f][f'] += (-1)^{|H'|} D'_k' K[f][H'_k'], the terms of one f' summed in registers first
-        static_for<0, NFT>([&](auto fc) {
-            constexpr int fp = decltype(fc)::value;
-            double acc[NFU];
-#pragma unroll
-            for (int f = 0; f < NFU; ++f) acc[f] = 0.0;
-            static_for<0, NTT>([&](auto kc) {
-                constexpr int k = decltype(kc)::value;
-                if constexpr (term_fn(TT, k) == fp) {
-                    constexpr int hp = term_h(TT, k);
-                    double ct = __ldg(tp + kRecCoef + k);
-                    if constexpr (h_parity(hp) != 0) ct = -ct;
-#pragma unroll
-                    for (int f = 0; f < NFU; ++f) acc[f] = fma(ct, K[f][hp], acc[f]);
-                }
-            });
-#pragma unroll
-            for (int f = 0; f < NFU; ++f) {
-                if constexpr (OUT_SMEM) res[(f * NFT + fp) * 32] += acc[f];
-                else out_r[f * NFT + fp] += acc[f];
-            }
-        });
-    }
-    if constexpr (!OUT_SMEM) {
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) res[o * 32] = out_r[o];
-    }
-    return nquart;
-}
-
-// warp-cooperative zero fill of out[0..n): 128-bit stores, the run may start on an odd element
-__device__ __forceinline__ void zero_run(double* __restrict__ p, int64_t n, int lane) {
-    if (n <= 0) return;
-    const int64_t head = (reinterpret_cast<uintptr_t>(p) & 15) ? 1 : 0;
-    if (head && lane == 0) p[0] = 0.0;
-    double2* q = reinterpret_cast<double2*>(p + head);
-    const int64_t n2 = (n - head) >> 1;
-    for (int64_t x = lane; x < n2; x += 32) q[x] = make_double2(0.0, 0.0);
-    if (((n - head) & 1) && lane == 0) p[n - 1] = 0.0;
-}
-
-// per-warp view of the shared-memory areas
-template <class C>
-struct WarpMem {
-    double* ubuf;
-    uint64_t* bar;
-    int* rowi;
-    int* rowj;
-    long long* rbase;
-    int* pend;  // [NLIST][64] items (C << 16 | D)
-    int* desc;  // [MAXCH][DESC]
-    double* res;
-    __device__ __forceinline__ explicit WarpMem(unsigned char* w) {
-        ubuf = reinterpret_cast<double*>(w);
-        bar = reinterpret_cast<uint64_t*>(w + C::W_BAR);
-        rowi = reinterpret_cast<int*>(w + C::W_ROW);
-        rowj = rowi + 16;
-        rbase = reinterpret_cast<long long*>(w + C::W_ROW + 128);
-        pend = reinterpret_cast<int*>(w + C::W_PEND);
-        desc = reinterpret_cast<int*>(w + C::W_DESC);
-        res = reinterpret_cast<double*>(w + C::W_RES);
-    }
+struct Cfg {
+    static constexpr int LT = UT + TT;
+    static constexpr int Q = 3 * LT;  // Boys start order, int2e.f90:654-658,668
+    static constexpr int NR = h_count(LT);
+    static constexpr int NHT = tt_nh(TT);
+    static constexpr int NFU = (USL >= 0) ? 4 : tt_nf(UT);
+    static constexpr int NFU_FULL = tt_nf(UT);
+    static constexpr int NFT = tt_nf(TT);
+    static constexpr int NTU = tt_nterm(UT);
+    static constexpr int NTT = tt_nterm(TT);
+    static constexpr int FU = tt_nfield(UT);
+    static constexpr int FT = tt_nfield(TT);
+    static constexpr int NOUT = NFU * NFT;
+    static constexpr bool OUT_SMEM = (NOUT > 16);
+    // lanes = lane-side primitives of a quartet (instead of quartets) for the classes with 64 integrals per lane
+    static constexpr bool UNITS = OUT_SMEM;
+    // 128-thread CTAs for every class: (S SP|S SP) needs 140 registers, and a 256-thread CTA of it
+    // would leave an SM with a single resident CTA (8 warps); four-warp CTAs pack 3 per SM
+    static constexpr int NTHREADS = 128;
+    static constexpr int NWARPS = NTHREADS / 32;
+    // resident CTAs per SM the register allocation is held to: 72 / 80 / 128 / 140 registers for the
+    // four small classes, two CTAs for the two large ones
+    static constexpr int MINB = (LT == 0) ? 7 : (LT == 1) ? 6 : (UT == 0 && TT == 2) ? 4 : (LT == 2) ? 3 : 2;
+    static constexpr uint32_t U_BYTES = 9 * FU * 8;
+    // shared memory: Taylor table | exp table | per-warp U double buffers | mbarriers | out staging
+    static constexpr size_t OFF_EXP = 121 * 8 * 8;
+    static constexpr size_t OFF_U = OFF_EXP + 608 * 16;
+    static constexpr size_t OFF_BAR = OFF_U + (size_t)NWARPS * 2 * U_BYTES;
+    static constexpr bool LANE_AOS = (UT >= 1);  // measured: pays for {1,1},{1,2},{2,2}, costs for {0,x}
+    static constexpr int TASKP = class_task_pairs(UT, TT);                 // lane-side pairs per task
+    static constexpr size_t OFF_SORT = OFF_BAR + (size_t)NWARPS * 2 * 8;   // per warp: TASKP idx + 64 bins (int)
+    static constexpr size_t OFF_OUT = OFF_SORT + (size_t)NWARPS * (TASKP + 64) * 4;
+    static constexpr size_t SMEM = OFF_OUT + (OUT_SMEM ? (size_t)NOUT * NTHREADS * 8 : 0);
 };
-
-// stores the parked integrals of one chunk (kind TD) into the packed rows of the owner
-template <int UT, int TC, int TD, int USL>
-__device__ __forceinline__ void scatter_chunk(const StripArgs& a, const WarpMem<SCfg<UT, TC, USL>>& m, const int* __restrict__ d,
-                                              int n, int lane) {
-    using C = SCfg<UT, TC, USL>;
-    constexpr int NFU = C::NFU, NFT = tt_nf(TC + TD);
-    if (lane >= n) return;
-    const int item = d[lane];
-    const int Cs = item >> 16, Ds = item & 0xffff;
-    const int4 fc = __ldg(a.sh_fn + Cs);
-    const int4 fd = __ldg(a.sh_fn + Ds);
-    const double* __restrict__ col = m.res + d[33] + lane;
-    long long cb[C::NK];
-#pragma unroll
-    for (int kc = 0; kc < C::NK; ++kc) cb[kc] = col_base64(slot_of(fc, kc), a.norb);
-#pragma unroll
-    for (int f = 0; f < NFU; ++f) {
-        const int i = m.rowi[f];
-        if (i < 0) continue;  // the row does not exist (absent function, or the duplicate half of a diagonal pair)
-        const int j = m.rowj[f];
-        const long long rb = m.rbase[f];
-#pragma unroll
-        for (int fp = 0; fp < NFT; ++fp) {
-            const int kc = fp_kc<TC, TD>(fp), ldx = fp_ld<TC, TD>(fp);
-            const int k = slot_of(fc, kc), l = slot_of(fd, ldx);
-            // the element exists in row (i,j) iff (k,l) is an orbital pair with k <= l at or after (i,j)
-            if (k < 0 || l < 0 || k > l || k < i || (k == i && l < j)) continue;
-            a.out[rb + cb[kc] + l] = col[(f * NFT + fp) * 32];
-        }
-    }
-}
 
 }  // namespace
 
-template <int UT, int TC, int USL>
-__global__ void __launch_bounds__(SCfg<UT, TC, USL>::NTHREADS, SCfg<UT, TC, USL>::MINB) eri_strip_kernel(const __grid_constant__ StripArgs a) {
-    using C = SCfg<UT, TC, USL>;
-    constexpr int NFU = C::NFU, NK = C::NK, FU = C::FU;
-    constexpr int CH0 = 32 * C::NOUT0, CH1 = 32 * C::NOUT1;
-    constexpr int Q0 = 3 * (UT + TC), Q1 = Q0 + 3;
-    (void)Q0; (void)Q1;
+template <int UT, int TT, int USL>
+__global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::MINB) eri_class_kernel(const ClassArgs a) {
+    using C = Cfg<UT, TT, USL>;
+    constexpr int LT = C::LT, Q = C::Q, NR = C::NR, NHT = C::NHT, NFU = C::NFU, NFT = C::NFT;
+    constexpr int NTU = C::NTU, NTT = C::NTT, FU = C::FU, FT = C::FT, NOUT = C::NOUT;
+    constexpr int NTHREADS = C::NTHREADS;
+    constexpr bool OUT_SMEM = C::OUT_SMEM;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* s_ft = reinterpret_cast<double*>(smem_raw);
+    double2* s_exp = reinterpret_cast<double2*>(smem_raw + C::OFF_EXP);
+    double* s_out = reinterpret_cast<double*>(smem_raw + C::OFF_OUT);
+
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const double* ft0 = a.ftab_q[0];
-    const double* ft1 = a.ftab_q[1];
-    if constexpr (C::FT_SMEM) {
-        double* s_ft = reinterpret_cast<double*>(smem_raw);
-        for (int i = tid; i < 121 * 8; i += C::NTHREADS) { s_ft[i] = a.ftab_q[0][i]; s_ft[121 * 8 + i] = a.ftab_q[1][i]; }
-        ft0 = s_ft;
-        ft1 = s_ft + 121 * 8;
-    }
-    double2* s_exp = reinterpret_cast<double2*>(smem_raw + C::OFF_EXP);
-    for (int i = tid; i < 601; i += C::NTHREADS) s_exp[i] = a.exptab[i];
-    const WarpMem<C> m(smem_raw + C::OFF_WARP + (size_t)warp * C::W_BYTES);
+    double* s_ubuf = reinterpret_cast<double*>(smem_raw + C::OFF_U) + (size_t)warp * 2 * 9 * FU;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + C::OFF_BAR) + warp * 2;
+    int* s_vidx = reinterpret_cast<int*>(smem_raw + C::OFF_SORT) + warp * (C::TASKP + 64);
+    int* s_bin = s_vidx + C::TASKP;
+
+    for (int i = tid; i < 121 * 8; i += NTHREADS) s_ft[i] = a.ftab_q[i];
+    for (int i = tid; i < 601; i += NTHREADS) s_exp[i] = a.exptab[i];
     if (lane == 0) {
-#pragma unroll
-        for (int b = 0; b < C::NBUF; ++b) mbar_init(&m.bar[b], 1);
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    const int ns = a.ns, nblk = a.nblk;
-
-    // ---- warp-autonomous task loop; the owner records of the next task arrive by TMA meanwhile ----
-    auto fetch = [&](int slot, int& t, int4& task, int& urec) {
-        t = 0; urec = -1; task = make_int4(0, 0, 0, 0);
-        if (lane == 0) {
-            t = atomicAdd(a.counter, 1);
-            if (t < a.ntasks) {
-                task = a.tasks[t];
-                urec = __ldg(a.pair_rec + (size_t)(task.x & 0xffff) * ns + (task.x >> 16));
-                if (urec >= 0) {
-                    mbar_expect_tx(&m.bar[slot], C::U_BYTES);
-                    tma_bulk_g2s(m.ubuf + (size_t)slot * 9 * FU, a.u_aos + (size_t)urec * 9 * FU, C::U_BYTES, &m.bar[slot]);
-                }
-            }
+    // ---- warp-autonomous task loop with a two-deep TMA prefetch ------------------------------
+    // task = (row u, lane-side range [vb0, vend)): rows are cut into pieces of at most
+    // kTaskPairs lane-side pairs so that no warp owns more than a sliver of the launch.
+    int t = 0;
+    int4 task = make_int4(0, 0, 0, 0);
+    if (lane == 0) {
+        t = atomicAdd(a.row_counter, 1);
+        if (t < a.ntasks) {
+            task = a.tasks[t];
+            mbar_expect_tx(&s_bar[0], C::U_BYTES);
+            tma_bulk_g2s(s_ubuf, a.u_aos + (size_t)task.x * 9 * FU, C::U_BYTES, &s_bar[0]);
         }
-        t = __shfl_sync(0xffffffffu, t, 0);
-        urec = __shfl_sync(0xffffffffu, urec, 0);
-        task.x = __shfl_sync(0xffffffffu, task.x, 0);
-        task.y = __shfl_sync(0xffffffffu, task.y, 0);
-        task.z = __shfl_sync(0xffffffffu, task.z, 0);
-        task.w = __shfl_sync(0xffffffffu, task.w, 0);
-    };
-    int t, urec, buf = 0;
-    int4 task;
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    task.x = __shfl_sync(0xffffffffu, task.x, 0);
+    task.y = __shfl_sync(0xffffffffu, task.y, 0);
+    task.z = __shfl_sync(0xffffffffu, task.z, 0);
+    int buf = 0;
     uint32_t parity0 = 0, parity1 = 0;
-    fetch(0, t, task, urec);
     while (t < a.ntasks) {
-        int tn = 0, urecn = -1;
+        int tn = 0;
         int4 taskn = make_int4(0, 0, 0, 0);
-        if constexpr (C::NBUF == 2) fetch(buf ^ 1, tn, taskn, urecn);
-        // task = {A | B << 16, first index into clist, end index, b0 | b1 << 16}: the span runs from block b0 of the
-        // first C through block b1-1 of the last C (b0 = block of the first C and b1 = nblk for whole runs)
-        const int A = task.x & 0xffff, B = task.x >> 16;
-        const int c_lo = task.y, c_hi = task.z, b_lo = task.w & 0xffff, b_hi = task.w >> 16;
-        // ---- the packed rows of the owner: orbitals (i,j), and the offset that turns a pair index P(k,l) into an address
-        if (lane < 16) {
-            int i = -1, j = -1;
-            long long rb = 0;
-            if (lane < NFU) {
-                const int4 fa4 = __ldg(a.sh_fn + A), fb4 = __ldg(a.sh_fn + B);
-                const int fa[4] = {fa4.x, fa4.y, fa4.z, fa4.w}, fb[4] = {fb4.x, fb4.y, fb4.z, fb4.w};
-                const bool a_is_sp = (UT == 1) && a.sh_type[A] == 1;
-                if (owner_row(UT, USL, a_is_sp, A == B, fa, fb, lane, &i, &j)) {
-                    const long long P1 = pair_index64(i, j, a.norb);
-                    rb = row_start64(P1, a.npair) - P1 - a.out_offset;
-                } else {
-                    i = -1;
+        if (lane == 0) {
+            tn = atomicAdd(a.row_counter, 1);
+            if (tn < a.ntasks) {
+                taskn = a.tasks[tn];
+                mbar_expect_tx(&s_bar[buf ^ 1], C::U_BYTES);
+                tma_bulk_g2s(s_ubuf + (size_t)(buf ^ 1) * 9 * FU, a.u_aos + (size_t)taskn.x * 9 * FU, C::U_BYTES,
+                             &s_bar[buf ^ 1]);
+            }
+        }
+        tn = __shfl_sync(0xffffffffu, tn, 0);
+        taskn.x = __shfl_sync(0xffffffffu, taskn.x, 0);
+        taskn.y = __shfl_sync(0xffffffffu, taskn.y, 0);
+        taskn.z = __shfl_sync(0xffffffffu, taskn.z, 0);
+        const int u = task.x;
+        const int v0 = task.y;
+        const int ntv = task.z;
+        const int npu = a.u_nprim[u];
+        int P1[NFU];
+#pragma unroll
+        for (int f = 0; f < NFU; ++f) P1[f] = a.u_pidx[(size_t)u * C::NFU_FULL + ((USL >= 0) ? (4 * USL + f) : f)];
+        if (buf == 0) { mbar_wait(&s_bar[0], parity0); parity0 ^= 1; }
+        else          { mbar_wait(&s_bar[1], parity1); parity1 ^= 1; }
+        const double* s_u = s_ubuf + (size_t)buf * 9 * FU;
+        const double eu_max = s_u[4];
+
+        // ---- order the task's lane-side pairs by their distance from the row's pair -----------
+        // The Boys regime of a primitive quartet is set by alpha*|P-Q|^2; pairs of one task are of
+        // one kind (same exponents), so after a counting sort on |P-Q|^2 the 32 lanes of a chunk
+        // take the same branch.  Which lane gets which pair does not affect any result.
+        const int nitem = ntv - v0;
+        if (C::TASKP > 32 && nitem > 32) {
+            const double Px = s_u[1], Py = s_u[2], Pz = s_u[3];
+            double key[C::TASKP / 32];
+            double kmin = 1.0e300, kmax = 0.0;
+#pragma unroll
+            for (int i = 0; i < C::TASKP / 32; ++i) {
+                const int v = v0 + i * 32 + lane;
+                key[i] = -1.0;
+                if (v < ntv) {
+                    double dx, dy, dz;
+                    if constexpr (C::LANE_AOS) {
+                        const double* r0 = a.t_aos + (size_t)v * 9 * FT;
+                        dx = Px - __ldg(r0 + 1);
+                        dy = Py - __ldg(r0 + 2);
+                        dz = Pz - __ldg(r0 + 3);
+                    } else {
+                        dx = Px - a.t_soa[(size_t)a.t_npad + v];
+                        dy = Py - a.t_soa[2 * (size_t)a.t_npad + v];
+                        dz = Pz - a.t_soa[3 * (size_t)a.t_npad + v];
+                    }
+                    key[i] = fma(dx, dx, fma(dy, dy, dz * dz));
+                    kmin = fmin(kmin, key[i]);
+                    kmax = fmax(kmax, key[i]);
                 }
             }
-            m.rowi[lane] = i; m.rowj[lane] = j; m.rbase[lane] = rb;
-        }
-        int npu = 0;
-        double eu_max = 0.0;
-        const double* s_u = m.ubuf + (size_t)buf * 9 * FU;
-        if (urec >= 0) {
-            npu = __ldg(a.u_nprim + urec);
-            if (buf == 0) { mbar_wait(&m.bar[0], parity0); parity0 ^= 1; }
-            else          { mbar_wait(&m.bar[C::NBUF - 1], parity1); parity1 ^= 1; }
-            eu_max = s_u[4];
-        }
-        __syncwarp();
-
-        // ---- the warp's state machine for one task.  Everything before (zci, zb) has been written
-        // (zb < 0: from the start of that C); (pci, pb) is the last block enumerated.  Each pass of the
-        // loop does one thing: flush, evaluate one chunk of 32 quartets, take up to 32 partners from the
-        // current segment, or move the cursor (class -> block -> first shell).
-        // Partners: for every first shell C and block b of second shells, the D >= C of one shell class that form a
-        // live pair with C are listed by decreasing emax(C,D) (same exponents: by increasing distance), so the
-        // partners that pass the bound emax_u*emax_v >= 1e-14 are a prefix of the segment, and the 32 quartets a
-        // chunk evaluates have the same partner exponents and similar distances (same primitive survival, same
-        // Boys regime).  pc = eight pending counts (two kinds x four survival bins), one byte each (always < 64).
-        int zci = c_lo, zb = b_lo;
-        int nch = 0, used = 0;
-        unsigned long long pc = 0ull;
-        unsigned tq0 = 0, tq1 = 0;
-        long long span = 0;
-        int ci = c_lo - 1, Cs = 0, b = 0, bfirst_c = 0, bend = 0, cls = a.ncls;
-        int sbase = 0, send = 0, skind = 0;
-        bool blk_live = false;
-        int pci = c_lo, pb = b_lo - 1;  // last block whose partners have all been listed
-        int fci = c_lo, fb = b_lo - 1;  // newest block a parked chunk holds integrals of: a flush must reach it
-        bool finishing = false;
-        if (urec < 0) { finishing = true; pci = c_hi - 1; pb = b_hi - 1; }  // dead owner: its rows are zeros
-        for (;;) {
-            int L = -1;
-            {
-                const unsigned long long r = pc & 0xE0E0E0E0E0E0E0E0ull;  // lists with >= 32 pending
-                if (r) L = (__ffsll((long long)r) - 1) >> 3;
-                else if (finishing && pc) L = (__ffsll((long long)pc) - 1) >> 3;
-            }
-            const int kind = L >> 2;  // 0: D is an S shell, 1: D is an SP shell (meaningful when L >= 0)
-            bool do_flush = false, last = false;
-            if (L >= 0) do_flush = (used + (kind ? CH1 : CH0) > C::RES_CAP) || (nch == C::MAXCH);
-            else if (finishing) { do_flush = true; last = true; }
-            // bound the span one flush zero-fills, so that the integrals stored right after it meet their sectors in L2
-            else if (span > (256 << 10) && nch > 0) do_flush = true;
-            if (do_flush) {
-                // ---- zeros over the span from (zci,zb) through (tci,tb), then the parked integrals into it.  The span
-                // ends at the newest block the parked chunks touch (blocks after it are zero-filled together with
-                // their own integrals, by a later flush); the last flush of a task runs to the task's end.
-                const int tci = last ? pci : fci, tb = last ? pb : fb;
-                for (int f = 0; f < NFU; ++f) {
-                    const int i = m.rowi[f];
-                    if (i < 0) continue;
-                    const int j = m.rowj[f];
-                    const long long rb = m.rbase[f];
-                    long long pa = 0, pcount = 0;
-                    for (int c2 = zci; c2 <= tci; ++c2) {
-                        const int C2 = __ldg(a.clist + c2);
-                        const int bfirst = C2 / kBlockShells;
-                        const int blo = (c2 == zci && zb >= 0) ? zb : bfirst;
-                        const int bhi = (c2 == tci) ? tb : nblk - 1;
-                        if (blo > bhi) continue;
-                        const int llo = (blo == bfirst) ? 0 : __ldg(a.sh_first + blo * kBlockShells);
-                        const int lhi = (bhi == nblk - 1) ? a.norb : __ldg(a.sh_first + (bhi + 1) * kBlockShells);
-                        const int4 fc = __ldg(a.sh_fn + C2);
 #pragma unroll
-                        for (int kc = 0; kc < NK; ++kc) {
-                            const int k = slot_of(fc, kc);
-                            if (k < 0) continue;
-                            int l0;
-                            const int n = row_piece(i, j, k, llo, lhi, &l0);
-                            if (n == 0) continue;
-                            const long long addr = rb + col_base64(k, a.norb) + l0;
-                            if (addr == pa + pcount) { pcount += n; }
-                            else { zero_run(a.out + pa, pcount, lane); pa = addr; pcount = n; }
+            for (int o = 16; o > 0; o >>= 1) {
+                kmin = fmin(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                kmax = fmax(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+            }
+            const double scale = 63.999 / (kmax - kmin + 1.0e-300);
+            s_bin[lane] = 0;
+            s_bin[lane + 32] = 0;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < C::TASKP / 32; ++i)
+                if (key[i] >= 0.0) atomicAdd(&s_bin[(int)((key[i] - kmin) * scale)], 1);
+            __syncwarp();
+            // exclusive scan of the 64 bin counts (two bins per lane)
+            const int c0 = s_bin[2 * lane], c1 = s_bin[2 * lane + 1];
+            int incl = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            __syncwarp();
+            s_bin[2 * lane] = incl - c0 - c1;
+            s_bin[2 * lane + 1] = incl - c1;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < C::TASKP / 32; ++i)
+                if (key[i] >= 0.0) s_vidx[atomicAdd(&s_bin[(int)((key[i] - kmin) * scale)], 1)] = v0 + i * 32 + lane;
+            __syncwarp();
+        } else {
+            s_vidx[lane] = v0 + lane;
+            __syncwarp();
+        }
+
+        // One lane-side primitive (record tp) against the row's primitives: K[f][H'] over the row primitives
+        // (step A), then the lane-side coefficients folded in (step B); every out[f][f'] contribution goes to
+        // sink(f, f', value).  Returns false when the primitive is below the screen against the whole row.
+        bool any = false;
+        const size_t ld = C::LANE_AOS ? (size_t)1 : (size_t)a.t_npad;
+        auto contract_prim = [&](const double* tp, bool has_next, auto&& sink) -> bool {
+            double et, q, Qx, Qy, Qz, cfar;
+            if constexpr (C::LANE_AOS) {
+                const double2 t45 = __ldg(reinterpret_cast<const double2*>(tp) + 2);
+                et = t45.x;
+                if (eu_max * et < kScreen) return false;  // primitives are sorted by E, descending
+                const double2 t01 = __ldg(reinterpret_cast<const double2*>(tp));
+                const double2 t23 = __ldg(reinterpret_cast<const double2*>(tp) + 1);
+                if (has_next) {
+#pragma unroll
+                    for (int b = 0; b < FT * 8; b += 128)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(tp + FT) + b));
+                }
+                q = t01.x; Qx = t01.y; Qy = t23.x; Qz = t23.y;
+                cfar = kHalfSqrtPi * t45.y;  // sqrt(pi)/2 / sqrt(q)
+            } else {
+                et = tp[4 * ld];
+                if (eu_max * et < kScreen) return false;  // primitives are sorted by E, descending
+                q = tp[0];
+                Qx = tp[ld]; Qy = tp[2 * ld]; Qz = tp[3 * ld];
+                cfar = kHalfSqrtPi * tp[5 * ld];  // sqrt(pi)/2 / sqrt(q)
+            }
+            double K[NFU][NHT];
+#pragma unroll
+            for (int f = 0; f < NFU; ++f)
+#pragma unroll
+                for (int h = 0; h < NHT; ++h) K[f][h] = 0.0;
+
+            for (int ku = 0; ku < npu; ++ku) {
+                const double* up = s_u + ku * FU;
+                if (up[4] * et < kScreen) break;  // IF (EGH*EIJ .LT. 1.0D-14) CYCLE  (int2e.f90:257)
+                any = true;
+                const double p = up[0];
+                const double X = up[1] - Qx, Y = up[2] - Qy, Z = up[3] - Qz;
+                const double R2 = fma(X, X, fma(Y, Y, Z * Z));
+                const double s = p + q;
+                const double pq = p * q;
+                const double w = pq * R2;  // T*(p+q)
+                double G[LT + 1];
+                if (w >= (double)(2 * Q + 36) * s) {
+                    // Boys3 (auxilary.f90:194-215): G_j = sqrt(pi)/2 /sqrt(pq) (2j-1)!! (-1)^j R^-(2j+1)
+                    const double rinv = rsqrt_pos(R2);
+                    const double m = -(rinv * rinv);
+                    double g = cfar * up[5] * rinv;
+                    G[0] = g;
+#pragma unroll
+                    for (int j = 1; j <= LT; ++j) {
+                        g *= (double)(2 * j - 1) * m;
+                        G[j] = g;
+                    }
+                } else {
+                    const double rs = rsqrt_pos(s);
+                    const double alpha = pq * (rs * rs);
+                    boys_near_mid<Q, LT>(alpha * R2, alpha, rs, G, s_ft, s_exp);
+                }
+                double R[NR];
+                build_R<LT>(G, X, Y, Z, R);
+                // step A: K[f][H'] += D_k * R[H_k + H']
+                static_for<0, NTU>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    constexpr int f = term_fn(UT, k);
+                    if constexpr (USL < 0 || f / 4 == USL) {
+                        constexpr int lf = (USL >= 0) ? (f % 4) : f;
+                        constexpr int hk = term_h(UT, k);
+                        const double cu = up[kRecCoef + k];
+                        static_for<0, NHT>([&](auto hc) {
+                            constexpr int hp = decltype(hc)::value;
+                            constexpr int ri = h_add(hk, hp);
+                            K[lf][hp] = fma(cu, R[ri], K[lf][hp]);
+                        });
+                    }
+                });
+            }
+            // step B: out[f][f'] += (-1)^{|H'|} D'_k' K[f][H'_k'], the terms of one f' summed in registers first
+            static_for<0, NFT>([&](auto fc) {
+                constexpr int fp = decltype(fc)::value;
+                double acc[NFU];
+#pragma unroll
+                for (int f = 0; f < NFU; ++f) acc[f] = 0.0;
+                static_for<0, NTT>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
+                    if constexpr (term_fn(TT, k) == fp) {
+                        constexpr int hp = term_h(TT, k);
+                        double ct = C::LANE_AOS ? __ldg(tp + kRecCoef + k) : tp[(size_t)(kRecCoef + k) * ld];
+                        if constexpr (h_parity(hp) != 0) ct = -ct;
+#pragma unroll
+                        for (int f = 0; f < NFU; ++f) acc[f] = fma(ct, K[f][hp], acc[f]);
+                    }
+                });
+                static_for<0, NFU>([&](auto ffc) { sink(ffc, fc, acc[decltype(ffc)::value]); });
+            });
+            return true;
+        };
+
+        if constexpr (C::UNITS) {
+            // ---- (S SP|SP SP) and the (SP SP|SP SP) slices: one LANE PER LANE-SIDE PRIMITIVE of a quartet.  A quartet
+            // with n surviving lane-side primitives takes n consecutive lanes; each lane contracts its primitive
+            // against the row (64 partial integrals, parked in its shared-memory column) and the n lanes then add
+            // their columns, lane j taking the integrals o = j, j+n, ...  A warp is full with ~4-8 quartets and a
+            // quartet is done after at most 9 primitive quartets instead of 81.
+            unsigned char* s_cnt = reinterpret_cast<unsigned char*>(s_bin);  // the sort bins are free again
+            __syncwarp();
+            for (int slot = lane; slot < nitem; slot += 32) {
+                const int v = s_vidx[slot];
+                const int npt = a.t_nprim[v];
+                const double* trec = a.t_aos + (size_t)v * 9 * FT;
+                int ns = 0;
+                for (int kt = 0; kt < npt; ++kt) {
+                    if (eu_max * __ldg(trec + kt * FT + 4) < kScreen) break;
+                    ++ns;
+                }
+                s_cnt[slot] = (unsigned char)ns;
+            }
+            __syncwarp();
+            const int wbase = tid - lane;
+            int s0 = 0;
+            while (s0 < nitem) {
+                // chunk = slots [s0, s1) with at most 32 primitives in all (a quartet stays in one chunk)
+                int s1 = s0, tot = 0;
+                while (s1 < nitem && tot + (int)s_cnt[s1] <= 32) { tot += (int)s_cnt[s1]; ++s1; }
+                int slot = -1, kt = 0, first = 0, n = 0;
+                for (int s = s0, accn = 0; s < s1; ++s) {
+                    const int c = (int)s_cnt[s];
+                    if (lane >= accn && lane < accn + c) { slot = s; kt = lane - accn; first = accn; n = c; }
+                    accn += c;
+                }
+                int v = 0;
+                if (slot >= 0) {
+                    v = s_vidx[slot];
+                    const double* tp = a.t_aos + (size_t)v * 9 * FT + kt * FT;
+                    contract_prim(tp, false, [&](auto fc, auto fpc, double val) {
+                        s_out[(decltype(fc)::value * NFT + decltype(fpc)::value) * NTHREADS + tid] = val;
+                    });
+                }
+                __syncwarp();
+                if (slot >= 0) {
+                    const bool same_pair = a.tri && (v == u);
+                    const int64_t np = a.npair;
+                    for (int o = lane - first; o < NOUT; o += n) {
+                        const int f = o / NFT, fp = o % NFT;
+                        int P1f = P1[0];
+#pragma unroll
+                        for (int g = 1; g < NFU; ++g) P1f = (f == g) ? P1[g] : P1f;
+                        const int P2 = __ldg(a.t_pidx + (size_t)v * NFT + fp);
+                        if (P1f < 0 || P2 < 0 || (same_pair && P1f > P2)) continue;
+                        double sum = 0.0;
+                        const double* col = s_out + (size_t)o * NTHREADS + wbase + first;
+                        for (int t2 = 0; t2 < n; ++t2) sum += col[t2];
+                        const int64_t lo = P1f < P2 ? P1f : P2;
+                        const int64_t hi = P1f < P2 ? P2 : P1f;
+                        store_eri(a.out + (lo * np - ((lo * (lo - 1)) >> 1) + (hi - lo) - a.out_offset), sum);
+                    }
+                }
+                __syncwarp();
+                s0 = s1;
+            }
+        } else {
+        for (int ib = 0; ib < nitem; ib += 32) {
+            if (ib + lane < nitem) {
+                const int v = s_vidx[ib + lane];
+                double out_r[OUT_SMEM ? 1 : NOUT];
+                if constexpr (OUT_SMEM) {
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) s_out[o * NTHREADS + tid] = 0.0;
+                } else {
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) out_r[o] = 0.0;
+                }
+                any = false;
+                const int npt = a.t_nprim[v];
+                // Lane-side records.  Small classes read the structure-of-arrays copy (a task's pairs are
+                // a contiguous range, so the 8 chunks of a task share its lines in L1).  The classes with
+                // many Hermite coefficients read the lane's own contiguous [9][FT] block instead: one base
+                // pointer and compile-time offsets instead of a 64-bit multiply-add per field, and the next
+                // primitive's lines are prefetched into L1 while this one is contracted.
+                const double* trec = C::LANE_AOS ? a.t_aos + (size_t)v * 9 * FT : a.t_soa + v;
+                for (int kt = 0; kt < npt; ++kt) {
+                    const double* tp = C::LANE_AOS ? trec + kt * FT : trec + (size_t)kt * FT * ld;
+                    const bool live = contract_prim(tp, kt + 1 < npt, [&](auto fc, auto fpc, double val) {
+                        constexpr int o = decltype(fc)::value * NFT + decltype(fpc)::value;
+                        if constexpr (OUT_SMEM) s_out[o * NTHREADS + tid] += val;
+                        else out_r[o] += val;
+                    });
+                    if (!live) break;
+                }
+                // store the distinct canonical integrals of this shell quartet (the slice was zero
+                // filled: quartets the screen removes entirely keep the reference's exact zeros)
+                if (any) {
+                    const bool same_pair = a.tri && (v == u);
+                    const int64_t np = a.npair;
+                    int P2[NFT];
+#pragma unroll
+                    for (int fp = 0; fp < NFT; ++fp) P2[fp] = a.t_pidx[(size_t)v * NFT + fp];
+#pragma unroll
+                    for (int f = 0; f < NFU; ++f) {
+                        if (P1[f] < 0) continue;
+#pragma unroll
+                        for (int fp = 0; fp < NFT; ++fp) {
+                            if (P2[fp] < 0) continue;
+                            if (same_pair && P1[f] > P2[fp]) continue;
+                            const int64_t lo = P1[f] < P2[fp] ? P1[f] : P2[fp];
+                            const int64_t hi = P1[f] < P2[fp] ? P2[fp] : P1[f];
+                            const int64_t idx = lo * np - ((lo * (lo - 1)) >> 1) + (hi - lo) - a.out_offset;
+                            store_eri(a.out + idx, OUT_SMEM ? s_out[(f * NFT + fp) * NTHREADS + tid] : out_r[f * NFT + fp]);
                         }
                     }
-                    zero_run(a.out + pa, pcount, lane);
                 }
-                __syncwarp();  // orders the zeros before the integrals stored below by other lanes
-                for (int ch = 0; ch < nch; ++ch) {
-                    const int* d = m.desc + ch * C::DESC;
-                    const int hdr = d[32];
-                    if ((hdr & 1) == 0) scatter_chunk<UT, TC, 0, USL>(a, m, d, hdr >> 8, lane);
-                    else scatter_chunk<UT, TC, 1, USL>(a, m, d, hdr >> 8, lane);
-                }
-                __syncwarp();
-                nch = 0; used = 0; span = 0;
-                if (tb >= nblk - 1) { zci = tci + 1; zb = -1; }
-                else { zci = tci; zb = tb + 1; }
-                if (last) break;
-                continue;
             }
-            if (L >= 0) {
-                // ---- evaluate the first (up to) 32 pending quartets of list L and park their integrals
-                int* pl = m.pend + L * 64;
-                const int pn = (int)((pc >> (8 * L)) & 0xffull);
-                const int n = pn < 32 ? pn : 32;
-                int* d = m.desc + nch * C::DESC;
-                int item = 0;
-                if (lane < n) item = pl[lane];
-                const int keep = (lane + 32 < pn) ? pl[lane + 32] : 0;
-                __syncwarp();
-                if (lane + 32 < pn) pl[lane] = keep;
-                d[lane] = item;
-                if (lane == 0) { d[32] = kind | (n << 8); d[33] = used; }
-                unsigned nq = 0;
-                if (lane < n) {
-                    const int v = __ldg(a.pair_rec + (size_t)(item >> 16) * ns + (item & 0xffff));
-                    if (kind == 0) {
-                        constexpr int FT = tt_nfield(TC);
-                        nq = quartet_lane<UT, TC, USL>(s_u, npu, eu_max, a.t_aos[0] + (size_t)v * 9 * FT, __ldg(a.t_nprim[0] + v), ft0,
-                                                       s_exp, m.res + used + lane);
-                    } else {
-                        constexpr int FT = tt_nfield(TC + 1);
-                        nq = quartet_lane<UT, TC + 1, USL>(s_u, npu, eu_max, a.t_aos[1] + (size_t)v * 9 * FT, __ldg(a.t_nprim[1] + v), ft1,
-                                                           s_exp, m.res + used + lane);
-                    }
-                }
-                if (kind) tq1 += nq; else tq0 += nq;
-                // the chunk may hold partners of the block the cursor is in
-                if (ci >= c_lo && ci < c_hi && b >= bfirst_c && b < bend) { fci = ci; fb = b; }
-                else { fci = pci; fb = pb; }
-                __syncwarp();
-                pc -= (unsigned long long)n << (8 * L);
-                used += kind ? CH1 : CH0;
-                ++nch;
-                continue;
-            }
-            if (sbase < send) {
-                // ---- up to 32 partners of the current segment: those that pass the pair-level bound (a prefix).
-                // Each goes to the pending list of its kind and of the number of its primitives that survive
-                // against this owner (1-2, 3-4, 5-6, 7-9): the lanes of a chunk then run about the same number of
-                // primitive quartets.  ep = {E(1) = emax, E(3), E(5), E(7)} of the partner's sorted prefactors.
-                const int e = sbase + lane;
-                double2 ep01 = make_double2(0.0, 0.0), ep23 = make_double2(0.0, 0.0);
-                if (e < send) {
-                    ep01 = __ldg(a.seg_eprof + 2 * (size_t)e);
-                    ep23 = __ldg(a.seg_eprof + 2 * (size_t)e + 1);
-                }
-                const bool ok = eu_max * ep01.x >= kScreen;
-                const int bin = C::BINS ? (eu_max * ep01.y >= kScreen ? 1 : 0) + (eu_max * ep23.x >= kScreen ? 1 : 0) + (eu_max * ep23.y >= kScreen ? 1 : 0) : 0;
-                const unsigned mk = __ballot_sync(0xffffffffu, ok);
-                const int cnt = __popc(mk);
-                const unsigned lt = (1u << lane) - 1u;
-                int item = 0;
-                if (ok) item = (Cs << 16) | (int)__ldg(a.seg_d + e);
-#pragma unroll
-                for (int j = 0; j < (C::BINS ? 4 : 1); ++j) {
-                    const unsigned mj = __ballot_sync(0xffffffffu, ok && bin == j);
-                    const int L2 = skind * 4 + j;
-                    const int pn = (int)((pc >> (8 * L2)) & 0xffull);
-                    if (ok && bin == j) m.pend[L2 * 64 + pn + __popc(mj & lt)] = item;
-                    pc += (unsigned long long)__popc(mj) << (8 * L2);
-                }
-                sbase = (cnt == 32) ? sbase + 32 : send;
-                __syncwarp();
-                continue;
-            }
-            // ---- move the cursor
-            if (blk_live && cls + 1 < a.ncls) {
-                ++cls;
-                const size_t sidx = ((size_t)Cs * nblk + b) * a.ncls + cls;
-                sbase = __ldg(a.seg_start + sidx);
-                send = __ldg(a.seg_start + sidx + 1);
-                skind = __ldg(a.cls_kind + cls);
-                continue;
-            }
-            if (ci >= c_lo && b >= bfirst_c && b < bend) { pci = ci; pb = b; }  // block (ci,b) has been enumerated
-            if (ci >= c_lo && b + 1 < bend) {
-                ++b;
-                blk_live = eu_max * __ldg(a.blk_emax + (size_t)Cs * nblk + b) >= kScreen;
-                cls = -1;
-                continue;
-            }
-            if (ci >= c_lo) span += (long long)NFU * NK * (a.norb - __ldg(a.sh_first + Cs)) * 8;  // C is done
-            ++ci;
-            if (ci >= c_hi) { finishing = true; continue; }
-            Cs = __ldg(a.clist + ci);
-            bend = (ci == c_hi - 1) ? b_hi : nblk;
-            bfirst_c = (ci == c_lo) ? b_lo : Cs / kBlockShells;
-            b = bfirst_c - 1;
-            blk_live = false;
-            cls = a.ncls;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            tq0 += __shfl_xor_sync(0xffffffffu, tq0, o);
-            tq1 += __shfl_xor_sync(0xffffffffu, tq1, o);
         }
-        if (lane == 0) {
-            if (tq0) atomicAdd(a.stats, (unsigned long long)tq0);
-            if (tq1) atomicAdd(a.stats + 1, (unsigned long long)tq1);
-        }
-
-        __syncwarp();  // every lane is done with the owner records before the next TMA reuses the buffer
-        if constexpr (C::NBUF == 1) fetch(0, tn, taskn, urecn);
-        t = tn; task = taskn; urec = urecn;
-        if constexpr (C::NBUF == 2) buf ^= 1;
+        __syncwarp();  // every lane is done with this buffer before the TMA two tasks ahead reuses it
+        t = tn;
+        task = taskn;
+        buf ^= 1;
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// dense XX(i,j,g,h) (column-major, i fastest) for h in [h0,h1) from the packed array: the fillsym pass of the
+__global__ void fill_zero_kernel(double* __restrict__ out, int64_t n, int* __restrict__ counters, int ncounters) {
+    // 128-bit stores, grid-stride; a slice may start on an odd element.  Also resets the per-launch
+    // row counters of the class kernels that follow on the same stream.
+    if (blockIdx.x == 0)
+        for (int c = threadIdx.x; c < ncounters; c += blockDim.x) counters[c] = 0;
+    const int64_t head = ((reinterpret_cast<uintptr_t>(out) & 15) != 0 && n > 0) ? 1 : 0;
+    const int64_t n2 = (n - head) / 2;
+    double2* o2 = reinterpret_cast<double2*>(out + head);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride)
+        o2[i] = make_double2(0.0, 0.0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (head) out[0] = 0.0;
+        if ((n - head) & 1) out[n - 1] = 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Screened zero fill.  An element (P,P') of the packed array is written by a class kernel iff its
+// two shell pairs pass the reference's test on their largest prefactors,
+// fl(emax_P * emax_P') >= 1e-14 (int2e.f90:257); the product is monotone in each factor, so with
+// rk[] = rank of emax in the descending list of all shell-pair prefactors and cut[P] = number of
+// list entries whose product with emax_P passes, the test is the integer compare rk[P'] < cut[P].
+// This kernel writes the zeros of exactly the other elements: every element of the slice is
+// written once, by one kernel, and the fill needs no ordering against the FP64 kernels -- it runs
+// next to them (HBM-write bound next to DFMA bound) instead of in front of them.
+//
+// Work unit = kFillRows packed rows x kFillCols columns; thread t owns columns cb*kFillCols +
+// j*256 + t and keeps their ranks in registers for all rows of the unit, so rk[] is read once per
+// unit, and a warp writes 256 contiguous bytes per store.  Units are enumerated column block by
+// column block (ucb[] = prefix sums of the row blocks each column block needs: only rows <= the
+// block's last column exist in the upper triangle) and pulled from a global counter.
+constexpr int kFillThreads = 256;
+constexpr int kFillColsPerThread = kFillCols / kFillThreads;
+constexpr int kFillUcbSmem = 1024;  // column-block prefix entries cached in shared memory
+
+__global__ void __launch_bounds__(kFillThreads) fill_screened_kernel(const FillArgs a) {
+    __shared__ int s_unit[2];
+    __shared__ int s_ucb[kFillUcbSmem];
+    const int tid = threadIdx.x;
+    const int64_t np = a.npair;
+    const bool ucb_smem = a.ncb + 1 <= kFillUcbSmem;
+    if (ucb_smem)
+        for (int i = tid; i <= a.ncb; i += kFillThreads) s_ucb[i] = a.ucb[i];
+    // thread 0 claims units; with pacing it first waits until the class kernels have got far enough
+    bool pace = a.nprog > 0;  // thread 0 only
+    auto claim = [&]() -> int {
+        if (pace) {
+            unsigned long long t_wait0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_wait0));
+            for (;;) {
+                float p = 0.0f;
+                for (int k = 0; k < a.nprog; ++k) {
+                    const int n = a.prog_n[k];
+                    int c = *reinterpret_cast<const volatile int*>(a.counters + a.prog_idx[k]);
+                    c = c < n ? c : n;
+                    p += a.prog_w[k] * (float)c / (float)n;
+                }
+                // a little ahead of the compute (tasks are sorted heaviest first, so the task count
+                // lags the time), everything once the class kernels are done (p == 1 -> 1.2)
+                const float allowed = (0.04f + 1.16f * p) * (float)a.nunits;
+                const int cur = *reinterpret_cast<const volatile int*>(a.counter);
+                if ((float)cur < allowed || p >= 0.999f) break;
+                // safety net: never wait more than 2 ms on the class kernels (they advance every few
+                // microseconds when they run; if they cannot run, throttling must not become a deadlock)
+                unsigned long long t_now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+                if (t_now - t_wait0 > 2000000ull) { pace = false; break; }
+                __nanosleep(2000);
+            }
+        }
+        return atomicAdd(a.counter, 1);
+    };
+    if (tid == 0) s_unit[0] = claim();
+    __syncthreads();
+    int unit = s_unit[0];
+    for (int it = 0; unit < a.nunits; ++it) {
+        // the next unit is claimed while this one is written (one barrier per unit)
+        if (tid == 0) s_unit[(it + 1) & 1] = claim();
+        // column block of this unit: last cb with ucb[cb] <= unit
+        int lo = 0, hi = a.ncb;
+        if (ucb_smem) {
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_ucb[mid] <= unit) lo = mid; else hi = mid;
+            }
+        } else {
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(a.ucb + mid) <= unit) lo = mid; else hi = mid;
+            }
+        }
+        const int ulo = ucb_smem ? s_ucb[lo] : __ldg(a.ucb + lo);
+        const int64_t r0 = a.row_lo + (int64_t)(unit - ulo) * kFillRows;
+        const int64_t c0 = (int64_t)(a.cb0 + lo) * kFillCols;
+        int rk[kFillColsPerThread];
+#pragma unroll
+        for (int j = 0; j < kFillColsPerThread; ++j) {
+            const int64_t c = c0 + j * kFillThreads + tid;
+            rk[j] = c < np ? __ldg(a.rk + c) : -1;  // -1: column does not exist, never stored
+        }
+        int64_t rend = r0 + kFillRows;
+        if (rend > a.row_hi) rend = a.row_hi;
+        const bool interior = (r0 + kFillRows - 1 <= c0);  // every row of the unit is <= every column
+        // element (r,c) lives at out[off(r) - out_offset + (c - r)], off(r) = r*np - r(r-1)/2
+        double* o = a.out + (r0 * np - ((r0 * (r0 - 1)) >> 1) - a.out_offset - r0 + c0 + tid);
+        int64_t r = r0;
+        if (interior) {
+            for (; r + 4 <= rend; r += 4) {
+                int cut[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cut[i] = a.all ? 0 : __ldg(a.cut + r + i);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int j = 0; j < kFillColsPerThread; ++j)
+                        if (rk[j] >= cut[i]) __stcs(o + j * kFillThreads, 0.0);
+                    o += np - (r + i) - 1;  // off(r+1) - (r+1) - (off(r) - r)
+                }
+                if (a.sleep_ns > 0) __nanosleep(a.sleep_ns);
+            }
+        }
+        for (; r < rend; ++r) {
+            const int cut = a.all ? 0 : __ldg(a.cut + r);
+#pragma unroll
+            for (int j = 0; j < kFillColsPerThread; ++j)
+                if (rk[j] >= cut && c0 + j * kFillThreads + tid >= r) __stcs(o + j * kFillThreads, 0.0);
+            o += np - r - 1;
+        }
+        __syncthreads();
+        unit = s_unit[(it + 1) & 1];
+    }
+}
+
+// dense XX(i,j,g,h) (column-major, i fastest) from the packed array: the fillsym pass of the
 // reference (int2e.f90:290-304,540-554) done as a gather so that the 8n^4-byte stream is written
-// once, coalesced.
+// once, coalesced.  [h0,h1) selects the slab XX(:,:,:,h0:h1-1) (one slab per device in the multi-GPU dense path).
 __global__ void expand_dense_kernel(const double* __restrict__ packed, int norb, int h0, int h1, double* __restrict__ xx) {
     const int64_t n = norb;
     const int64_t npair = n * (n + 1) / 2;
@@ -681,23 +713,46 @@ int launch_chunk_push(const double* out, int64_t n, const unsigned char* flags, 
 }
 
 // ------------------------------------------------------------------------------------------
-// Kernel attributes are set (and the kernels loaded: CUDA loads modules lazily) once per device.
-constexpr int kNumVariants = 9;  // (0,0) (0,1) (1,0) (1,1) (2,0) (2,1)x4
-template <int UT, int TC, int USL>
+// Kernels that are meant to share SMs (the class kernels and the screened fill) must ask for the
+// same L1/shared split; with the default fill mode the split of every kernel is left to the driver
+// (a larger L1 is worth ~2 % on the small classes).
+static bool common_carveout() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MYQC_FILL_MODE");
+        v = (e && e[0] == 's') ? 1 : 0;
+    }
+    return v == 1;
+}
+
+// Kernel attributes are set (and the kernels loaded: CUDA loads modules lazily, and a first-time load
+// cannot complete while the paced fill kernel is waiting on the device for that very kernel) once
+// per device, before the first launch of a plan.
+template <int UT, int TT, int USL>
 static int prepare_one(int* occ_out) {
-    using C = SCfg<UT, TC, USL>;
-    auto kern = eri_strip_kernel<UT, TC, USL>;
+    using C = Cfg<UT, TT, USL>;
+    auto kern = eri_class_kernel<UT, TT, USL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return (int)e;
+    // Every kernel of a plan asks for the same (maximum) shared-memory carve-out: an SM cannot hold
+    // CTAs of kernels with different L1/shared splits at the same time (measured:
+    // tools/probes/concurrency_probe.cu), and the class kernels and the screened fill share SMs.
+    if (common_carveout()) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+    }
     int occ = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NTHREADS, C::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
     if (e != cudaSuccess) return (int)e;
     *occ_out = occ < 1 ? 1 : occ;
     return 0;
 }
 
 constexpr int kMaxDevices = 64;
-static int g_occ[kMaxDevices][kNumVariants];
+static int g_occ[kMaxDevices][10];
 static bool g_prepared[kMaxDevices];
 
 int prepare_kernels() {
@@ -709,55 +764,97 @@ int prepare_kernels() {
     int e = 0;
     if (!e) e = prepare_one<0, 0, -1>(&g_occ[dev][0]);
     if (!e) e = prepare_one<0, 1, -1>(&g_occ[dev][1]);
-    if (!e) e = prepare_one<1, 0, -1>(&g_occ[dev][2]);
+    if (!e) e = prepare_one<0, 2, -1>(&g_occ[dev][2]);
     if (!e) e = prepare_one<1, 1, -1>(&g_occ[dev][3]);
-    if (!e) e = prepare_one<2, 0, -1>(&g_occ[dev][4]);
-    if (!e) e = prepare_one<2, 1, 0>(&g_occ[dev][5]);
-    if (!e) e = prepare_one<2, 1, 1>(&g_occ[dev][6]);
-    if (!e) e = prepare_one<2, 1, 2>(&g_occ[dev][7]);
-    if (!e) e = prepare_one<2, 1, 3>(&g_occ[dev][8]);
+    if (!e) e = prepare_one<1, 2, -1>(&g_occ[dev][4]);
+    if (!e) e = prepare_one<2, 2, 0>(&g_occ[dev][5]);
+    if (!e) e = prepare_one<2, 2, 1>(&g_occ[dev][6]);
+    if (!e) e = prepare_one<2, 2, 2>(&g_occ[dev][7]);
+    if (!e) e = prepare_one<2, 2, 3>(&g_occ[dev][8]);
     if (e) return e;
+    if (common_carveout()) {
+        ce = cudaFuncSetAttribute(fill_screened_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared);
+        if (ce != cudaSuccess) return (int)ce;
+    }
+    cudaFuncAttributes fa;
+    ce = cudaFuncGetAttributes(&fa, fill_screened_kernel);
+    if (ce != cudaSuccess) return (int)ce;
     g_prepared[dev] = true;
     return 0;
 }
 
-template <int UT, int TC, int USL>
-static int launch_one(const StripArgs& a, int num_sms, cudaStream_t st, int slot) {
-    if (a.ntasks <= 0) return 0;
-    using C = SCfg<UT, TC, USL>;
-    auto kern = eri_strip_kernel<UT, TC, USL>;
+template <int UT, int TT, int USL>
+static int launch_one(const ClassArgs& a, int num_sms, cudaStream_t st, int slot) {
+    if (a.nU <= 0 || a.nT <= 0 || a.ntasks <= 0) return 0;
+    using C = Cfg<UT, TT, USL>;
+    auto kern = eri_class_kernel<UT, TT, USL>;
     int dev = 0;
     cudaGetDevice(&dev);
     int e0 = prepare_kernels();
     if (e0) return e0;
-    int grid = num_sms * g_occ[dev][slot];
+    const int occ = g_occ[dev][slot];
+    int grid = num_sms * occ;
     const int need = (a.ntasks + C::NWARPS - 1) / C::NWARPS;
     if (grid > need) grid = need;
     kern<<<grid, C::NTHREADS, C::SMEM, st>>>(a);
     return (int)cudaGetLastError();
 }
 
-int strip_nslices(int UT, int TC) { return (UT == 2 && TC == 1) ? 4 : 1; }
+int class_nlaunch(int UT, int TT) { return (UT == 2 && TT == 2) ? 4 : 1; }
 
-int launch_strip(int UT, int TC, int slice, const StripArgs& a, int num_sms, void* stream) {
+int launch_class(int UT, int TT, int slice, const ClassArgs& a0, int num_sms, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (UT == 0 && TC == 0) return launch_one<0, 0, -1>(a, num_sms, st, 0);
-    if (UT == 0 && TC == 1) return launch_one<0, 1, -1>(a, num_sms, st, 1);
-    if (UT == 1 && TC == 0) return launch_one<1, 0, -1>(a, num_sms, st, 2);
-    if (UT == 1 && TC == 1) return launch_one<1, 1, -1>(a, num_sms, st, 3);
-    if (UT == 2 && TC == 0) return launch_one<2, 0, -1>(a, num_sms, st, 4);
-    if (UT == 2 && TC == 1) {
-        if (slice == 0) return launch_one<2, 1, 0>(a, num_sms, st, 5);
-        if (slice == 1) return launch_one<2, 1, 1>(a, num_sms, st, 6);
-        if (slice == 2) return launch_one<2, 1, 2>(a, num_sms, st, 7);
-        if (slice == 3) return launch_one<2, 1, 3>(a, num_sms, st, 8);
+    ClassArgs a = a0;
+    a.row_counter = a0.row_counter + slice;
+    if (UT == 0 && TT == 0) return launch_one<0, 0, -1>(a, num_sms, st, 0);
+    if (UT == 0 && TT == 1) return launch_one<0, 1, -1>(a, num_sms, st, 1);
+    if (UT == 0 && TT == 2) return launch_one<0, 2, -1>(a, num_sms, st, 2);
+    if (UT == 1 && TT == 1) return launch_one<1, 1, -1>(a, num_sms, st, 3);
+    if (UT == 1 && TT == 2) return launch_one<1, 2, -1>(a, num_sms, st, 4);
+    if (UT == 2 && TT == 2) {  // four mu-slices, each with its own task counter
+        if (slice == 0) return launch_one<2, 2, 0>(a, num_sms, st, 5);
+        if (slice == 1) return launch_one<2, 2, 1>(a, num_sms, st, 6);
+        if (slice == 2) return launch_one<2, 2, 2>(a, num_sms, st, 7);
+        if (slice == 3) return launch_one<2, 2, 3>(a, num_sms, st, 8);
     }
     return (int)cudaErrorInvalidValue;
 }
 
-int launch_expand_dense(const double* packed, int norb, int h0, int h1, double* xx_slab, int num_sms, void* stream) {
+int launch_fill_zero(double* out, int64_t n, int* counters, int ncounters, int num_sms, void* stream) {
+    // A small footprint (default 2 CTAs of 256 threads per SM) is enough to saturate HBM with
+    // 128-bit stores and leaves the SMs to the FP64 kernels that run next to a later region's fill.
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        const char* e = getenv("MYQC_FILL_CTAS");
+        ctas_per_sm = e ? atoi(e) : 2;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    fill_zero_kernel<<<num_sms * ctas_per_sm, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, counters, ncounters);
+    return (int)cudaGetLastError();
+}
+
+int launch_fill_screened(const FillArgs& a, int num_sms, void* stream) {
+    if (a.nunits <= 0) return 0;
+    // persistent: a few CTAs per SM are enough to keep HBM busy with posted stores, and leave the
+    // register file to the FP64 kernels that run next to the fill
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        const char* e = getenv("MYQC_FILL_CTAS");
+        ctas_per_sm = e ? atoi(e) : 1;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    int grid = num_sms * ctas_per_sm;
+    if (grid > a.nunits) grid = a.nunits;
+    const int e0 = prepare_kernels();
+    if (e0) return e0;
+    fill_screened_kernel<<<grid, kFillThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return (int)cudaGetLastError();
+}
+
+int launch_expand_dense(const double* packed, int norb, int h0, int h1, double* xx, int num_sms, void* stream) {
     if (h1 <= h0) return 0;
-    expand_dense_kernel<<<num_sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(packed, norb, h0, h1, xx_slab);
+    expand_dense_kernel<<<num_sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(packed, norb, h0, h1, xx);
     return (int)cudaGetLastError();
 }
 

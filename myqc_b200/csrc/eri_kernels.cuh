@@ -1,4 +1,4 @@
-// Device-side interface of the owner-row strip kernels (see eri_kernels.cu).
+// Device-side interface of the quartet-class kernel family (see eri_kernels.cu).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -6,60 +6,84 @@
 
 namespace myqc {
 
-constexpr int kBlockShells = 128;  // partner second shells D are handled in blocks of this many consecutive shells
+constexpr int kTaskPairs = 256;  // most lane-side pairs per task (8 warp chunks)
+// The heavier the class, the shorter the tasks: a task is executed by one warp from start to finish,
+// so its duration bounds the tail of the launch (a 256-pair (SP SP|SP SP) task with all 81 primitive
+// quartets alive would run for more than a millisecond).
+constexpr int class_task_pairs(int UT, int TT) {
+    return (UT + TT <= 1) ? 256 : (UT + TT == 2) ? 128 : (UT + TT == 3) ? 64 : 32;
+}
 
-// One launch of eri_strip_kernel<UT,TC,USL>: every task (owner shell pair u = (A,B) of type UT;
-// a range of partner first shells C of type TC) computes all quartets (u | C D), D >= C, and writes
-// the part of u's packed rows whose columns start in C -- values and zeros -- exactly once.
-struct StripArgs {
-    // shells, ordered by first orbital
-    const int4* sh_fn;         // [ns] orbital ids of the slots (s,px,py,pz), -1 where absent
-    const signed char* sh_type;  // [ns] 0 = S, 1 = SP
-    const int32_t* sh_first;   // [ns+1] first orbital of each shell; sh_first[ns] = norb
-    int ns, nblk, norb;        // nblk = ceil(ns / kBlockShells)
-    int64_t npair;
-    // shell-pair tables, entry (C,D), C <= D, at C*ns + D
-    const int32_t* pair_rec;   // record index inside the pair's kind list, -1: no primitive pair survives
-    const double* pair_emax;   // largest primitive prefactor (0 where pair_rec < 0)
-    const double* blk_emax;    // [ns][nblk] max of pair_emax over D in a block, D >= C
-    // partner segments: for (C, block b, shell class c) the D >= C of class c in block b that form a live pair with C,
-    // by decreasing emax(C,D): entries seg_start[(C*nblk + b)*ncls + c] .. seg_start[.. + 1]
-    const int32_t* seg_start;
-    const unsigned short* seg_d;
-    const double2* seg_eprof;  // per entry two double2: {E(1) = emax, E(3)}, {E(5), E(7)}: the pair's primitive prefactors by rank (0 past the last)
-    const int32_t* cls_kind;   // [ncls] 0: shells of the class are S shells, 1: SP shells
-    int ncls;
-    // first shells C this launch handles: the shells of type TC in ascending order
-    const int32_t* clist;
-    // uniform side: records of kind UT, [n][9][nfield(UT)]
+// One launch = all quartets (u, v) with u in a "uniform-side" pair list (records staged to
+// shared memory by TMA bulk copy, one row of the quartet space per CTA iteration) and v in a
+// "lane-side" pair list (structure-of-arrays, one pair per lane).
+struct ClassArgs {
+    // uniform side (AoS records [nU][9][nfield(UT)])
     const double* u_aos;
-    const int32_t* u_nprim;
-    // lane side, partner kinds TC + TD for TD = 0 (D is an S shell) and 1 (D is an SP shell)
-    const double* t_aos[2];    // [n][9][nfield]
-    const int32_t* t_nprim[2];
-    // Boys Taylor tables [121][8] = {Ft(t,Q+k)/k!} for the two start orders, and {exp(-k/10), k/10}
-    const double* ftab_q[2];
-    const double2* exptab;
-    // tasks {A | B << 16, first index into clist, end index, b0 | b1 << 16}: owner pair (A,B), partner first shells
-    // clist[first..end), starting at partner block b0 of the first and ending before block b1 of the last;
-    // pulled by warps from *counter
+    const int32_t* u_nprim;  // [nU]
+    const int32_t* u_pidx;   // [nU][nf(UT)] packed pair index of each function pair, -1 = not stored
+    int nU;
+    // work list: task = {row u, first lane-side pair, end lane-side pair, 0}; rows are cut into
+    // pieces of at most kTaskPairs lane-side pairs (longest rows first)
     const int4* tasks;
     int ntasks;
-    int* counter;
-    unsigned long long* stats;  // [2] primitive quartets evaluated per TD (atomics, one per chunk)
-    double* out;                // this shard's slice of the packed array
-    int64_t out_offset;         // packed index of out[0]
+    // lane side (SoA [9][nfield(TT)][t_npad])
+    const double* t_soa;
+    const double* t_aos;     // the same records as [nT][9][nfield(TT)]: one lane reads its own pair contiguously
+    const int32_t* t_nprim;  // [nT]
+    const int32_t* t_pidx;   // [nT][nf(TT)]
+    int t_npad;
+    int nT;
+    int tri;  // lists are the same list: take v >= u only, and P1 <= P2 when v == u
+    // Boys Taylor table for this class's start order Q: [121][8] = {Ft(t,Q+k)/k!, k=0..6 ; 0}
+    const double* ftab_q;
+    // [601] {exp(-k/10), k/10}
+    const double2* exptab;
+    // global row counter of this launch (zeroed by the fill kernel that precedes it)
+    int* row_counter;
+    // output
+    double* out;         // this shard's slice of the packed array
+    int64_t out_offset;  // packed index of out[0]
+    int64_t npair;
 };
 
-// Kernel variants: UT in 0..2, TC in 0..1; the SP.SP owner with SP first partner shells runs as four
-// launches, one per first function of the owner (slice 0..3).
-int strip_nslices(int UT, int TC);
-// returns cudaError_t as int
-int launch_strip(int UT, int TC, int slice, const StripArgs& a, int num_sms, void* stream);
+// Screened zero fill (see fill_screened_kernel): rows [row_lo,row_hi) of the packed upper triangle
+constexpr int kFillRows = 64;
+constexpr int kFillCols = 2048;
+struct FillArgs {
+    double* out;         // this slice of the packed array
+    int64_t out_offset;  // packed index of out[0]
+    int64_t npair;
+    int64_t row_lo, row_hi;
+    const int32_t* rk;   // [npair] rank of the function pair's shell-pair prefactor (INT32_MAX: no shell pair kept)
+    const int32_t* cut;  // [npair] number of ranks that pass the screen against this row
+    const int32_t* ucb;  // [ncb+1] prefix sums of row blocks per column block, column blocks cb0..cb0+ncb-1
+    int cb0, ncb, nunits;
+    int* counter;        // unit counter (zeroed before the launch)
+    int all;             // experiments: ignore the screen, zero every element (only valid before the class kernels)
+    // pacing: the fill is throttled to the progress of the class kernels that run next to it, so that
+    // its stores are spread over their whole duration instead of saturating the memory pipeline up front.
+    // progress = sum_k prog_w[k] * min(counters[prog_idx[k]], prog_n[k]) / prog_n[k]  (weights sum to 1);
+    // nprog = 0: no pacing (serial timing pass, or nothing to pace against)
+    const int* counters;
+    const int32_t* prog_idx;
+    const int32_t* prog_n;
+    const float* prog_w;
+    int nprog;
+    int sleep_ns;  // experiments: fixed delay per four rows written (a constant-rate fill)
+};
+int launch_fill_screened(const FillArgs& a, int num_sms, void* stream);
 // sets the kernel attributes and forces the (lazily loaded) kernels of the current device to load
 int prepare_kernels();
 
+// returns cudaError_t as int; `slice` < class_nlaunch(UT,TT) selects the mu-slice of (2,2) (0 otherwise);
+// slice k uses the task counter a.row_counter + k
+int launch_class(int UT, int TT, int slice, const ClassArgs& a, int num_sms, void* stream);
+// number of kernel launches launch_class issues for (UT,TT)
+int class_nlaunch(int UT, int TT);
+
 int measure_dfma_peak(int num_sms, double* tflops);
+int launch_fill_zero(double* out, int64_t n, int* counters, int ncounters, int num_sms, void* stream);
 // dense XX(:,:,:,h0:h1-1) (column-major, all 8 images) gathered from the whole packed array
 int launch_expand_dense(const double* packed, int norb, int h0, int h1, double* xx_slab, int num_sms, void* stream);
 

@@ -83,22 +83,8 @@ int build_shells(int nnuc, int nset, int setl, const int32_t* setinfo, int ops,
             if (sh.fn[k] >= 0) sh.first_fn = std::min(sh.first_fn, sh.fn[k]);
         shells.push_back(sh);
     }
-    for (Shell& sh : shells) {
+    for (const Shell& sh : shells)
         if ((int)sh.sets.size() > 3) { err = "more than 3 primitives per shell"; return MYQC_ERR_UNSUPPORTED; }
-        int cnt = 0, mx = -1;
-        for (int k = 0; k < 4; ++k)
-            if (sh.fn[k] >= 0) { ++cnt; mx = std::max(mx, sh.fn[k]); }
-        sh.end_fn = mx + 1;
-        // the strip engine addresses a shell's orbitals as one run of the packed array
-        if (mx - sh.first_fn + 1 != cnt) { err = "orbital ids of a shell are not contiguous"; return MYQC_ERR_UNSUPPORTED; }
-        for (int k = 1; k < 4; ++k)
-            if (sh.fn[k] >= 0 && sh.fn[k] != sh.first_fn + (sh.fn[0] >= 0 ? k : k - 1)) {
-                err = "orbitals of a shell are not in (s,px,py,pz) order"; return MYQC_ERR_UNSUPPORTED;
-            }
-    }
-    std::stable_sort(shells.begin(), shells.end(), [](const Shell& x, const Shell& y) { return x.first_fn < y.first_fn; });
-    for (size_t h = 1; h < shells.size(); ++h)
-        if (shells[h].first_fn < shells[h - 1].end_fn) { err = "orbital ranges of two shells overlap"; return MYQC_ERR_UNSUPPORTED; }
     return MYQC_OK;
 }
 
@@ -108,6 +94,20 @@ struct PrimRec {
     double E;
     double f[kCoefField + 46 + 2];
 };
+
+// 30-bit Morton code of a point inside the bounding box [lo, lo+ext]^3
+uint32_t morton3(const double* r, const double* lo, double ext) {
+    uint32_t code = 0;
+    uint32_t q[3];
+    for (int c = 0; c < 3; ++c) {
+        double t = ext > 0 ? (r[c] - lo[c]) / ext : 0.0;
+        t = t < 0 ? 0 : (t > 1 ? 1 : t);
+        q[c] = (uint32_t)(t * 1023.0);
+    }
+    for (int b = 9; b >= 0; --b)
+        for (int c = 0; c < 3; ++c) code = (code << 1) | ((q[c] >> b) & 1u);
+    return code;
+}
 
 // contraction coefficient of function slot mu (0=s,1..3=p) of `shell` in primitive set `s`
 double slot_coef(const Shell& sh, int s, int mu, const int32_t* setinfo, int setl, int ops,
@@ -126,10 +126,19 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
                 const std::vector<Shell>& shells, PairList lists[3], std::string& err) {
     const double tol = 0.1e-15;  // auxilary.f90:573
     struct Tmp {
-        int type, A, B, nprim;
+        int type, A, B, nprim, bucket;
+        uint32_t morton;
         double emax;
+        double centre[3];
         std::vector<PrimRec> prims;
     };
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < nnuc; ++i)
+        for (int c = 0; c < 3; ++c) {
+            lo[c] = std::min(lo[c], xyz[i + nnuc * c]);
+            hi[c] = std::max(hi[c], xyz[i + nnuc * c]);
+        }
+    const double ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
     const bool trace = std::getenv("MYQC_TRACE") != nullptr;
     auto tprev = std::chrono::steady_clock::now();
     auto stage = [&](const char* name) {
@@ -227,6 +236,9 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
             std::stable_sort(t.prims.begin(), t.prims.end(), [](const PrimRec& x, const PrimRec& y) { return x.E > y.E; });
             t.nprim = (int)t.prims.size();
             if (t.nprim > kMaxPrim) { rcA[A] = MYQC_ERR_UNSUPPORTED; return; }
+            t.bucket = emax_bucket(t.emax);
+            for (int c = 0; c < 3; ++c) t.centre[c] = t.prims[0].f[1 + c];  // centre of the dominant primitive
+            t.morton = morton3(t.centre, lo, ext);
             outA.push_back(std::move(t));
         }
     };
@@ -252,26 +264,112 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
     }
     stage("merge");
     for (int type = 0; type < 3; ++type) {
-        // perA[] was filled in (A,B) order, so each list is already (A,B) row-major
         std::vector<Tmp>& v = tmp[type];
+        std::stable_sort(v.begin(), v.end(), [](const Tmp& x, const Tmp& y) {
+            if (x.bucket != y.bucket) return x.bucket < y.bucket;
+            return x.morton < y.morton;
+        });
         PairList& pl = lists[type];
         pl = PairList();
         pl.type = type;
         pl.n = (int)v.size();
-        const int nfield = pt_nfield(type);
-        pl.emax.resize(pl.n); pl.nprim.resize(pl.n);
-        pl.shA.resize(pl.n); pl.shB.resize(pl.n);
+        pl.npad = (pl.n + 31) / 32 * 32;
+        const int nf = pt_nf(type), nfield = pt_nfield(type);
+        pl.emax.resize(pl.n); pl.nprim.resize(pl.n); pl.bucket.resize(pl.n);
+        pl.shA.resize(pl.n); pl.shB.resize(pl.n); pl.owner_fn.resize(pl.n);
+        pl.pidx.assign((size_t)pl.n * nf, -1);
         pl.aos.assign((size_t)pl.n * kMaxPrim * nfield, 0.0);
+        pl.soa.assign((size_t)kMaxPrim * nfield * pl.npad, 0.0);
+        const int64_t norb = basinfo[1];
         for (int k = 0; k < pl.n; ++k) {
             const Tmp& t = v[k];
-            pl.emax[k] = t.emax; pl.nprim[k] = t.nprim;
+            const Shell& sa = shells[t.A];
+            const Shell& sb = shells[t.B];
+            pl.emax[k] = t.emax; pl.nprim[k] = t.nprim; pl.bucket[k] = t.bucket;
             pl.shA[k] = t.A; pl.shB[k] = t.B;
+            pl.owner_fn[k] = std::min(sa.first_fn, sb.first_fn);
+            for (int f = 0; f < nf; ++f) {
+                int fi, fj;
+                if (type == PT_SS) { fi = sa.fn[0]; fj = sb.fn[0]; }
+                else if (type == PT_SSP) {
+                    const bool a_is_sp = (sa.type == 1);
+                    fi = a_is_sp ? sa.fn[f] : sa.fn[0];
+                    fj = a_is_sp ? sb.fn[0] : sb.fn[f];
+                } else { fi = sa.fn[f / 4]; fj = sb.fn[f % 4]; }
+                if (fi < 0 || fj < 0) continue;            // absent function (p-only set)
+                if (t.A == t.B && fi > fj) continue;       // (j,i) duplicate inside a diagonal shell pair
+                const int64_t i = std::min(fi, fj), j = std::max(fi, fj);
+                pl.pidx[(size_t)k * nf + f] = (int32_t)(i * norb - i * (i - 1) / 2 + (j - i));
+            }
             for (int q = 0; q < t.nprim; ++q)
                 std::memcpy(&pl.aos[((size_t)k * kMaxPrim + q) * nfield], t.prims[q].f, sizeof(double) * nfield);
+        }
+        // structure-of-arrays copy: tiles of 32 pairs so that both sides of the transpose stay in cache
+        for (int k0 = 0; k0 < pl.n; k0 += 32) {
+            const int k1 = std::min(pl.n, k0 + 32);
+            for (int q = 0; q < kMaxPrim; ++q)
+                for (int f = 0; f < nfield; ++f) {
+                    double* dst = &pl.soa[((size_t)q * nfield + f) * pl.npad];
+                    for (int k = k0; k < k1; ++k) dst[k] = pl.aos[((size_t)k * kMaxPrim + q) * nfield + f];
+                }
         }
     }
     stage("sort + layout");
     return MYQC_OK;
+}
+
+PairList sublist(const PairList& src, const std::vector<char>& pred) {
+    PairList d;
+    d.type = src.type;
+    const int nf = pt_nf(src.type), nfield = pt_nfield(src.type);
+    std::vector<int> idx;
+    for (int k = 0; k < src.n; ++k)
+        if (pred[k]) idx.push_back(k);
+    d.n = (int)idx.size();
+    d.npad = (d.n + 31) / 32 * 32;
+    d.emax.resize(d.n); d.nprim.resize(d.n); d.bucket.resize(d.n);
+    d.shA.resize(d.n); d.shB.resize(d.n); d.owner_fn.resize(d.n);
+    d.pidx.resize((size_t)d.n * nf);
+    d.aos.assign((size_t)d.n * kMaxPrim * nfield, 0.0);
+    d.soa.assign((size_t)kMaxPrim * nfield * d.npad, 0.0);
+    for (int k = 0; k < d.n; ++k) {
+        const int s = idx[k];
+        d.emax[k] = src.emax[s]; d.nprim[k] = src.nprim[s]; d.bucket[k] = src.bucket[s];
+        d.shA[k] = src.shA[s]; d.shB[k] = src.shB[s]; d.owner_fn[k] = src.owner_fn[s];
+        for (int f = 0; f < nf; ++f) d.pidx[(size_t)k * nf + f] = src.pidx[(size_t)s * nf + f];
+        std::memcpy(&d.aos[(size_t)k * kMaxPrim * nfield], &src.aos[(size_t)s * kMaxPrim * nfield],
+                    sizeof(double) * kMaxPrim * nfield);
+        for (int q = 0; q < kMaxPrim; ++q)
+            for (int f = 0; f < nfield; ++f)
+                d.soa[((size_t)q * nfield + f) * d.npad + k] = src.soa[((size_t)q * nfield + f) * src.npad + s];
+    }
+    return d;
+}
+
+int emax_bucket(double emax) {
+    // Fine groups: symmetry-equivalent pairs share emax up to rounding noise, so a 1e-6 relative
+    // grid keeps pairs of one kind (same primitive survival pattern) together while the Morton
+    // order inside a group keeps them spatially close.
+    if (!(emax > 0.0)) return 1 << 30;
+    const double b = std::floor(-std::log(emax) * 1.0e6);
+    return b < 0 ? 0 : (b > 1.0e9 ? 1000000000 : (int)b);
+}
+
+std::vector<int32_t> row_prefix(const PairList& U, const PairList& T) {
+    // suffix maximum of T.emax is non-increasing: binary search for the last index that can still
+    // hold a pair passing emax_u*emax_v >= 1e-14
+    std::vector<double> smax(T.n + 1, 0.0);
+    for (int k = T.n - 1; k >= 0; --k) smax[k] = std::max(smax[k + 1], T.emax[k]);
+    std::vector<int32_t> out(U.n, 0);
+    for (int u = 0; u < U.n; ++u) {
+        int lo = 0, hi = T.n;  // first index with emax_u*smax < 1e-14
+        while (lo < hi) {
+            const int mid = (lo + hi) / 2;
+            if (U.emax[u] * smax[mid] < 1.0e-14) hi = mid; else lo = mid + 1;
+        }
+        out[u] = lo;
+    }
+    return out;
 }
 
 }  // namespace myqc

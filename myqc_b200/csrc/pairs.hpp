@@ -2,14 +2,12 @@
 //
 // Replaces the per-(a,b) / per-(c,d) work of the reference's quartet loop
 // (src/integrals/int2e.f90:192-263: p, P, PA, PB, EIJ, getcoef, getDk) by tables built once:
-// contracted shells are recovered from the reference's "set" arrays and ordered by their first
-// orbital; every shell pair (A <= B) with at least one primitive pair of prefactor >= 1e-14 gets
-// its primitive-pair records (exponent sum, centre, prefactor, Hermite coefficients folded with
-// normalisation and contraction coefficients).  Pairs are classed by the number of SP sets
-// (0: S.S, 1: S.SP, 2: SP.SP) and stored in (A,B) row-major order, so the partners (C,D) of one
-// first shell C are consecutive records.  The largest prefactor of a pair, emax, bounds the
-// reference's EIJ*EGH >= 1e-14 rule (int2e.f90:257) exactly: fl(x*y) is monotone, so a quartet
-// of pairs with fl(emax_u*emax_v) < 1e-14 has no surviving primitive quartet.
+// contracted shells are recovered from the reference's "set" arrays, every shell pair gets its
+// primitive-pair records (exponent sum, centre, prefactor, Hermite coefficients folded with
+// normalisation and contraction coefficients), pairs are classed by the number of SP sets
+// (0: S.S, 1: S.SP, 2: SP.SP) and sorted by their largest prefactor so that the reference's
+// EIJ*EGH >= 1e-14 screen becomes a prefix of the list (a Schwarz-like bound that is *exactly*
+// the reference's inclusion rule).
 #pragma once
 #include <cstdint>
 #include <string>
@@ -35,28 +33,54 @@ struct Shell {
     int type;         // 0 = S (one s function), 1 = SP (s,px,py,pz; s may be absent)
     int fn[4];        // orbital ids of (s,px,py,pz); -1 if absent (S shells use fn[0] only)
     std::vector<int> sets;  // primitive sets (indices into set[]) in reference order
-    int first_fn;     // smallest orbital id
-    int end_fn;       // one past the largest orbital id
+    int first_fn;     // smallest orbital id (ownership of packed rows)
 };
 
 struct PairList {
     int type = 0;
-    int n = 0;     // number of shell pairs kept (emax >= 1e-14)
-    std::vector<double> emax;     // largest primitive prefactor of the pair
-    std::vector<int32_t> nprim;   // primitive pairs with E >= 1e-14, sorted by E descending
-    std::vector<int32_t> shA, shB;  // shell indices (A <= B) in the sorted shell order
-    std::vector<double> aos;  // [n][kMaxPrim][nfield]: one contiguous block per pair (TMA source on the owner side, per-lane reads on the partner side)
+    int n = 0;     // number of shell pairs kept
+    int npad = 0;  // n rounded up to 32 (SoA leading dimension)
+    // Order: groups of decreasing largest-prefactor (emax equal to 1e-6 relative, i.e. pairs of
+    // one symmetry-equivalent kind), and inside a group the Morton order of the pair centre, so
+    // that the 32 pairs a warp holds are of one kind (same primitive survival pattern) and
+    // spatially close (same Boys regime against a given row).
+    std::vector<double> emax;
+    std::vector<int32_t> bucket;  // [n] non-decreasing bucket id
+    std::vector<int32_t> nprim;
+    std::vector<int32_t> pidx;    // [n][nf] packed pair index P(i,j) of each function pair; -1: not stored
+                                  // (absent function, or the (j,i) duplicate of a diagonal shell pair)
+    std::vector<int32_t> shA, shB;
+    std::vector<int32_t> owner_fn;  // min(first_fn(A), first_fn(B)) -> shard ownership key
+    // primitive records (prims sorted by E descending inside each pair, unused slots zero)
+    std::vector<double> aos;  // [n][kMaxPrim][nfield]   (uniform / TMA side)
+    std::vector<double> soa;  // [kMaxPrim][nfield][npad] (per-lane side)
 };
 
-// Returns 0 or a negative MYQC_ERR_* code; err receives a message.  Shells come out ordered by
-// their first orbital; each shell's orbitals must form one contiguous range (what buildBasis
-// produces, basis.f90:101-205), and the ranges must not interleave.
+struct Basis {
+    int nnuc = 0, nset = 0, norb = 0;
+    std::vector<Shell> shells;
+    PairList lists[3];
+};
+
+// Returns 0 or a negative MYQC_ERR_* code; err receives a message.
 int build_shells(int nnuc, int nset, int setl, const int32_t* setinfo, int ops,
                  const int32_t* basinfo, std::vector<Shell>& shells, std::string& err);
 
-// Build the three pair lists ((A,B) row-major inside each list).
+// Group id of a largest-prefactor value (1e-6 relative grid, emax = 1 -> group 0).
+int emax_bucket(double emax);
+
+// For every row u of `U`: the number of leading pairs of `T` that must be visited so that every
+// pair v with emax_u*emax_v >= 1e-14 is included (pairs inside the prefix that fail the product
+// test simply find no surviving primitive quartet).
+std::vector<int32_t> row_prefix(const PairList& U, const PairList& T);
+
+// Build the three pair lists restricted to shells for which keep_shell[s] != 0 on BOTH sides
+// (keep_shell == nullptr keeps all).
 int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* setinfo,
                 int setl, int ops, const double* bas, const int32_t* basinfo,
                 const std::vector<Shell>& shells, PairList lists[3], std::string& err);
+
+// Select a sub-list (keeping order) of the pairs for which pred[k] != 0.
+PairList sublist(const PairList& src, const std::vector<char>& pred);
 
 }  // namespace myqc

@@ -533,25 +533,26 @@ static void row_sink(void *c, int i, int j, int g, int h, double v) {
     else { if (Pp == d->P && P != Pp) d->row[P] += v; }
 }
 
-int oracle_int2e_rows(int nnuc, const double *xyz, const double *set, const int *setinfo,
-                      const double *bas, const int *basinfo, const double *ft, int nrows,
-                      const long long *rows, double *out) {
+typedef struct {
+    int nnuc; const double *xyz, *set; const int *setinfo; const double *bas; const int *basinfo; const double *ft;
+    int nrows; const long long *rows; double *out; const double *Eall;
+    int tid, nthreads;
+} rows_job;
+
+static void *rows_worker(void *arg) {
+    rows_job *J = (rows_job *)arg;
+    const int *setinfo = J->setinfo;
     int nset = setinfo[0], setl = setinfo[1];
-    long long norb = basinfo[1], npair = norb * (norb + 1) / 2;
-    memset(out, 0, sizeof(double) * (size_t)nrows * npair);
-    /* set membership of each orbital */
+    long long norb = J->basinfo[1], npair = norb * (norb + 1) / 2;
     setpair_t *ab = (setpair_t *)malloc(sizeof(setpair_t));
     setpair_t *cd = (setpair_t *)malloc(sizeof(setpair_t));
-    double *Eall = (double *)malloc(sizeof(double) * (size_t)nset * nset);
-    for (int c = 0; c < nset; ++c)
-        for (int d = 0; d < nset; ++d) Eall[(size_t)c * nset + d] = setpair_E(c, d, nnuc, xyz, set, setinfo);
-    for (int r = 0; r < nrows; ++r) {
-        long long P = rows[r];
+    for (int r = J->tid; r < J->nrows; r += J->nthreads) {
+        long long P = J->rows[r];
         /* invert P -> (i,j) */
         long long i = 0;
         while (pair_index(i + 1, i + 1, norb) <= P) ++i;
         long long j = i + (P - pair_index(i, i, norb));
-        row_ctx ctx = {&out[(size_t)r * npair], norb, npair, P, 0};
+        row_ctx ctx = {&J->out[(size_t)r * npair], norb, npair, P, 0};
         for (int a = 0; a < nset; ++a) {
             const int *sa = &setinfo[1 + a * setl + 1];
             int has_i = 0; for (int k = 0; k < sa[0]; ++k) if (sa[3 + k] == i) has_i = 1;
@@ -560,20 +561,53 @@ int oracle_int2e_rows(int nnuc, const double *xyz, const double *set, const int 
                 const int *sb = &setinfo[1 + b * setl + 1];
                 int has_j = 0; for (int k = 0; k < sb[0]; ++k) if (sb[3 + k] == j) has_j = 1;
                 if (!has_j) continue;
-                if (Eall[(size_t)a * nset + b] < 1.0e-14) continue;
-                make_setpair(ab, a, b, nnuc, xyz, set, setinfo, bas, basinfo);
+                if (J->Eall[(size_t)a * nset + b] < 1.0e-14) continue;
+                make_setpair(ab, a, b, J->nnuc, J->xyz, J->set, setinfo, J->bas, J->basinfo);
                 for (int c = 0; c < nset; ++c)
                     for (int d = 0; d < nset; ++d) {
-                        if (Eall[(size_t)c * nset + d] * ab->E < 1.0e-14) continue;
-                        make_setpair(cd, c, d, nnuc, xyz, set, setinfo, bas, basinfo);
-                        ctx.want_lower = 0; clmnew(ab, cd, (int)norb, ft, row_sink, &ctx); /* (P|P'>=P) */
-                        ctx.want_lower = 1; clmnew(cd, ab, (int)norb, ft, row_sink, &ctx); /* (P'<P|P) */
+                        if (J->Eall[(size_t)c * nset + d] * ab->E < 1.0e-14) continue;
+                        make_setpair(cd, c, d, J->nnuc, J->xyz, J->set, setinfo, J->bas, J->basinfo);
+                        ctx.want_lower = 0; clmnew(ab, cd, (int)norb, J->ft, row_sink, &ctx); /* (P|P'>=P) */
+                        ctx.want_lower = 1; clmnew(cd, ab, (int)norb, J->ft, row_sink, &ctx); /* (P'<P|P) */
                     }
             }
         }
     }
-    free(ab); free(cd); free(Eall);
+    free(ab); free(cd);
+    return NULL;
+}
+
+/* rows are independent: nthreads workers take every nthreads-th row (test infrastructure: lets the parity
+ * tests of the large configs compare hundreds of complete rows in a minute) */
+int oracle_int2e_rows_mt(int nnuc, const double *xyz, const double *set, const int *setinfo,
+                         const double *bas, const int *basinfo, const double *ft, int nrows,
+                         const long long *rows, double *out, int nthreads) {
+    int nset = setinfo[0];
+    long long norb = basinfo[1], npair = norb * (norb + 1) / 2;
+    memset(out, 0, sizeof(double) * (size_t)nrows * npair);
+    double *Eall = (double *)malloc(sizeof(double) * (size_t)nset * nset);
+    for (int c = 0; c < nset; ++c)
+        for (int d = 0; d < nset; ++d) Eall[(size_t)c * nset + d] = setpair_E(c, d, nnuc, xyz, set, setinfo);
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    if (nthreads > nrows) nthreads = nrows > 0 ? nrows : 1;
+    rows_job J[256];
+    pthread_t th[256];
+    for (int t = 0; t < nthreads; ++t) {
+        rows_job j = {nnuc, xyz, set, setinfo, bas, basinfo, ft, nrows, rows, out, Eall, t, nthreads};
+        J[t] = j;
+    }
+    for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, rows_worker, &J[t]);
+    rows_worker(&J[0]);
+    for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+    free(Eall);
     return 0;
+}
+
+int oracle_int2e_rows(int nnuc, const double *xyz, const double *set, const int *setinfo,
+                      const double *bas, const int *basinfo, const double *ft, int nrows,
+                      const long long *rows, double *out) {
+    return oracle_int2e_rows_mt(nnuc, xyz, set, setinfo, bas, basinfo, ft, nrows, rows, out, 1);
 }
 
 /* ------------------------------------------------------------------ */

@@ -256,14 +256,18 @@ def int2e_packed(mol, b, ft):
     return out
 
 
-def int2e_rows(mol, b, ft, rows):
+def int2e_rows(mol, b, ft, rows, nthreads=None):
+    """Complete rows (P|all P') of the packed array; rows are independent and go to `nthreads` workers
+    (default: all host threads)."""
     keep, a = _args(mol, b, ft)
     n = b.norb
     npair = n * (n + 1) // 2
     rows = np.ascontiguousarray(rows, dtype=np.int64)
     out = np.zeros((len(rows), npair))
-    assert lib().oracle_int2e_rows(*a, len(rows), rows.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
-                                   _dp(out)) == 0
+    if nthreads is None:
+        nthreads = os.cpu_count() or 1
+    assert lib().oracle_int2e_rows_mt(*a, len(rows), rows.ctypes.data_as(ctypes.POINTER(ctypes.c_longlong)),
+                                      _dp(out), int(nthreads)) == 0
     return out
 
 
