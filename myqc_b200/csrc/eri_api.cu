@@ -112,9 +112,9 @@ struct myqc_eri_plan {
     int ncounters = 0;
     // internal streams: the zero fill of sub-shard k+1 overlaps the FP64 kernels of sub-shard k,
     // and class kernels of one sub-shard overlap each other's tails
-    static constexpr int kNumCompute = 4;
-    cudaStream_t s_fill = nullptr, s_comp[kNumCompute] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t e_start = nullptr, e_done[kNumCompute + 1] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    static constexpr int kNumCompute = 9;  // one per launch of an unsharded step: small launches run side by side
+    cudaStream_t s_fill = nullptr, s_comp[kNumCompute] = {};
+    cudaEvent_t e_start = nullptr, e_done[kNumCompute + 1] = {};
     std::vector<cudaEvent_t> e_fill;
     // stats (canonical primitive-quartet counts of the whole shard)
     int64_t nquartets[6] = {0, 0, 0, 0, 0, 0};
@@ -183,7 +183,17 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
     const std::vector<int32_t> ntv = row_prefix(U.host, T.host);
     // segments of the lane-side list: at most kTaskPairs pairs, cut at group boundaries once a
     // segment holds >= 64 pairs, so that a task holds pairs of (mostly) one kind
-    const int maxpairs = class_task_pairs(U.type, T.type);
+    // A task is one warp's unit of work and lasts as long as its longest lane.  When the whole launch has fewer
+    // tasks than a few per resident warp (small and medium molecules) its duration is that of ONE task, so the
+    // tasks are cut finer, down to a single chunk of 32 lane-side pairs.
+    int maxpairs = class_task_pairs(U.type, T.type);
+    {
+        static const int occ_class[3][3] = {{7, 6, 4}, {6, 3, 2}, {4, 2, 2}};  // resident CTAs per SM (launch bounds of the class kernels)
+        const double warps = 4.0 * pl->num_sms * occ_class[U.type][T.type];
+        double total_pairs = 0.0;
+        for (int u = 0; u < U.n; ++u) total_pairs += std::max(0, ntv[u] - (tri ? u : 0));
+        while (maxpairs > 32 && total_pairs / maxpairs < 4.0 * warps) maxpairs /= 2;
+    }
     const int mingroup = std::min(64, maxpairs);
     std::vector<int> seg;  // segment start offsets, terminated by T.n
     seg.push_back(0);
@@ -856,7 +866,7 @@ int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
     for (Sub& sub : plan->subs) {
         double* d_sub = d_out + (sub.out_offset - plan->out_offset);
         for (int r = 0; r < (int)sub.region_end.size(); ++r, ++ef) {
-            bool waited[myqc_eri_plan::kNumCompute] = {false, false, false, false};
+            bool waited[myqc_eri_plan::kNumCompute] = {};
             for (Launch& L : sub.launches) {
                 if (L.region_task[r + 1] <= L.region_task[r]) continue;
                 // the mu-slices of (SP SP|SP SP) are independent launches: one internal stream each
@@ -1203,7 +1213,9 @@ static int run_packed_host(int nnuc, const double* xyz, int nset, int setl, cons
                            const double* ftab, double* packed, int ngpu) {
     const int ndev = myqc_device_count();
     if (ndev == 0) return fail(MYQC_ERR_NO_DEVICE, "no CUDA device: the ERI engine has no CPU fallback");
-    if (ngpu <= 0 || ngpu > ndev) ngpu = ndev;
+    // MYQC_OVERSUBSCRIBE=1 (test hook): more shards than devices, mapped round-robin onto the devices there are
+    const bool oversub = std::getenv("MYQC_OVERSUBSCRIBE") != nullptr;
+    if (ngpu <= 0 || (ngpu > ndev && !oversub)) ngpu = ndev;
     if (!packed) return fail(MYQC_ERR_BAD_ARG, "null output");
     std::vector<int64_t> off(ngpu + 1, 0);
     int rc = myqc_eri_shard_layout(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ngpu, off.data());
@@ -1212,7 +1224,7 @@ static int run_packed_host(int nnuc, const double* xyz, int nset, int setl, cons
     std::vector<std::string> errs(ngpu);
     auto work = [&](int g) {
         rcs[g] = myqc_eri_packed_shard(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, ftab,
-                                       packed + off[g], g, g, ngpu, nullptr);
+                                       packed + off[g], g % ndev, g, ngpu, nullptr);
         if (rcs[g]) errs[g] = g_last_error;
     };
     if (ngpu == 1) work(0);
@@ -1246,7 +1258,8 @@ int myqc_eri_dense(int nnuc, const double* xyz, int nset, int setl, const double
     if (!xx) return fail(MYQC_ERR_BAD_ARG, "null output");
     const int ndev = myqc_device_count();
     if (ndev == 0) return fail(MYQC_ERR_NO_DEVICE, "no CUDA device: the ERI engine has no CPU fallback");
-    if (ngpu <= 0 || ngpu > ndev) ngpu = ndev;
+    const bool oversub = std::getenv("MYQC_OVERSUBSCRIBE") != nullptr;
+    if (ngpu <= 0 || (ngpu > ndev && !oversub)) ngpu = ndev;
     const int64_t n = basinfo[1];
     const int64_t npair = n * (n + 1) / 2, nunique = npair * (npair + 1) / 2;
     if (ngpu > n) ngpu = (int)n;
@@ -1282,8 +1295,8 @@ int myqc_eri_dense(int nnuc, const double* xyz, int nset, int setl, const double
         const size_t slab = (size_t)(n * n * n) * (size_t)(h1 - h0);
         double *d_packed = nullptr, *d_slab = nullptr;
         int sms = 0;
-        cudaError_t e = cudaSetDevice(g);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g);
+        cudaError_t e = cudaSetDevice(g % ndev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g % ndev);
         if (e == cudaSuccess) e = cudaMalloc((void**)&d_packed, (size_t)nunique * sizeof(double));
         if (e == cudaSuccess) e = cudaMalloc((void**)&d_slab, slab * sizeof(double));
         if (e == cudaSuccess) e = cudaMemcpy(d_packed, packed.data(), (size_t)nunique * sizeof(double), cudaMemcpyHostToDevice);

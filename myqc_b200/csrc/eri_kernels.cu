@@ -115,8 +115,6 @@ struct Cfg {
     static constexpr int FT = tt_nfield(TT);
     static constexpr int NOUT = NFU * NFT;
     static constexpr bool OUT_SMEM = (NOUT > 16);
-    // lanes = lane-side primitives of a quartet (instead of quartets) for the classes with 64 integrals per lane
-    static constexpr bool UNITS = OUT_SMEM;
     // 128-thread CTAs for every class: (S SP|S SP) needs 140 registers, and a 256-thread CTA of it
     // would leave an SM with a single resident CTA (8 warps); four-warp CTAs pack 3 per SM
     static constexpr int NTHREADS = 128;
@@ -378,69 +376,6 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
             return true;
         };
 
-        if constexpr (C::UNITS) {
-            // ---- (S SP|SP SP) and the (SP SP|SP SP) slices: one LANE PER LANE-SIDE PRIMITIVE of a quartet.  A quartet
-            // with n surviving lane-side primitives takes n consecutive lanes; each lane contracts its primitive
-            // against the row (64 partial integrals, parked in its shared-memory column) and the n lanes then add
-            // their columns, lane j taking the integrals o = j, j+n, ...  A warp is full with ~4-8 quartets and a
-            // quartet is done after at most 9 primitive quartets instead of 81.
-            unsigned char* s_cnt = reinterpret_cast<unsigned char*>(s_bin);  // the sort bins are free again
-            __syncwarp();
-            for (int slot = lane; slot < nitem; slot += 32) {
-                const int v = s_vidx[slot];
-                const int npt = a.t_nprim[v];
-                const double* trec = a.t_aos + (size_t)v * 9 * FT;
-                int ns = 0;
-                for (int kt = 0; kt < npt; ++kt) {
-                    if (eu_max * __ldg(trec + kt * FT + 4) < kScreen) break;
-                    ++ns;
-                }
-                s_cnt[slot] = (unsigned char)ns;
-            }
-            __syncwarp();
-            const int wbase = tid - lane;
-            int s0 = 0;
-            while (s0 < nitem) {
-                // chunk = slots [s0, s1) with at most 32 primitives in all (a quartet stays in one chunk)
-                int s1 = s0, tot = 0;
-                while (s1 < nitem && tot + (int)s_cnt[s1] <= 32) { tot += (int)s_cnt[s1]; ++s1; }
-                int slot = -1, kt = 0, first = 0, n = 0;
-                for (int s = s0, accn = 0; s < s1; ++s) {
-                    const int c = (int)s_cnt[s];
-                    if (lane >= accn && lane < accn + c) { slot = s; kt = lane - accn; first = accn; n = c; }
-                    accn += c;
-                }
-                int v = 0;
-                if (slot >= 0) {
-                    v = s_vidx[slot];
-                    const double* tp = a.t_aos + (size_t)v * 9 * FT + kt * FT;
-                    contract_prim(tp, false, [&](auto fc, auto fpc, double val) {
-                        s_out[(decltype(fc)::value * NFT + decltype(fpc)::value) * NTHREADS + tid] = val;
-                    });
-                }
-                __syncwarp();
-                if (slot >= 0) {
-                    const bool same_pair = a.tri && (v == u);
-                    const int64_t np = a.npair;
-                    for (int o = lane - first; o < NOUT; o += n) {
-                        const int f = o / NFT, fp = o % NFT;
-                        int P1f = P1[0];
-#pragma unroll
-                        for (int g = 1; g < NFU; ++g) P1f = (f == g) ? P1[g] : P1f;
-                        const int P2 = __ldg(a.t_pidx + (size_t)v * NFT + fp);
-                        if (P1f < 0 || P2 < 0 || (same_pair && P1f > P2)) continue;
-                        double sum = 0.0;
-                        const double* col = s_out + (size_t)o * NTHREADS + wbase + first;
-                        for (int t2 = 0; t2 < n; ++t2) sum += col[t2];
-                        const int64_t lo = P1f < P2 ? P1f : P2;
-                        const int64_t hi = P1f < P2 ? P2 : P1f;
-                        store_eri(a.out + (lo * np - ((lo * (lo - 1)) >> 1) + (hi - lo) - a.out_offset), sum);
-                    }
-                }
-                __syncwarp();
-                s0 = s1;
-            }
-        } else {
         for (int ib = 0; ib < nitem; ib += 32) {
             if (ib + lane < nitem) {
                 const int v = s_vidx[ib + lane];
@@ -492,7 +427,6 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
                     }
                 }
             }
-        }
         }
         __syncwarp();  // every lane is done with this buffer before the TMA two tasks ahead reuses it
         t = tn;

@@ -604,6 +604,74 @@ int oracle_int2e_rows_mt(int nnuc, const double *xyz, const double *set, const i
     return 0;
 }
 
+/* Diagonal integrals (P|P) of every function pair P = (i,j) WITHOUT the EIJ*EGH screen: the Schwarz factors
+ * sqrt((ij|ij)) used by tools/schwarz_probe.py.  (The screened diagonal is exactly zero once E_ij < 1e-7, which would
+ * make a Schwarz bound built from it unsafe.)  Test / analysis infrastructure only. */
+typedef struct { double acc; long long norb, P; } diag_ctx;
+static void diag_sink(void *c, int i, int j, int g, int h, double v) {
+    diag_ctx *d = (diag_ctx *)c;
+    if (pair_index(i, j, d->norb) == d->P && pair_index(g, h, d->norb) == d->P) d->acc += v;
+}
+typedef struct {
+    int nnuc; const double *xyz, *set; const int *setinfo; const double *bas; const int *basinfo; const double *ft;
+    double *out; int tid, nthreads;
+} diag_job;
+static void *diag_worker(void *arg) {
+    diag_job *J = (diag_job *)arg;
+    const int *setinfo = J->setinfo;
+    int nset = setinfo[0], setl = setinfo[1];
+    long long norb = J->basinfo[1];
+    setpair_t *ab = (setpair_t *)malloc(sizeof(setpair_t));
+    setpair_t *cd = (setpair_t *)malloc(sizeof(setpair_t));
+    long long P = 0;
+    for (long long i = 0; i < norb; ++i)
+        for (long long j = i; j < norb; ++j, ++P) {
+            if (P % J->nthreads != J->tid) continue;
+            diag_ctx ctx = {0.0, norb, P};
+            for (int a = 0; a < nset; ++a) {
+                const int *sa = &setinfo[1 + a * setl + 1];
+                int has_i = 0; for (int k = 0; k < sa[0]; ++k) if (sa[3 + k] == i) has_i = 1;
+                if (!has_i) continue;
+                for (int b = 0; b < nset; ++b) {
+                    const int *sb = &setinfo[1 + b * setl + 1];
+                    int has_j = 0; for (int k = 0; k < sb[0]; ++k) if (sb[3 + k] == j) has_j = 1;
+                    if (!has_j) continue;
+                    make_setpair(ab, a, b, J->nnuc, J->xyz, J->set, setinfo, J->bas, J->basinfo);
+                    for (int c = 0; c < nset; ++c) {
+                        const int *sc = &setinfo[1 + c * setl + 1];
+                        int ci = 0; for (int k = 0; k < sc[0]; ++k) if (sc[3 + k] == i) ci = 1;
+                        if (!ci) continue;
+                        for (int d = 0; d < nset; ++d) {
+                            const int *sd = &setinfo[1 + d * setl + 1];
+                            int dj = 0; for (int k = 0; k < sd[0]; ++k) if (sd[3 + k] == j) dj = 1;
+                            if (!dj) continue;
+                            make_setpair(cd, c, d, J->nnuc, J->xyz, J->set, setinfo, J->bas, J->basinfo);
+                            clmnew(ab, cd, (int)norb, J->ft, diag_sink, &ctx);
+                        }
+                    }
+                }
+            }
+            J->out[P] = ctx.acc;
+        }
+    free(ab); free(cd);
+    return NULL;
+}
+int oracle_int2e_diag_unscreened(int nnuc, const double *xyz, const double *set, const int *setinfo,
+                                 const double *bas, const int *basinfo, const double *ft, double *out, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    diag_job J[256];
+    pthread_t th[256];
+    for (int t = 0; t < nthreads; ++t) {
+        diag_job j = {nnuc, xyz, set, setinfo, bas, basinfo, ft, out, t, nthreads};
+        J[t] = j;
+    }
+    for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, diag_worker, &J[t]);
+    diag_worker(&J[0]);
+    for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+    return 0;
+}
+
 int oracle_int2e_rows(int nnuc, const double *xyz, const double *set, const int *setinfo,
                       const double *bas, const int *basinfo, const double *ft, int nrows,
                       const long long *rows, double *out) {

@@ -271,6 +271,19 @@ def int2e_rows(mol, b, ft, rows, nthreads=None):
     return out
 
 
+def int2e_diag_unscreened(mol, b, ft, nthreads=None):
+    """(P|P) for every function pair P without the EIJ*EGH screen (Schwarz factors; analysis only)."""
+    keep, a = _args(mol, b, ft)
+    n = b.norb
+    out = np.zeros(n * (n + 1) // 2)
+    if nthreads is None:
+        nthreads = os.cpu_count() or 1
+    L = lib()
+    L.oracle_int2e_diag_unscreened.restype = ctypes.c_int
+    assert L.oracle_int2e_diag_unscreened(*a, _dp(out), int(nthreads)) == 0
+    return out
+
+
 def int2e_sample(mol, b, ft, a_list, b_list, nthreads=1):
     """Time-only run of the reference's per-(a,b) work for the listed ordered set pairs.
     Returns (seconds, surviving ordered quartets processed)."""

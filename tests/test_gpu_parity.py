@@ -69,6 +69,57 @@ def test_int2e_drop_in_writes_the_reference_xx_record(name, tmp_path, oracle_inp
         assert abs(E - (-183.32315970625)) < 1e-9  # 1e-9 Eh, north star
 
 
+def test_int2e_executable_found_on_path_like_the_driver_does(tmp_path, oracle_inputs):
+    """The reference driver runs `int2e` by name in the job directory (CALL EXECUTE_COMMAND_LINE('int2e'),
+    src/myQC/myQC.f90:54) and then only looks for the `error` file (:55-59).  Same here: PATH lookup, cwd = job
+    directory, no arguments; a second run finds XX and leaves it alone (int2e.f90:58-63)."""
+    import subprocess
+    s = product_system("HF", tmp_path)
+    exe_dir = os.path.join(os.path.dirname(Q.__file__), "csrc")
+    assert os.path.exists(os.path.join(exe_dir, "int2e"))
+    env = dict(os.environ, PATH=exe_dir + os.pathsep + os.environ.get("PATH", ""))
+    out = subprocess.run("int2e", shell=True, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and not (tmp_path / "error").exists(), out.stdout + out.stderr
+    n = s.norb
+    xx = Q.read_xx(str(tmp_path / "XX"), n)
+    mol, b, ft = oracle_system("HF", oracle_inputs)
+    ref, _ = O.int2e_dense(mol, b, ft)
+    assert np.abs(xx - ref).max() < TOL
+    stamp = os.stat(tmp_path / "XX").st_mtime_ns
+    again = subprocess.run("int2e", shell=True, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=300)
+    assert again.returncode == 0 and os.stat(tmp_path / "XX").st_mtime_ns == stamp
+    # failure path: without Ftab the program touches `error`, as the reference does (int2e.f90:174-178)
+    os.remove(tmp_path / "XX")
+    os.remove(tmp_path / "Ftab")
+    subprocess.run("int2e", shell=True, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=300)
+    assert (tmp_path / "error").exists() and not (tmp_path / "XX").exists()
+
+
+@pytest.mark.parametrize("name,ngpu", [("CO2", 2), ("h2o_4", 3)])
+def test_dense_xx_assembled_in_slabs_matches_single_device(name, ngpu, tmp_path, monkeypatch):
+    """myqc_eri_dense(ngpu > 1): shards of the packed array, then one slab XX(:,:,:,h0:h1) per device.  With fewer
+    devices than shards MYQC_OVERSUBSCRIBE=1 maps them round-robin onto the devices there are (test hook), so the
+    in-process multi-device path runs on a one-GPU box too; on a multi-GPU box it uses distinct devices."""
+    s = product_system(name, tmp_path)
+    one = Q.eri_dense(s, ngpu=1)
+    if Q.device_count() < ngpu:
+        monkeypatch.setenv("MYQC_OVERSUBSCRIBE", "1")
+    many = Q.eri_dense(s, ngpu=ngpu)
+    assert np.abs(many - one).max() < 1e-13 and np.array_equal(many == 0.0, one == 0.0)
+    packed = Q.eri_packed(s, ngpu=ngpu)
+    assert np.abs(packed - Q.eri_packed(s, ngpu=1)).max() < 1e-13
+
+
+def test_int2e_main_with_all_devices(tmp_path, oracle_inputs):
+    """`int2e <ngpu>` / MYQC_NGPU: the drop-in program on every visible device (0 = all)."""
+    s = product_system("CO2", tmp_path)
+    assert Q.int2e_main(str(tmp_path), 0) == 0
+    xx = Q.read_xx(str(tmp_path / "XX"), s.norb)
+    mol, b, ft = oracle_system("CO2", oracle_inputs)
+    ref, _ = O.int2e_dense(mol, b, ft)
+    assert np.abs(xx - ref).max() < TOL
+
+
 @pytest.mark.parametrize("name", ["h2o", "h2o_4", "c4h10", "h2o_8"])
 def test_small_clusters_full_compare(name, tmp_path, oracle_inputs):
     s = product_system(name, tmp_path)
@@ -91,32 +142,65 @@ def test_h2o16_baseline_config_full_compare(tmp_path, oracle_inputs):
     assert np.array_equal(got == 0.0, ref == 0.0) or np.abs(got[ref == 0.0]).max(initial=0.0) < 1e-14
 
 
+def _stratified_rows(s, nrows, seed=20261017):
+    """A fixed sample of packed rows P = (i,j) that covers every kind of row the kernels produce: rows of
+    same-centre pairs (dense, every quartet class lands in them), rows of bonded / neighbouring pairs, rows of
+    distant pairs (a handful of integrals), for s-s, s-p and p-p function pairs alike, plus the first and last row."""
+    n = s.norb
+    setl = int(s.setinfo[1])
+    cen = np.zeros(n, dtype=int)
+    lfn = np.zeros(n, dtype=int)
+    for o in range(n):
+        lfn[o] = int(s.basinfo[2 + 5 * o + 1])
+        cen[o] = int(s.basinfo[2 + 5 * o + 4])
+    xyz = np.array(s.xyz).reshape(3, s.nnuc).T
+    rng = np.random.default_rng(seed)
+    ii, jj = np.triu_indices(n)
+    d = np.linalg.norm(xyz[cen[ii]] - xyz[cen[jj]], axis=1)
+    kind = lfn[ii] + lfn[jj]                       # 0: s-s, 1: s-p, 2: p-p
+    band = np.digitize(d, [1e-9, 3.0, 7.0, 12.0])  # same centre | bonded | near | mid | far (bohr)
+    P = ii * n - ii * (ii - 1) // 2 + (jj - ii)
+    rows = [0, s.npair - 1]
+    per = max(1, nrows // 15)
+    for k in range(3):
+        for b in range(5):
+            cand = P[(kind == k) & (band == b)]
+            if len(cand):
+                rows.extend(rng.choice(cand, size=min(per, len(cand)), replace=False).tolist())
+    return np.unique(np.array(rows, dtype=np.int64))
+
+
 def _rows_check(name, tmp_path, oracle_inputs, nrows):
-    """Full-size configs: the whole packed array stays on the device side of the call; a fixed
-    sample of complete rows is compared with the row oracle, plus size-independent properties."""
+    """Full-size configs: the whole packed array stays on the device side of the call; a fixed stratified
+    sample of complete rows is compared with the (multithreaded) row oracle, plus size-independent properties."""
     s = product_system(name, tmp_path)
     got = Q.eri_packed(s)
     mol, b, ft = oracle_system(name, oracle_inputs)
     npair = s.npair
-    rng = np.random.default_rng(20261017)
-    rows = np.unique(np.concatenate([[0, npair - 1], rng.integers(0, npair, nrows)]))
+    rows = _stratified_rows(s, nrows)
     ref = O.int2e_rows(mol, b, ft, rows)
 
     def packed_index(P, Pp):
         lo, hi = np.minimum(P, Pp), np.maximum(P, Pp)
         return lo * npair - lo * (lo - 1) // 2 + (hi - lo)
     cols = np.arange(npair, dtype=np.int64)
-    worst = 0.0
+    worst, nonempty, nnz = 0.0, 0, 0
     for r, P in enumerate(rows):
         g = got[packed_index(np.int64(P), cols)]
         worst = max(worst, float(np.abs(g - ref[r]).max()))
+        assert np.array_equal(g == 0.0, ref[r] == 0.0) or np.abs(g[ref[r] == 0.0]).max(initial=0.0) < 1e-14
+        k = int(np.count_nonzero(ref[r]))
+        nnz += k
+        nonempty += k > 0
     assert worst < TOL, worst
+    # rows of distant pairs are (nearly) empty on purpose: they pin the exact zeros; most rows are not
+    assert nonempty >= 0.5 * len(rows) and nnz > 50 * len(rows), (nonempty, len(rows), nnz)
     # Schwarz inequality |(P|P')| <= sqrt((P|P)(P'|P')) on the sampled rows (size independent).
     # Slack 1e-6: the reference's EIJ*EGH >= 1e-14 rule zeroes a diagonal (P'|P') once E_P' < 1e-7
     # while (P|P') with a compact P survives, so the inequality only holds up to ~E_P' itself.
     diag = got[packed_index(cols, cols)]
     assert diag.min() > -1e-12
-    for P in rows:
+    for P in rows[::4]:
         g = got[packed_index(np.int64(P), cols)]
         assert np.all(np.abs(g) <= np.sqrt(np.abs(diag[P]) * np.abs(diag)) + 1e-6)
     return s, got
@@ -124,13 +208,13 @@ def _rows_check(name, tmp_path, oracle_inputs, nrows):
 
 def test_c20h42_rows(tmp_path, oracle_inputs):
     """BASELINE.json configs[3]: C20H42, 142 basis functions."""
-    s, got = _rows_check("c20h42", tmp_path, oracle_inputs, 24)
+    s, got = _rows_check("c20h42", tmp_path, oracle_inputs, 300)
     assert (s.norb, s.nunique) == (142, 51546781)
 
 
 def test_h2o64_rows(tmp_path, oracle_inputs):
     """BASELINE.json configs[4]: (H2O)_64, 448 basis functions, 5.06e9 unique integrals (40.5 GB)."""
-    s, got = _rows_check("h2o_64", tmp_path, oracle_inputs, 10)
+    s, got = _rows_check("h2o_64", tmp_path, oracle_inputs, 150)
     assert (s.norb, s.nunique) == (448, 5057816176)
     # translation invariance of the lattice: molecule (0,0,0) and molecule (1,0,0) have the same
     # intramolecular integrals (7 functions each, 16 molecules apart in orbital order)
