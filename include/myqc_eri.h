@@ -144,6 +144,13 @@ int myqc_eri_plan_launch_count(const myqc_eri_plan *plan);
 int myqc_eri_plan_launch_info(const myqc_eri_plan *plan, int k, int *cls, int *tri, int64_t *rows);
 int myqc_eri_plan_execute_timed(myqc_eri_plan *plan, double *d_out, void *stream, float *ms);
 
+/* After an execute (synchronises the device): primitive quartets the class kernels evaluated, per class in the order of
+ * nquartets[] above.  It is the canonical count of the reference's rule minus what the Schwarz skip leaves out:
+ * a contracted quartet (u|v) is skipped when Q_u*Q_v < tau, Q = sqrt(max (ij|ij)) over the pair's function pairs
+ * (unscreened diagonals, computed on the device at plan creation), so that every skipped integral is < tau in
+ * magnitude.  tau defaults to 1e-12 (MYQC_SCHWARZ_TAU; 0 = the reference's rule alone) and is returned in *schwarz_tau. */
+int myqc_eri_plan_executed_quartets(myqc_eri_plan *plan, int64_t *nq, double *schwarz_tau);
+
 /* Register-resident DFMA microbenchmark: the FP64 (non-tensor) roofline denominator, measured
  * on the device the plan runs on (MEASURED_PEAKS.json has no FP64 figure).                    */
 int myqc_fp64_peak(int device, double *tflops);

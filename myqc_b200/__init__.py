@@ -37,7 +37,7 @@ EXPORTS = [
     "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main", "myqc_eri_shard_layout",
     "myqc_eri_canonical_stats", "myqc_eri_plan_launch_count", "myqc_eri_plan_launch_info",
     "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard", "myqc_write_xx_ex", "myqc_eri_last_d2h_bytes",
-    "myqc_eri_release_cache",
+    "myqc_eri_release_cache", "myqc_eri_plan_executed_quartets",
     # include/myqc_fock.h
     "myqc_fock_rhf", "myqc_fock_uhf", "myqc_fock_rhf_host", "myqc_fock_uhf_host",
     "myqc_fock_mask_words", "myqc_fock_mask_build", "myqc_fock_rhf_masked", "myqc_fock_uhf_masked",
@@ -108,6 +108,7 @@ def lib() -> ctypes.CDLL:
     L.myqc_eri_packed_shard.argtypes = common + [_dp, c_int, c_int, c_int, _i64p]
     L.myqc_eri_last_d2h_bytes.argtypes = []
     L.myqc_eri_last_d2h_bytes.restype = ctypes.c_int64
+    L.myqc_eri_plan_executed_quartets.argtypes = [c_void_p, _i64p, _dp]
     L.myqc_eri_release_cache.argtypes = []
     L.myqc_eri_release_cache.restype = None
     c_i64 = ctypes.c_int64
@@ -361,6 +362,13 @@ class Plan:
         ms = (ctypes.c_float * n)()
         _check(lib().myqc_eri_plan_execute_timed(self._h, ctypes.c_void_p(d_out_ptr), ctypes.c_void_p(stream), ms))
         return list(ms)
+
+    def executed_quartets(self):
+        """After an execute: (primitive quartets evaluated per class, Schwarz threshold in use)."""
+        nq = (ctypes.c_int64 * 6)()
+        tau = ctypes.c_double()
+        _check(lib().myqc_eri_plan_executed_quartets(self._h, nq, ctypes.byref(tau)))
+        return list(nq), tau.value
 
     def stats(self):
         nq = (ctypes.c_int64 * 6)()

@@ -65,7 +65,7 @@ static int class_id(int la, int lb) {
 
 struct DevList {  // device copy of a PairList
     int type = 0, n = 0, npad = 0;
-    double *aos = nullptr, *soa = nullptr;
+    double *aos = nullptr, *soa = nullptr, *q = nullptr;
     int32_t *nprim = nullptr, *pidx = nullptr;
     PairList host;  // host copy (without the bulky record arrays) for the prefix computation
 };
@@ -127,6 +127,8 @@ struct myqc_eri_plan {
     int in_nnuc = 0, in_setl = 0;
     bool stats_done = false, stats_whole = false;
     bool screened_fill = true;
+    double schwarz_tau = 0.0;                 // 0: only the reference's own rule
+    unsigned long long* d_pq = nullptr;       // primitive quartets evaluated, one counter per class launch
     int32_t *d_rk = nullptr, *d_cut = nullptr;
     std::vector<int32_t> h_rk, h_cut;
     int nrank = 0;
@@ -148,11 +150,13 @@ static int upload(myqc_eri_plan* pl, const std::vector<T>& h, T** d) {
 static int upload_list(myqc_eri_plan* pl, const PairList& src, DevList& d) {
     d.type = src.type; d.n = src.n; d.npad = src.npad;
     d.host.type = src.type; d.host.n = src.n; d.host.emax = src.emax; d.host.bucket = src.bucket; d.host.pidx = src.pidx; d.host.nprim = src.nprim;
+    d.host.qmax = src.qmax;
     int rc;
     if ((rc = upload(pl, src.aos, &d.aos))) return rc;
     if ((rc = upload(pl, src.soa, &d.soa))) return rc;
     if ((rc = upload(pl, src.nprim, &d.nprim))) return rc;
     if ((rc = upload(pl, src.pidx, &d.pidx))) return rc;
+    if ((rc = upload(pl, src.qmax, &d.q))) return rc;
     return MYQC_OK;
 }
 
@@ -180,7 +184,7 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
     ClassArgs& a = L.args;
     std::memset(&a, 0, sizeof(a));
     a.u_aos = U.aos; a.u_nprim = U.nprim; a.u_pidx = U.pidx; a.nU = U.n;
-    const std::vector<int32_t> ntv = row_prefix(U.host, T.host);
+    const std::vector<int32_t> ntv = row_prefix(U.host, T.host, pl->schwarz_tau);
     // segments of the lane-side list: at most kTaskPairs pairs, cut at group boundaries once a
     // segment holds >= 64 pairs, so that a task holds pairs of (mostly) one kind
     // A task is one warp's unit of work and lasts as long as its longest lane.  When the whole launch has fewer
@@ -295,6 +299,9 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
     a.ntasks = (int)tasks.size();
     a.t_soa = T.soa; a.t_aos = T.aos; a.t_nprim = T.nprim; a.t_pidx = T.pidx;
     a.t_npad = T.npad; a.nT = T.n; a.tri = tri ? 1 : 0;
+    a.u_q = U.q; a.t_q = T.q;
+    a.tau = (U.q && T.q) ? pl->schwarz_tau : 0.0;
+    a.pq_counter = pl->d_pq + pl->ncounters;  // one per launch (slices of a launch share it)
     a.ftab_q = pl->d_ftab + (size_t)(U.type + T.type) * 121 * 8;
     a.exptab = reinterpret_cast<const double2*>(pl->d_exptab);
     const int ncnt = class_nlaunch(L.UT, L.TT) * nregion;  // one task counter per launch and region
@@ -604,9 +611,62 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
         if ((rc = upload(pl.get(), ex, &pl->d_exptab))) return rc;
         std::vector<int> zeros(kMaxCounters, 0);
         if ((rc = upload(pl.get(), zeros, &pl->d_counters))) return rc;
+        std::vector<unsigned long long> zq(kMaxCounters, 0ull);
+        if ((rc = upload(pl.get(), zq, &pl->d_pq))) return rc;
     }
     if (pl->screened_fill && (rc = build_screen_ranks(pl.get(), all))) return rc;
     stage("tables");
+    // ---- Schwarz factors (north star (1); SURVEY.md 7 "Parity vs. screening").  A contracted quartet (u|v) is left out
+    // when Q_u*Q_v < tau, Q = an upper bound of sqrt((ij|ij)) over the pair's function pairs: every integral of the
+    // quartet is then below tau in magnitude, and an integral belongs to exactly one contracted quartet, so the
+    // omission per integral is < tau (default 1e-12, two orders below the 1e-10 parity bar; MYQC_SCHWARZ_TAU=0 keeps
+    // the reference's rule alone).  The diagonals come from a device pass WITHOUT the reference's screen; the primitive
+    // pairs the builder dropped (E < 1e-14) are covered by the additive term below.
+    {
+        const char* et = std::getenv("MYQC_SCHWARZ_TAU");
+        pl->schwarz_tau = et ? std::atof(et) : 1.0e-12;
+        if (!(pl->schwarz_tau > 0.0)) pl->schwarz_tau = 0.0;
+    }
+    if (pl->schwarz_tau > 0.0) {
+        double* d_diag = nullptr;
+        CU(cudaMalloc((void**)&d_diag, (size_t)pl->npair * sizeof(double)));
+        CU(cudaMemset(d_diag, 0, (size_t)pl->npair * sizeof(double)));
+        std::vector<void*> tmp;
+        int e = 0;
+        for (int t = 0; t < 3 && !e; ++t) {
+            if (all[t].n == 0) continue;
+            double* d_aos = nullptr; int32_t *d_np = nullptr, *d_px = nullptr;
+            cudaError_t ce = cudaMalloc((void**)&d_aos, all[t].aos.size() * sizeof(double));
+            if (ce == cudaSuccess) { tmp.push_back(d_aos); ce = cudaMalloc((void**)&d_np, all[t].nprim.size() * sizeof(int32_t)); }
+            if (ce == cudaSuccess) { tmp.push_back(d_np); ce = cudaMalloc((void**)&d_px, all[t].pidx.size() * sizeof(int32_t)); }
+            if (ce == cudaSuccess) { tmp.push_back(d_px); ce = cudaMemcpy(d_aos, all[t].aos.data(), all[t].aos.size() * sizeof(double), cudaMemcpyHostToDevice); }
+            if (ce == cudaSuccess) ce = cudaMemcpy(d_np, all[t].nprim.data(), all[t].nprim.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+            if (ce == cudaSuccess) ce = cudaMemcpy(d_px, all[t].pidx.data(), all[t].pidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+            if (ce != cudaSuccess) { e = (int)ce; break; }
+            pl->h2d_bytes += (int64_t)(all[t].aos.size() * sizeof(double) + (all[t].nprim.size() + all[t].pidx.size()) * sizeof(int32_t));
+            e = launch_diag(t, d_aos, d_np, d_px, all[t].n, pl->d_ftab + (size_t)(2 * t) * 121 * 8,
+                            reinterpret_cast<const double2*>(pl->d_exptab), d_diag, nullptr);
+        }
+        std::vector<double> diag((size_t)pl->npair, 0.0);
+        if (!e) e = (int)cudaMemcpy(diag.data(), d_diag, diag.size() * sizeof(double), cudaMemcpyDeviceToHost);
+        for (void* p : tmp) cudaFree(p);
+        cudaFree(d_diag);
+        if (e) return cuda_fail((cudaError_t)e, "Schwarz diagonal pass");
+        for (int t = 0; t < 3; ++t) {
+            const int nf = pt_nf(t);
+            all[t].qmax.assign(all[t].n, 0.0);
+            for (int k = 0; k < all[t].n; ++k) {
+                double q2 = 0.0;
+                for (int f = 0; f < nf; ++f) {
+                    const int32_t P = all[t].pidx[(size_t)k * nf + f];
+                    if (P >= 0) q2 = std::max(q2, diag[(size_t)P]);
+                }
+                // + what the dropped primitive pairs (E < 1e-14, at most 80 quartets of O(1) x E x 1e-14 each) could add
+                all[t].qmax[k] = std::sqrt(q2 + 1.0e-11 * all[t].emax[k]) * (1.0 + 1.0e-9);
+            }
+        }
+        stage("Schwarz diagonals");
+    }
 
     // ---- sharding: contiguous blocks of packed rows, cut where a shell's functions start -------
     // External shards (one per GPU) are cut first; this plan's shard is then cut again into
@@ -846,6 +906,7 @@ int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
         tl.emplace_back(name, e);
     };
     if (plan->screened_fill) CU(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)plan->ncounters, st));
+    CU(cudaMemsetAsync(plan->d_pq, 0, sizeof(unsigned long long) * (size_t)kMaxCounters, st));
     mark("start", st);
     // fork: internal streams start after whatever is already queued on the caller's stream
     CU(cudaEventRecord(plan->e_start, st));
@@ -939,6 +1000,7 @@ int myqc_eri_plan_execute_timed(myqc_eri_plan* plan, double* d_out, void* stream
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) CU(cudaEventCreate(&e));
     if (plan->screened_fill) CU(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)plan->ncounters, st));
+    CU(cudaMemsetAsync(plan->d_pq, 0, sizeof(unsigned long long) * (size_t)kMaxCounters, st));
     CU(cudaEventRecord(ev[0], st));
     int idx = 0;
     for (Sub& sub : plan->subs) {
@@ -957,6 +1019,25 @@ int myqc_eri_plan_execute_timed(myqc_eri_plan* plan, double* d_out, void* stream
     CU(cudaEventSynchronize(ev[n]));
     for (int k = 0; k < n; ++k) CU(cudaEventElapsedTime(&ms[k], ev[k], ev[k + 1]));
     for (auto& x : ev) cudaEventDestroy(x);
+    return MYQC_OK;
+}
+
+// After an execute (synchronises the device): primitive quartets the class kernels actually evaluated, per class
+// {0,0},{0,1},{0,2},{1,1},{1,2},{2,2} -- the reference's rule minus what the Schwarz skip left out (the (SP SP|SP SP)
+// slices each evaluate every quartet of their class: their common counter is divided by four).
+int myqc_eri_plan_executed_quartets(myqc_eri_plan* plan, int64_t* nq, double* schwarz_tau) {
+    if (!plan || !nq) return fail(MYQC_ERR_BAD_ARG, "null plan/output");
+    CU(cudaSetDevice(plan->device));
+    CU(cudaDeviceSynchronize());
+    std::vector<unsigned long long> h(kMaxCounters, 0ull);
+    CU(cudaMemcpy(h.data(), plan->d_pq, sizeof(unsigned long long) * (size_t)kMaxCounters, cudaMemcpyDeviceToHost));
+    for (int c = 0; c < 6; ++c) nq[c] = 0;
+    for (const Sub& sub : plan->subs)
+        for (const Launch& L : sub.launches) {
+            const size_t idx = (size_t)(L.args.pq_counter - plan->d_pq);
+            nq[class_id(L.UT, L.TT)] += (int64_t)(h[idx] / (unsigned long long)class_nlaunch(L.UT, L.TT));
+        }
+    if (schwarz_tau) *schwarz_tau = plan->schwarz_tau;
     return MYQC_OK;
 }
 

@@ -281,6 +281,8 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
         // (step A), then the lane-side coefficients folded in (step B); every out[f][f'] contribution goes to
         // sink(f, f', value).  Returns false when the primitive is below the screen against the whole row.
         bool any = false;
+        unsigned npq = 0;  // primitive quartets this lane evaluated in this task
+        const double qu = (a.tau > 0.0) ? __ldg(a.u_q + u) : 0.0;
         const size_t ld = C::LANE_AOS ? (size_t)1 : (size_t)a.t_npad;
         auto contract_prim = [&](const double* tp, bool has_next, auto&& sink) -> bool {
             double et, q, Qx, Qy, Qz, cfar;
@@ -314,6 +316,7 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
                 const double* up = s_u + ku * FU;
                 if (up[4] * et < kScreen) break;  // IF (EGH*EIJ .LT. 1.0D-14) CYCLE  (int2e.f90:257)
                 any = true;
+                ++npq;
                 const double p = up[0];
                 const double X = up[1] - Qx, Y = up[2] - Qy, Z = up[3] - Qz;
                 const double R2 = fma(X, X, fma(Y, Y, Z * Z));
@@ -388,7 +391,10 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
                     for (int o = 0; o < NOUT; ++o) out_r[o] = 0.0;
                 }
                 any = false;
-                const int npt = a.t_nprim[v];
+                // Schwarz skip: every integral of the quartet is below tau in magnitude (|(ij|kl)| <= sqrt((ij|ij)(kl|kl)));
+                // the slice was zero filled, so the quartet is simply left out
+                const bool skip = (a.tau > 0.0) && (qu * __ldg(a.t_q + v) < a.tau);
+                const int npt = skip ? 0 : a.t_nprim[v];
                 // Lane-side records.  Small classes read the structure-of-arrays copy (a task's pairs are
                 // a contiguous range, so the 8 chunks of a task share its lines in L1).  The classes with
                 // many Hermite coefficients read the lane's own contiguous [9][FT] block instead: one base
@@ -428,11 +434,86 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
                 }
             }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) npq += __shfl_xor_sync(0xffffffffu, npq, o);
+        if (lane == 0 && npq) atomicAdd(a.pq_counter, (unsigned long long)npq);
         __syncwarp();  // every lane is done with this buffer before the TMA two tasks ahead reuses it
         t = tn;
         task = taskn;
         buf ^= 1;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Schwarz factors.  (f|f) for every function pair f of the shell pairs of kind T, one thread per shell pair, over
+// ALL primitive quartets of the pair with itself: no EIJ*EGH screen here, because the reference's own diagonal is
+// exactly zero once E < 1e-7 and a bound built from it would not bound anything.  Same Boys / R arithmetic as the
+// class kernels; only the terms of one function pair against themselves are contracted.
+template <int T>
+__global__ void __launch_bounds__(128) eri_diag_kernel(const double* __restrict__ aos, const int32_t* __restrict__ nprim,
+                                                       const int32_t* __restrict__ pidx, int n, const double* __restrict__ ftab_q,
+                                                       const double2* __restrict__ exptab, double* __restrict__ diag) {
+    constexpr int LT = 2 * T, Q = 3 * LT, NR = h_count(LT), NF = tt_nf(T), NT = tt_nterm(T), FT = tt_nfield(T);
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n) return;
+    const double* rec = aos + (size_t)u * 9 * FT;
+    const int np = nprim[u];
+    double acc[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) acc[f] = 0.0;
+    for (int k1 = 0; k1 < np; ++k1) {
+        const double* r1 = rec + k1 * FT;
+        for (int k2 = 0; k2 < np; ++k2) {
+            const double* r2 = rec + k2 * FT;
+            const double p = r1[0], q = r2[0];
+            const double X = r1[1] - r2[1], Y = r1[2] - r2[2], Z = r1[3] - r2[3];
+            const double R2 = fma(X, X, fma(Y, Y, Z * Z));
+            const double s = p + q, pq = p * q, w = pq * R2;
+            double G[LT + 1];
+            if (w >= (double)(2 * Q + 36) * s) {
+                const double rinv = rsqrt_pos(R2);
+                const double m = -(rinv * rinv);
+                double g = kHalfSqrtPi * r2[5] * r1[5] * rinv;
+                G[0] = g;
+#pragma unroll
+                for (int j = 1; j <= LT; ++j) { g *= (double)(2 * j - 1) * m; G[j] = g; }
+            } else {
+                const double rs = rsqrt_pos(s);
+                const double alpha = pq * (rs * rs);
+                boys_near_mid<Q, LT>(alpha * R2, alpha, rs, G, ftab_q, exptab);
+            }
+            double R[NR];
+            build_R<LT>(G, X, Y, Z, R);
+            static_for<0, NT>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                static_for<0, NT>([&](auto kc2) {
+                    constexpr int kk = decltype(kc2)::value;
+                    if constexpr (term_fn(T, k) == term_fn(T, kk)) {
+                        constexpr int ri = h_add(term_h(T, k), term_h(T, kk));
+                        const double c = r1[kRecCoef + k] * r2[kRecCoef + kk];
+                        if constexpr (h_parity(term_h(T, kk)) != 0) acc[term_fn(T, k)] = fma(-c, R[ri], acc[term_fn(T, k)]);
+                        else acc[term_fn(T, k)] = fma(c, R[ri], acc[term_fn(T, k)]);
+                    }
+                });
+            });
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const int P = pidx[(size_t)u * NF + f];
+        if (P >= 0) diag[P] = acc[f];
+    }
+}
+
+int launch_diag(int T, const double* aos, const int32_t* nprim, const int32_t* pidx, int n, const double* ftab_q,
+                const double2* exptab, double* diag, void* stream) {
+    if (n <= 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = (n + 127) / 128;
+    if (T == 0) eri_diag_kernel<0><<<grid, 128, 0, st>>>(aos, nprim, pidx, n, ftab_q, exptab, diag);
+    else if (T == 1) eri_diag_kernel<1><<<grid, 128, 0, st>>>(aos, nprim, pidx, n, ftab_q, exptab, diag);
+    else eri_diag_kernel<2><<<grid, 128, 0, st>>>(aos, nprim, pidx, n, ftab_q, exptab, diag);
+    return (int)cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------

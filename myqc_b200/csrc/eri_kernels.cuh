@@ -41,6 +41,11 @@ struct ClassArgs {
     const double2* exptab;
     // global row counter of this launch (zeroed by the fill kernel that precedes it)
     int* row_counter;
+    // Schwarz skip (tau = 0: off): lanes leave out the quartets with u_q[u]*t_q[v] < tau
+    const double* u_q;   // [nU] Schwarz factor of the uniform-side pairs
+    const double* t_q;   // [nT] of the lane-side pairs
+    double tau;
+    unsigned long long* pq_counter;  // primitive quartets this launch evaluated (one atomic per task)
     // output
     double* out;         // this shard's slice of the packed array
     int64_t out_offset;  // packed index of out[0]
@@ -81,6 +86,10 @@ int prepare_kernels();
 int launch_class(int UT, int TT, int slice, const ClassArgs& a, int num_sms, void* stream);
 // number of kernel launches launch_class issues for (UT,TT)
 int class_nlaunch(int UT, int TT);
+
+// unscreened diagonal integrals (f|f) of the shell pairs of kind T (0..2) into diag[packed pair index]
+int launch_diag(int T, const double* aos, const int32_t* nprim, const int32_t* pidx, int n, const double* ftab_q,
+                const double2* exptab, double* diag, void* stream);
 
 int measure_dfma_peak(int num_sms, double* tflops);
 int launch_fill_zero(double* out, int64_t n, int* counters, int ncounters, int num_sms, void* stream);

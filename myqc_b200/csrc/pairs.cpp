@@ -328,6 +328,7 @@ PairList sublist(const PairList& src, const std::vector<char>& pred) {
     d.n = (int)idx.size();
     d.npad = (d.n + 31) / 32 * 32;
     d.emax.resize(d.n); d.nprim.resize(d.n); d.bucket.resize(d.n);
+    if (!src.qmax.empty()) d.qmax.resize(d.n);
     d.shA.resize(d.n); d.shB.resize(d.n); d.owner_fn.resize(d.n);
     d.pidx.resize((size_t)d.n * nf);
     d.aos.assign((size_t)d.n * kMaxPrim * nfield, 0.0);
@@ -335,6 +336,7 @@ PairList sublist(const PairList& src, const std::vector<char>& pred) {
     for (int k = 0; k < d.n; ++k) {
         const int s = idx[k];
         d.emax[k] = src.emax[s]; d.nprim[k] = src.nprim[s]; d.bucket[k] = src.bucket[s];
+        if (!src.qmax.empty()) d.qmax[k] = src.qmax[s];
         d.shA[k] = src.shA[s]; d.shB[k] = src.shB[s]; d.owner_fn[k] = src.owner_fn[s];
         for (int f = 0; f < nf; ++f) d.pidx[(size_t)k * nf + f] = src.pidx[(size_t)s * nf + f];
         std::memcpy(&d.aos[(size_t)k * kMaxPrim * nfield], &src.aos[(size_t)s * kMaxPrim * nfield],
@@ -355,17 +357,29 @@ int emax_bucket(double emax) {
     return b < 0 ? 0 : (b > 1.0e9 ? 1000000000 : (int)b);
 }
 
-std::vector<int32_t> row_prefix(const PairList& U, const PairList& T) {
+std::vector<int32_t> row_prefix(const PairList& U, const PairList& T, double tau) {
     // suffix maximum of T.emax is non-increasing: binary search for the last index that can still
-    // hold a pair passing emax_u*emax_v >= 1e-14
+    // hold a pair passing emax_u*emax_v >= 1e-14; same for the Schwarz factors when they are there
     std::vector<double> smax(T.n + 1, 0.0);
     for (int k = T.n - 1; k >= 0; --k) smax[k] = std::max(smax[k + 1], T.emax[k]);
+    const bool schwarz = tau > 0.0 && (int)U.qmax.size() == U.n && (int)T.qmax.size() == T.n;
+    std::vector<double> sq(T.n + 1, 0.0);
+    if (schwarz)
+        for (int k = T.n - 1; k >= 0; --k) sq[k] = std::max(sq[k + 1], T.qmax[k]);
     std::vector<int32_t> out(U.n, 0);
     for (int u = 0; u < U.n; ++u) {
         int lo = 0, hi = T.n;  // first index with emax_u*smax < 1e-14
         while (lo < hi) {
             const int mid = (lo + hi) / 2;
             if (U.emax[u] * smax[mid] < 1.0e-14) hi = mid; else lo = mid + 1;
+        }
+        if (schwarz) {
+            int l2 = 0, h2 = lo;  // first index with qmax_u*sq < tau
+            while (l2 < h2) {
+                const int mid = (l2 + h2) / 2;
+                if (U.qmax[u] * sq[mid] < tau) h2 = mid; else l2 = mid + 1;
+            }
+            lo = l2;
         }
         out[u] = lo;
     }

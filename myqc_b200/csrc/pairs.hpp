@@ -51,6 +51,9 @@ struct PairList {
                                   // (absent function, or the (j,i) duplicate of a diagonal shell pair)
     std::vector<int32_t> shA, shB;
     std::vector<int32_t> owner_fn;  // min(first_fn(A), first_fn(B)) -> shard ownership key
+    // Schwarz factor of the pair: an upper bound of sqrt((ij|ij)) over its function pairs (empty: no Schwarz skip).
+    // Filled by the plan from a device pass over the unscreened diagonal quartets (eri_diag_kernel).
+    std::vector<double> qmax;
     // primitive records (prims sorted by E descending inside each pair, unused slots zero)
     std::vector<double> aos;  // [n][kMaxPrim][nfield]   (uniform / TMA side)
     std::vector<double> soa;  // [kMaxPrim][nfield][npad] (per-lane side)
@@ -72,7 +75,9 @@ int emax_bucket(double emax);
 // For every row u of `U`: the number of leading pairs of `T` that must be visited so that every
 // pair v with emax_u*emax_v >= 1e-14 is included (pairs inside the prefix that fail the product
 // test simply find no surviving primitive quartet).
-std::vector<int32_t> row_prefix(const PairList& U, const PairList& T);
+// With Schwarz factors on both lists and tau > 0 the prefix also ends where qmax_u*qmax_v < tau for every later
+// pair: |(ij|kl)| <= sqrt((ij|ij)(kl|kl)) < tau for all their integrals (SURVEY.md 7 "Parity vs. screening").
+std::vector<int32_t> row_prefix(const PairList& U, const PairList& T, double tau = 0.0);
 
 // Build the three pair lists restricted to shells for which keep_shell[s] != 0 on BOTH sides
 // (keep_shell == nullptr keeps all).

@@ -277,6 +277,35 @@ def test_plan_api_device_buffers(tmp_path):
     plan.close()
 
 
+@pytest.mark.parametrize("name", ["CO2", "h2o_8", "c4h10"])
+def test_schwarz_skip_omits_less_than_tau_and_can_be_turned_off(name, tmp_path, monkeypatch):
+    """The Schwarz skip (Q_u*Q_v < tau, Q from unscreened diagonals) leaves every omitted integral below tau;
+    MYQC_SCHWARZ_TAU=0 evaluates exactly the reference's set: the device counters then equal the canonical
+    counts of SURVEY.md 8d class by class."""
+    import torch
+    s = product_system(name, tmp_path)
+    nq, _ = Q.canonical_stats(s)
+
+    def run(tau):
+        monkeypatch.setenv("MYQC_SCHWARZ_TAU", tau)
+        plan = Q.Plan(s, device=0)
+        out = torch.full((plan.out_elems,), float("nan"), dtype=torch.float64, device="cuda:0")
+        plan.execute(out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        ex, t = plan.executed_quartets()
+        plan.close()
+        return out.cpu().numpy(), ex, t
+    exact, ex0, t0 = run("0")
+    assert t0 == 0.0 and list(ex0) == [int(x) for x in nq]
+    for tau in ("1e-12", "1e-11"):
+        got, ex, t = run(tau)
+        assert t == float(tau)
+        assert np.abs(got - exact).max() < float(tau)
+        assert all(a <= b for a, b in zip(ex, ex0))
+        assert np.array_equal(got[exact == 0.0], exact[exact == 0.0])
+    if name != "CO2":
+        assert sum(ex) < sum(ex0)  # the last run (tau = 1e-11) did leave quartets out
+
+
 def test_permuting_atoms_permutes_integrals(tmp_path, oracle_inputs):
     """Relabelling the nuclei only relabels the integrals (size-independent property)."""
     zm = example_zmat("h2o_2").splitlines()

@@ -156,3 +156,44 @@ def test_mp2_energy_of_co2_against_the_cfour_output_the_reference_ships(oracle_i
     fu = O.ao2mo_files("mp2_uhf", xx, C, C, nA, nB)
     s1, s2, s3, tot = O.mp2_uhf_energy(fu, eps, eps, nA, nB, b.norb)
     assert abs(s1 - e_aa) < 1e-12 and abs(s2 - e_aa) < 1e-12 and abs(s3 - e_ab) < 1e-12 and abs(tot - e2) < 1e-12
+
+
+CFOUR_SCF = json.load(open(os.path.join(GOLDEN, "cfour_scf.json")))
+
+
+@pytest.mark.parametrize("name,lo,hi", [("HeH", 5e-8, 3e-7), ("OH", 2e-6, 3e-5), ("CO2", 2e-5, 2e-4)])
+def test_cfour_scf_energies_at_their_stated_distance(name, lo, hi, oracle_inputs):
+    """CFOUR (an independent program, true pi, exact Boys function) against the oracle's SCF on the oracle's
+    integrals.  The two differ by what the reference's float32 pi and Ftab errors do:
+    1.2e-7 Eh for HeH, 9e-6 for OH, 6.7e-5 for CO2 -- no less (the oracle must carry the reference's quirks) and no more.
+    (examples/H2/cfour was run at R = 1.0 A, the myQC input at 0.5 A: not comparable, not used.)"""
+    E, _, _, _ = _scf(name, oracle_inputs)
+    d = abs(E - CFOUR_SCF[name]["E(SCF)"])
+    assert lo < d < hi, (name, E, CFOUR_SCF[name]["E(SCF)"], d)
+
+
+def test_no_uhf_densities_from_the_reference_cui_file(oracle_inputs):
+    """examples/NO/Cui holds myQC's own converged UHF orbitals (alpha then beta).  Orbital phases and the mixing inside
+    the degenerate pi pair are arbitrary, the spin densities are not: D = C_occ C_occ^T from the file against the
+    oracle's SCF on the oracle's integrals (the reference stopped at SCF_Conv = 7, hence 1e-5)."""
+    cui = np.load(os.path.join(GOLDEN, "NO_Cui.npy"))
+    mol, b, ft = oracle_system("NO", oracle_inputs)
+    xx, _ = O.int2e_dense(mol, b, ft)
+    S, H = O.int1e(mol, b, ft)
+    nA, nB = O.electrons(mol)
+    out = O.scf_uhf(S, H, xx, nA, nB, O.nuclear_repulsion(mol), orbitals=True)
+    Ca, Cb = out[-2], out[-1]
+    sig = [0, 1, 4, 5, 6, 9]          # s and pz functions (the molecule lies on z): the sigma space
+    px, py = [2, 7], [3, 8]
+    for C_ref, C, nocc in ((cui[0].T, Ca, nA), (cui[1].T, Cb, nB)):
+        # the file's orbitals are S-orthonormal
+        assert np.abs(C_ref.T @ S @ C_ref - np.eye(b.norb)).max() < 1e-6
+        D_ref = C_ref[:, :nocc] @ C_ref[:, :nocc].T
+        D = C[:, :nocc] @ C[:, :nocc].T
+        # the odd electron sits in one of the two degenerate pi* orbitals; which combination of (x,y) is a matter of the
+        # starting guess, so compare what a rotation about z leaves alone: the sigma block and the x+y traces of the pi block
+        assert np.abs(D[np.ix_(sig, sig)] - D_ref[np.ix_(sig, sig)]).max() < 1e-5
+        pi = D[np.ix_(px, px)] + D[np.ix_(py, py)]
+        pi_ref = D_ref[np.ix_(px, px)] + D_ref[np.ix_(py, py)]
+        assert np.abs(pi - pi_ref).max() < 1e-5
+        assert abs(np.sum(D * S) - nocc) < 1e-9 and abs(np.sum(D_ref * S) - nocc) < 1e-6

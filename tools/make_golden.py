@@ -10,6 +10,8 @@ box has no /root/reference).
                               BASELINE.md section 2 (recorded there from the survey session)
   tests/golden/packed_<mol>.npy    oracle packed ERIs of the small examples (GPU parity fixtures)
   tests/golden/cfour_mp2.json      MP2 energies of the CFOUR output the reference ships (examples/CO2/cfour/out)
+  tests/golden/cfour_scf.json      CFOUR SCF energies (HeH, OH, CO2) the reference ships
+  tests/golden/NO_Cui.npy          myQC's own UHF orbital coefficients of NO (examples/NO/Cui)
   tests/golden/ao2mo_CO2.npz       Cui / eig of the oracle's CO2 SCF and its (ia|jb) block: the ao2mo fixture
                                    (`python tools/make_golden.py ao2mo` regenerates only these two)
 """
@@ -93,9 +95,28 @@ def ao2mo_golden():
     print(vals, E, e_aa, e_ab, e2)
 
 
+def cfour_and_cui_golden():
+    """Independent SCF numbers the reference ships: CFOUR total energies (examples/{HeH,OH,CO2}/cfour/out; examples/H2/cfour
+    is another geometry, R = 1.0 A, and is not used) and myQC's own UHF orbital coefficients of NO (examples/NO/Cui,
+    written by scf.f90:1082-1083 as CuiA(:,:) then CuiB(:,:), list-directed, column-major)."""
+    vals = {}
+    for name in ("HeH", "OH", "CO2"):
+        out = open(os.path.join(REF, "examples", name, "cfour", "out")).read()
+        vals[name] = {"E(SCF)": float(re.search(r"E\(SCF\)\s*=\s*(-?\d+\.\d+)", out).group(1)),
+                      "source": f"examples/{name}/cfour/out"}
+    json.dump(vals, open(os.path.join(G, "cfour_scf.json"), "w"), indent=1)
+    cui = np.array([float(x.replace("D", "E")) for x in open(os.path.join(REF, "examples", "NO", "Cui")).read().split()])
+    assert cui.size == 200
+    np.save(os.path.join(G, "NO_Cui.npy"), cui.reshape(2, 10, 10))  # [spin][MO i][AO u]: Cui(u,i), u fastest
+    print(vals)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ao2mo":
         ao2mo_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "cfour":
+        cfour_and_cui_golden()
     else:
         main()
         ao2mo_golden()
+        cfour_and_cui_golden()
