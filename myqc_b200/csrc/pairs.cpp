@@ -168,8 +168,12 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
             const int nterm = pt_nterm(type);
             Tmp t;
             t.type = type; t.A = A; t.B = B; t.emax = 0.0;
-            for (int a : sa.sets) {
-                for (int b : sb.sets) {
+            for (size_t ia = 0; ia < sa.sets.size(); ++ia) {
+                for (size_t ib = 0; ib < sb.sets.size(); ++ib) {
+                    // A shell with itself: the set pairs (a,b) and (b,a) have the same p, P and E and differ only in
+                    // their coefficients, which add; one record with the summed coefficients does the work of two.
+                    if (A == B && ib < ia) continue;
+                    const int a = sa.sets[ia], b = sb.sets[ib];
                     // int2e.f90:215-223
                     const double aa = set[a], bb = set[b];
                     const int u = sa.centre, v = sb.centre;
@@ -194,24 +198,18 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
                         d[w][1][1][1] = PA[w] / (2.0 * p) + PB[w] * half;
                         d[w][1][1][2] = half / (2.0 * p);
                     }
-                    const double ga[2] = {g0[a], g1[a]};
-                    const double gb[2] = {g0[b], g1[b]};
-                    double ca[4], cb[4];  // contraction coefficients of the four function slots
-                    for (int mu = 0; mu < 4; ++mu) {
-                        ca[mu] = slot_coef(sa, a, mu, setinfo, setl, ops, bas);
-                        cb[mu] = slot_coef(sb, b, mu, setinfo, setl, ops, bas);
-                    }
                     // 2 Pi^2.5 / (p q sqrt(p+q)) is split as scale(p)*scale(q)/sqrt(p+q)
                     const double scale = std::sqrt(2.0) * std::pow(kPiRef, 1.25) / p;
-                    auto term = [&](int mu, int nu, int N, int L, int M) -> double {
+                    // coefficient of term (mu,nu;N,L,M) with the first function in set sa_ and the second in set sb_
+                    auto term = [&](int sa_, int sb_, int mu, int nu, int N, int L, int M) -> double {
                         // mu,nu in {0=s,1=x,2=y,3=z}; getDk, auxilary.f90:610-622
                         int n[3] = {mu == 1, mu == 2, mu == 3};
                         int nb[3] = {nu == 1, nu == 2, nu == 3};
                         const double cx = d[0][n[0]][nb[0]][N], cy = d[1][n[1]][nb[1]][L], cz = d[2][n[2]][nb[2]][M];
                         if (std::fabs(cz) < tol || std::fabs(cy) < tol || std::fabs(cx) < tol) return 0.0;
                         double Dk = cx * cy * cz;
-                        Dk = Dk * EIJ * ga[mu != 0] * gb[nu != 0];
-                        Dk = Dk * ca[mu] * cb[nu];
+                        Dk = Dk * EIJ * (mu != 0 ? g1[sa_] : g0[sa_]) * (nu != 0 ? g1[sb_] : g0[sb_]);
+                        Dk = Dk * slot_coef(sa, sa_, mu, setinfo, setl, ops, bas) * slot_coef(sb, sb_, nu, setinfo, setl, ops, bas);
                         return Dk * scale;
                     };
                     PrimRec r;
@@ -226,7 +224,8 @@ int build_pairs(int nnuc, const double* xyz, const double* set, const int32_t* s
                         int mu = 0, nu = 0;
                         if (type == PT_SSP) { mu = a_is_sp ? f : 0; nu = a_is_sp ? 0 : f; }
                         else if (type == PT_SPSP) { mu = f / 4; nu = f % 4; }
-                        c[k] = term(mu, nu, h_N(h), h_L(h), h_M(h));
+                        c[k] = term(a, b, mu, nu, h_N(h), h_L(h), h_M(h));
+                        if (A == B && ia != ib) c[k] += term(b, a, mu, nu, h_N(h), h_L(h), h_M(h));  // same centre: PA = PB = 0 both ways
                     }
                     t.prims.push_back(r);
                     t.emax = std::max(t.emax, EIJ);
