@@ -334,8 +334,11 @@ def run_ours(args):
     kernels = []
     for cls, t in sorted(per_class_ms.items()):
         if cls < 0:
+            # cls -2: compose_kernel (writes every element of the slice once: algorithmic bytes = 8 B per unique ERI);
+            # cls -1: fill_zero_kernel of the scatter mode (MYQC_OUTPUT_MODE=scatter)
             gb = 8.0 * fill_elems / 1e9
-            kernels.append({"kernel": "fill_zero", "zeros_written": fill_elems, "ms": t, "bound": "hbm", "share_of_step": t / serial_ms,
+            kernels.append({"kernel": "compose" if cls == -2 else "fill_zero", "elements_written": fill_elems, "ms": t, "bound": "hbm",
+                            "share_of_step": t / serial_ms,
                             "achieved": gb / (t * 1e-3) if t > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s"})
         else:
             # canonical primitive quartets of the class x W(class); for a shard the class counts of the whole molecule

@@ -96,6 +96,11 @@ struct Sub {  // one virtual sub-shard: a contiguous piece of the plan's slice w
     // kernel writes, so it needs no ordering against them
     FillArgs fill;
     int64_t fill_zero_elems = 0;  // zeros the screened fill writes (slice elements minus screened-in ones)
+    // compose mode: pair ids g of this piece = position in [mine S.S | mine S.SP | mine SP.SP | later S.S | ...]
+    ComposeArgs comp;
+    int listbase[6] = {0, 0, 0, 0, 0, 0};
+    int ng = 0;
+    std::vector<uint32_t> h_rowrel;  // [ng][6], see ComposeArgs::rowrel
 };
 
 struct myqc_eri_plan {
@@ -127,6 +132,10 @@ struct myqc_eri_plan {
     int in_nnuc = 0, in_setl = 0;
     bool stats_done = false, stats_whole = false;
     bool screened_fill = true;
+    // compose mode (MYQC_OUTPUT_MODE=compose): class kernels stage quartet blocks, compose_kernel writes the slice once
+    bool compose = false;
+    double* d_stage = nullptr;
+    int64_t stage_elems = 0;
     double schwarz_tau = 0.0;                 // 0: only the reference's own rule
     unsigned long long* d_pq = nullptr;       // primitive quartets evaluated, one counter per class launch
     int32_t *d_rk = nullptr, *d_cut = nullptr;
@@ -175,7 +184,8 @@ static std::vector<int32_t> prefix_counts(const std::vector<double>& eu, const s
     return out;
 }
 
-static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
+// ukind / tkind: 0 = the piece's own ("mine") list, 1 = its "later" list
+static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri, int ukind = 0, int tkind = 0) {
     const DevList& U = pl->lists[ui];
     const DevList& T = pl->lists[ti];
     if (U.n == 0 || T.n == 0) return MYQC_OK;
@@ -312,6 +322,28 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri) {
     a.out = nullptr;
     a.out_offset = sub.out_offset;
     a.npair = pl->npair;
+    if (pl->compose) {
+        // quartet blocks of this launch in the staging array: row u holds the blocks of v in [lo_u, ntv[u]) one after
+        // the other; stage_row[u] is the position its v = 0 block would have, so block(u,v) = stage_row[u] + v*blk
+        const int64_t blk = (int64_t)pt_nf(U.type) * pt_nf(T.type);
+        std::vector<int64_t> srow(U.n, INT64_MIN);
+        int64_t pos = (pl->stage_elems + 15) & ~(int64_t)15;
+        const int64_t lbase = pos;
+        const int lidu = 2 * U.type + ukind, lidt = 2 * T.type + tkind;
+        sub.comp.launch_base[lidu * 6 + lidt] = lbase;
+        for (int u = 0; u < U.n; ++u) {
+            const int lo = tri ? u : 0, hi = ntv[u];
+            if (lo >= hi) continue;
+            srow[u] = pos - (int64_t)lo * blk;
+            pos += (int64_t)(hi - lo) * blk;
+            sub.h_rowrel[(size_t)(sub.listbase[lidu] + u) * 6 + lidt] = (uint32_t)(srow[u] - lbase);  // mod 2^32, see ComposeArgs
+        }
+        if (pos - lbase >= ((int64_t)1 << 32)) return fail(MYQC_ERR_UNSUPPORTED, "one class launch stages more than 2^32 integrals");
+        pl->stage_elems = pos;
+        int64_t* d_srow = nullptr;
+        if ((rc = upload(pl, srow, &d_srow))) return rc;
+        a.stage_row = d_srow;
+    }
     sub.launches.push_back(L);
     pl->nlaunch += class_nlaunch(L.UT, L.TT) * nregion;
     return MYQC_OK;
@@ -601,6 +633,14 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
         // kernels' scattered stores and the fill compete for DRAM, the co-run takes the sum of both.
         const char* fm = std::getenv("MYQC_FILL_MODE");
         pl->screened_fill = (fm && std::strcmp(fm, "screened") == 0);
+        // Default ("scatter"): zero fill of the slice, then the class kernels store their integrals into it.
+        // MYQC_OUTPUT_MODE=compose: the class kernels stage dense quartet blocks and compose_kernel writes every element
+        // of the slice exactly once (DRAM traffic 1.2x the algorithmic bytes instead of 1.5x, class kernels 8.2 instead
+        // of 10.9 ms on (H2O)_64) -- but the element-wise gather of the compose pass costs 12 ms against 6.5 ms for
+        // the plain fill, so the step is slower (20.3 against 17.1 ms; profiles/r2_notes.md section 3).
+        const char* om = std::getenv("MYQC_OUTPUT_MODE");
+        pl->compose = (om && std::strcmp(om, "compose") == 0) && !pl->screened_fill;
+
     }
 
     // Boys tables for the five start orders Q = 0,3,6,9,12: row t = {Ft(t,Q+k)/k!, k<7 ; t/10}
@@ -614,7 +654,7 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
         std::vector<unsigned long long> zq(kMaxCounters, 0ull);
         if ((rc = upload(pl.get(), zq, &pl->d_pq))) return rc;
     }
-    if (pl->screened_fill && (rc = build_screen_ranks(pl.get(), all))) return rc;
+    if ((pl->screened_fill || pl->compose) && (rc = build_screen_ranks(pl.get(), all))) return rc;
     stage("tables");
     // ---- Schwarz factors (north star (1); SURVEY.md 7 "Parity vs. screening").  A contracted quartet (u|v) is left out
     // when Q_u*Q_v < tau, Q = an upper bound of sqrt((ij|ij)) over the pair's function pairs: every integral of the
@@ -722,7 +762,7 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
             // well (persistent grids starve each other): 23.2 / 24.2 / 24.8 ms for 1 / 2 / 4 regions
             // (profiles/r1_notes.md).  MYQC_FILL_REGIONS overrides it for experiments.
             int nreg = envr ? std::atoi(envr) : 1;
-            if (nreg < 1 || pl->screened_fill) nreg = 1;
+            if (nreg < 1 || pl->screened_fill || pl->compose) nreg = 1;
             if (nreg > 16) nreg = 16;
             sub.region_end.resize(nreg);
             for (int r = 0; r < nreg; ++r) {
@@ -754,19 +794,88 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
             }
         }
         stage("list upload");
+        // pair ids of this piece (compose mode): lists in the order lid = 2*type + kind
+        std::vector<int32_t> fpinfo;
+        if (pl->compose) {
+            std::memset(&sub.comp, 0, sizeof(sub.comp));
+            for (auto& b : sub.comp.launch_base) b = INT64_MIN;
+            sub.ng = 0;
+            for (int lid = 0; lid < 6; ++lid) {
+                sub.listbase[lid] = sub.ng;
+                const int id = (lid & 1) == 0 ? mine_id[lid >> 1] : later_id[lid >> 1];
+                if (id >= 0) sub.ng += pl->lists[id].n;
+            }
+            if (sub.ng >= (1 << 25)) return fail(MYQC_ERR_UNSUPPORTED, "too many shell pairs for the compose pass");
+            sub.h_rowrel.assign((size_t)sub.ng * 6, 0u);
+        }
         // launches.  Class (ta,tb), ta <= tb, uniform side = ta, lane side = tb.
         for (int ta = 0; ta < 3; ++ta)
             for (int tb = ta; tb < 3; ++tb) {
                 if (ta == tb) {
-                    if ((rc = add_launch(pl.get(), sub, mine_id[ta], mine_id[ta], true))) return rc;
-                    if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), sub, mine_id[ta], later_id[ta], false))) return rc;
+                    if ((rc = add_launch(pl.get(), sub, mine_id[ta], mine_id[ta], true, 0, 0))) return rc;
+                    if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), sub, mine_id[ta], later_id[ta], false, 0, 1))) return rc;
                 } else {
-                    if ((rc = add_launch(pl.get(), sub, mine_id[ta], mine_id[tb], false))) return rc;
-                    if (later_id[tb] >= 0 && (rc = add_launch(pl.get(), sub, mine_id[ta], later_id[tb], false))) return rc;
-                    if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), sub, later_id[ta], mine_id[tb], false))) return rc;
+                    if ((rc = add_launch(pl.get(), sub, mine_id[ta], mine_id[tb], false, 0, 0))) return rc;
+                    if (later_id[tb] >= 0 && (rc = add_launch(pl.get(), sub, mine_id[ta], later_id[tb], false, 0, 1))) return rc;
+                    if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), sub, later_id[ta], mine_id[tb], false, 1, 0))) return rc;
                 }
             }
-        pl->nlaunch += (int)sub.region_end.size();  // zero fills of this piece
+        if (pl->compose) {
+            // tables of the compose pass: function pair -> (pair id, slot), pair id -> (list index, type, list kind),
+            // Schwarz factors, stage rows; work units of kCompRows rows x kCompCols columns, row block by row block
+            ComposeArgs& c = sub.comp;
+            fpinfo.assign((size_t)pl->npair, -1);
+            std::vector<int2> pmeta((size_t)sub.ng, make_int2(0, 0));
+            std::vector<double> pq((size_t)sub.ng, 0.0);
+            for (int lid = 0; lid < 6; ++lid) {
+                const int t = lid >> 1;
+                const int id = (lid & 1) == 0 ? mine_id[t] : later_id[t];
+                if (id < 0) continue;
+                const PairList& h = pl->lists[id].host;
+                const int nf = pt_nf(t);
+                for (int k = 0; k < h.n; ++k) {
+                    const int g = sub.listbase[lid] + k;
+                    pmeta[g] = make_int2(k * nf, lid);
+                    if ((int)h.qmax.size() == h.n) pq[g] = h.qmax[k];
+                    for (int f = 0; f < nf; ++f) {
+                        const int32_t P = h.pidx[(size_t)k * nf + f];
+                        if (P >= 0) fpinfo[(size_t)P] = (g << 4) | f;
+                    }
+                }
+            }
+            int32_t *d_fp = nullptr, *d_urb = nullptr;
+            int2* d_pm = nullptr;
+            double* d_pq = nullptr;
+            uint32_t* d_rb = nullptr;
+            if ((rc = upload(pl.get(), fpinfo, &d_fp))) return rc;
+            if ((rc = upload(pl.get(), pmeta, &d_pm))) return rc;
+            if (pl->schwarz_tau > 0.0 && (rc = upload(pl.get(), pq, &d_pq))) return rc;
+            if ((rc = upload(pl.get(), sub.h_rowrel, &d_rb))) return rc;
+            const int64_t n = pl->norb;
+            c.row_lo = (int64_t)fn_lo * n - (int64_t)fn_lo * (fn_lo - 1) / 2;
+            c.row_hi = fn_hi >= n ? pl->npair : (int64_t)fn_hi * n - (int64_t)fn_hi * (fn_hi - 1) / 2;
+            const int64_t ncb_all = (pl->npair + kCompCols - 1) / kCompCols;
+            c.nrb = (int)((c.row_hi - c.row_lo + kCompRows - 1) / kCompRows);
+            std::vector<int32_t> urb((size_t)c.nrb + 1, 0);
+            for (int rb = 0; rb < c.nrb; ++rb) {
+                const int64_t r0 = c.row_lo + (int64_t)rb * kCompRows;
+                const int64_t ncb = ncb_all - r0 / kCompCols;
+                if ((int64_t)urb[rb] + ncb > INT32_MAX) return fail(MYQC_ERR_UNSUPPORTED, "too many compose units");
+                urb[rb + 1] = urb[rb] + (int32_t)ncb;
+            }
+            c.nunits = urb[c.nrb];
+            if ((rc = upload(pl.get(), urb, &d_urb))) return rc;
+            c.out_offset = sub.out_offset; c.npair = pl->npair;
+            c.rk = pl->d_rk; c.cut = pl->d_cut; c.fpinfo = d_fp; c.pmeta = d_pm; c.pq = d_pq; c.rowrel = d_rb;
+            c.tau = d_pq ? pl->schwarz_tau : 0.0;
+            c.urb = d_urb;
+            c.all_zero = std::getenv("MYQC_COMPOSE_ZERO") ? std::atoi(std::getenv("MYQC_COMPOSE_ZERO")) : 0;
+            if (pl->ncounters + 1 > kMaxCounters) return fail(MYQC_ERR_UNSUPPORTED, "too many launches in one plan");
+            c.counter = pl->d_counters + pl->ncounters;
+            pl->ncounters += 1;
+            sub.h_rowrel.clear(); sub.h_rowrel.shrink_to_fit();
+        }
+        pl->nlaunch += (int)sub.region_end.size();  // zero fills of this piece (compose mode: the compose launch)
         if (pl->screened_fill) {
             // pacing table: one entry per class-kernel task counter, weighted by the launch's estimated
             // duration (upper bound of its primitive quartets x measured time per quartet of its class)
@@ -801,6 +910,16 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
     }
     pl->h_rk.clear(); pl->h_rk.shrink_to_fit();
     pl->h_cut.clear(); pl->h_cut.shrink_to_fit();
+    if (pl->compose && pl->stage_elems > 0) {
+        // zeroed once: blocks of quartets that are never evaluated are never written, and the compose pass may read them
+        cudaError_t e = cudaMalloc((void**)&pl->d_stage, (size_t)pl->stage_elems * sizeof(double));
+        if (e != cudaSuccess)
+            return fail(MYQC_ERR_NOMEM, std::string("device allocation of the quartet staging array (") +
+                                            std::to_string(8e-9 * (double)pl->stage_elems) + " GB): " + cudaGetErrorString(e));
+        pl->dev_allocs.push_back(pl->d_stage);
+        CU(cudaMemset(pl->d_stage, 0, (size_t)pl->stage_elems * sizeof(double)));
+        if (trace) std::fprintf(stderr, "[myqc trace]   staging array %.3f GB for a slice of %.3f GB\n", 8e-9 * (double)pl->stage_elems, 8e-9 * (double)pl->out_elems);
+    }
     stage("task lists");
     // internal streams and events
     CU(cudaStreamCreateWithFlags(&pl->s_fill, cudaStreamNonBlocking));
@@ -860,7 +979,8 @@ int64_t myqc_eri_plan_out_elems(const myqc_eri_plan* plan) { return plan ? plan-
 // kernels restricted to the tasks of that region
 static int plan_launch_total(const myqc_eri_plan* plan) {
     int n = 0;
-    for (const Sub& sub : plan->subs) n += (int)sub.region_end.size() * (1 + (int)sub.launches.size());
+    for (const Sub& sub : plan->subs)
+        n += (int)sub.region_end.size() * (1 + (int)sub.launches.size());
     return n;
 }
 
@@ -869,7 +989,8 @@ static int launch_region(myqc_eri_plan* plan, Sub& sub, Launch& L, int r, int sl
     const int t0 = L.region_task[r], t1 = L.region_task[r + 1];
     if (t1 <= t0) return 0;
     ClassArgs a = L.args;
-    a.out = d_sub_out;
+    a.out = plan->compose ? nullptr : d_sub_out;
+    a.stage = plan->compose ? plan->d_stage : nullptr;
     a.tasks = L.args.tasks + t0;
     a.ntasks = t1 - t0;
     a.row_counter = L.args.row_counter + r * class_nlaunch(L.UT, L.TT);
@@ -890,6 +1011,13 @@ static int fill_region(myqc_eri_plan* plan, Sub& sub, int r, double* d_sub_out, 
                             plan->num_sms, st);
 }
 
+static int compose_sub(myqc_eri_plan* plan, Sub& sub, double* d_sub_out, cudaStream_t st) {
+    ComposeArgs c = sub.comp;
+    c.out = d_sub_out;
+    c.stage = plan->d_stage;
+    return launch_compose(c, plan->num_sms, st);
+}
+
 int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
     if (!plan || (!d_out && plan->out_elems > 0)) return fail(MYQC_ERR_BAD_ARG, "null plan or output");
     CU(cudaSetDevice(plan->device));
@@ -905,9 +1033,43 @@ int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
         cudaEventRecord(e, s);
         tl.emplace_back(name, e);
     };
-    if (plan->screened_fill) CU(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)plan->ncounters, st));
+    if (plan->screened_fill || plan->compose) CU(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)plan->ncounters, st));
     CU(cudaMemsetAsync(plan->d_pq, 0, sizeof(unsigned long long) * (size_t)kMaxCounters, st));
     mark("start", st);
+    if (plan->compose) {
+        // class kernels of all pieces side by side on the internal streams (they only write the staging array),
+        // then one compose launch per piece on the caller's stream
+        CU(cudaEventRecord(plan->e_start, st));
+        for (auto& sc : plan->s_comp) CU(cudaStreamWaitEvent(sc, plan->e_start, 0));
+        int rr = 0;
+        for (Sub& sub : plan->subs)
+            for (Launch& L : sub.launches)
+                for (int slice = 0; slice < class_nlaunch(L.UT, L.TT); ++slice) {
+                    const int si = rr++ % myqc_eri_plan::kNumCompute;
+                    int e = launch_region(plan, sub, L, 0, slice, nullptr, plan->s_comp[si]);
+                    if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+                    mark("class{" + std::to_string(L.UT) + "," + std::to_string(L.TT) + "} on stream " + std::to_string(si), plan->s_comp[si]);
+                }
+        for (int i = 0; i < myqc_eri_plan::kNumCompute; ++i) {
+            CU(cudaEventRecord(plan->e_done[i], plan->s_comp[i]));
+            CU(cudaStreamWaitEvent(st, plan->e_done[i], 0));
+        }
+        for (Sub& sub : plan->subs) {
+            int e = compose_sub(plan, sub, d_out + (sub.out_offset - plan->out_offset), st);
+            if (e) return cuda_fail((cudaError_t)e, "compose launch");
+            mark("compose", st);
+        }
+        if (timeline) {
+            cudaDeviceSynchronize();
+            for (size_t k = 1; k < tl.size(); ++k) {
+                float t = 0;
+                cudaEventElapsedTime(&t, tl[0].second, tl[k].second);
+                std::fprintf(stderr, "[myqc timeline] %-28s done at %8.3f ms\n", tl[k].first.c_str(), t);
+            }
+            for (auto& x : tl) cudaEventDestroy(x.second);
+        }
+        return MYQC_OK;
+    }
     // fork: internal streams start after whatever is already queued on the caller's stream
     CU(cudaEventRecord(plan->e_start, st));
     CU(cudaStreamWaitEvent(plan->s_fill, plan->e_start, 0));
@@ -974,6 +1136,15 @@ int myqc_eri_plan_launch_info(const myqc_eri_plan* plan, int k, int* cls, int* t
         for (int r = 0; r < (int)sub.region_end.size(); ++r) {
             const int n = 1 + (int)sub.launches.size();
             if (k >= n) { k -= n; continue; }
+            if (plan->compose) {  // class launches first, the compose launch of the piece last (cls = -2)
+                if (k == n - 1) {
+                    if (cls) *cls = -2;
+                    if (tri) *tri = 0;
+                    if (rows) *rows = sub.out_elems;
+                    return MYQC_OK;
+                }
+                ++k;
+            }
             if (k == 0) {  // the zero fill of this region
                 if (cls) *cls = -1;
                 if (tri) *tri = 0;
@@ -999,12 +1170,24 @@ int myqc_eri_plan_execute_timed(myqc_eri_plan* plan, double* d_out, void* stream
     const int n = plan_launch_total(plan);
     std::vector<cudaEvent_t> ev(n + 1);
     for (auto& e : ev) CU(cudaEventCreate(&e));
-    if (plan->screened_fill) CU(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)plan->ncounters, st));
+    if (plan->screened_fill || plan->compose) CU(cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)plan->ncounters, st));
     CU(cudaMemsetAsync(plan->d_pq, 0, sizeof(unsigned long long) * (size_t)kMaxCounters, st));
     CU(cudaEventRecord(ev[0], st));
     int idx = 0;
     for (Sub& sub : plan->subs) {
         double* d_sub = d_out + (sub.out_offset - plan->out_offset);
+        if (plan->compose) {
+            int e = 0;
+            for (Launch& L : sub.launches) {
+                for (int slice = 0; slice < class_nlaunch(L.UT, L.TT) && !e; ++slice) e = launch_region(plan, sub, L, 0, slice, nullptr, st);
+                if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
+                CU(cudaEventRecord(ev[++idx], st));
+            }
+            e = compose_sub(plan, sub, d_sub, st);
+            if (e) return cuda_fail((cudaError_t)e, "compose launch");
+            CU(cudaEventRecord(ev[++idx], st));
+            continue;
+        }
         for (int r = 0; r < (int)sub.region_end.size(); ++r) {
             int e = fill_region(plan, sub, r, d_sub, st);
             if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");

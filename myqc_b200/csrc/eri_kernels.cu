@@ -33,6 +33,7 @@
 //     between lane-side primitives.
 #include <cuda_runtime.h>
 
+#include <climits>
 #include <cstdint>
 #include <cstdlib>
 #include <type_traits>
@@ -410,7 +411,27 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
                     });
                     if (!live) break;
                 }
-                // store the distinct canonical integrals of this shell quartet (the slice was zero
+                if (a.stage != nullptr) {
+                    // compose mode: the quartet's block [f_u][f_v] of the staging array, written whole with 128-bit
+                    // stores (every sector it touches is covered).  Quartets the screen or the Schwarz skip leave out
+                    // write nothing: their blocks keep the zeros of plan creation -- except the one-double blocks of
+                    // (S S|S S), whose sectors are shared by four quartets and are therefore always written.
+                    if (any || NOUT == 1) {
+                        double* dst = a.stage + (__ldg(a.stage_row + u) + (int64_t)v * (C::NFU_FULL * NFT) + ((USL >= 0) ? USL * 4 * NFT : 0));
+                        if constexpr (NOUT == 1) {
+                            dst[0] = out_r[0];
+                        } else {
+#pragma unroll
+                            for (int o = 0; o < NOUT; o += 2) {
+                                double2 w;
+                                if constexpr (OUT_SMEM) w = make_double2(s_out[o * NTHREADS + tid], s_out[(o + 1) * NTHREADS + tid]);
+                                else w = make_double2(out_r[o], out_r[o + 1]);
+                                reinterpret_cast<double2*>(dst)[o >> 1] = w;
+                            }
+                        }
+                    }
+                } else
+                // scatter mode: store the distinct canonical integrals of this shell quartet (the slice was zero
                 // filled: quartets the screen removes entirely keep the reference's exact zeros)
                 if (any) {
                     const bool same_pair = a.tri && (v == u);
@@ -651,6 +672,191 @@ __global__ void __launch_bounds__(kFillThreads) fill_screened_kernel(const FillA
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Compose pass.  The class kernels leave every evaluated shell quartet (u|v) as a dense block [f_u][f_v] in the
+// staging array (u = uniform side of its launch).  This kernel writes the packed slice once, row by row, with
+// 256-byte warp stores: element (P,P') is an exact zero unless the shell pairs U of P and V of P' pass the
+// reference's rule on their largest prefactors (fl(emax_U*emax_V) >= 1e-14, int2e.f90:257, as the integer compare
+// rk[P'] < cut[P]) and the Schwarz test Q_U*Q_V >= tau; otherwise it is read from the quartet's block: the uniform
+// side of the quartet is the pair of the lower type, or for equal types the pair that comes first in its list
+// ("mine" before "later"), exactly the rule the launches were built with.
+//
+// Work unit = kCompRows packed rows x kCompCols columns; a thread owns kCompColsPerThread columns (stride
+// kCompThreads, so a warp stores 256 contiguous bytes) and keeps their pair data in registers for all rows of the
+// unit; the rows' pair data sit in shared memory.  Units are enumerated row block by row block (urb[] = prefix
+// sums of the column blocks of each row block: only columns >= the block's first row exist) and pulled from a
+// global counter, so that concurrently running CTAs work on neighbouring rows and columns and the 32-byte sectors
+// of a quartet block that several rows share are fetched from DRAM once.
+// Gathers go through cp.async (LDGSTS) into a per-thread landing area in shared memory: the packed array is ~90 %
+// zeros, so the few loads a thread needs are spread over many rows; with register loads only a handful are in flight
+// per warp while the stores wait on them (measured: 12 ms, long-scoreboard bound), with cp.async every needed
+// element of kSub rows x 4 columns is in flight at once, two such groups deep, and costs no registers.  A thread only
+// ever reads the slots it filled itself, so cp.async.wait_group is the only synchronisation.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int kSub>
+__global__ void __launch_bounds__(kCompThreads) compose_kernel(const ComposeArgs a) {
+    static_assert(kSub * kCompColsPerThread <= 32, "one mask bit per landing slot");
+    extern __shared__ __align__(16) double s_land[];  // [2][kSub][kCompCols]
+    __shared__ int s_unit[2];
+    __shared__ int s_cut[kCompRows], s_g[kCompRows], s_iun[kCompRows], s_pk[kCompRows];
+    __shared__ double s_q[kCompRows];
+    __shared__ uint32_t s_rel[kCompRows][8];       // rowrel of the unit's row pairs, by lane list
+    __shared__ uint32_t s_crel[3][kCompCols];      // rowrel of the unit's column pairs against the own list of each type
+    __shared__ long long s_lb[36];
+    const int tid = threadIdx.x;
+    const int64_t np = a.npair;
+    const bool schwarz = a.tau > 0.0 && a.pq != nullptr;
+    if (tid < 36) s_lb[tid] = a.launch_base[tid];
+    if (tid == 0) s_unit[0] = atomicAdd(a.counter, 1);
+    __syncthreads();
+    int unit = s_unit[0];
+    for (int it = 0; unit < a.nunits; ++it) {
+        if (tid == 0) s_unit[(it + 1) & 1] = atomicAdd(a.counter, 1);  // the next unit is claimed while this one is written
+        int lo = 0, hi = a.nrb;  // row block of this unit: last rb with urb[rb] <= unit
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(a.urb + mid) <= unit) lo = mid; else hi = mid;
+        }
+        const int64_t r0 = a.row_lo + (int64_t)lo * kCompRows;
+        const int64_t c0 = ((r0 / kCompCols) + (unit - __ldg(a.urb + lo))) * kCompCols;
+        int64_t rend = r0 + kCompRows;
+        if (rend > a.row_hi) rend = a.row_hi;
+        const int nrow = (int)(rend - r0);
+        // rows of the unit -> shared memory.  pk = f | (2*type) << 4 | lid << 8
+        if (tid < kCompRows) {
+            int cut = 0, g = 0, iun = 0, pk = 0;
+            double q = 0.0;
+            const int info = tid < nrow ? __ldg(a.fpinfo + r0 + tid) : -1;
+            if (info >= 0) {
+                g = info >> 4;
+                cut = a.all_zero ? 0 : __ldg(a.cut + r0 + tid);
+                const int2 m = __ldg(a.pmeta + g);
+                iun = m.x;
+                pk = (info & 15) | ((m.y >> 1) << 5) | (m.y << 8);
+                if (schwarz) q = __ldg(a.pq + g);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) s_rel[tid][k] = __ldg(a.rowrel + (size_t)g * 6 + k);
+            }
+            s_cut[tid] = cut; s_g[tid] = g; s_iun[tid] = iun; s_pk[tid] = pk; s_q[tid] = q;
+        }
+        // columns of this thread -> registers (and their rowrel -> shared memory)
+        int c_rk[kCompColsPerThread], c_g[kCompColsPerThread], c_ivn[kCompColsPerThread], c_pk[kCompColsPerThread];
+        int c_imax[kCompColsPerThread];  // last row of the unit in which the column exists (column >= row)
+        double c_q[kCompColsPerThread];
+#pragma unroll
+        for (int j = 0; j < kCompColsPerThread; ++j) {
+            const int64_t c = c0 + j * kCompThreads + tid;
+            c_rk[j] = INT32_MAX; c_g[j] = 0; c_ivn[j] = 0; c_pk[j] = 0; c_q[j] = 0.0;
+            c_imax[j] = -1;
+            if (c < np) {
+                c_imax[j] = (c - r0 < nrow - 1) ? (int)(c - r0) : nrow - 1;
+                const int info = __ldg(a.fpinfo + c);
+                if (info >= 0) {
+                    const int g = info >> 4;
+                    const int2 m = __ldg(a.pmeta + g);
+                    c_rk[j] = __ldg(a.rk + c);
+                    c_g[j] = g;
+                    c_ivn[j] = m.x;
+                    c_pk[j] = (info & 15) | ((m.y >> 1) << 5) | (m.y << 8);
+                    if (schwarz) c_q[j] = __ldg(a.pq + g);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) s_crel[k][j * kCompThreads + tid] = __ldg(a.rowrel + (size_t)g * 6 + 2 * k);
+                }
+            }
+        }
+        __syncthreads();
+        // element (r,c) lives at out[off(r) - out_offset + (c - r)], off(r) = r*np - r(r-1)/2
+        double* o = a.out + (r0 * np - ((r0 * (r0 - 1)) >> 1) - a.out_offset - r0 + c0 + tid);
+
+        // issue the gathers of rows [i0, i0+kSub) into landing buffer sb; returns the mask of the slots in use
+        auto issue = [&](int sb, int i0) -> uint32_t {
+            uint32_t mask = 0;
+            double* land = s_land + (size_t)sb * kSub * kCompCols + tid;
+#pragma unroll
+            for (int ii = 0; ii < kSub; ++ii) {
+                const int i = i0 + ii;
+                if (i < nrow) {
+                    const int cut = s_cut[i];
+#pragma unroll
+                    for (int j = 0; j < kCompColsPerThread; ++j) {
+                        if (c_rk[j] < cut) {  // skipped by the whole warp when none of its 32 columns passes the reference's rule
+                            if (!(schwarz && s_q[i] * c_q[j] < a.tau)) {
+                                const int pu = s_pk[i], pv = c_pk[j];
+                                const int fu = pu & 15, tu2 = (pu >> 4) & 6, lidu = pu >> 8;
+                                const int fv = pv & 15, tv2 = (pv >> 4) & 6, lidv = pv >> 8;
+                                // the uniform side of the quartet is the pair with the smaller id (lower type; equal
+                                // types: own list before later list, then list order): the rule the launches were built with
+                                const bool u_uni = s_g[i] <= c_g[j];
+                                const uint32_t w = u_uni ? s_rel[i][lidv] + (uint32_t)(fu << tv2) + ((uint32_t)c_ivn[j] << tu2) + (uint32_t)fv
+                                                         : s_crel[tu2 >> 1][j * kCompThreads + tid] + (uint32_t)(fv << tu2) + ((uint32_t)s_iun[i] << tv2) + (uint32_t)fu;
+                                const long long lb = s_lb[u_uni ? lidu * 6 + lidv : lidv * 6 + lidu];
+                                if ((int)(lb >> 32) != INT32_MIN) {
+                                    cp_async8(land + (ii * kCompCols + j * kCompThreads), a.stage + (lb + (long long)w));
+                                    mask |= 1u << (ii * kCompColsPerThread + j);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            cp_async_commit();
+            return mask;
+        };
+        const int nsub = (nrow + kSub - 1) / kSub;
+        uint32_t m_cur = issue(0, 0);
+        for (int sidx = 0; sidx < nsub; ++sidx) {
+            uint32_t m_next = 0;
+            if (sidx + 1 < nsub) { m_next = issue((sidx + 1) & 1, (sidx + 1) * kSub); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
+            const double* land = s_land + (size_t)(sidx & 1) * kSub * kCompCols + tid;
+#pragma unroll
+            for (int ii = 0; ii < kSub; ++ii) {
+                const int i = sidx * kSub + ii;
+#pragma unroll
+                for (int j = 0; j < kCompColsPerThread; ++j) {
+                    const double val = ((m_cur >> (ii * kCompColsPerThread + j)) & 1u) ? land[ii * kCompCols + j * kCompThreads] : 0.0;
+                    if (i <= c_imax[j]) __stcs(o + j * kCompThreads, val);
+                }
+                o += np - (r0 + i) - 1;  // off(r+1) - (r+1) - (off(r) - r)
+            }
+            m_cur = m_next;
+        }
+        __syncthreads();
+        unit = s_unit[(it + 1) & 1];
+    }
+}
+
+int launch_compose(const ComposeArgs& a, int num_sms, void* stream) {
+    if (a.nunits <= 0) return 0;
+    static int ctas_per_sm = 0, sub = 0;
+    if (ctas_per_sm == 0) {
+        const char* e = getenv("MYQC_COMPOSE_CTAS");
+        ctas_per_sm = e ? atoi(e) : 6;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        e = getenv("MYQC_COMPOSE_SUB");
+        sub = e ? atoi(e) : 4;
+    }
+    int grid = num_sms * ctas_per_sm;
+    if (grid > a.nunits) grid = a.nunits;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (sub == 4) {
+        const size_t sm = 2ull * 4 * kCompCols * sizeof(double);
+        compose_kernel<4><<<grid, kCompThreads, sm, st>>>(a);
+    } else {
+        const size_t sm = 2ull * 8 * kCompCols * sizeof(double);
+        const int e0 = prepare_kernels();  // raises the dynamic shared-memory limit of compose_kernel<8> on this device
+        if (e0) return e0;
+        compose_kernel<8><<<grid, kCompThreads, sm, st>>>(a);
+    }
+    return (int)cudaGetLastError();
+}
+
 // dense XX(i,j,g,h) (column-major, i fastest) from the packed array: the fillsym pass of the
 // reference (int2e.f90:290-304,540-554) done as a gather so that the 8n^4-byte stream is written
 // once, coalesced.  [h0,h1) selects the slab XX(:,:,:,h0:h1-1) (one slab per device in the multi-GPU dense path).
@@ -794,6 +1000,8 @@ int prepare_kernels() {
     }
     cudaFuncAttributes fa;
     ce = cudaFuncGetAttributes(&fa, fill_screened_kernel);
+    if (ce != cudaSuccess) return (int)ce;
+    ce = cudaFuncSetAttribute(compose_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2ull * 8 * kCompCols * sizeof(double)));
     if (ce != cudaSuccess) return (int)ce;
     g_prepared[dev] = true;
     return 0;

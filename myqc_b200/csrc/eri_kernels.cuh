@@ -47,10 +47,48 @@ struct ClassArgs {
     double tau;
     unsigned long long* pq_counter;  // primitive quartets this launch evaluated (one atomic per task)
     // output
-    double* out;         // this shard's slice of the packed array
+    double* out;         // this shard's slice of the packed array (scatter mode; nullptr in compose mode)
     int64_t out_offset;  // packed index of out[0]
     int64_t npair;
+    // compose mode: every quartet (u, v) of the launch owns a block of nf(UT)*nf(TT) doubles, [f_u][f_v], at
+    // stage + stage_row[u] + v*nf(UT)*nf(TT); the lane that evaluates the quartet writes the whole block with 128-bit
+    // stores and compose_kernel gathers the packed array from the blocks.  stage == nullptr: scatter into `out`.
+    double* stage;
+    const int64_t* stage_row;  // [nU]
 };
+
+// Compose pass (compose_kernel): the packed slice is written ONCE, in order, by 256-byte warp stores: exact zeros
+// where the reference's rule (or the Schwarz skip) leaves a quartet out, else the value gathered from the quartet
+// blocks the class kernels staged.  Work unit = kCompRows packed rows x kCompCols columns.
+constexpr int kCompRows = 64;
+constexpr int kCompThreads = 128;
+constexpr int kCompColsPerThread = 4;
+constexpr int kCompCols = kCompThreads * kCompColsPerThread;
+struct ComposeArgs {
+    double* out;         // this slice of the packed array
+    int64_t out_offset;  // packed index of out[0]
+    int64_t npair;
+    int64_t row_lo, row_hi;  // packed rows of the slice
+    // reference rule as an integer compare (see build_screen_ranks): (P,P') is kept iff rk[P'] < cut[P]
+    const int32_t* rk;       // [npair]
+    const int32_t* cut;      // [npair]
+    // Shell pairs of the piece are numbered g = 0..ng-1 list by list, lists in the order lid = 2*type + kind
+    // (kind 0: the piece's own pairs, 1: pairs of later pieces), so that the uniform side of a quartet is simply
+    // the pair with the smaller g.
+    const int32_t* fpinfo;   // [npair] (g << 4) | function-pair slot f inside the shell pair; -1: no shell pair kept
+    const int2* pmeta;       // [ng] {list index * nf(type), lid}
+    const double* pq;        // [ng] Schwarz factors (nullptr when tau == 0)
+    // block(u,v) = stage + launch_base[lid_u][lid_v] + (rowrel[g_u][lid_v] + v*nf_u*nf_v + f_u*nf_v + f_v mod 2^32)
+    const uint32_t* rowrel;  // [ng][6]
+    int64_t launch_base[36]; // [lid_u*6 + lid_v]; INT64_MIN: no such launch
+    const double* stage;
+    double tau;
+    const int32_t* urb;      // [nrb+1] prefix sums of column blocks per row block
+    int nrb, nunits;
+    int* counter;            // unit counter (zeroed before the launch)
+    int all_zero;            // experiments (MYQC_COMPOSE_ZERO=1): write zeros only, the ceiling of the store pattern
+};
+int launch_compose(const ComposeArgs& a, int num_sms, void* stream);
 
 // Screened zero fill (see fill_screened_kernel): rows [row_lo,row_hi) of the packed upper triangle
 constexpr int kFillRows = 64;

@@ -141,6 +141,12 @@ int myqc_build_basis(const char* mybasis_path, int bkey, int nnuc, const int32_t
     const int Omax = std::atoi(rows[start + 1][2].c_str());
     const int almax = std::atoi(rows[start + 1][3].c_str());
     const int OpS = std::atoi(rows[start + 1][4].c_str());  // :101
+    // Callers size set/bas/setinfo for 4 orbitals per set (s or s,px,py,pz: all the ERI engine evaluates, and what the
+    // reference's mybasis holds); any other header value is refused here instead of overrunning their buffers.
+    if (OpS != 4) {
+        g_last_error = "mybasis: orbitals per set must be 4 (s / sp sets), found " + std::to_string(OpS);
+        return MYQC_ERR_UNSUPPORTED;
+    }
     const int mN = std::atoi(rows[start + 2][0].c_str()), mL = std::atoi(rows[start + 2][1].c_str());  // :102
     if (maxN) *maxN = mN;
     if (maxL) *maxL = mL;

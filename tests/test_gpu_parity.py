@@ -234,7 +234,8 @@ def test_h2o64_rows(tmp_path, oracle_inputs):
         assert abs(a - bshift) < 1e-11
 
 
-@pytest.mark.parametrize("name,nsh", [("CO2", 2), ("h2o_4", 3), ("h2o_8", 4), ("h2o_16", 8)])
+# ("CO2", 8), ("h2o", 7): more shards than shells, so some shards own no packed row at all (out_elems == 0)
+@pytest.mark.parametrize("name,nsh", [("CO2", 2), ("h2o_4", 3), ("h2o_8", 4), ("h2o_16", 8), ("CO2", 8), ("h2o", 7)])
 def test_shards_reproduce_the_unsharded_array(name, nsh, tmp_path):
     """Multi-GPU path on one device: every shard computes its slice independently.  A quartet that
     straddles two ownership lists is evaluated with bra and ket roles possibly exchanged with
@@ -340,3 +341,25 @@ def test_sparse_host_transfer_is_bit_identical(nsh, shift, tmp_path, monkeypatch
         Q.eri_packed_shard(s, dst, shard=sh, nshards=nsh)
         assert np.array_equal(dst.view(np.int64), plain.view(np.int64))
         assert np.isnan(pinned.numpy()[shift + nloc])  # nothing written past the slice
+
+
+@pytest.mark.parametrize("name,nsh", [("CO2", 1), ("h2o_8", 1), ("c4h10", 1), ("h2o_8", 3), ("CO2", 8), ("h2o_16", 1)])
+def test_compose_mode_equals_scatter_mode(name, nsh, tmp_path, monkeypatch):
+    """MYQC_OUTPUT_MODE=compose (class kernels stage dense quartet blocks, compose_kernel writes every element of the
+    slice once) produces the array of the default scatter mode bit for bit: the same lanes evaluate the same quartets
+    in the same order, only the way the integrals reach the packed array differs."""
+    s = product_system(name, tmp_path)
+    off = Q.shard_layout(s, nsh)
+
+    def run():
+        Q.release_cache()
+        out = np.full(int(off[-1]), np.nan)
+        for k in range(nsh):
+            Q.eri_packed_shard(s, out[off[k]:off[k + 1]], device=0, shard=k, nshards=nsh)
+        return out
+    ref = run()
+    monkeypatch.setenv("MYQC_OUTPUT_MODE", "compose")
+    got = run()
+    Q.release_cache()
+    assert not np.isnan(got).any()
+    assert np.array_equal(got, ref)
