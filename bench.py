@@ -371,12 +371,12 @@ def run_ours(args):
     else:
         achieved, peak, unit = (model_flops / world) / (ms_local * 1e-3) / 1e12, fp64_peak, "TFLOP/s"
     traffic = None
-    tfile = os.path.join(ROOT, "profiles", "r2_h2o64_dram_traffic_bytes.json")
+    tfile = os.path.join(ROOT, "profiles", "r2f_h2o64_dram_traffic_bytes.json")
     if args.workload == "h2o_64" and world == 1 and os.path.exists(tfile):
         traffic = float(sum(json.load(open(tfile)).values()))
     roofline = {"kernel": "step (zero fill + all class launches of one execute)", "bound": bound, "achieved": achieved, "peak": peak,
                 "unit": unit, "frac": achieved / peak if peak else None, "traffic": traffic,
-                "traffic_source": "sum over the step's launches of dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r2_h2o64_ncu_full.json)",
+                "traffic_source": "sum over the step's launches of dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r2f_h2o64_ncu_full.json)",
                 "peak_source": peak_src if bound == "hbm" else "measured DFMA microbenchmark in this run (myqc_fp64_peak)",
                 "algorithmic_bytes": bytes_alg, "model_flops": model_flops / world,
                 "hbm_frac": bytes_alg / 1e9 / (ms_local * 1e-3) / hbm_peak,

@@ -1,5 +1,5 @@
 """Turn an .ncu-rep (ncu --set full) and a launch-list CSV into the committed summaries under profiles/.
-usage: ncu_profile_summary.py <report.ncu-rep> <launches.csv> <out_prefix>"""
+usage: ncu_profile_summary.py <report.ncu-rep | raw.csv> <launches.csv> <out_prefix>"""
 import collections
 import csv
 import json
@@ -7,7 +7,8 @@ import subprocess
 import sys
 
 rep, launches, out = sys.argv[1:4]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# a raw-page CSV exported on the GPU box (ncu -i x.ncu-rep --page raw --csv) is accepted in place of the report
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 WANT = [
