@@ -72,6 +72,9 @@ struct DevList {  // device copy of a PairList
 
 struct Launch {
     int UT, TT;
+    // host copies of the tasks of each part until finalize_launches() merges and uploads them:
+    // {task, weight of the task's row} in the part's own order (rows heaviest first, tasks of a row adjacent)
+    std::vector<std::pair<int4, double>> part_tasks[kMaxParts];
     ClassArgs args;                // args.tasks/ntasks describe the whole need-sorted task array
     std::vector<int> region_task;  // [nregion+1] task ranges: region r = tasks whose writes end inside fill region r
     double weight = 0.0;           // sum over tasks of (primitives of the row) x (primitives of the lane-side range)
@@ -189,11 +192,25 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri, int
     const DevList& U = pl->lists[ui];
     const DevList& T = pl->lists[ti];
     if (U.n == 0 || T.n == 0) return MYQC_OK;
-    Launch L;
-    L.UT = U.type; L.TT = T.type;
+    const int nregion = (int)sub.region_end.size();
+    // Parts of one class are merged into one launch (one tail per class and shard instead of up to three) unless the
+    // fill-region experiments (MYQC_FILL_REGIONS > 1) need a task range per region and launch.
+    Launch* Lp = nullptr;
+    if (nregion == 1)
+        for (Launch& x : sub.launches)
+            if (x.UT == U.type && x.TT == T.type && x.args.nparts < kMaxParts) Lp = &x;
+    Launch Lnew;
+    if (!Lp) {
+        Lnew.UT = U.type; Lnew.TT = T.type;
+        std::memset(&Lnew.args, 0, sizeof(Lnew.args));
+        Lp = &Lnew;
+    }
+    Launch& L = *Lp;
     ClassArgs& a = L.args;
-    std::memset(&a, 0, sizeof(a));
-    a.u_aos = U.aos; a.u_nprim = U.nprim; a.u_pidx = U.pidx; a.nU = U.n;
+    const int ip = a.nparts;  // index of this part
+    PartArgs pa;
+    std::memset(&pa, 0, sizeof(pa));
+    pa.u_aos = U.aos; pa.u_nprim = U.nprim; pa.u_pidx = U.pidx;
     const std::vector<int32_t> ntv = row_prefix(U.host, T.host, pl->schwarz_tau);
     // segments of the lane-side list: at most kTaskPairs pairs, cut at group boundaries once a
     // segment holds >= 64 pairs, so that a task holds pairs of (mostly) one kind
@@ -229,7 +246,6 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri, int
     struct TaskN { int4 t; int64_t need; int region; double weight; };
     std::vector<double> tprim_prefix(T.n + 1, 0.0);  // prefix sums of lane-side primitive counts
     for (int k = 0; k < T.n; ++k) tprim_prefix[k + 1] = tprim_prefix[k] + T.host.nprim[k];
-    const int nregion = (int)sub.region_end.size();
     // MYQC_TASK_ORDER=0: plain heaviest-task-first order (23.5 ms on (H2O)_64 against 22.5 ms, profiles/r1_notes.md)
     static const int task_order = std::getenv("MYQC_TASK_ORDER") ? std::atoi(std::getenv("MYQC_TASK_ORDER")) : 1;
     auto emit_row = [&](int u, std::vector<TaskN>& dst) {
@@ -239,13 +255,15 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri, int
         for (; si + 1 < seg.size() && seg[si] < hi; ++si) {
             const int b = std::max(seg[si], lo), e = std::min(seg[si + 1], hi);
             if (b < e)
-                dst.push_back({make_int4(u, b, e, 0), need_u[u], 0,
+                dst.push_back({make_int4(u, b, e, ip), need_u[u], 0,
                                (double)U.host.nprim[u] * (tprim_prefix[e] - tprim_prefix[b])});
         }
     };
     std::vector<TaskN> tn;
     std::vector<int4> tasks;
-    L.region_task.assign(nregion + 1, 0);
+    std::vector<double> task_roww;  // weight of the row each task belongs to (merge key)
+    double part_weight = 0.0;
+    std::vector<int> region_task(nregion + 1, 0);
     if (task_order == 1 && nregion == 1) {
         // Rows heaviest first, the tasks of one row adjacent (in lane-side order): everything a launch
         // stores into the packed rows of one uniform-side pair is stored within a short time, so
@@ -263,9 +281,9 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri, int
         for (int u : order) {
             tn.clear();
             emit_row(u, tn);
-            for (const TaskN& t : tn) { tasks.push_back(t.t); L.weight += t.weight; }
+            for (const TaskN& t : tn) { tasks.push_back(t.t); task_roww.push_back(roww[u]); part_weight += t.weight; }
         }
-        L.region_task[1] = (int)tasks.size();
+        region_task[1] = (int)tasks.size();
     } else {
         for (int u = 0; u < U.n; ++u) emit_row(u, tn);
         // region of a task = first fill region that covers everything the task can write; inside a
@@ -293,35 +311,32 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri, int
             });
         }
         tasks.resize(tn.size());
-        for (size_t k = 0; k < tn.size(); ++k) { tasks[k] = tn[k].t; L.weight += tn[k].weight; }
-        L.region_task.assign(nregion + 1, (int)tn.size());
-        L.region_task[0] = 0;
+        task_roww.resize(tn.size());
+        for (size_t k = 0; k < tn.size(); ++k) { tasks[k] = tn[k].t; task_roww[k] = tn[k].weight; part_weight += tn[k].weight; }
+        region_task.assign(nregion + 1, (int)tn.size());
+        region_task[0] = 0;
         for (size_t k = 0, r = 0; r < (size_t)nregion; ++r) {
             while (k < tn.size() && tn[k].region <= (int)r) ++k;
-            L.region_task[r + 1] = (int)k;
+            region_task[r + 1] = (int)k;
         }
     }
     if (tasks.empty()) return MYQC_OK;
-    int4* d_tasks = nullptr;
-    int rc = upload(pl, tasks, &d_tasks);
-    if (rc) return rc;
-    a.tasks = d_tasks;
-    a.ntasks = (int)tasks.size();
-    a.t_soa = T.soa; a.t_aos = T.aos; a.t_nprim = T.nprim; a.t_pidx = T.pidx;
-    a.t_npad = T.npad; a.nT = T.n; a.tri = tri ? 1 : 0;
-    a.u_q = U.q; a.t_q = T.q;
-    a.tau = (U.q && T.q) ? pl->schwarz_tau : 0.0;
-    a.pq_counter = pl->d_pq + pl->ncounters;  // one per launch (slices of a launch share it)
-    a.ftab_q = pl->d_ftab + (size_t)(U.type + T.type) * 121 * 8;
-    a.exptab = reinterpret_cast<const double2*>(pl->d_exptab);
-    const int ncnt = class_nlaunch(L.UT, L.TT) * nregion;  // one task counter per launch and region
-    if (pl->ncounters + ncnt > kMaxCounters) return fail(MYQC_ERR_UNSUPPORTED, "too many launches in one plan");
-    a.row_counter = pl->d_counters + pl->ncounters;
-    pl->ncounters += ncnt;
-    sub.ncounters += ncnt;
-    a.out = nullptr;
-    a.out_offset = sub.out_offset;
-    a.npair = pl->npair;
+    int rc = MYQC_OK;
+    pa.t_soa = T.soa; pa.t_aos = T.aos; pa.t_nprim = T.nprim; pa.t_pidx = T.pidx;
+    pa.t_npad = T.npad; pa.tri = tri ? 1 : 0;
+    pa.u_q = U.q; pa.t_q = T.q;
+    if (ip == 0) {
+        a.tau = (U.q && T.q) ? pl->schwarz_tau : 0.0;
+        a.ftab_q = pl->d_ftab + (size_t)(U.type + T.type) * 121 * 8;
+        a.exptab = reinterpret_cast<const double2*>(pl->d_exptab);
+        a.out = nullptr;
+        a.out_offset = sub.out_offset;
+        a.npair = pl->npair;
+        L.region_task = region_task;
+    }
+    L.part_tasks[ip].resize(tasks.size());
+    for (size_t k = 0; k < tasks.size(); ++k) L.part_tasks[ip][k] = {tasks[k], task_roww[k]};
+    L.weight += part_weight;
     if (pl->compose) {
         // quartet blocks of this launch in the staging array: row u holds the blocks of v in [lo_u, ntv[u]) one after
         // the other; stage_row[u] is the position its v = 0 block would have, so block(u,v) = stage_row[u] + v*blk
@@ -342,10 +357,53 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri, int
         pl->stage_elems = pos;
         int64_t* d_srow = nullptr;
         if ((rc = upload(pl, srow, &d_srow))) return rc;
-        a.stage_row = d_srow;
+        pa.stage_row = d_srow;
     }
-    sub.launches.push_back(L);
-    pl->nlaunch += class_nlaunch(L.UT, L.TT) * nregion;
+    a.part[ip] = pa;
+    a.nparts = ip + 1;
+    if (Lp == &Lnew) sub.launches.push_back(Lnew);
+    return MYQC_OK;
+}
+
+// After all parts of a piece are known: merge the task lists of every launch (rows heaviest first across the parts,
+// the tasks of a row still adjacent), upload them, and give the launch its task and work counters.
+static int finalize_launches(myqc_eri_plan* pl, Sub& sub) {
+    const int nregion = (int)sub.region_end.size();
+    for (Launch& L : sub.launches) {
+        ClassArgs& a = L.args;
+        std::vector<int4> tasks;
+        if (a.nparts == 1) {
+            tasks.reserve(L.part_tasks[0].size());
+            for (const auto& t : L.part_tasks[0]) tasks.push_back(t.first);
+        } else {
+            size_t pos[kMaxParts] = {0, 0, 0}, total = 0;
+            for (int k = 0; k < a.nparts; ++k) total += L.part_tasks[k].size();
+            tasks.reserve(total);
+            while (tasks.size() < total) {
+                int best = -1;
+                for (int k = 0; k < a.nparts; ++k)
+                    if (pos[k] < L.part_tasks[k].size() && (best < 0 || L.part_tasks[k][pos[k]].second > L.part_tasks[best][pos[best]].second)) best = k;
+                // the whole row (its tasks are adjacent and carry the same row weight)
+                const int u = L.part_tasks[best][pos[best]].first.x;
+                while (pos[best] < L.part_tasks[best].size() && L.part_tasks[best][pos[best]].first.x == u) tasks.push_back(L.part_tasks[best][pos[best]++].first);
+            }
+            L.region_task.assign(2, 0);
+            L.region_task[1] = (int)tasks.size();
+        }
+        for (auto& v : L.part_tasks) { v.clear(); v.shrink_to_fit(); }
+        int4* d_tasks = nullptr;
+        int rc = upload(pl, tasks, &d_tasks);
+        if (rc) return rc;
+        a.tasks = d_tasks;
+        a.ntasks = (int)tasks.size();
+        const int ncnt = class_nlaunch(L.UT, L.TT) * nregion;  // one task counter per launch and region
+        if (pl->ncounters + ncnt > kMaxCounters) return fail(MYQC_ERR_UNSUPPORTED, "too many launches in one plan");
+        a.pq_counter = pl->d_pq + pl->ncounters;  // one per launch (slices of a launch share it)
+        a.row_counter = pl->d_counters + pl->ncounters;
+        pl->ncounters += ncnt;
+        sub.ncounters += ncnt;
+        pl->nlaunch += class_nlaunch(L.UT, L.TT) * nregion;
+    }
     return MYQC_OK;
 }
 
@@ -513,9 +571,10 @@ static int build_cut_table(const std::vector<Shell>& shells, const PairList all[
             }
             mean_prim /= B.n;
             for (int c = nc - 1; c >= 0; --c) ge[c] = ge[c + 1] + hist[c];
-            // seconds per primitive quartet: model flops / (measured class efficiency x DFMA peak);
-            // efficiencies from profiles/r1_notes.md ((H2O)_64, one B200)
-            static const double kEff[6] = {0.34, 0.31, 0.23, 0.23, 0.20, 0.12};
+            // seconds per primitive quartet: model flops / (class efficiency x DFMA peak).  The efficiencies are machine
+            // constants of these kernels on a B200 (fraction of the DFMA peak in model flops when a launch fills the
+            // machine: profiles/r2f_bench.json); only their ratios to each other and to the fill rate below enter the cuts.
+            static const double kEff[6] = {0.46, 0.47, 0.32, 0.36, 0.30, 0.27};
             const int cid = class_id(ta, tb);
             const double wq = kW[cid] / (kEff[cid] * 34.2e12) * mean_prim / B.n;
             for (int u = 0; u < A.n; ++u) {
@@ -820,6 +879,7 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
                     if (later_id[ta] >= 0 && (rc = add_launch(pl.get(), sub, later_id[ta], mine_id[tb], false, 1, 0))) return rc;
                 }
             }
+        if ((rc = finalize_launches(pl.get(), sub))) return rc;
         if (pl->compose) {
             // tables of the compose pass: function pair -> (pair id, slot), pair id -> (list index, type, list kind),
             // Schwarz factors, stage rows; work units of kCompRows rows x kCompCols columns, row block by row block
@@ -1153,7 +1213,7 @@ int myqc_eri_plan_launch_info(const myqc_eri_plan* plan, int k, int* cls, int* t
             }
             const Launch& L = sub.launches[k - 1];
             if (cls) *cls = class_id(L.UT, L.TT);
-            if (tri) *tri = L.args.tri;
+            if (tri) *tri = L.args.part[0].tri;
             if (rows) *rows = L.region_task[r + 1] - L.region_task[r];
             return MYQC_OK;
         }

@@ -137,8 +137,10 @@ struct Cfg {
 
 }  // namespace
 
-template <int UT, int TT, int USL>
-__global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::MINB) eri_class_kernel(const ClassArgs a) {
+// MULTI: the launch has several parts (a shard's own x own, own x later, later x own lists) and task.w selects one;
+// with MULTI = false every reference to the part is a kernel-parameter operand at a fixed offset, as before the merge.
+template <int UT, int TT, int USL, bool MULTI>
+__global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::MINB) eri_class_kernel(const __grid_constant__ ClassArgs a) {
     using C = Cfg<UT, TT, USL>;
     constexpr int LT = C::LT, Q = C::Q, NR = C::NR, NHT = C::NHT, NFU = C::NFU, NFT = C::NFT;
     constexpr int NTU = C::NTU, NTT = C::NTT, FU = C::FU, FT = C::FT, NOUT = C::NOUT;
@@ -177,13 +179,14 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
         if (t < a.ntasks) {
             task = a.tasks[t];
             mbar_expect_tx(&s_bar[0], C::U_BYTES);
-            tma_bulk_g2s(s_ubuf, a.u_aos + (size_t)task.x * 9 * FU, C::U_BYTES, &s_bar[0]);
+            tma_bulk_g2s(s_ubuf, a.part[MULTI ? task.w : 0].u_aos + (size_t)task.x * 9 * FU, C::U_BYTES, &s_bar[0]);
         }
     }
     t = __shfl_sync(0xffffffffu, t, 0);
     task.x = __shfl_sync(0xffffffffu, task.x, 0);
     task.y = __shfl_sync(0xffffffffu, task.y, 0);
     task.z = __shfl_sync(0xffffffffu, task.z, 0);
+    if (MULTI) task.w = __shfl_sync(0xffffffffu, task.w, 0);
     int buf = 0;
     uint32_t parity0 = 0, parity1 = 0;
     while (t < a.ntasks) {
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
             if (tn < a.ntasks) {
                 taskn = a.tasks[tn];
                 mbar_expect_tx(&s_bar[buf ^ 1], C::U_BYTES);
-                tma_bulk_g2s(s_ubuf + (size_t)(buf ^ 1) * 9 * FU, a.u_aos + (size_t)taskn.x * 9 * FU, C::U_BYTES,
+                tma_bulk_g2s(s_ubuf + (size_t)(buf ^ 1) * 9 * FU, a.part[MULTI ? taskn.w : 0].u_aos + (size_t)taskn.x * 9 * FU, C::U_BYTES,
                              &s_bar[buf ^ 1]);
             }
         }
@@ -202,13 +205,15 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
         taskn.x = __shfl_sync(0xffffffffu, taskn.x, 0);
         taskn.y = __shfl_sync(0xffffffffu, taskn.y, 0);
         taskn.z = __shfl_sync(0xffffffffu, taskn.z, 0);
+        if (MULTI) taskn.w = __shfl_sync(0xffffffffu, taskn.w, 0);
+        const PartArgs& S = a.part[MULTI ? task.w : 0];
         const int u = task.x;
         const int v0 = task.y;
         const int ntv = task.z;
-        const int npu = a.u_nprim[u];
+        const int npu = S.u_nprim[u];
         int P1[NFU];
 #pragma unroll
-        for (int f = 0; f < NFU; ++f) P1[f] = a.u_pidx[(size_t)u * C::NFU_FULL + ((USL >= 0) ? (4 * USL + f) : f)];
+        for (int f = 0; f < NFU; ++f) P1[f] = S.u_pidx[(size_t)u * C::NFU_FULL + ((USL >= 0) ? (4 * USL + f) : f)];
         if (buf == 0) { mbar_wait(&s_bar[0], parity0); parity0 ^= 1; }
         else          { mbar_wait(&s_bar[1], parity1); parity1 ^= 1; }
         const double* s_u = s_ubuf + (size_t)buf * 9 * FU;
@@ -230,14 +235,14 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
                 if (v < ntv) {
                     double dx, dy, dz;
                     if constexpr (C::LANE_AOS) {
-                        const double* r0 = a.t_aos + (size_t)v * 9 * FT;
+                        const double* r0 = S.t_aos + (size_t)v * 9 * FT;
                         dx = Px - __ldg(r0 + 1);
                         dy = Py - __ldg(r0 + 2);
                         dz = Pz - __ldg(r0 + 3);
                     } else {
-                        dx = Px - a.t_soa[(size_t)a.t_npad + v];
-                        dy = Py - a.t_soa[2 * (size_t)a.t_npad + v];
-                        dz = Pz - a.t_soa[3 * (size_t)a.t_npad + v];
+                        dx = Px - S.t_soa[(size_t)S.t_npad + v];
+                        dy = Py - S.t_soa[2 * (size_t)S.t_npad + v];
+                        dz = Pz - S.t_soa[3 * (size_t)S.t_npad + v];
                     }
                     key[i] = fma(dx, dx, fma(dy, dy, dz * dz));
                     kmin = fmin(kmin, key[i]);
@@ -283,8 +288,8 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
         // sink(f, f', value).  Returns false when the primitive is below the screen against the whole row.
         bool any = false;
         unsigned npq = 0;  // primitive quartets this lane evaluated in this task
-        const double qu = (a.tau > 0.0) ? __ldg(a.u_q + u) : 0.0;
-        const size_t ld = C::LANE_AOS ? (size_t)1 : (size_t)a.t_npad;
+        const double qu = (a.tau > 0.0) ? __ldg(S.u_q + u) : 0.0;
+        const size_t ld = C::LANE_AOS ? (size_t)1 : (size_t)S.t_npad;
         auto contract_prim = [&](const double* tp, bool has_next, auto&& sink) -> bool {
             double et, q, Qx, Qy, Qz, cfar;
             if constexpr (C::LANE_AOS) {
@@ -394,14 +399,14 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
                 any = false;
                 // Schwarz skip: every integral of the quartet is below tau in magnitude (|(ij|kl)| <= sqrt((ij|ij)(kl|kl)));
                 // the slice was zero filled, so the quartet is simply left out
-                const bool skip = (a.tau > 0.0) && (qu * __ldg(a.t_q + v) < a.tau);
-                const int npt = skip ? 0 : a.t_nprim[v];
+                const bool skip = (a.tau > 0.0) && (qu * __ldg(S.t_q + v) < a.tau);
+                const int npt = skip ? 0 : S.t_nprim[v];
                 // Lane-side records.  Small classes read the structure-of-arrays copy (a task's pairs are
                 // a contiguous range, so the 8 chunks of a task share its lines in L1).  The classes with
                 // many Hermite coefficients read the lane's own contiguous [9][FT] block instead: one base
                 // pointer and compile-time offsets instead of a 64-bit multiply-add per field, and the next
                 // primitive's lines are prefetched into L1 while this one is contracted.
-                const double* trec = C::LANE_AOS ? a.t_aos + (size_t)v * 9 * FT : a.t_soa + v;
+                const double* trec = C::LANE_AOS ? S.t_aos + (size_t)v * 9 * FT : S.t_soa + v;
                 for (int kt = 0; kt < npt; ++kt) {
                     const double* tp = C::LANE_AOS ? trec + kt * FT : trec + (size_t)kt * FT * ld;
                     const bool live = contract_prim(tp, kt + 1 < npt, [&](auto fc, auto fpc, double val) {
@@ -417,7 +422,7 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
                     // write nothing: their blocks keep the zeros of plan creation -- except the one-double blocks of
                     // (S S|S S), whose sectors are shared by four quartets and are therefore always written.
                     if (any || NOUT == 1) {
-                        double* dst = a.stage + (__ldg(a.stage_row + u) + (int64_t)v * (C::NFU_FULL * NFT) + ((USL >= 0) ? USL * 4 * NFT : 0));
+                        double* dst = a.stage + (__ldg(S.stage_row + u) + (int64_t)v * (C::NFU_FULL * NFT) + ((USL >= 0) ? USL * 4 * NFT : 0));
                         if constexpr (NOUT == 1) {
                             dst[0] = out_r[0];
                         } else {
@@ -434,11 +439,11 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
                 // scatter mode: store the distinct canonical integrals of this shell quartet (the slice was zero
                 // filled: quartets the screen removes entirely keep the reference's exact zeros)
                 if (any) {
-                    const bool same_pair = a.tri && (v == u);
+                    const bool same_pair = S.tri && (v == u);
                     const int64_t np = a.npair;
                     int P2[NFT];
 #pragma unroll
-                    for (int fp = 0; fp < NFT; ++fp) P2[fp] = a.t_pidx[(size_t)v * NFT + fp];
+                    for (int fp = 0; fp < NFT; ++fp) P2[fp] = S.t_pidx[(size_t)v * NFT + fp];
 #pragma unroll
                     for (int f = 0; f < NFU; ++f) {
                         if (P1[f] < 0) continue;
@@ -949,10 +954,10 @@ static bool common_carveout() {
 // Kernel attributes are set (and the kernels loaded: CUDA loads modules lazily, and a first-time load
 // cannot complete while the paced fill kernel is waiting on the device for that very kernel) once
 // per device, before the first launch of a plan.
-template <int UT, int TT, int USL>
+template <int UT, int TT, int USL, bool MULTI>
 static int prepare_one(int* occ_out) {
     using C = Cfg<UT, TT, USL>;
-    auto kern = eri_class_kernel<UT, TT, USL>;
+    auto kern = eri_class_kernel<UT, TT, USL, MULTI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     if (e != cudaSuccess) return (int)e;
     // Every kernel of a plan asks for the same (maximum) shared-memory carve-out: an SM cannot hold
@@ -973,7 +978,7 @@ static int prepare_one(int* occ_out) {
 }
 
 constexpr int kMaxDevices = 64;
-static int g_occ[kMaxDevices][10];
+static int g_occ[kMaxDevices][20];  // [slot] one-part kernels, [10 + slot] multi-part kernels
 static bool g_prepared[kMaxDevices];
 
 int prepare_kernels() {
@@ -983,15 +988,24 @@ int prepare_kernels() {
     if (dev < 0 || dev >= kMaxDevices) return (int)cudaErrorInvalidDevice;
     if (g_prepared[dev]) return 0;
     int e = 0;
-    if (!e) e = prepare_one<0, 0, -1>(&g_occ[dev][0]);
-    if (!e) e = prepare_one<0, 1, -1>(&g_occ[dev][1]);
-    if (!e) e = prepare_one<0, 2, -1>(&g_occ[dev][2]);
-    if (!e) e = prepare_one<1, 1, -1>(&g_occ[dev][3]);
-    if (!e) e = prepare_one<1, 2, -1>(&g_occ[dev][4]);
-    if (!e) e = prepare_one<2, 2, 0>(&g_occ[dev][5]);
-    if (!e) e = prepare_one<2, 2, 1>(&g_occ[dev][6]);
-    if (!e) e = prepare_one<2, 2, 2>(&g_occ[dev][7]);
-    if (!e) e = prepare_one<2, 2, 3>(&g_occ[dev][8]);
+    if (!e) e = prepare_one<0, 0, -1, false>(&g_occ[dev][0]);
+    if (!e) e = prepare_one<0, 0, -1, true>(&g_occ[dev][10 + 0]);
+    if (!e) e = prepare_one<0, 1, -1, false>(&g_occ[dev][1]);
+    if (!e) e = prepare_one<0, 1, -1, true>(&g_occ[dev][10 + 1]);
+    if (!e) e = prepare_one<0, 2, -1, false>(&g_occ[dev][2]);
+    if (!e) e = prepare_one<0, 2, -1, true>(&g_occ[dev][10 + 2]);
+    if (!e) e = prepare_one<1, 1, -1, false>(&g_occ[dev][3]);
+    if (!e) e = prepare_one<1, 1, -1, true>(&g_occ[dev][10 + 3]);
+    if (!e) e = prepare_one<1, 2, -1, false>(&g_occ[dev][4]);
+    if (!e) e = prepare_one<1, 2, -1, true>(&g_occ[dev][10 + 4]);
+    if (!e) e = prepare_one<2, 2, 0, false>(&g_occ[dev][5]);
+    if (!e) e = prepare_one<2, 2, 0, true>(&g_occ[dev][10 + 5]);
+    if (!e) e = prepare_one<2, 2, 1, false>(&g_occ[dev][6]);
+    if (!e) e = prepare_one<2, 2, 1, true>(&g_occ[dev][10 + 6]);
+    if (!e) e = prepare_one<2, 2, 2, false>(&g_occ[dev][7]);
+    if (!e) e = prepare_one<2, 2, 2, true>(&g_occ[dev][10 + 7]);
+    if (!e) e = prepare_one<2, 2, 3, false>(&g_occ[dev][8]);
+    if (!e) e = prepare_one<2, 2, 3, true>(&g_occ[dev][10 + 8]);
     if (e) return e;
     if (common_carveout()) {
         ce = cudaFuncSetAttribute(fill_screened_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -1007,21 +1021,27 @@ int prepare_kernels() {
     return 0;
 }
 
-template <int UT, int TT, int USL>
-static int launch_one(const ClassArgs& a, int num_sms, cudaStream_t st, int slot) {
-    if (a.nU <= 0 || a.nT <= 0 || a.ntasks <= 0) return 0;
+template <int UT, int TT, int USL, bool MULTI>
+static int launch_impl(const ClassArgs& a, int num_sms, cudaStream_t st, int slot) {
     using C = Cfg<UT, TT, USL>;
-    auto kern = eri_class_kernel<UT, TT, USL>;
+    auto kern = eri_class_kernel<UT, TT, USL, MULTI>;
     int dev = 0;
     cudaGetDevice(&dev);
     int e0 = prepare_kernels();
     if (e0) return e0;
-    const int occ = g_occ[dev][slot];
+    const int occ = g_occ[dev][slot + (MULTI ? 10 : 0)];
     int grid = num_sms * occ;
     const int need = (a.ntasks + C::NWARPS - 1) / C::NWARPS;
     if (grid > need) grid = need;
     kern<<<grid, C::NTHREADS, C::SMEM, st>>>(a);
     return (int)cudaGetLastError();
+}
+
+template <int UT, int TT, int USL>
+static int launch_one(const ClassArgs& a, int num_sms, cudaStream_t st, int slot) {
+    if (a.ntasks <= 0 || a.nparts <= 0) return 0;
+    if (a.nparts > 1) return launch_impl<UT, TT, USL, true>(a, num_sms, st, slot);
+    return launch_impl<UT, TT, USL, false>(a, num_sms, st, slot);
 }
 
 int class_nlaunch(int UT, int TT) { return (UT == 2 && TT == 2) ? 4 : 1; }

@@ -17,24 +17,37 @@ constexpr int class_task_pairs(int UT, int TT) {
 // One launch = all quartets (u, v) with u in a "uniform-side" pair list (records staged to
 // shared memory by TMA bulk copy, one row of the quartet space per CTA iteration) and v in a
 // "lane-side" pair list (structure-of-arrays, one pair per lane).
-struct ClassArgs {
+// The pair lists one part of a launch works on.  An unsharded plan has one part per class; a shard has up to three
+// (own x own, own x later, later x own), merged into ONE launch per class so that a shard pays one launch tail per
+// class, not three: task.w selects the part.
+struct PartArgs {
     // uniform side (AoS records [nU][9][nfield(UT)])
     const double* u_aos;
     const int32_t* u_nprim;  // [nU]
     const int32_t* u_pidx;   // [nU][nf(UT)] packed pair index of each function pair, -1 = not stored
-    int nU;
-    // work list: task = {row u, first lane-side pair, end lane-side pair, 0}; rows are cut into
-    // pieces of at most kTaskPairs lane-side pairs (longest rows first)
-    const int4* tasks;
-    int ntasks;
+    const double* u_q;       // [nU] Schwarz factor of the uniform-side pairs
     // lane side (SoA [9][nfield(TT)][t_npad])
     const double* t_soa;
     const double* t_aos;     // the same records as [nT][9][nfield(TT)]: one lane reads its own pair contiguously
     const int32_t* t_nprim;  // [nT]
     const int32_t* t_pidx;   // [nT][nf(TT)]
+    const double* t_q;       // [nT] Schwarz factor of the lane-side pairs
+    const int64_t* stage_row;  // [nU] compose mode, see below
     int t_npad;
-    int nT;
     int tri;  // lists are the same list: take v >= u only, and P1 <= P2 when v == u
+};
+constexpr int kMaxParts = 3;
+
+// One launch = all quartets (u, v) with u in a "uniform-side" pair list (records staged to
+// shared memory by TMA bulk copy, one row of the quartet space per CTA iteration) and v in a
+// "lane-side" pair list (structure-of-arrays, one pair per lane).
+struct ClassArgs {
+    PartArgs part[kMaxParts];
+    int nparts;
+    // work list: task = {row u, first lane-side pair, end lane-side pair, part}; rows are cut into
+    // pieces of at most kTaskPairs lane-side pairs (longest rows first)
+    const int4* tasks;
+    int ntasks;
     // Boys Taylor table for this class's start order Q: [121][8] = {Ft(t,Q+k)/k!, k=0..6 ; 0}
     const double* ftab_q;
     // [601] {exp(-k/10), k/10}
@@ -42,19 +55,16 @@ struct ClassArgs {
     // global row counter of this launch (zeroed by the fill kernel that precedes it)
     int* row_counter;
     // Schwarz skip (tau = 0: off): lanes leave out the quartets with u_q[u]*t_q[v] < tau
-    const double* u_q;   // [nU] Schwarz factor of the uniform-side pairs
-    const double* t_q;   // [nT] of the lane-side pairs
     double tau;
     unsigned long long* pq_counter;  // primitive quartets this launch evaluated (one atomic per task)
     // output
     double* out;         // this shard's slice of the packed array (scatter mode; nullptr in compose mode)
     int64_t out_offset;  // packed index of out[0]
     int64_t npair;
-    // compose mode: every quartet (u, v) of the launch owns a block of nf(UT)*nf(TT) doubles, [f_u][f_v], at
+    // compose mode: every quartet (u, v) of a part owns a block of nf(UT)*nf(TT) doubles, [f_u][f_v], at
     // stage + stage_row[u] + v*nf(UT)*nf(TT); the lane that evaluates the quartet writes the whole block with 128-bit
     // stores and compose_kernel gathers the packed array from the blocks.  stage == nullptr: scatter into `out`.
     double* stage;
-    const int64_t* stage_row;  // [nU]
 };
 
 // Compose pass (compose_kernel): the packed slice is written ONCE, in order, by 256-byte warp stores: exact zeros
