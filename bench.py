@@ -310,7 +310,8 @@ def run_ours(args):
         d2h = int(allsum(float(Q.last_d2h_bytes())))  # what crossed PCIe (sparse route: nonzero chunks + flags)
         e2e = {"value": s.nunique / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": d2h, "host_bytes_written_per_step": int(8 * s.nunique),
-               "d2h_route": "sparse push of nonzero 2 KB chunks + host zero fill" if d2h < 8 * s.nunique else "cudaMemcpy",
+               "d2h_route": "sparse push of the nonzero 256-byte chunks by the GPU + zeros of the other chunks by host threads (streaming stores)"
+               if d2h < 8 * s.nunique else "cudaMemcpy",
                "ms_per_step": dt * 1e3, "steps": ne2e,
                "host_checksum": float(allsum(float(harr[:nloc].sum())))}
     except Exception as exc:  # report, do not hide
@@ -324,6 +325,13 @@ def run_ours(args):
     # ---- per-kernel breakdown and the rooflines of the step ------------------------------------------
     # One execute() = the zero fill + the six quartet-class kernels ((SP SP|SP SP) as four mu-slices).  Times are
     # CUDA events around every launch of a serialised pass; launches of one kernel family are added up.
+    # the zero fill is the driver's cudaMemsetAsync by default (7.35 TB/s on a B200 against 6.2-6.55 TB/s for every SM
+    # fill kernel tried; MYQC_FILL_ENGINE=kernel selects the repo's fill_zero_kernel): write-only, so its rate can
+    # exceed MEASURED_PEAKS' copy (read + write) bandwidth, and it is not one of this repo's kernel launches
+    fill_engine = os.environ.get("MYQC_FILL_ENGINE", "memset")
+    if fill_engine not in ("kernel", "copy") or os.environ.get("MYQC_OUTPUT_MODE") == "compose":
+        fill_engine = "memset" if os.environ.get("MYQC_OUTPUT_MODE") != "compose" else "kernel"
+    own_launches = nlaunch - (0 if fill_engine == "kernel" else sum(1 for (cls, tri, rows) in launches if cls == -1))
     per_class_ms = {}
     fill_elems = 0
     for (cls, tri, rows), t in zip(launches, acc):
@@ -337,7 +345,9 @@ def run_ours(args):
             # cls -2: compose_kernel (writes every element of the slice once: algorithmic bytes = 8 B per unique ERI);
             # cls -1: fill_zero_kernel of the scatter mode (MYQC_OUTPUT_MODE=scatter)
             gb = 8.0 * fill_elems / 1e9
-            kernels.append({"kernel": "compose" if cls == -2 else "fill_zero", "elements_written": fill_elems, "ms": t, "bound": "hbm",
+            kernels.append({"kernel": "compose" if cls == -2 else ("fill_zero" if fill_engine == "kernel" else
+                                                                   "zero fill (cudaMemsetAsync)" if fill_engine == "memset" else
+                                                                   "zero fill (device-to-device copies of a zero buffer)"), "elements_written": fill_elems, "ms": t, "bound": "hbm",
                             "share_of_step": t / serial_ms,
                             "achieved": gb / (t * 1e-3) if t > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s"})
         else:
@@ -376,7 +386,9 @@ def run_ours(args):
         traffic = float(sum(json.load(open(tfile)).values()))
     roofline = {"kernel": "step (zero fill + all class launches of one execute)", "bound": bound, "achieved": achieved, "peak": peak,
                 "unit": unit, "frac": achieved / peak if peak else None, "traffic": traffic,
-                "traffic_source": "sum over the step's launches of dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/r2f_h2o64_ncu_full.json)",
+                "traffic_source": "sum over the step's launches of dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full "
+                                  "(profiles/r2f_h2o64_ncu_full.json; captured with the repo's fill kernel, ncu does not see the driver's memset, "
+                                  "which writes the same 8 B per element)",
                 "peak_source": peak_src if bound == "hbm" else "measured DFMA microbenchmark in this run (myqc_fp64_peak)",
                 "algorithmic_bytes": bytes_alg, "model_flops": model_flops / world,
                 "hbm_frac": bytes_alg / 1e9 / (ms_local * 1e-3) / hbm_peak,
@@ -409,7 +421,8 @@ def run_ours(args):
                          "output slice per step (%.1f GB) is larger than L2" % (8 * plan.out_elems / 1e9),
                    "parallelism": f"quartet-space row shards x{world}, no collective"},
         "roofline": roofline, "kernels": kernels, "whole_step": whole,
-        "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(nlaunch * args.steps),
+        "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(own_launches * args.steps),
+        "zero_fill_engine": fill_engine,
         "clocks": clk, "fp64_peak_tflops_measured": fp64_peak, "checksum": checksum, "per_rank": per_rank,
     }
     _emit(args._stdout, json.dumps(line))

@@ -124,6 +124,14 @@ struct myqc_eri_plan {
     cudaStream_t s_fill = nullptr, s_comp[kNumCompute] = {};
     cudaEvent_t e_start = nullptr, e_done[kNumCompute + 1] = {};
     std::vector<cudaEvent_t> e_fill;
+    // zero fill by the copy engines (fill_engine 1: cudaMemsetAsync, 2: device-to-device copies from a small zero
+    // buffer on fill_nstreams streams) -- no SM takes part, so the fill of piece k+1 can run under the FP64 kernels of piece k
+    static constexpr int kMaxFillStreams = 4;
+    int fill_engine = 1, fill_nstreams = 1;
+    void* d_zero = nullptr;
+    size_t zero_bytes = 0;
+    cudaStream_t s_fillx[kMaxFillStreams] = {};
+    cudaEvent_t e_fork = nullptr, e_join[kMaxFillStreams] = {};
     // stats (canonical primitive-quartet counts of the whole shard)
     int64_t nquartets[6] = {0, 0, 0, 0, 0, 0};
     double model_flops = 0.0;
@@ -993,6 +1001,29 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
         for (auto& e : pl->e_fill) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
 
+    {
+        const char* fe = std::getenv("MYQC_FILL_ENGINE");
+        // Default: cudaMemsetAsync.  On a B200 the driver's fill writes 7.35 TB/s; thirty variants of an SM fill kernel
+        // (128/256-bit stores, tiles, cache operators, TMA bulk stores of a zeroed shared-memory tile) all end at
+        // 6.2-6.55 TB/s (profiles/r2_notes.md section 6).  MYQC_FILL_ENGINE=kernel keeps the repo's fill_zero_kernel,
+        // =copy uses device-to-device copies from a zero buffer on the copy engines (4.5 TB/s, measured).
+        pl->fill_engine = fe ? (std::strcmp(fe, "kernel") == 0 ? 0 : std::strcmp(fe, "copy") == 0 ? 2 : 1) : 1;
+        if (pl->screened_fill || pl->compose) pl->fill_engine = 0;
+        const char* fs = std::getenv("MYQC_FILL_STREAMS");
+        pl->fill_nstreams = fs ? std::max(1, std::min((int)myqc_eri_plan::kMaxFillStreams, std::atoi(fs))) : 1;
+        if (pl->fill_engine == 2) {
+            const char* zm = std::getenv("MYQC_ZERO_MB");
+            pl->zero_bytes = (size_t)(zm ? std::max(1, std::atoi(zm)) : 32) << 20;
+            CU(cudaMalloc(&pl->d_zero, pl->zero_bytes));
+            pl->dev_allocs.push_back(pl->d_zero);
+            CU(cudaMemset(pl->d_zero, 0, pl->zero_bytes));
+        }
+        if (pl->fill_engine) {
+            for (int i = 1; i < pl->fill_nstreams; ++i) CU(cudaStreamCreateWithFlags(&pl->s_fillx[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&pl->e_fork, cudaEventDisableTiming));
+            for (int i = 1; i < pl->fill_nstreams; ++i) CU(cudaEventCreateWithFlags(&pl->e_join[i], cudaEventDisableTiming));
+        }
+    }
     stage("streams + events");
     // the canonical work statistics cost ~8 ms of host time: evaluated when plan_stats asks for them
     pl->stats_whole = (nshards == 1);
@@ -1066,6 +1097,38 @@ static int fill_region(myqc_eri_plan* plan, Sub& sub, int r, double* d_sub_out, 
         return launch_fill_screened(f, plan->num_sms, st);
     }
     const int64_t b = r == 0 ? 0 : sub.region_end[r - 1], e = sub.region_end[r];
+    if (plan->fill_engine) {
+        if (r == 0 && sub.ncounters > 0) {
+            cudaError_t ce = cudaMemsetAsync(plan->d_counters + sub.counter_base, 0, sizeof(int) * (size_t)sub.ncounters, st);
+            if (ce != cudaSuccess) return (int)ce;
+        }
+        char* p0 = reinterpret_cast<char*>(d_sub_out + b);
+        const size_t bytes = (size_t)(e - b) * sizeof(double);
+        const int ns = plan->fill_nstreams;
+        if (ns > 1) {
+            cudaEventRecord(plan->e_fork, st);
+            for (int i = 1; i < ns; ++i) cudaStreamWaitEvent(plan->s_fillx[i], plan->e_fork, 0);
+        }
+        // stream i takes the i-th part (cut at 1 MB); copies go in pieces of the zero buffer's size
+        const size_t part = ((bytes + ns - 1) / ns + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        for (int i = 0; i < ns; ++i) {
+            const size_t lo = std::min(bytes, part * i), hi = std::min(bytes, part * (i + 1));
+            cudaStream_t si = i == 0 ? st : plan->s_fillx[i];
+            cudaError_t ce = cudaSuccess;
+            if (plan->fill_engine == 1) {
+                if (hi > lo) ce = cudaMemsetAsync(p0 + lo, 0, hi - lo, si);
+            } else {
+                for (size_t o = lo; o < hi && ce == cudaSuccess; o += plan->zero_bytes)
+                    ce = cudaMemcpyAsync(p0 + o, plan->d_zero, std::min(plan->zero_bytes, hi - o), cudaMemcpyDeviceToDevice, si);
+            }
+            if (ce != cudaSuccess) return (int)ce;
+        }
+        for (int i = 1; i < ns; ++i) {
+            cudaEventRecord(plan->e_join[i], plan->s_fillx[i]);
+            cudaStreamWaitEvent(st, plan->e_join[i], 0);
+        }
+        return (int)cudaGetLastError();
+    }
     // the first fill of a sub-shard also resets all of its task counters
     return launch_fill_zero(d_sub_out + b, e - b, plan->d_counters + sub.counter_base, r == 0 ? sub.ncounters : 0,
                             plan->num_sms, st);
@@ -1320,6 +1383,9 @@ void myqc_eri_plan_destroy(myqc_eri_plan* plan) {
     if (plan->e_start) cudaEventDestroy(plan->e_start);
     for (auto& e : plan->e_done) if (e) cudaEventDestroy(e);
     for (auto& e : plan->e_fill) if (e) cudaEventDestroy(e);
+    for (auto& st : plan->s_fillx) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    if (plan->e_fork) cudaEventDestroy(plan->e_fork);
+    for (auto& e : plan->e_join) if (e) cudaEventDestroy(e);
     for (void* p : plan->dev_allocs) cudaFree(p);
     delete plan;
 }
@@ -1342,6 +1408,9 @@ int myqc_eri_expand_dense(const double* d_packed, int norb, double* d_xx, void* 
 // benchmark loop, pays for the pair tables, the task lists and a 40 GB cudaMalloc/cudaFree once.
 // myqc_eri_release_cache() drops them; MYQC_NO_CACHE=1 turns the cache off.
 namespace myqc {
+
+void host_zero_stream(double* p, size_t n);  // hostmem.cpp
+void host_zero_fence();
 
 struct CacheEntry {
     uint64_t key = 0;
@@ -1457,7 +1526,13 @@ int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const
                       pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr;
         cudaGetLastError();  // an unregistered pointer may leave a sticky-free error code behind
         if (sparse) {
-            const int64_t nchunk = (n + myqc::kXferChunk - 1) / myqc::kXferChunk;
+            // chunk size of the sparse route in doubles (MYQC_XFER_CHUNK = 32 / 64 / 128 / 256)
+            int chunk = myqc::kXferChunkDefault;
+            if (const char* ec = std::getenv("MYQC_XFER_CHUNK")) { const int c = std::atoi(ec); if (myqc::xfer_chunk_ok(c)) chunk = c; }
+            // measurement hooks (the result is then incomplete): leave out the host-side zeros or the device-side push
+            const bool plain_memset = std::getenv("MYQC_HOST_MEMSET") != nullptr;  // measurement hook: glibc memset instead of streaming stores
+            const bool no_host = std::getenv("MYQC_XFER_NOHOST") != nullptr, no_push = std::getenv("MYQC_XFER_NOPUSH") != nullptr;
+            const int64_t nchunk = (n + chunk - 1) / chunk;
             cudaError_t e = cudaSuccess;
             if (nchunk > ce.flags_cap) {
                 if (ce.d_flags) { cudaFree(ce.d_flags); ce.d_flags = nullptr; }
@@ -1473,12 +1548,13 @@ int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const
             int sms = 0;
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_flags, cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-            if (e == cudaSuccess) e = (cudaError_t)myqc::launch_chunk_flags(d_out, n, d_flags, sms, nullptr);
+            if (e == cudaSuccess) e = (cudaError_t)myqc::launch_chunk_flags(d_out, n, chunk, d_flags, sms, nullptr);
             if (e == cudaSuccess) e = cudaMemcpyAsync(h_flags, d_flags, (size_t)nchunk, cudaMemcpyDeviceToHost, nullptr);
             if (e == cudaSuccess) e = cudaEventRecord(ev_flags, nullptr);
-            if (e == cudaSuccess)
-                e = (cudaError_t)myqc::launch_chunk_push(d_out, n, d_flags, static_cast<double*>(pa.devicePointer), sms, nullptr);
+            if (e == cudaSuccess && !no_push)
+                e = (cudaError_t)myqc::launch_chunk_push(d_out, n, chunk, d_flags, static_cast<double*>(pa.devicePointer), sms, nullptr);
             if (e == cudaSuccess) e = cudaEventSynchronize(ev_flags);
+            const auto tf = now();
             if (e == cudaSuccess) {
                 // zeros of the unflagged chunks, written by host threads while the push kernel runs:
                 // half the hardware threads, shared between the shards of one box, at most 8 (measured on the
@@ -1493,10 +1569,14 @@ int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const
                         if (h_flags[c]) { ++mine; ++c; continue; }
                         int64_t r = c;
                         while (r < c1 && !h_flags[r]) ++r;
-                        const int64_t e0 = c * myqc::kXferChunk, e1 = std::min<int64_t>(n, r * myqc::kXferChunk);
-                        std::memset(packed_slice + e0, 0, (size_t)(e1 - e0) * sizeof(double));
+                        const int64_t e0 = c * chunk, e1 = std::min<int64_t>(n, r * chunk);
+                        if (!no_host) {
+                            if (plain_memset) std::memset(packed_slice + e0, 0, (size_t)(e1 - e0) * sizeof(double));
+                            else myqc::host_zero_stream(packed_slice + e0, (size_t)(e1 - e0));
+                        }
                         c = r;
                     }
+                    myqc::host_zero_fence();
                     sent += mine;
                 };
                 std::vector<std::thread> th;
@@ -1505,10 +1585,14 @@ int myqc_eri_packed_shard(int nnuc, const double* xyz, int nset, int setl, const
                     if (t * per < nchunk) th.emplace_back(zero_range, t * per, std::min<int64_t>(nchunk, (t + 1) * per));
                 zero_range(0, std::min<int64_t>(nchunk, per));
                 for (auto& t : th) t.join();
+                const auto th1 = now();
                 xfer_frac = (double)sent.load() / (double)nchunk;
-                myqc::g_last_d2h_bytes = sent.load() * myqc::kXferChunk * (int64_t)sizeof(double) + nchunk;
+                myqc::g_last_d2h_bytes = sent.load() * chunk * (int64_t)sizeof(double) + nchunk;
                 xfer_kind = "sparse push";
                 e = cudaStreamSynchronize(nullptr);
+                if (trace)
+                    std::fprintf(stderr, "[myqc trace]   sparse route: chunk %d B, flags ready after %.1f ms, host zeros %.1f ms (%d threads), push done %.1f ms after the zeros\n",
+                                 chunk * 8, ms(t3, tf), ms(tf, th1), nthr, ms(th1, now()));
             }
             if (ev_flags) cudaEventDestroy(ev_flags);
             if (e != cudaSuccess) rc = cuda_fail(e, "sparse transfer of the packed slice to the host");

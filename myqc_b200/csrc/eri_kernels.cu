@@ -886,55 +886,86 @@ __global__ void expand_dense_kernel(const double* __restrict__ packed, int norb,
 }
 
 // ------------------------------------------------------------------------------------------
-// Sparse transfer to the host.  A warp owns a chunk of kXferChunk consecutive elements of the slice.
+// Sparse transfer to the host.  The slice is cut into chunks of CH consecutive elements (CH = 32 ... 256, a multiple of
+// the 32 elements = 256 bytes one warp store covers).  A warp walks groups of 256 elements (eight warp rows), so that
+// eight independent loads are in flight per lane whatever the chunk size.
+template <int CH>
 __global__ void __launch_bounds__(256) chunk_flags_kernel(const double* __restrict__ out, int64_t n, unsigned char* __restrict__ flags) {
+    constexpr int RPC = CH / 32;  // warp rows per chunk
     const int lane = threadIdx.x & 31;
-    const int64_t nchunk = (n + kXferChunk - 1) / kXferChunk;
+    const int64_t ngroup = (n + 255) / 256;
+    const int64_t nchunk = (n + CH - 1) / CH;
     const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nchunk; c += nwarp) {
-        const int64_t base = c * kXferChunk;
-        long long bits = 0;
+    for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ngroup; g += nwarp) {
+        const int64_t base = g * 256;
+        long long bits[8];
 #pragma unroll
-        for (int j = 0; j < kXferChunk / 32; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const int64_t e = base + j * 32 + lane;
-            if (e < n) bits |= __double_as_longlong(__ldcs(out + e));
+            bits[j] = e < n ? __double_as_longlong(__ldcs(out + e)) : 0ll;
         }
-        const bool any = __any_sync(0xffffffffu, bits != 0);
-        if (lane == 0) flags[c] = any ? 1 : 0;
+#pragma unroll
+        for (int c = 0; c < 8 / RPC; ++c) {
+            long long b = 0;
+#pragma unroll
+            for (int j = 0; j < RPC; ++j) b |= bits[c * RPC + j];
+            const bool any = __any_sync(0xffffffffu, b != 0);
+            const int64_t ci = g * (8 / RPC) + c;
+            if (lane == 0 && ci < nchunk) flags[ci] = any ? 1 : 0;
+        }
     }
 }
 
+template <int CH>
 __global__ void __launch_bounds__(256) chunk_push_kernel(const double* __restrict__ out, int64_t n, const unsigned char* __restrict__ flags,
                                                          double* __restrict__ host) {
+    constexpr int RPC = CH / 32;
     const int lane = threadIdx.x & 31;
-    const int64_t nchunk = (n + kXferChunk - 1) / kXferChunk;
+    const int64_t ngroup = (n + 255) / 256;
+    const int64_t nchunk = (n + CH - 1) / CH;
     const int64_t nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nchunk; c += nwarp) {
-        if (!flags[c]) continue;
-        const int64_t base = c * kXferChunk;
-        double v[kXferChunk / 32];
+    for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ngroup; g += nwarp) {
+        const int64_t base = g * 256;
+        // the group's flags: one byte per chunk, read by the first lanes and broadcast as a bit mask
+        const int64_t c0 = g * (8 / RPC);
+        const bool f = lane < 8 / RPC && c0 + lane < nchunk && flags[c0 + lane] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (m == 0) continue;
+        double v[8];
 #pragma unroll
-        for (int j = 0; j < kXferChunk / 32; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const int64_t e = base + j * 32 + lane;
-            v[j] = e < n ? __ldcs(out + e) : 0.0;
+            v[j] = ((m >> (j / RPC)) & 1u) && e < n ? __ldcs(out + e) : 0.0;
         }
 #pragma unroll
-        for (int j = 0; j < kXferChunk / 32; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const int64_t e = base + j * 32 + lane;
-            if (e < n) host[e] = v[j];  // 256 contiguous bytes per warp store, posted over PCIe
+            if (((m >> (j / RPC)) & 1u) && e < n) host[e] = v[j];  // 256 contiguous bytes per warp store, posted over PCIe
         }
     }
 }
 
-int launch_chunk_flags(const double* out, int64_t n, unsigned char* flags, int num_sms, void* stream) {
+int xfer_chunk_ok(int chunk) { return chunk == 32 || chunk == 64 || chunk == 128 || chunk == 256; }
+
+int launch_chunk_flags(const double* out, int64_t n, int chunk, unsigned char* flags, int num_sms, void* stream) {
     if (n <= 0) return 0;
-    chunk_flags_kernel<<<num_sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, flags);
+    if (!xfer_chunk_ok(chunk)) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (chunk == 32) chunk_flags_kernel<32><<<num_sms * 8, 256, 0, st>>>(out, n, flags);
+    else if (chunk == 64) chunk_flags_kernel<64><<<num_sms * 8, 256, 0, st>>>(out, n, flags);
+    else if (chunk == 128) chunk_flags_kernel<128><<<num_sms * 8, 256, 0, st>>>(out, n, flags);
+    else chunk_flags_kernel<256><<<num_sms * 8, 256, 0, st>>>(out, n, flags);
     return (int)cudaGetLastError();
 }
 
-int launch_chunk_push(const double* out, int64_t n, const unsigned char* flags, double* host, int num_sms, void* stream) {
+int launch_chunk_push(const double* out, int64_t n, int chunk, const unsigned char* flags, double* host, int num_sms, void* stream) {
     if (n <= 0) return 0;
-    chunk_push_kernel<<<num_sms * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, flags, host);
+    if (!xfer_chunk_ok(chunk)) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (chunk == 32) chunk_push_kernel<32><<<num_sms * 8, 256, 0, st>>>(out, n, flags, host);
+    else if (chunk == 64) chunk_push_kernel<64><<<num_sms * 8, 256, 0, st>>>(out, n, flags, host);
+    else if (chunk == 128) chunk_push_kernel<128><<<num_sms * 8, 256, 0, st>>>(out, n, flags, host);
+    else chunk_push_kernel<256><<<num_sms * 8, 256, 0, st>>>(out, n, flags, host);
     return (int)cudaGetLastError();
 }
 

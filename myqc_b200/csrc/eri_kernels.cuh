@@ -145,10 +145,11 @@ int launch_fill_zero(double* out, int64_t n, int* counters, int ncounters, int n
 int launch_expand_dense(const double* packed, int norb, int h0, int h1, double* xx_slab, int num_sms, void* stream);
 
 // Sparse device -> host transfer of a packed slice (most of a large molecule's integrals are exact zeros):
-// chunks of kXferChunk doubles; flags[c] = 1 iff chunk c holds a nonzero bit pattern; the push kernel
-// stores the flagged chunks straight into device-accessible (pinned) host memory.
-constexpr int kXferChunk = 256;
-int launch_chunk_flags(const double* out, int64_t n, unsigned char* flags, int num_sms, void* stream);
-int launch_chunk_push(const double* out, int64_t n, const unsigned char* flags, double* host, int num_sms, void* stream);
+// chunks of `chunk` doubles (32, 64, 128 or 256); flags[c] = 1 iff chunk c holds a nonzero bit pattern; the push
+// kernel stores the flagged chunks straight into device-accessible (pinned) host memory.
+constexpr int kXferChunkDefault = 32;  // 256 bytes: one warp store; measured best end to end (profiles/r2_notes.md section 7)
+int xfer_chunk_ok(int chunk);
+int launch_chunk_flags(const double* out, int64_t n, int chunk, unsigned char* flags, int num_sms, void* stream);
+int launch_chunk_push(const double* out, int64_t n, int chunk, const unsigned char* flags, double* host, int num_sms, void* stream);
 
 }  // namespace myqc

@@ -320,12 +320,12 @@ def test_permuting_atoms_permutes_integrals(tmp_path, oracle_inputs):
     assert np.abs(x1 - x2[np.ix_(p, p, p, p)]).max() < 1e-12
 
 
-@pytest.mark.parametrize("nsh,shift", [(1, 0), (2, 1)])
-def test_sparse_host_transfer_is_bit_identical(nsh, shift, tmp_path, monkeypatch):
+@pytest.mark.parametrize("nsh,shift,chunk", [(1, 0, None), (2, 1, None), (1, 1, 32), (2, 0, 64), (1, 3, 128), (2, 1, 256)])
+def test_sparse_host_transfer_is_bit_identical(nsh, shift, chunk, tmp_path, monkeypatch):
     """Pinned destination: only the chunks that hold a nonzero cross PCIe (stored by the GPU into the host
     buffer), host threads write the zeros.  Same bytes as the plain cudaMemcpy path, for whole arrays and
-    shards, at odd element offsets of the destination, and with a poisoned destination (every element
-    must be written by one side or the other)."""
+    shards, at odd element offsets of the destination (the streaming-store zeroing has a scalar head and tail),
+    for every chunk size, and with a poisoned destination (every element must be written by one side or the other)."""
     import torch
     s = product_system("h2o_16", tmp_path)
     off = Q.shard_layout(s, nsh)
@@ -336,11 +336,36 @@ def test_sparse_host_transfer_is_bit_identical(nsh, shift, tmp_path, monkeypatch
         plain = np.empty(nloc)
         Q.eri_packed_shard(s, plain, shard=sh, nshards=nsh)
         monkeypatch.delenv("MYQC_SPARSE_D2H")
+        if chunk is not None:
+            monkeypatch.setenv("MYQC_XFER_CHUNK", str(chunk))  # doubles per chunk (default 32 = one 256-byte warp store)
         pinned = torch.full((nloc + 2,), float("nan"), dtype=torch.float64).pin_memory()
         dst = pinned.numpy()[shift:shift + nloc]
         Q.eri_packed_shard(s, dst, shard=sh, nshards=nsh)
         assert np.array_equal(dst.view(np.int64), plain.view(np.int64))
         assert np.isnan(pinned.numpy()[shift + nloc])  # nothing written past the slice
+
+
+@pytest.mark.parametrize("engine", ["kernel", "copy"])
+@pytest.mark.parametrize("name,nsh", [("CO2", 1), ("h2o_8", 3), ("h2o_16", 1)])
+def test_fill_engines_agree(name, nsh, engine, tmp_path, monkeypatch):
+    """The zero fill of the slice by cudaMemsetAsync (default), by the repo's fill kernel (MYQC_FILL_ENGINE=kernel) and
+    by device-to-device copies from a zero buffer on several streams (=copy) give the same bytes."""
+    s = product_system(name, tmp_path)
+    off = Q.shard_layout(s, nsh)
+
+    def run():
+        Q.release_cache()
+        out = np.full(int(off[-1]), np.nan)
+        for k in range(nsh):
+            Q.eri_packed_shard(s, out[off[k]:off[k + 1]], device=0, shard=k, nshards=nsh)
+        return out
+    ref = run()
+    monkeypatch.setenv("MYQC_FILL_ENGINE", engine)
+    monkeypatch.setenv("MYQC_FILL_STREAMS", "3")
+    monkeypatch.setenv("MYQC_ZERO_MB", "1")
+    got = run()
+    Q.release_cache()
+    assert np.array_equal(got.view(np.int64), ref.view(np.int64))
 
 
 @pytest.mark.parametrize("name,nsh", [("CO2", 1), ("h2o_8", 1), ("c4h10", 1), ("h2o_8", 3), ("CO2", 8), ("h2o_16", 1)])
