@@ -594,7 +594,7 @@ static int build_cut_table(const std::vector<Shell>& shells, const PairList all[
                 for (int c = 0; c < cu; ++c) ct.w[c] += wr * hist[c];
             }
         }
-    // plus the zero fill of the rows the block owns (HBM bound, ~6.2 TB/s)
+    // plus the zero fill of the rows the block owns (HBM bound; cudaMemsetAsync writes ~7.3 TB/s on a B200)
     {
         int norb = 0;
         for (const Shell& sh : shells)
@@ -602,7 +602,7 @@ static int build_cut_table(const std::vector<Shell>& shells, const PairList all[
         for (int c = 0; c < nc; ++c) {
             const int64_t b = packed_row_offset(c == 0 ? 0 : cuts[c], norb);
             const int64_t e = packed_row_offset(c + 1 < nc ? cuts[c + 1] : norb, norb);
-            ct.w[c] += 8.0 * (double)(e - b) / 6.2e12;
+            ct.w[c] += 8.0 * (double)(e - b) / 7.3e12;
         }
     }
     return MYQC_OK;

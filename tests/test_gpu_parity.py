@@ -338,7 +338,7 @@ def test_sparse_host_transfer_is_bit_identical(nsh, shift, chunk, tmp_path, monk
         monkeypatch.delenv("MYQC_SPARSE_D2H")
         if chunk is not None:
             monkeypatch.setenv("MYQC_XFER_CHUNK", str(chunk))  # doubles per chunk (default 32 = one 256-byte warp store)
-        pinned = torch.full((nloc + 2,), float("nan"), dtype=torch.float64).pin_memory()
+        pinned = torch.full((nloc + 4,), float("nan"), dtype=torch.float64).pin_memory()
         dst = pinned.numpy()[shift:shift + nloc]
         Q.eri_packed_shard(s, dst, shard=sh, nshards=nsh)
         assert np.array_equal(dst.view(np.int64), plain.view(np.int64))
