@@ -78,7 +78,17 @@ struct Launch {
     ClassArgs args;                // args.tasks/ntasks describe the whole need-sorted task array
     std::vector<int> region_task;  // [nregion+1] task ranges: region r = tasks whose writes end inside fill region r
     double weight = 0.0;           // sum over tasks of (primitives of the row) x (primitives of the lane-side range)
+    bool warp = false;             // (SP SP|SP SP) only: the warp-cooperative kernel (one launch) instead of four mu-slices
 };
+
+// Below these numbers of contracted quartets per piece the warp-cooperative kernels are used (profiles/r2_notes.md
+// section 9).  (SP SP|SP SP): 3 582 quartets 0.239 -> 0.057 ms, 6 481: 0.359 -> 0.104 ms, 118 708: 0.72 -> 1.06 ms.
+// (S SP|SP SP) has 10x the quartets of the same molecule and the class kernel fills its lanes: the warp kernel lost on
+// all three configurations (0.118 -> 0.149, 0.170 -> 0.252, 2.25 -> 3.99 ms) and is never chosen automatically.
+constexpr int64_t kWarpQuartetsPP = 20000, kWarpQuartetsSP = 0;
+
+// kernel launches one class launch issues
+static inline int launch_count(const Launch& L) { return L.warp ? 1 : class_nlaunch(L.UT, L.TT); }
 
 constexpr int kMaxCounters = 1024;
 
@@ -104,6 +114,8 @@ struct Sub {  // one virtual sub-shard: a contiguous piece of the plan's slice w
     int listbase[6] = {0, 0, 0, 0, 0, 0};
     int ng = 0;
     std::vector<uint32_t> h_rowrel;  // [ng][6], see ComposeArgs::rowrel
+    bool pp_warp = false, sp_warp = false;       // (SP SP|SP SP) / (S SP|SP SP) of this piece run on the warp-cooperative kernel
+    int64_t pp_quartets = 0, sp_quartets = 0;    // their contracted quartets (reference rule + Schwarz prefix)
 };
 
 struct myqc_eri_plan {
@@ -210,6 +222,7 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri, int
     Launch Lnew;
     if (!Lp) {
         Lnew.UT = U.type; Lnew.TT = T.type;
+        Lnew.warp = T.type == 2 && ((U.type == 2 && sub.pp_warp) || (U.type == 1 && sub.sp_warp));
         std::memset(&Lnew.args, 0, sizeof(Lnew.args));
         Lp = &Lnew;
     }
@@ -232,6 +245,12 @@ static int add_launch(myqc_eri_plan* pl, Sub& sub, int ui, int ti, bool tri, int
         double total_pairs = 0.0;
         for (int u = 0; u < U.n; ++u) total_pairs += std::max(0, ntv[u] - (tri ? u : 0));
         while (maxpairs > 32 && total_pairs / maxpairs < 4.0 * warps) maxpairs /= 2;
+        if (T.type == 2 && ((U.type == 2 && sub.pp_warp) || (U.type == 1 && sub.sp_warp))) {
+            // warp-cooperative kernel: a warp works through the quartets of a task one after the other (each is one to
+            // three batches of 32 primitive quartets), so tasks are a few quartets long
+            maxpairs = 8;
+            while (maxpairs > 1 && total_pairs / maxpairs < 4.0 * warps) maxpairs /= 2;
+        }
     }
     const int mingroup = std::min(64, maxpairs);
     std::vector<int> seg;  // segment start offsets, terminated by T.n
@@ -404,13 +423,13 @@ static int finalize_launches(myqc_eri_plan* pl, Sub& sub) {
         if (rc) return rc;
         a.tasks = d_tasks;
         a.ntasks = (int)tasks.size();
-        const int ncnt = class_nlaunch(L.UT, L.TT) * nregion;  // one task counter per launch and region
+        const int ncnt = launch_count(L) * nregion;  // one task counter per launch and region
         if (pl->ncounters + ncnt > kMaxCounters) return fail(MYQC_ERR_UNSUPPORTED, "too many launches in one plan");
         a.pq_counter = pl->d_pq + pl->ncounters;  // one per launch (slices of a launch share it)
         a.row_counter = pl->d_counters + pl->ncounters;
         pl->ncounters += ncnt;
         sub.ncounters += ncnt;
-        pl->nlaunch += class_nlaunch(L.UT, L.TT) * nregion;
+        pl->nlaunch += launch_count(L) * nregion;
     }
     return MYQC_OK;
 }
@@ -875,6 +894,31 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
             if (sub.ng >= (1 << 25)) return fail(MYQC_ERR_UNSUPPORTED, "too many shell pairs for the compose pass");
             sub.h_rowrel.assign((size_t)sub.ng * 6, 0u);
         }
+        // (SP SP|SP SP): which kernel.  The class kernel gives a contracted quartet to one lane, so it needs tens of
+        // thousands of quartets to fill the machine and lasts ~0.23 ms however few there are; the warp-cooperative
+        // kernel spreads the primitive quartets of ONE quartet over a warp and wins for small pieces (kWarpQuartetsPP).
+        // MYQC_PP_KERNEL=warp / slices and MYQC_SP_KERNEL=warp / class force one of them.
+        {
+            auto count = [&](int ui, int ti, bool tri) -> int64_t {
+                if (ui < 0 || ti < 0) return 0;
+                const DevList& U = pl->lists[ui];
+                const DevList& T = pl->lists[ti];
+                if (U.n == 0 || T.n == 0) return 0;
+                const std::vector<int32_t> ntv = row_prefix(U.host, T.host, pl->schwarz_tau);
+                int64_t n = 0;
+                for (int u = 0; u < U.n; ++u) n += std::max(0, ntv[u] - (tri ? u : 0));
+                return n;
+            };
+            sub.pp_quartets = count(mine_id[2], mine_id[2], true) + count(mine_id[2], later_id[2], false);
+            const int mode = pp_kernel_mode();
+            sub.pp_warp = mode == 1 || (mode < 0 && sub.pp_quartets < kWarpQuartetsPP);
+            sub.sp_quartets = count(mine_id[1], mine_id[2], false) + count(mine_id[1], later_id[2], false) + count(later_id[1], mine_id[2], false);
+            const int smode = sp_kernel_mode();
+            sub.sp_warp = smode == 1 || (smode < 0 && sub.sp_quartets < kWarpQuartetsSP);
+            if (trace) std::fprintf(stderr, "[myqc trace]   (SP SP|SP SP): %lld contracted quartets -> %s kernel; (S SP|SP SP): %lld -> %s kernel\n",
+                                    (long long)sub.pp_quartets, sub.pp_warp ? "warp-cooperative" : "mu-slice class",
+                                    (long long)sub.sp_quartets, sub.sp_warp ? "warp-cooperative" : "class");
+        }
         // launches.  Class (ta,tb), ta <= tb, uniform side = ta, lane side = tb.
         for (int ta = 0; ta < 3; ++ta)
             for (int tb = ta; tb < 3; ++tb) {
@@ -952,7 +996,7 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
             std::vector<float> pw;
             double wsum = 0.0;
             for (const Launch& L : sub.launches) {
-                const int ns = class_nlaunch(L.UT, L.TT);
+                const int ns = launch_count(L);
                 const double w = L.weight * kPsPerQuartet[class_id(L.UT, L.TT)] / ns;
                 for (int k = 0; k < ns; ++k) {
                     pidx.push_back((int32_t)(L.args.row_counter - pl->d_counters) + k);
@@ -1084,8 +1128,8 @@ static int launch_region(myqc_eri_plan* plan, Sub& sub, Launch& L, int r, int sl
     a.stage = plan->compose ? plan->d_stage : nullptr;
     a.tasks = L.args.tasks + t0;
     a.ntasks = t1 - t0;
-    a.row_counter = L.args.row_counter + r * class_nlaunch(L.UT, L.TT);
-    return launch_class(L.UT, L.TT, slice, a, plan->num_sms, st);
+    a.row_counter = L.args.row_counter + r * launch_count(L);
+    return launch_class(L.UT, L.TT, L.warp ? -1 : slice, a, plan->num_sms, st);
 }
 
 static int fill_region(myqc_eri_plan* plan, Sub& sub, int r, double* d_sub_out, cudaStream_t st, bool paced = false) {
@@ -1167,7 +1211,7 @@ int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
         int rr = 0;
         for (Sub& sub : plan->subs)
             for (Launch& L : sub.launches)
-                for (int slice = 0; slice < class_nlaunch(L.UT, L.TT); ++slice) {
+                for (int slice = 0; slice < launch_count(L); ++slice) {
                     const int si = rr++ % myqc_eri_plan::kNumCompute;
                     int e = launch_region(plan, sub, L, 0, slice, nullptr, plan->s_comp[si]);
                     if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
@@ -1216,7 +1260,7 @@ int myqc_eri_plan_execute(myqc_eri_plan* plan, double* d_out, void* stream) {
             for (Launch& L : sub.launches) {
                 if (L.region_task[r + 1] <= L.region_task[r]) continue;
                 // the mu-slices of (SP SP|SP SP) are independent launches: one internal stream each
-                for (int slice = 0; slice < class_nlaunch(L.UT, L.TT); ++slice) {
+                for (int slice = 0; slice < launch_count(L); ++slice) {
                     const int si = rr++ % myqc_eri_plan::kNumCompute;
                     // plain fill: the slice must be zeroed before a class kernel stores into it; the
                     // screened fill writes a disjoint set of elements and needs no ordering
@@ -1302,7 +1346,7 @@ int myqc_eri_plan_execute_timed(myqc_eri_plan* plan, double* d_out, void* stream
         if (plan->compose) {
             int e = 0;
             for (Launch& L : sub.launches) {
-                for (int slice = 0; slice < class_nlaunch(L.UT, L.TT) && !e; ++slice) e = launch_region(plan, sub, L, 0, slice, nullptr, st);
+                for (int slice = 0; slice < launch_count(L) && !e; ++slice) e = launch_region(plan, sub, L, 0, slice, nullptr, st);
                 if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
                 CU(cudaEventRecord(ev[++idx], st));
             }
@@ -1316,7 +1360,7 @@ int myqc_eri_plan_execute_timed(myqc_eri_plan* plan, double* d_out, void* stream
             if (e) return cuda_fail((cudaError_t)e, "fill_zero launch");
             CU(cudaEventRecord(ev[++idx], st));
             for (Launch& L : sub.launches) {
-                for (int slice = 0; slice < class_nlaunch(L.UT, L.TT) && !e; ++slice) e = launch_region(plan, sub, L, r, slice, d_sub, st);
+                for (int slice = 0; slice < launch_count(L) && !e; ++slice) e = launch_region(plan, sub, L, r, slice, d_sub, st);
                 if (e) return cuda_fail((cudaError_t)e, "class kernel launch");
                 CU(cudaEventRecord(ev[++idx], st));
             }
@@ -1341,7 +1385,7 @@ int myqc_eri_plan_executed_quartets(myqc_eri_plan* plan, int64_t* nq, double* sc
     for (const Sub& sub : plan->subs)
         for (const Launch& L : sub.launches) {
             const size_t idx = (size_t)(L.args.pq_counter - plan->d_pq);
-            nq[class_id(L.UT, L.TT)] += (int64_t)(h[idx] / (unsigned long long)class_nlaunch(L.UT, L.TT));
+            nq[class_id(L.UT, L.TT)] += (int64_t)(h[idx] / (unsigned long long)launch_count(L));
         }
     if (schwarz_tau) *schwarz_tau = plan->schwarz_tau;
     return MYQC_OK;

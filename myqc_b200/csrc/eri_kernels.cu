@@ -471,6 +471,314 @@ __global__ void __launch_bounds__(Cfg<UT, TT, USL>::NTHREADS, Cfg<UT, TT, USL>::
 }
 
 // ------------------------------------------------------------------------------------------
+// Warp-cooperative (SP SP|SP SP) kernel (MYQC_PP_KERNEL=warp).  The class kernel above gives a whole contracted
+// quartet -- up to 81 primitive quartets x four mu-slices -- to ONE lane, so a launch with a few thousand quartets
+// (C20H42, (H2O)_16) lasts as long as its longest lane (~0.3 ms) however empty the machine is.  Here a warp takes ONE
+// contracted quartet at a time and its lanes take the PRIMITIVE quartets (row primitive ku, lane-side primitive kt)
+// that pass the reference's test, 32 at a time:
+//   * both pair records sit in shared memory (row: TMA bulk copy two tasks ahead as above; lane side: one coalesced
+//     copy per quartet); a lane reads the coefficients of its own (ku, kt);
+//   * per lane: Boys values and R_{NLM} (35 values) once, then for each mu-slice step A (K[4][10]) and step B -- the
+//     full 16 x 16 contribution of the primitive quartet, 32 values at a time;
+//   * the 32 values of every lane go through a [32][33] shared-memory tile and lane l adds up column l (fixed order:
+//     primitive quartets in (kt, ku) order), so after eight tiles every lane holds 8 of the quartet's 256 integrals;
+//   * stores: lane l owns f' = l % 8 (+8) and f = 4 mu + l / 8, so the 16 f' of one f -- four runs of four adjacent
+//     packed columns -- leave in one warp instruction.
+// Same screens, same Boys / R arithmetic, same term tables as the class kernel; only the order in which the
+// primitive quartets of one integral are added differs (|difference| ~ 1e-16 relative).
+// UT = 2: (SP SP|SP SP), four mu-slices of the row pair; UT = 1: (S SP|SP SP), one slice.  The lane side is SP.SP.
+template <int UT>
+struct PPW {
+    static constexpr int LT = UT + 2, Q = 3 * LT, NR = h_count(LT), NHT = tt_nh(2), NT = tt_nterm(2), FU = tt_nfield(2);
+    static constexpr int NTU = tt_nterm(UT), NFU = tt_nf(UT), NSL = NFU / 4, FUU = tt_nfield(UT);
+    static constexpr int NTHREADS = 128, NWARPS = 4;
+    static constexpr uint32_t U_BYTES = 9 * FUU * 8;
+    // Primitive records sit LD doubles apart in shared memory (52 in global memory): lanes read the same field of
+    // different primitives, and with a stride of 54 doubles primitives 0..7 fall into different banks (52: 0, 4, 8 collide)
+    static constexpr int LD = FU + 2;
+    static constexpr int LDU = (FUU % 8 == 4) ? FUU + 2 : FUU;  // 54 for SP.SP rows; S.SP rows (14 doubles) need no padding
+    static constexpr int RED_LD = 33;
+    static constexpr size_t OFF_EXP = 121 * 8 * 8;
+    static constexpr size_t OFF_U = OFF_EXP + 608 * 16;                          // per warp: two row buffers
+    static constexpr size_t OFF_V = OFF_U + (size_t)NWARPS * 2 * 9 * LDU * 8;    // per warp: the lane-side record
+    static constexpr size_t OFF_RED = OFF_V + (size_t)NWARPS * 9 * LD * 8;       // per warp: [32][33] reduction tile
+    static constexpr size_t OFF_BAR = OFF_RED + (size_t)NWARPS * 32 * RED_LD * 8;
+    static constexpr size_t SMEM = OFF_BAR + (size_t)NWARPS * 2 * 8;
+};
+
+template <int UT, bool MULTI>
+__global__ void __launch_bounds__(PPW<UT>::NTHREADS, 2) eri_ppw_kernel(const __grid_constant__ ClassArgs a) {
+    using C = PPW<UT>;
+    constexpr int LT = C::LT, Q = C::Q, NR = C::NR, NHT = C::NHT, NT = C::NT, FU = C::FU, LD = C::LD;
+    constexpr int NTU = C::NTU, NFU = C::NFU, NSL = C::NSL, FUU = C::FUU, LDU = C::LDU;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* s_ft = reinterpret_cast<double*>(smem_raw);
+    double2* s_exp = reinterpret_cast<double2*>(smem_raw + C::OFF_EXP);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    double* s_ubuf = reinterpret_cast<double*>(smem_raw + C::OFF_U) + (size_t)warp * 2 * 9 * LDU;
+    double* s_v = reinterpret_cast<double*>(smem_raw + C::OFF_V) + (size_t)warp * 9 * LD;
+    double* s_red = reinterpret_cast<double*>(smem_raw + C::OFF_RED) + (size_t)warp * 32 * C::RED_LD;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + C::OFF_BAR) + warp * 2;
+
+    for (int i = tid; i < 121 * 8; i += C::NTHREADS) s_ft[i] = a.ftab_q[i];
+    for (int i = tid; i < 601; i += C::NTHREADS) s_exp[i] = a.exptab[i];
+    if (lane == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    int t = 0;
+    int4 task = make_int4(0, 0, 0, 0);
+    if (lane == 0) {
+        t = atomicAdd(a.row_counter, 1);
+        if (t < a.ntasks) {
+            task = a.tasks[t];
+            mbar_expect_tx(&s_bar[0], C::U_BYTES);
+            const double* src = a.part[MULTI ? task.w : 0].u_aos + (size_t)task.x * 9 * FUU;
+            if constexpr (LDU == FUU) tma_bulk_g2s(s_ubuf, src, C::U_BYTES, &s_bar[0]);
+            else {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) tma_bulk_g2s(s_ubuf + k * LDU, src + k * FUU, FUU * 8, &s_bar[0]);
+            }
+        }
+    }
+    t = __shfl_sync(0xffffffffu, t, 0);
+    task.x = __shfl_sync(0xffffffffu, task.x, 0);
+    task.y = __shfl_sync(0xffffffffu, task.y, 0);
+    task.z = __shfl_sync(0xffffffffu, task.z, 0);
+    if (MULTI) task.w = __shfl_sync(0xffffffffu, task.w, 0);
+    int buf = 0;
+    uint32_t parity0 = 0, parity1 = 0;
+    // this lane's 2 NSL integrals of a quartet: slot 2*mu + hh is (f, f') = (4 mu + lane / 8, 8 hh + lane % 8)
+    const int fl = lane >> 3, fpl = lane & 7;
+    while (t < a.ntasks) {
+        int tn = 0;
+        int4 taskn = make_int4(0, 0, 0, 0);
+        if (lane == 0) {
+            tn = atomicAdd(a.row_counter, 1);
+            if (tn < a.ntasks) {
+                taskn = a.tasks[tn];
+                mbar_expect_tx(&s_bar[buf ^ 1], C::U_BYTES);
+                const double* src = a.part[MULTI ? taskn.w : 0].u_aos + (size_t)taskn.x * 9 * FUU;
+                double* dstb = s_ubuf + (size_t)(buf ^ 1) * 9 * LDU;
+                if constexpr (LDU == FUU) tma_bulk_g2s(dstb, src, C::U_BYTES, &s_bar[buf ^ 1]);
+                else {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) tma_bulk_g2s(dstb + k * LDU, src + k * FUU, FUU * 8, &s_bar[buf ^ 1]);
+                }
+            }
+        }
+        tn = __shfl_sync(0xffffffffu, tn, 0);
+        taskn.x = __shfl_sync(0xffffffffu, taskn.x, 0);
+        taskn.y = __shfl_sync(0xffffffffu, taskn.y, 0);
+        taskn.z = __shfl_sync(0xffffffffu, taskn.z, 0);
+        if (MULTI) taskn.w = __shfl_sync(0xffffffffu, taskn.w, 0);
+        const PartArgs& S = a.part[MULTI ? task.w : 0];
+        const int u = task.x;
+        const int npu = S.u_nprim[u];
+        int P1[NSL];
+#pragma unroll
+        for (int m = 0; m < NSL; ++m) P1[m] = S.u_pidx[(size_t)u * NFU + 4 * m + fl];
+        if (buf == 0) { mbar_wait(&s_bar[0], parity0); parity0 ^= 1; }
+        else          { mbar_wait(&s_bar[1], parity1); parity1 ^= 1; }
+        const double* s_u = s_ubuf + (size_t)buf * 9 * LDU;
+        const double eu_max = s_u[4];
+        const double qu = (a.tau > 0.0) ? __ldg(S.u_q + u) : 0.0;
+        unsigned long long npq_task = 0;
+
+        for (int v = task.y; v < task.z; ++v) {
+            // Schwarz skip (warp uniform): every integral of the quartet is below tau
+            if (a.tau > 0.0 && qu * __ldg(S.t_q + v) < a.tau) continue;
+            const int npt = S.t_nprim[v];
+            __syncwarp();  // the previous quartet's readers of s_v are done
+            {
+                const double* src = S.t_aos + (size_t)v * 9 * FU;
+                for (int i = lane; i < npt * FU; i += 32) s_v[(i / FU) * LD + i % FU] = __ldg(src + i);
+            }
+            __syncwarp();
+            // lane kt < npt: number of row primitives that pass IF (EGH*EIJ .LT. 1.0D-14) CYCLE (int2e.f90:257) against
+            // lane-side primitive kt (both lists are sorted by prefactor, so the survivors are a prefix)
+            int nk = 0;
+            if (lane < npt) {
+                const double et = s_v[lane * LD + 4];
+                if (!(eu_max * et < kScreen))
+                    for (int ku = 0; ku < npu; ++ku) {
+                        if (s_u[ku * LDU + 4] * et < kScreen) break;
+                        ++nk;
+                    }
+            }
+            int incl = nk;
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const int npq = __shfl_sync(0xffffffffu, incl, 15);  // at most nine lanes hold a count
+            if (npq == 0) continue;
+            const int excl = incl - nk;
+            npq_task += (unsigned long long)npq;
+            double out[2 * NSL];
+#pragma unroll
+            for (int o = 0; o < 2 * NSL; ++o) out[o] = 0.0;
+
+            for (int base = 0; base < npq; base += 32) {
+                const int i = base + lane;
+                const bool active = i < npq;
+                int kt = 0, ku = 0;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const int ek = __shfl_sync(0xffffffffu, excl, k), ik = __shfl_sync(0xffffffffu, incl, k);
+                    if (i >= ek && i < ik) { kt = k; ku = i - ek; }
+                }
+                const int nact = min(32, npq - base);
+                const int nsum = (nact + 7) & ~7;  // lanes without a primitive quartet write zeros
+                const double* up = s_u + ku * LDU;
+                const double* tp = s_v + kt * LD;
+                double R[NR];
+                if (active) {
+                    const double p = up[0], q = tp[0];
+                    const double X = up[1] - tp[1], Y = up[2] - tp[2], Z = up[3] - tp[3];
+                    const double R2 = fma(X, X, fma(Y, Y, Z * Z));
+                    const double sm = p + q;
+                    const double pq = p * q;
+                    const double w = pq * R2;  // T*(p+q)
+                    double G[LT + 1];
+                    if (w >= (double)(2 * Q + 36) * sm) {
+                        const double rinv = rsqrt_pos(R2);
+                        const double m = -(rinv * rinv);
+                        double g = (kHalfSqrtPi * tp[5]) * up[5] * rinv;
+                        G[0] = g;
+#pragma unroll
+                        for (int j = 1; j <= LT; ++j) {
+                            g *= (double)(2 * j - 1) * m;
+                            G[j] = g;
+                        }
+                    } else {
+                        const double rs = rsqrt_pos(sm);
+                        const double alpha = pq * (rs * rs);
+                        boys_near_mid<Q, LT>(alpha * R2, alpha, rs, G, s_ft, s_exp);
+                    }
+                    build_R<LT>(G, X, Y, Z, R);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) R[r] = 0.0;
+                }
+                // The four mu-slices run through ONE copy of the step-B / reduction code (a run-time loop; only step A,
+                // whose R indices differ from slice to slice, exists four times): the first version unrolled everything
+                // into 100 KB of straight-line code and spent 37 % of its stall samples waiting for instructions.
+                // Lanes without a primitive quartet carry R = 0 and so produce exact zeros without a branch.
+#pragma unroll 1
+                for (int mu = 0; mu < NSL; ++mu) {
+                    // step A: K[f][H'] = sum_k D_k R[H_k + H'] over the terms of the four function pairs of this slice
+                    double K[4][NHT];
+                    auto step_a = [&](auto mc) {
+                        constexpr int m = decltype(mc)::value;
+                        static_for<0, NTU>([&](auto kc) {
+                            constexpr int k = decltype(kc)::value;
+                            constexpr int f = term_fn(UT, k);
+                            if constexpr (f / 4 == m) {
+                                constexpr int hk = term_h(UT, k);
+                                constexpr bool fst = (k == 0) || (term_fn(UT, k > 0 ? k - 1 : 0) != f);  // first term of its function pair
+                                const double cu = up[kRecCoef + k];
+                                static_for<0, NHT>([&](auto hc) {
+                                    constexpr int hp = decltype(hc)::value;
+                                    if constexpr (fst) K[f % 4][hp] = cu * R[h_add(hk, hp)];
+                                    else K[f % 4][hp] = fma(cu, R[h_add(hk, hp)], K[f % 4][hp]);
+                                });
+                            }
+                        });
+                    };
+                    if constexpr (NSL == 1) step_a(std::integral_constant<int, 0>{});
+                    else
+                        switch (mu) {
+                            case 0: step_a(std::integral_constant<int, 0>{}); break;
+                            case 1: step_a(std::integral_constant<int, 1>{}); break;
+                            case 2: step_a(std::integral_constant<int, 2>{}); break;
+                            default: step_a(std::integral_constant<int, 3>{}); break;
+                        }
+                    // step B, eight f' at a time: this primitive quartet's share of 32 integrals into the tile
+                    static_for<0, 2>([&](auto hhc) {
+                        constexpr int hh = decltype(hhc)::value;
+                        static_for<0, 8>([&](auto fc) {
+                            constexpr int fp = 8 * hh + decltype(fc)::value;
+                            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                            static_for<0, NT>([&](auto kc) {
+                                constexpr int k = decltype(kc)::value;
+                                if constexpr (term_fn(2, k) == fp) {
+                                    constexpr int hp = term_h(2, k);
+                                    double ct = tp[kRecCoef + k];
+                                    if constexpr (h_parity(hp) != 0) ct = -ct;
+#pragma unroll
+                                    for (int f = 0; f < 4; ++f) acc[f] = fma(ct, K[f][hp], acc[f]);
+                                }
+                            });
+#pragma unroll
+                            for (int f = 0; f < 4; ++f) s_red[(f * 8 + decltype(fc)::value) * C::RED_LD + lane] = acc[f];
+                        });
+                        __syncwarp();
+                        // lane l adds up column l = (f, f') = (l / 8, l % 8) over the primitive quartets of the batch
+                        {
+                            const double* col = s_red + lane * C::RED_LD;
+                            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 1
+                            for (int r = 0; r < nsum; r += 8) {
+                                const double c0 = col[r], c1 = col[r + 1], c2 = col[r + 2], c3 = col[r + 3];
+                                const double c4 = col[r + 4], c5 = col[r + 5], c6 = col[r + 6], c7 = col[r + 7];
+                                s0 += c0 + c4;
+                                s1 += c1 + c5;
+                                s2 += c2 + c6;
+                                s3 += c3 + c7;
+                            }
+                            const double sum = (s0 + s1) + (s2 + s3);
+#pragma unroll
+                            for (int m = 0; m < NSL; ++m)
+                                if (mu == m) out[2 * m + hh] += sum;
+                        }
+                        __syncwarp();
+                    });
+                }
+            }
+
+            if (a.stage != nullptr) {
+                // compose mode: this quartet's dense block [f][f'] of the staging array
+                double* dst = a.stage + (__ldg(S.stage_row + u) + (int64_t)v * (NFU * 16));
+#pragma unroll
+                for (int m = 0; m < NSL; ++m)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) dst[(4 * m + fl) * 16 + 8 * hh + fpl] = out[2 * m + hh];
+            } else {
+                const bool same_pair = S.tri && (v == u);
+                const int64_t np = a.npair;
+                const int P2a = S.t_pidx[(size_t)v * 16 + fpl], P2b = S.t_pidx[(size_t)v * 16 + 8 + fpl];
+#pragma unroll
+                for (int m = 0; m < NSL; ++m) {
+                    if (P1[m] < 0) continue;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int P2 = hh ? P2b : P2a;
+                        if (P2 < 0) continue;
+                        if (same_pair && P1[m] > P2) continue;
+                        const int64_t lo = P1[m] < P2 ? P1[m] : P2;
+                        const int64_t hi = P1[m] < P2 ? P2 : P1[m];
+                        const int64_t idx = lo * np - ((lo * (lo - 1)) >> 1) + (hi - lo) - a.out_offset;
+                        store_eri(a.out + idx, out[2 * m + hh]);
+                    }
+                }
+            }
+        }
+        if (lane == 0 && npq_task) atomicAdd(a.pq_counter, npq_task);
+        __syncwarp();  // every lane is done with this row buffer before the TMA two tasks ahead reuses it
+        t = tn;
+        task = taskn;
+        buf ^= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Schwarz factors.  (f|f) for every function pair f of the shell pairs of kind T, one thread per shell pair, over
 // ALL primitive quartets of the pair with itself: no EIJ*EGH screen here, because the reference's own diagonal is
 // exactly zero once E < 1e-7 and a bound built from it would not bound anything.  Same Boys / R arithmetic as the
@@ -1008,8 +1316,20 @@ static int prepare_one(int* occ_out) {
     return 0;
 }
 
+template <int UT, bool MULTI>
+static int prepare_ppw(int* occ_out) {
+    auto kern = eri_ppw_kernel<UT, MULTI>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PPW<UT>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, PPW<UT>::NTHREADS, PPW<UT>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    *occ_out = occ < 1 ? 1 : occ;
+    return 0;
+}
+
 constexpr int kMaxDevices = 64;
-static int g_occ[kMaxDevices][20];  // [slot] one-part kernels, [10 + slot] multi-part kernels
+static int g_occ[kMaxDevices][24];  // [slot] one-part kernels, [12 + slot] multi-part kernels; slots 9, 10: warp-cooperative kernels
 static bool g_prepared[kMaxDevices];
 
 int prepare_kernels() {
@@ -1020,23 +1340,27 @@ int prepare_kernels() {
     if (g_prepared[dev]) return 0;
     int e = 0;
     if (!e) e = prepare_one<0, 0, -1, false>(&g_occ[dev][0]);
-    if (!e) e = prepare_one<0, 0, -1, true>(&g_occ[dev][10 + 0]);
+    if (!e) e = prepare_one<0, 0, -1, true>(&g_occ[dev][12 + 0]);
     if (!e) e = prepare_one<0, 1, -1, false>(&g_occ[dev][1]);
-    if (!e) e = prepare_one<0, 1, -1, true>(&g_occ[dev][10 + 1]);
+    if (!e) e = prepare_one<0, 1, -1, true>(&g_occ[dev][12 + 1]);
     if (!e) e = prepare_one<0, 2, -1, false>(&g_occ[dev][2]);
-    if (!e) e = prepare_one<0, 2, -1, true>(&g_occ[dev][10 + 2]);
+    if (!e) e = prepare_one<0, 2, -1, true>(&g_occ[dev][12 + 2]);
     if (!e) e = prepare_one<1, 1, -1, false>(&g_occ[dev][3]);
-    if (!e) e = prepare_one<1, 1, -1, true>(&g_occ[dev][10 + 3]);
+    if (!e) e = prepare_one<1, 1, -1, true>(&g_occ[dev][12 + 3]);
     if (!e) e = prepare_one<1, 2, -1, false>(&g_occ[dev][4]);
-    if (!e) e = prepare_one<1, 2, -1, true>(&g_occ[dev][10 + 4]);
+    if (!e) e = prepare_one<1, 2, -1, true>(&g_occ[dev][12 + 4]);
     if (!e) e = prepare_one<2, 2, 0, false>(&g_occ[dev][5]);
-    if (!e) e = prepare_one<2, 2, 0, true>(&g_occ[dev][10 + 5]);
+    if (!e) e = prepare_one<2, 2, 0, true>(&g_occ[dev][12 + 5]);
     if (!e) e = prepare_one<2, 2, 1, false>(&g_occ[dev][6]);
-    if (!e) e = prepare_one<2, 2, 1, true>(&g_occ[dev][10 + 6]);
+    if (!e) e = prepare_one<2, 2, 1, true>(&g_occ[dev][12 + 6]);
     if (!e) e = prepare_one<2, 2, 2, false>(&g_occ[dev][7]);
-    if (!e) e = prepare_one<2, 2, 2, true>(&g_occ[dev][10 + 7]);
+    if (!e) e = prepare_one<2, 2, 2, true>(&g_occ[dev][12 + 7]);
     if (!e) e = prepare_one<2, 2, 3, false>(&g_occ[dev][8]);
-    if (!e) e = prepare_one<2, 2, 3, true>(&g_occ[dev][10 + 8]);
+    if (!e) e = prepare_one<2, 2, 3, true>(&g_occ[dev][12 + 8]);
+    if (!e) e = prepare_ppw<2, false>(&g_occ[dev][9]);
+    if (!e) e = prepare_ppw<2, true>(&g_occ[dev][12 + 9]);
+    if (!e) e = prepare_ppw<1, false>(&g_occ[dev][10]);
+    if (!e) e = prepare_ppw<1, true>(&g_occ[dev][12 + 10]);
     if (e) return e;
     if (common_carveout()) {
         ce = cudaFuncSetAttribute(fill_screened_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -1060,7 +1384,7 @@ static int launch_impl(const ClassArgs& a, int num_sms, cudaStream_t st, int slo
     cudaGetDevice(&dev);
     int e0 = prepare_kernels();
     if (e0) return e0;
-    const int occ = g_occ[dev][slot + (MULTI ? 10 : 0)];
+    const int occ = g_occ[dev][slot + (MULTI ? 12 : 0)];
     int grid = num_sms * occ;
     const int need = (a.ntasks + C::NWARPS - 1) / C::NWARPS;
     if (grid > need) grid = need;
@@ -1075,11 +1399,42 @@ static int launch_one(const ClassArgs& a, int num_sms, cudaStream_t st, int slot
     return launch_impl<UT, TT, USL, false>(a, num_sms, st, slot);
 }
 
+// MYQC_PP_KERNEL=warp: (SP SP|SP SP) always by the warp-cooperative kernel (one launch); =slices: always four mu-slices
+// of the class kernel; unset: the plan decides per piece from its number of contracted quartets.  1 / 0 / -1.
+int pp_kernel_mode() {  // read at plan creation (not cached: tests switch it between plans)
+    const char* e = getenv("MYQC_PP_KERNEL");
+    return !e ? -1 : (e[0] == 'w') ? 1 : (e[0] == 's') ? 0 : -1;
+}
+// the same for (S SP|SP SP): MYQC_SP_KERNEL = warp (1) / class (0) / unset (-1)
+int sp_kernel_mode() {
+    const char* e = getenv("MYQC_SP_KERNEL");
+    return !e ? -1 : (e[0] == 'w') ? 1 : (e[0] == 'c') ? 0 : -1;
+}
+
+template <int UT, bool MULTI>
+static int launch_ppw(const ClassArgs& a, int num_sms, cudaStream_t st) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int e0 = prepare_kernels();
+    if (e0) return e0;
+    int grid = num_sms * g_occ[dev][(UT == 2 ? 9 : 10) + (MULTI ? 12 : 0)];
+    const int need = (a.ntasks + PPW<UT>::NWARPS - 1) / PPW<UT>::NWARPS;
+    if (grid > need) grid = need;
+    eri_ppw_kernel<UT, MULTI><<<grid, PPW<UT>::NTHREADS, PPW<UT>::SMEM, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
 int class_nlaunch(int UT, int TT) { return (UT == 2 && TT == 2) ? 4 : 1; }
 
 int launch_class(int UT, int TT, int slice, const ClassArgs& a0, int num_sms, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ClassArgs a = a0;
+    if (slice < 0) {  // warp-cooperative kernel of (S SP|SP SP) / (SP SP|SP SP): one launch, task counter 0
+        if (TT != 2 || UT < 1) return (int)cudaErrorInvalidValue;
+        if (a.ntasks <= 0 || a.nparts <= 0) return 0;
+        if (UT == 2) return a.nparts > 1 ? launch_ppw<2, true>(a, num_sms, st) : launch_ppw<2, false>(a, num_sms, st);
+        return a.nparts > 1 ? launch_ppw<1, true>(a, num_sms, st) : launch_ppw<1, false>(a, num_sms, st);
+    }
     a.row_counter = a0.row_counter + slice;
     if (UT == 0 && TT == 0) return launch_one<0, 0, -1>(a, num_sms, st, 0);
     if (UT == 0 && TT == 1) return launch_one<0, 1, -1>(a, num_sms, st, 1);

@@ -129,11 +129,16 @@ int launch_fill_screened(const FillArgs& a, int num_sms, void* stream);
 // sets the kernel attributes and forces the (lazily loaded) kernels of the current device to load
 int prepare_kernels();
 
-// returns cudaError_t as int; `slice` < class_nlaunch(UT,TT) selects the mu-slice of (2,2) (0 otherwise);
+// returns cudaError_t as int; `slice` < class_nlaunch(UT,TT) selects the mu-slice of (2,2) (0 otherwise; -1: see below);
 // slice k uses the task counter a.row_counter + k
 int launch_class(int UT, int TT, int slice, const ClassArgs& a, int num_sms, void* stream);
 // number of kernel launches launch_class issues for (UT,TT)
 int class_nlaunch(int UT, int TT);
+// (SP SP|SP SP) by the warp-cooperative kernel (a warp per contracted quartet, lanes over its primitive quartets):
+// launch_class(2, 2, slice = -1, ...).  pp_kernel_mode(): MYQC_PP_KERNEL = warp (1) / slices (0) / unset (-1: the plan
+// decides per piece from the number of contracted quartets)
+int pp_kernel_mode();
+int sp_kernel_mode();  // the same for (S SP|SP SP): MYQC_SP_KERNEL = warp / class
 
 // unscreened diagonal integrals (f|f) of the shell pairs of kind T (0..2) into diag[packed pair index]
 int launch_diag(int T, const double* aos, const int32_t* nprim, const int32_t* pidx, int n, const double* ftab_q,

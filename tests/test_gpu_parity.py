@@ -345,6 +345,33 @@ def test_sparse_host_transfer_is_bit_identical(nsh, shift, chunk, tmp_path, monk
         assert np.isnan(pinned.numpy()[shift + nloc])  # nothing written past the slice
 
 
+@pytest.mark.parametrize("name,nsh", [("CO2", 1), ("c4h10", 1), ("h2o_8", 3), ("h2o_16", 1)])
+def test_warp_cooperative_kernels_match_class_kernels(name, nsh, tmp_path, monkeypatch):
+    """(SP SP|SP SP) and (S SP|SP SP) by the warp-cooperative kernel (a warp per contracted quartet, lanes over its
+    primitive quartets, MYQC_PP_KERNEL / MYQC_SP_KERNEL = warp) against the class kernels (one lane per contracted
+    quartet): the same screens and arithmetic, only the order in which the primitive quartets of one integral are added
+    differs -- 1e-13 absolute, the same zero pattern; and the forced-warp array passes the oracle bar on CO2."""
+    s = product_system(name, tmp_path)
+    off = Q.shard_layout(s, nsh)
+
+    def run():
+        Q.release_cache()
+        out = np.full(int(off[-1]), np.nan)
+        for k in range(nsh):
+            Q.eri_packed_shard(s, out[off[k]:off[k + 1]], device=0, shard=k, nshards=nsh)
+        return out
+    monkeypatch.setenv("MYQC_PP_KERNEL", "slices")
+    monkeypatch.setenv("MYQC_SP_KERNEL", "class")
+    ref = run()
+    monkeypatch.setenv("MYQC_PP_KERNEL", "warp")
+    monkeypatch.setenv("MYQC_SP_KERNEL", "warp")
+    got = run()
+    Q.release_cache()
+    assert not np.isnan(got).any()
+    assert np.abs(got - ref).max() < 1e-13
+    assert np.array_equal(got == 0.0, ref == 0.0)
+
+
 @pytest.mark.parametrize("engine", ["kernel", "copy"])
 @pytest.mark.parametrize("name,nsh", [("CO2", 1), ("h2o_8", 3), ("h2o_16", 1)])
 def test_fill_engines_agree(name, nsh, engine, tmp_path, monkeypatch):

@@ -12,7 +12,7 @@ while [ $# -ge 2 ]; do
   tag=$1; defs=$2; shift 2
   $NVCC $FLAGS $defs -c eri_kernels.cu -o variants/eri_kernels_$tag.o
   $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o variants/libmyqc_eri_$tag.so variants/eri_kernels_$tag.o \
-     eri_api.o fock.o int1e.o ao2mo.o pairs.o qcio.o -cudart static -lpthread
+     eri_api.o fock.o int1e.o ao2mo.o pairs.o qcio.o parse.o hostmem.o -cudart static -lpthread
   rm -f variants/eri_kernels_$tag.o
   echo "built variants/libmyqc_eri_$tag.so ($defs)"
 done
