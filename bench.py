@@ -381,14 +381,21 @@ def run_ours(args):
     else:
         achieved, peak, unit = (model_flops / world) / (ms_local * 1e-3) / 1e12, fp64_peak, "TFLOP/s"
     traffic = None
-    tfile = os.path.join(ROOT, "profiles", "r2f_h2o64_dram_traffic_bytes.json")
+    traffic_src = None
+    tfile = os.path.join(ROOT, "profiles", "r2g_h2o_64_dram_traffic_bytes.json")
     if args.workload == "h2o_64" and world == 1 and os.path.exists(tfile):
-        traffic = float(sum(json.load(open(tfile)).values()))
+        per_kernel = json.load(open(tfile))
+        traffic = float(sum(per_kernel.values()))
+        traffic_src = ("sum over the step's class-kernel launches of dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                       "ncu --set full (profiles/r2g_h2o_64_ncu_full.json)")
+        if not any("fill" in k for k in per_kernel):
+            # ncu does not see the driver's memset; it writes every byte of the slice once (the repo's fill kernel,
+            # which ncu does see, moved 40.40 GB for 40.46 GB: profiles/r2f_h2o64_dram_traffic_bytes.json)
+            traffic += bytes_alg
+            traffic_src += " + 8 B per element for the cudaMemsetAsync zero fill, which ncu does not capture"
     roofline = {"kernel": "step (zero fill + all class launches of one execute)", "bound": bound, "achieved": achieved, "peak": peak,
                 "unit": unit, "frac": achieved / peak if peak else None, "traffic": traffic,
-                "traffic_source": "sum over the step's launches of dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full "
-                                  "(profiles/r2f_h2o64_ncu_full.json; captured with the repo's fill kernel, ncu does not see the driver's memset, "
-                                  "which writes the same 8 B per element)",
+                "traffic_source": traffic_src,
                 "peak_source": peak_src if bound == "hbm" else "measured DFMA microbenchmark in this run (myqc_fp64_peak)",
                 "algorithmic_bytes": bytes_alg, "model_flops": model_flops / world,
                 "hbm_frac": bytes_alg / 1e9 / (ms_local * 1e-3) / hbm_peak,
