@@ -82,9 +82,10 @@ int myqc_eri_packed_shard(int nnuc, const double *xyz, int nset, int setl, const
 
 /* Bytes that crossed the device -> host link in this thread's last myqc_eri_packed_shard call.  A
  * pinned (device-accessible) destination of at least 4 Mi elements takes the sparse route: the slice
- * is cut into 2 KB chunks, the GPU stores the chunks that hold a nonzero straight into the host buffer
- * and host threads write the zeros of the others (MYQC_SPARSE_D2H=0 turns it off, MYQC_HOST_THREADS
- * sets the number of zeroing threads); any other destination gets one cudaMemcpy of the slice.      */
+ * is cut into 256-byte chunks (MYQC_XFER_CHUNK = 32 / 64 / 128 / 256 doubles), the GPU stores the chunks
+ * that hold a nonzero straight into the host buffer and host threads write the zeros of the others with
+ * streaming stores (MYQC_SPARSE_D2H=0 turns it off, MYQC_HOST_THREADS sets the number of zeroing
+ * threads); any other destination gets one cudaMemcpy of the slice.                                  */
 int64_t myqc_eri_last_d2h_bytes(void);
 
 /* The one-shot calls (myqc_eri_packed, myqc_eri_packed_shard, multi-device myqc_eri_dense) keep the plan (pair
@@ -97,7 +98,13 @@ void myqc_eri_release_cache(void);
  * A plan holds the shell-pair tables of one shard of the canonical quartet space on one device.
  * Shard s of nshards owns a contiguous block of rows of the packed array (rows = bra pair index
  * P), cut at shell boundaries and balanced by model flops; shards are independent (no
- * collective).  nshards=1 is the whole problem.                                               */
+ * collective).  nshards=1 is the whole problem.
+ * Execution knobs read at plan creation (defaults are the measured best):
+ *   MYQC_FILL_ENGINE = memset (default: cudaMemsetAsync) | kernel (the repo's fill kernel) | copy (copy engines)
+ *   MYQC_PP_KERNEL   = warp | slices   (SP SP|SP SP) on the warp-cooperative kernel / four mu-slices of the class
+ *                      kernel; unset: per piece, warp below 20 000 contracted quartets
+ *   MYQC_SP_KERNEL   = warp | class    the same choice for (S SP|SP SP); unset: class
+ *   MYQC_OUTPUT_MODE = compose         staged quartet blocks + one pass that writes every element once       */
 typedef struct myqc_eri_plan myqc_eri_plan;
 
 int myqc_eri_plan_create(int nnuc, const double *xyz, int nset, int setl, const double *set,
