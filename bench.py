@@ -159,11 +159,28 @@ def cpu_sample(zm: str, seconds: float, nthreads: int, offset: int = 0):
     return nunique / full, desc, dt
 
 
+def make_config(workload, s, nq_total, model_flops, rank0_elems, world):
+    """The `config` object of the JSON line.  Both arms print the SAME object (the reference arm is timed on the GPU
+    arm's config), so it is built from host-side quantities only."""
+    need_flush = 8 * rank0_elems < 512e6
+    return {"workload": workload, "norb": s.norb, "nset": s.nset, "unique_eris": s.nunique,
+            "canonical_prim_quartets": int(nq_total), "model_flops": model_flops,
+            "l2": "flushed between steps (256 MB scratch write)" if need_flush else
+                  "output slice per step (%.1f GB) is larger than L2" % (8 * rank0_elems / 1e9),
+            "parallelism": f"quartet-space row shards x{world}, no collective"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     s, zm = build_system(args.workload)
+    # the GPU arm's config (host-only library calls: canonical work statistics and the shard layout)
+    import myqc_b200 as Q
+    world = max(1, int(os.environ.get("WORLD_SIZE", str(args.gpus))))
+    nq, model_flops = Q.canonical_stats(s)
+    off = Q.shard_layout(s, world)
+    config = make_config(args.workload, s, nq.sum(), model_flops, int(off[1] - off[0]), world)
     nthreads = os.cpu_count() or 1
     per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     for w in range(args.warmup):
@@ -179,8 +196,7 @@ def run_reference(args):
         "ms_per_step_is": "extrapolated from the timed sample to the whole molecule (see cpu_baseline.sample)",
         "sample_seconds_timed": t_tot,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": args.workload, "norb": s.norb, "nset": s.nset,
-                                          "unique_eris": s.nunique},
+        "data": "synthetic", "config": config,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": descs[-1]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -422,11 +438,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": args.workload, "norb": s.norb, "nset": s.nset, "unique_eris": s.nunique,
-                   "canonical_prim_quartets": int(nq.sum()), "model_flops": model_flops,
-                   "l2": "flushed between steps (256 MB scratch write)" if need_flush else
-                         "output slice per step (%.1f GB) is larger than L2" % (8 * plan.out_elems / 1e9),
-                   "parallelism": f"quartet-space row shards x{world}, no collective"},
+        "config": make_config(args.workload, s, nq.sum(), model_flops, plan.out_elems, world),
         "roofline": roofline, "kernels": kernels, "whole_step": whole,
         "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(own_launches * args.steps),
         "zero_fill_engine": fill_engine,
