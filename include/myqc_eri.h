@@ -138,6 +138,12 @@ int myqc_eri_shard_layout(int nnuc, const double *xyz, int nset, int setl, const
                           const int32_t *setinfo, int ops, const double *bas, const int32_t *basinfo,
                           int nshards, int64_t *offsets);
 
+/* Host only: what the shard-cut cost model expects of each of `nshards` shards -- seconds in the class kernels
+ * (class_s[nshards]) and in the zero fill (fill_s[nshards]); tools/exp_shard_times.py puts measured times next to them. */
+int myqc_eri_shard_model(int nnuc, const double *xyz, int nset, int setl, const double *set,
+                         const int32_t *setinfo, int ops, const double *bas, const int32_t *basinfo,
+                         int nshards, double *class_s, double *fill_s);
+
 /* Host-only: canonical surviving primitive-quartet counts per class and their model flops for
  * the whole molecule (same definition as myqc_eri_plan_stats).                  */
 int myqc_eri_canonical_stats(int nnuc, const double *xyz, int nset, int setl, const double *set,

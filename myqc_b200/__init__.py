@@ -34,7 +34,7 @@ EXPORTS = [
     "myqc_eri_plan_create", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
     "myqc_eri_plan_execute", "myqc_eri_plan_stats", "myqc_eri_plan_destroy",
     "myqc_eri_expand_dense", "myqc_read_env", "myqc_build_basis", "myqc_read_ftab",
-    "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main", "myqc_eri_shard_layout",
+    "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main", "myqc_eri_shard_layout", "myqc_eri_shard_model",
     "myqc_eri_canonical_stats", "myqc_eri_plan_launch_count", "myqc_eri_plan_launch_info",
     "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard", "myqc_write_xx_ex", "myqc_eri_last_d2h_bytes",
     "myqc_eri_release_cache", "myqc_eri_plan_executed_quartets",
@@ -100,6 +100,7 @@ def lib() -> ctypes.CDLL:
     L.myqc_write_xx_ex.argtypes = [c_char_p, _dp, c_int, ctypes.c_int64]
     L.myqc_int2e_main.argtypes = [c_char_p, c_int]
     L.myqc_eri_shard_layout.argtypes = common[:-1] + [c_int, _i64p]
+    L.myqc_eri_shard_model.argtypes = common[:-1] + [c_int, _dp, _dp]
     L.myqc_eri_canonical_stats.argtypes = [c_int, _dp, c_int, c_int, _dp, _ip, _i64p, _dp]
     L.myqc_eri_plan_launch_count.argtypes = [c_void_p]
     L.myqc_eri_plan_launch_info.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), _i64p]
@@ -400,6 +401,13 @@ def shard_layout(s: System, nshards: int) -> np.ndarray:
     off = np.zeros(nshards + 1, dtype=np.int64)
     _check(lib().myqc_eri_shard_layout(*s._common()[:-1], nshards, off.ctypes.data_as(_i64p)))
     return off
+
+
+def shard_model(s: System, nshards: int):
+    """Host-only: (class_seconds[nshards], fill_seconds[nshards]) the shard-cut cost model expects."""
+    cs, fs = np.zeros(nshards), np.zeros(nshards)
+    _check(lib().myqc_eri_shard_model(*s._common()[:-1], nshards, _d(cs), _d(fs)))
+    return cs, fs
 
 
 def canonical_stats(s: System):

@@ -563,10 +563,21 @@ static int64_t packed_row_offset(int64_t fn, int64_t norb) {
 // Pure host arithmetic: every rank computes the same answer independently.
 struct CutTable {
     std::vector<int> cuts;   // candidate cut points: first orbital of each shell, ascending
-    std::vector<double> w;   // estimated model flops owned by [cuts[c], cuts[c+1])
+    std::vector<double> w;   // estimated seconds of the block [cuts[c], cuts[c+1]): class kernels + zero fill
+    std::vector<double> wclass, wfill;  // the two parts of w
 };
 
-static int build_cut_table(const std::vector<Shell>& shells, const PairList all[3], CutTable& ct, std::string& err) {
+// Fenwick tree over doubles (prefix sums with point updates)
+struct Fenwick {
+    std::vector<double> t;
+    explicit Fenwick(int n) : t((size_t)n + 1, 0.0) {}
+    void add(int i, double v) { for (++i; i < (int)t.size(); i += i & -i) t[i] += v; }
+    double prefix(int n) const { double s = 0.0; for (int i = std::min(n, (int)t.size() - 1); i > 0; i -= i & -i) s += t[i]; return s; }  // sum of [0, n)
+    double range(int lo, int hi) const { return hi > lo ? prefix(hi) - prefix(lo) : 0.0; }
+};
+
+// nq_ref: canonical primitive-quartet counts of the whole molecule per class (canonical_stats), or nullptr
+static int build_cut_table(const std::vector<Shell>& shells, const PairList all[3], const int64_t* nq_ref, CutTable& ct, std::string& err) {
     for (const Shell& sh : shells) {  // row blocks are closed only for contiguous orbital ranges
         int cnt = 0, mx = -1;
         for (int k = 0; k < 4; ++k) if (sh.fn[k] >= 0) { ++cnt; mx = std::max(mx, sh.fn[k]); }
@@ -579,39 +590,62 @@ static int build_cut_table(const std::vector<Shell>& shells, const PairList all[
     cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
     const int nc = (int)cuts.size();
     auto cut_of = [&](int fn) { return (int)(std::upper_bound(cuts.begin(), cuts.end(), fn) - cuts.begin()) - 1; };
-    // weight of block c ~ model flops of the quartets it owns.  A row u of class (ta,tb) has
-    // cnt[u] partners (the emax prefix); the prefix is treated as an unbiased sample of owners, so
-    // the row's weight is split between cut(u) (partners with cut >= cut(u)) and the lower cuts
-    // in proportion to the partner histogram.
-    ct.w.assign(nc, 0.0);
+    // Class-kernel seconds of block c = (primitive quartets of the quartets it owns) x (seconds per primitive quartet
+    // of the class).  A quartet (u|v) belongs to the block min(cut(u), cut(v)); u's partners are the prefix [lo_u, L_u)
+    // of the lane-side list.  The count is taken with the separable proxy nprim(u) x nprim(v) per quartet, summed
+    // EXACTLY over the (row, partner) pairs with two sweeps over the blocks and a Fenwick tree each, and scaled per
+    // class to the canonical primitive-quartet count of the whole molecule.  (Until session 3 of round 2 the partners
+    // of a row were split over the blocks in proportion to ALL pairs of the list; the prefix holds the pairs with the
+    // largest prefactors -- near pairs, which are spread evenly over the blocks, while all pairs are front-loaded --
+    // so late blocks were under-weighted: the last of 8 shards of (H2O)_64 got 1.57x the primitive quartets of the first
+    // where the model meant 1.38x, and was 8 % slower than the rest at every N.)
+    ct.wclass.assign(nc, 0.0);
+    ct.wfill.assign(nc, 0.0);
     for (int ta = 0; ta < 3; ++ta)
         for (int tb = ta; tb < 3; ++tb) {
             const PairList& A = all[ta];
             const PairList& B = all[tb];
             if (A.n == 0 || B.n == 0) continue;
-            const std::vector<int32_t> cnt = row_prefix(A, B);
-            std::vector<double> hist(nc + 1, 0.0), ge(nc + 2, 0.0);
-            double mean_prim = 0.0;
-            for (int k = 0; k < B.n; ++k) {
-                hist[cut_of(B.owner_fn[k])] += 1.0;
-                mean_prim += B.nprim[k];
+            const bool tri = (ta == tb);
+            std::vector<int32_t> L = row_prefix(A, B);
+            for (int u = 1; u < A.n; ++u) L[u] = std::min(L[u], L[u - 1]);  // rows are in prefactor order: monotone up to rounding
+            std::vector<int> cA(A.n), cB(B.n);
+            std::vector<std::vector<int>> bktA(nc), bktB(nc);
+            for (int u = 0; u < A.n; ++u) { cA[u] = cut_of(A.owner_fn[u]); bktA[cA[u]].push_back(u); }
+            for (int v = 0; v < B.n; ++v) { cB[v] = cut_of(B.owner_fn[v]); bktB[cB[v]].push_back(v); }
+            std::vector<double> acc(nc, 0.0);
+            {   // quartets owned through the row: partners v in [lo_u, L_u) with cut(v) >= cut(u)
+                Fenwick fb(B.n);
+                for (int c = nc - 1; c >= 0; --c) {
+                    for (int v : bktB[c]) fb.add(v, (double)B.nprim[v]);
+                    for (int u : bktA[c]) acc[c] += (double)A.nprim[u] * fb.range(tri ? u : 0, L[u]);
+                }
             }
-            mean_prim /= B.n;
-            for (int c = nc - 1; c >= 0; --c) ge[c] = ge[c + 1] + hist[c];
+            {   // quartets owned through the partner: rows u with lo_u <= v < L_u and cut(u) > cut(v)
+                Fenwick fa(A.n);
+                for (int c = nc - 1; c >= 0; --c) {
+                    for (int v : bktB[c]) {
+                        // rows with L_u > v are a prefix of the (monotone) list
+                        int ustar = (int)(std::partition_point(L.begin(), L.end(), [&](int32_t l) { return l > v; }) - L.begin());
+                        if (tri) ustar = std::min(ustar, v + 1);
+                        acc[c] += (double)B.nprim[v] * fa.prefix(ustar);
+                    }
+                    for (int u : bktA[c]) fa.add(u, (double)A.nprim[u]);
+                }
+            }
             // seconds per primitive quartet: model flops / (class efficiency x DFMA peak).  The efficiencies are machine
             // constants of these kernels on a B200 (fraction of the DFMA peak in model flops when a launch fills the
             // machine: profiles/r2f_bench.json); only their ratios to each other and to the fill rate below enter the cuts.
             static const double kEff[6] = {0.46, 0.47, 0.32, 0.36, 0.30, 0.27};
             const int cid = class_id(ta, tb);
-            const double wq = kW[cid] / (kEff[cid] * 34.2e12) * mean_prim / B.n;
-            for (int u = 0; u < A.n; ++u) {
-                double nrow = cnt[u];
-                if (ta == tb) nrow = std::max(0.0, nrow - u);
-                const double wr = wq * nrow * (double)A.nprim[u];
-                const int cu = cut_of(A.owner_fn[u]);
-                ct.w[cu] += wr * ge[cu];
-                for (int c = 0; c < cu; ++c) ct.w[c] += wr * hist[c];
-            }
+            const double sec_per_pq = kW[cid] / (kEff[cid] * 34.2e12);
+            double proxy = 0.0;
+            for (int c = 0; c < nc; ++c) proxy += acc[c];
+            if (!(proxy > 0.0)) continue;
+            // the proxy counts every primitive pair of both sides; the reference's rule on primitives removes a
+            // class-dependent share of them, so the class total is taken from the canonical count when it is known
+            const double scale = (nq_ref && nq_ref[cid] > 0) ? (double)nq_ref[cid] / proxy : 1.0;
+            for (int c = 0; c < nc; ++c) ct.wclass[c] += acc[c] * scale * sec_per_pq;
         }
     // plus the zero fill of the rows the block owns (HBM bound; cudaMemsetAsync writes ~7.3 TB/s on a B200)
     {
@@ -621,9 +655,11 @@ static int build_cut_table(const std::vector<Shell>& shells, const PairList all[
         for (int c = 0; c < nc; ++c) {
             const int64_t b = packed_row_offset(c == 0 ? 0 : cuts[c], norb);
             const int64_t e = packed_row_offset(c + 1 < nc ? cuts[c + 1] : norb, norb);
-            ct.w[c] += 8.0 * (double)(e - b) / 7.3e12;
+            ct.wfill[c] = 8.0 * (double)(e - b) / 7.3e12;
         }
     }
+    ct.w.assign(nc, 0.0);
+    for (int c = 0; c < nc; ++c) ct.w[c] = ct.wclass[c] + ct.wfill[c];
     return MYQC_OK;
 }
 
@@ -816,7 +852,10 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
     std::vector<int> sub_fn(2, 0);
     sub_fn[1] = pl->norb;
     if (nshards > 1 || nvs > 1) {
-        if ((rc = build_cut_table(shells, all, ct, err))) return fail(rc, err);
+        int64_t nq_ref[6];
+        double fl_ref = 0.0;
+        canonical_stats(nnuc, xyz, nset, setl, set, setinfo, nq_ref, &fl_ref);
+        if ((rc = build_cut_table(shells, all, nq_ref, ct, err))) return fail(rc, err);
         const int nc = (int)ct.cuts.size();
         const std::vector<int> ext = split_range(ct, 0, nc, nshards);
         const std::vector<int> sub = split_range(ct, ext[shard], ext[shard + 1], nvs);
@@ -1101,9 +1140,39 @@ int myqc_eri_shard_layout(int nnuc, const double* xyz, int nset, int setl, const
     if ((rc = build_pairs(nnuc, xyz, set, setinfo, setl, ops, bas, basinfo, shells, all, err))) return fail(rc, err);
     CutTable ct;
     if (nshards == 1) { offsets[0] = 0; offsets[1] = packed_row_offset(basinfo[1], basinfo[1]); return MYQC_OK; }
-    if ((rc = build_cut_table(shells, all, ct, err))) return fail(rc, err);
+    int64_t nq_ref[6];
+    double fl_ref = 0.0;
+    canonical_stats(nnuc, xyz, nset, setl, set, setinfo, nq_ref, &fl_ref);
+    if ((rc = build_cut_table(shells, all, nq_ref, ct, err))) return fail(rc, err);
     const std::vector<int> ext = split_range(ct, 0, (int)ct.cuts.size(), nshards);
     for (int k = 0; k <= nshards; ++k) offsets[k] = packed_row_offset(cut_to_fn(ct, ext[k], basinfo[1]), basinfo[1]);
+    return MYQC_OK;
+}
+
+// Host only: what the cut model expects of each of `nshards` shards -- seconds in the class kernels and in the zero
+// fill (class_s[nshards], fill_s[nshards]).  For tools/exp_shard_times.py, which puts the measured times next to them.
+int myqc_eri_shard_model(int nnuc, const double* xyz, int nset, int setl, const double* set,
+                         const int32_t* setinfo, int ops, const double* bas, const int32_t* basinfo,
+                         int nshards, double* class_s, double* fill_s) {
+    static const double dummy_ft[1] = {0.0};
+    int rc = check_args(nnuc, xyz, nset, setl, set, setinfo, ops, bas, basinfo, dummy_ft);
+    if (rc) return rc;
+    if (nshards < 1 || !class_s || !fill_s) return fail(MYQC_ERR_BAD_ARG, "bad nshards/outputs");
+    std::string err;
+    std::vector<Shell> shells;
+    if ((rc = build_shells(nnuc, nset, setl, setinfo, ops, basinfo, shells, err))) return fail(rc, err);
+    PairList all[3];
+    if ((rc = build_pairs(nnuc, xyz, set, setinfo, setl, ops, bas, basinfo, shells, all, err))) return fail(rc, err);
+    CutTable ct;
+    int64_t nq_ref[6];
+    double fl_ref = 0.0;
+    canonical_stats(nnuc, xyz, nset, setl, set, setinfo, nq_ref, &fl_ref);
+    if ((rc = build_cut_table(shells, all, nq_ref, ct, err))) return fail(rc, err);
+    const std::vector<int> ext = split_range(ct, 0, (int)ct.cuts.size(), nshards);
+    for (int k = 0; k < nshards; ++k) {
+        class_s[k] = fill_s[k] = 0.0;
+        for (int c = ext[k]; c < ext[k + 1]; ++c) { class_s[k] += ct.wclass[c]; fill_s[k] += ct.wfill[c]; }
+    }
     return MYQC_OK;
 }
 
