@@ -577,7 +577,7 @@ struct Fenwick {
 };
 
 // nq_ref: canonical primitive-quartet counts of the whole molecule per class (canonical_stats), or nullptr
-static int build_cut_table(const std::vector<Shell>& shells, const PairList all[3], const int64_t* nq_ref, CutTable& ct, std::string& err) {
+static int build_cut_table(const std::vector<Shell>& shells, const PairList all[3], const int64_t* nq_ref, int nshards, CutTable& ct, std::string& err) {
     for (const Shell& sh : shells) {  // row blocks are closed only for contiguous orbital ranges
         int cnt = 0, mx = -1;
         for (int k = 0; k < 4; ++k) if (sh.fn[k] >= 0) { ++cnt; mx = std::max(mx, sh.fn[k]); }
@@ -638,7 +638,12 @@ static int build_cut_table(const std::vector<Shell>& shells, const PairList all[
             // machine: profiles/r2f_bench.json); only their ratios to each other and to the fill rate below enter the cuts.
             static const double kEff[6] = {0.46, 0.47, 0.32, 0.36, 0.30, 0.27};
             const int cid = class_id(ta, tb);
-            const double sec_per_pq = kW[cid] / (kEff[cid] * 34.2e12);
+            // Launches of a 1/N share run below the efficiency of the full-size launches the constants come from (tails,
+            // fewer tasks per warp): replays of the 2- / 4- / 8-way splits of (H2O)_64 on one GPU take 1.08 / 1.15 / 1.21x
+            // the model's class time in every shard alike (tools/exp_shard_times.py), i.e. 1 + 0.07 log2 N.  The factor
+            // only shifts weight between the class kernels and the zero fill of a shard.
+            const double small_launch = 1.0 + 0.07 * std::log2((double)std::max(1, nshards));
+            const double sec_per_pq = small_launch * kW[cid] / (kEff[cid] * 34.2e12);
             double proxy = 0.0;
             for (int c = 0; c < nc; ++c) proxy += acc[c];
             if (!(proxy > 0.0)) continue;
@@ -855,7 +860,7 @@ int myqc_eri_plan_create(int nnuc, const double* xyz, int nset, int setl, const 
         int64_t nq_ref[6];
         double fl_ref = 0.0;
         canonical_stats(nnuc, xyz, nset, setl, set, setinfo, nq_ref, &fl_ref);
-        if ((rc = build_cut_table(shells, all, nq_ref, ct, err))) return fail(rc, err);
+        if ((rc = build_cut_table(shells, all, nq_ref, nshards, ct, err))) return fail(rc, err);
         const int nc = (int)ct.cuts.size();
         const std::vector<int> ext = split_range(ct, 0, nc, nshards);
         const std::vector<int> sub = split_range(ct, ext[shard], ext[shard + 1], nvs);
@@ -1143,7 +1148,7 @@ int myqc_eri_shard_layout(int nnuc, const double* xyz, int nset, int setl, const
     int64_t nq_ref[6];
     double fl_ref = 0.0;
     canonical_stats(nnuc, xyz, nset, setl, set, setinfo, nq_ref, &fl_ref);
-    if ((rc = build_cut_table(shells, all, nq_ref, ct, err))) return fail(rc, err);
+    if ((rc = build_cut_table(shells, all, nq_ref, nshards, ct, err))) return fail(rc, err);
     const std::vector<int> ext = split_range(ct, 0, (int)ct.cuts.size(), nshards);
     for (int k = 0; k <= nshards; ++k) offsets[k] = packed_row_offset(cut_to_fn(ct, ext[k], basinfo[1]), basinfo[1]);
     return MYQC_OK;
@@ -1167,7 +1172,7 @@ int myqc_eri_shard_model(int nnuc, const double* xyz, int nset, int setl, const 
     int64_t nq_ref[6];
     double fl_ref = 0.0;
     canonical_stats(nnuc, xyz, nset, setl, set, setinfo, nq_ref, &fl_ref);
-    if ((rc = build_cut_table(shells, all, nq_ref, ct, err))) return fail(rc, err);
+    if ((rc = build_cut_table(shells, all, nq_ref, nshards, ct, err))) return fail(rc, err);
     const std::vector<int> ext = split_range(ct, 0, (int)ct.cuts.size(), nshards);
     for (int k = 0; k < nshards; ++k) {
         class_s[k] = fill_s[k] = 0.0;
