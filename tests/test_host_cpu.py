@@ -157,6 +157,28 @@ def test_shard_layout_tiles_the_packed_array(name, nsh, tmp_path):
         assert np.count_nonzero(np.diff(off)) == nsh  # no empty shard on the benchmark workloads
 
 
+@pytest.mark.parametrize("name,nsh", [("h2o_16", 4), ("c20h42", 4), ("h2o_64", 8)])
+def test_shard_cost_model_is_consistent_and_balanced(name, nsh, tmp_path):
+    """Host only (myqc_eri_shard_model): the seconds the cut model expects of every shard.  The fill part is the bytes
+    of the shard's slice over the fill rate; the class part of all shards adds up to the canonical primitive-quartet
+    counts times the per-class constants (the attribution to blocks only distributes it); and the cuts balance the
+    totals as well as cuts at shell starts allow."""
+    s = product_system(name, tmp_path)
+    cs, fs = Q.shard_model(s, nsh)
+    off = Q.shard_layout(s, nsh)
+    assert cs.shape == (nsh,) and fs.shape == (nsh,) and np.all(cs >= 0) and np.all(fs >= 0)
+    assert np.allclose(fs, 8.0 * np.diff(off) / 7.3e12, rtol=1e-12, atol=0)
+    nq, _ = Q.canonical_stats(s)
+    keff = np.array([0.46, 0.47, 0.32, 0.36, 0.30, 0.27])
+    want = float(np.sum(nq * np.array(Q.CLASS_W) / (keff * 34.2e12))) * (1.0 + 0.07 * np.log2(nsh))
+    assert abs(cs.sum() - want) < 1e-9 * want
+    one_c, one_f = Q.shard_model(s, 1)
+    assert abs(one_f[0] - 8.0 * s.nunique / 7.3e12) < 1e-15
+    tot = cs + fs
+    if name == "h2o_64":
+        assert tot.max() / tot.mean() < 1.05  # the benchmark workload: within 5 % of the mean in the model
+
+
 def test_synthetic_geometries(tmp_path):
     """deterministic lattices, atom order O,H,H, 3.0 A spacing."""
     atoms, xyz, _ = parse.parse_zmat(molecules.zmat("h2o_16"))
