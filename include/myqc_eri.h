@@ -88,6 +88,10 @@ int myqc_eri_packed_shard(int nnuc, const double *xyz, int nset, int setl, const
  * threads); any other destination gets one cudaMemcpy of the slice.                                  */
 int64_t myqc_eri_last_d2h_bytes(void);
 
+/* Host only: n doubles at p (8-byte aligned) become +0.0, written with the non-temporal stores the sparse route uses for
+ * the zeros of the unflagged chunks (scalar head and tail up to the first / after the last whole cache line). */
+void myqc_host_zero(double *p, int64_t n);
+
 /* The one-shot calls (myqc_eri_packed, myqc_eri_packed_shard, multi-device myqc_eri_dense) keep the plan (pair
  * tables, task lists) and the device slice of the last call per device, keyed on the bytes of every input, so a
  * caller that asks for the same integrals again pays for them once (MYQC_NO_CACHE=1 turns this off).  This

@@ -34,7 +34,7 @@ EXPORTS = [
     "myqc_eri_plan_create", "myqc_eri_plan_out_offset", "myqc_eri_plan_out_elems",
     "myqc_eri_plan_execute", "myqc_eri_plan_stats", "myqc_eri_plan_destroy",
     "myqc_eri_expand_dense", "myqc_read_env", "myqc_build_basis", "myqc_read_ftab",
-    "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main", "myqc_eri_shard_layout", "myqc_eri_shard_model",
+    "myqc_write_xx", "myqc_read_xx", "myqc_int2e_main", "myqc_eri_shard_layout", "myqc_eri_shard_model", "myqc_host_zero",
     "myqc_eri_canonical_stats", "myqc_eri_plan_launch_count", "myqc_eri_plan_launch_info",
     "myqc_eri_plan_execute_timed", "myqc_fp64_peak", "myqc_eri_packed_shard", "myqc_write_xx_ex", "myqc_eri_last_d2h_bytes",
     "myqc_eri_release_cache", "myqc_eri_plan_executed_quartets",
@@ -101,6 +101,8 @@ def lib() -> ctypes.CDLL:
     L.myqc_int2e_main.argtypes = [c_char_p, c_int]
     L.myqc_eri_shard_layout.argtypes = common[:-1] + [c_int, _i64p]
     L.myqc_eri_shard_model.argtypes = common[:-1] + [c_int, _dp, _dp]
+    L.myqc_host_zero.argtypes = [_dp, ctypes.c_int64]
+    L.myqc_host_zero.restype = None
     L.myqc_eri_canonical_stats.argtypes = [c_int, _dp, c_int, c_int, _dp, _ip, _i64p, _dp]
     L.myqc_eri_plan_launch_count.argtypes = [c_void_p]
     L.myqc_eri_plan_launch_info.argtypes = [c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), _i64p]
@@ -401,6 +403,12 @@ def shard_layout(s: System, nshards: int) -> np.ndarray:
     off = np.zeros(nshards + 1, dtype=np.int64)
     _check(lib().myqc_eri_shard_layout(*s._common()[:-1], nshards, off.ctypes.data_as(_i64p)))
     return off
+
+
+def host_zero(a: np.ndarray) -> None:
+    """Host only: zero a contiguous float64 array (or slice) with the streaming-store routine of the sparse route."""
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    lib().myqc_host_zero(a.ctypes.data_as(_dp), a.size)
 
 
 def shard_model(s: System, nshards: int):

@@ -42,3 +42,12 @@ void host_zero_stream(double* p, size_t n) {
 void host_zero_fence() { _mm_sfence(); }
 
 }  // namespace myqc
+
+// C-ABI entry (include/myqc_eri.h): n doubles at p become +0.0 with the streaming-store routine of the sparse
+// device -> host route, fenced before it returns.  Exposed so that the host-side tests can check heads, tails and
+// alignments without a GPU.
+extern "C" void myqc_host_zero(double* p, int64_t n) {
+    if (!p || n <= 0) return;
+    myqc::host_zero_stream(p, (size_t)n);
+    myqc::host_zero_fence();
+}

@@ -179,6 +179,19 @@ def test_shard_cost_model_is_consistent_and_balanced(name, nsh, tmp_path):
         assert tot.max() / tot.mean() < 1.05  # the benchmark workload: within 5 % of the mean in the model
 
 
+def test_streaming_host_zero_writes_exactly_its_range():
+    """The zeroing routine of the sparse device -> host route (non-temporal stores for whole cache lines, scalar head
+    and tail): every offset relative to a cache line, lengths around its thresholds, nothing outside the range."""
+    buf = np.empty(4096 + 64)
+    base = (-buf.ctypes.data // 8) % 8  # element index of a 64-byte boundary
+    for off in range(0, 9):
+        for n in [0, 1, 7, 8, 9, 31, 32, 33, 63, 64, 65, 255, 256, 257, 1000, 4000]:
+            buf[:] = np.nan
+            Q.host_zero(buf[base + off:base + off + n])
+            assert np.all(buf[base + off:base + off + n] == 0.0) and not np.signbit(buf[base + off:base + off + n]).any()
+            assert np.isnan(buf[:base + off]).all() and np.isnan(buf[base + off + n:]).all()
+
+
 def test_synthetic_geometries(tmp_path):
     """deterministic lattices, atom order O,H,H, 3.0 A spacing."""
     atoms, xyz, _ = parse.parse_zmat(molecules.zmat("h2o_16"))
